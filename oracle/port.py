@@ -1,0 +1,560 @@
+"""CPU oracle for the batched differentiable iLQR / MPC hot path.
+
+TEST INFRASTRUCTURE ONLY.  This file is a from-scratch restatement (torch CPU
+tensor arithmetic, batch-vectorised exactly like the reference so the
+batch-global control flow is reproduced) of the algorithm implemented by the
+reference repo josef-w/Differentiable-iLQR.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl
+reference`` legs may import it; the product (``differentiable-ilqr_b200``)
+never does and has no CPU fallback.
+
+Parity status: PINNED.  ``tests/test_oracle_vs_reference.py`` runs this port
+side by side with the real reference (imported through
+``oracle/ref_harness.py`` when ``/root/reference`` exists) and against the
+golden vectors in ``tests/golden`` (generated from the reference by
+``tests/golden/make_golden.py``; the two ``data/*.pkl`` expert-trajectory
+fixtures of the reference are included there).
+
+Every function cites the reference file:line it restates (paths relative to
+the reference root).
+"""
+from collections import namedtuple
+import math
+
+import torch
+
+QuadCost = namedtuple("QuadCost", "C c")      # definitions.py:3
+LinDx = namedtuple("LinDx", "F f")            # definitions.py:4
+
+
+# --------------------------------------------------------------------------
+# tiny batched helpers (util.py:42-72)
+# --------------------------------------------------------------------------
+def _mv(M, v):                       # util.py:46  bmv
+    return torch.bmm(M, v.unsqueeze(2)).squeeze(2)
+
+
+def _outer(a, b):                    # util.py:42  bger
+    return a.unsqueeze(2) * b.unsqueeze(1)
+
+
+def _quad(x, Q):                     # util.py:50  bquad
+    return torch.bmm(torch.bmm(x.unsqueeze(1), Q), x.unsqueeze(2)).reshape(-1)
+
+
+def _dot(a, b):                      # util.py:54  bdot
+    return torch.bmm(a.unsqueeze(1), b.unsqueeze(2)).reshape(-1)
+
+
+def _clamp(x, lo, hi):               # util.py:58-72 eclamp (out of place here)
+    x = x.clone()
+    lo_t = lo if torch.is_tensor(lo) else torch.full_like(x, float(lo))
+    hi_t = hi if torch.is_tensor(hi) else torch.full_like(x, float(hi))
+    m = x < lo_t
+    x[m] = lo_t[m]
+    m = x > hi_t
+    x[m] = hi_t[m]
+    return x
+
+
+def _bound(v, t):                    # lqr_step.py:264-272 get_bound
+    return v if isinstance(v, float) else v[t]
+
+
+# --------------------------------------------------------------------------
+# projected-Newton box QP  (pnqp.py:5-82)
+# --------------------------------------------------------------------------
+PnqpOut = namedtuple("PnqpOut", "x Hfree If n_iter converged")
+
+
+def pnqp(H, q, lower, upper, x_init=None, n_iter=20):
+    """min 1/2 x'Hx + q'x  s.t. lower <= x <= upper, batched, with the
+    reference's *batch-global* termination and Armijo logic (pnqp.py:56-76).
+    Returns the masked Hessian ``H_`` (not its LU) as ``Hfree``."""
+    GAMMA = 0.1
+    B, n, _ = H.shape
+    eye = 1e-11 * torch.eye(n, dtype=H.dtype).expand(B, n, n)
+
+    def obj(x):                                        # pnqp.py:11-12
+        return 0.5 * _quad(x, H) + _dot(q, x)
+
+    if x_init is None:                                 # pnqp.py:14-19
+        if n == 1:
+            x0 = -(1.0 / H.squeeze(2)) * q
+        else:
+            x0 = -torch.linalg.solve(H, q.unsqueeze(2)).squeeze(2)
+    else:
+        x0 = x_init.clone()
+    x = _clamp(x0, lower, upper)                       # pnqp.py:23
+    lo_t = lower if torch.is_tensor(lower) else torch.full_like(x, float(lower))
+    hi_t = upper if torch.is_tensor(upper) else torch.full_like(x, float(upper))
+
+    H_ = If = None
+    for i in range(n_iter):
+        g = _mv(H, x) + q                              # pnqp.py:29
+        Ic = (((x == lo_t) & (g > 0)) | ((x == hi_t) & (g < 0))).to(H.dtype)
+        If = 1 - Ic                                    # pnqp.py:32-33
+        Hff = _outer(If, If)
+        g_ = g * If                                    # pnqp.py:44-45
+        H_ = H * Hff + eye                             # pnqp.py:46-48
+        if n == 1:
+            dx = -(1.0 / H_.squeeze(2)) * g_           # pnqp.py:51
+        else:
+            dx = -torch.linalg.solve(H_, g_.unsqueeze(2)).squeeze(2)
+        J = torch.norm(dx, 2, 1) >= 1e-4               # pnqp.py:56
+        if int(J.sum()) == 0:                          # pnqp.py:57-59
+            return PnqpOut(x, H_, If, i, True)
+        alpha = torch.ones(B, dtype=H.dtype)
+        max_armijo = GAMMA
+        count = 0
+        while max_armijo <= GAMMA and count < 10:      # pnqp.py:65
+            maybe_x = _clamp(x + alpha.unsqueeze(1) * dx, lower, upper)
+            arm = torch.full((B,), GAMMA + 1e-6, dtype=H.dtype)
+            ratio = (obj(x) - obj(maybe_x)) / _dot(g, x - maybe_x)
+            arm[J] = ratio[J]                          # pnqp.py:71-72
+            alpha[arm <= GAMMA] *= 0.1                 # pnqp.py:73-74
+            max_armijo = torch.max(arm).item()
+            count += 1
+        x = maybe_x                                    # pnqp.py:78
+    return PnqpOut(x, H_, If, n_iter - 1, False)       # pnqp.py:81-82
+
+
+# --------------------------------------------------------------------------
+# Riccati backward recursion  (lqr_step.py:52-160, lqr_step_backup.py:163-259)
+# --------------------------------------------------------------------------
+def lqr_backward(C, c, F, f, u, n_state, n_ctrl, u_lower=None, u_upper=None,
+                 u_zero_I=None, gain_solve="pinv"):
+    """Returns (Ks, ks, n_total_qp_iter); Ks/ks are lists in *reverse* time
+    order exactly as the reference builds them (Ks[0] belongs to t=T-1).
+    ``gain_solve``: "pinv" (lqr_step.py:88-94) or "chol_reg"
+    (lqr_step_backup.py:202-205, Cholesky of Quu + 1e-6 I)."""
+    T = C.shape[0]
+    ns = n_state
+    Ks, ks = [], []
+    prev_k = None
+    n_qp = 0
+    V = v = None
+    for t in range(T - 1, -1, -1):
+        if t == T - 1:
+            Q, qv = C[t], c[t]
+        else:
+            Ft = F[t]
+            FtT = Ft.transpose(1, 2)
+            Q = C[t] + FtT.bmm(V).bmm(Ft)              # lqr_step.py:68
+            if f is None or f.nelement() == 0:
+                qv = c[t] + _mv(FtT, v)                # lqr_step.py:70
+            else:
+                qv = c[t] + _mv(FtT.bmm(V), f[t]) + _mv(FtT, v)
+        Qxx, Qxu = Q[:, :ns, :ns], Q[:, :ns, ns:]
+        Qux, Quu = Q[:, ns:, :ns], Q[:, ns:, ns:]
+        qx, qu = qv[:, :ns], qv[:, ns:]
+
+        if u_lower is None:
+            if n_ctrl == 1 and u_zero_I is None:       # lqr_step.py:84-86
+                K = -(1.0 / Quu) * Qux
+                k = -(1.0 / Quu.squeeze(2)) * qu
+            elif u_zero_I is None:
+                if gain_solve == "pinv":               # lqr_step.py:88-94
+                    inv = torch.stack([torch.pinverse(Quu[i])
+                                       for i in range(Quu.shape[0])])
+                    K = -inv.bmm(Qux)
+                    k = _mv(-inv, qu)
+                else:                                  # lqr_step_backup.py:202-205
+                    L = torch.linalg.cholesky(
+                        Quu + 1e-6 * torch.eye(n_ctrl, dtype=Quu.dtype))
+                    K = -torch.cholesky_solve(Qux, L)
+                    k = -torch.cholesky_solve(qu.unsqueeze(2), L).squeeze(2)
+            else:                                      # lqr_step.py:99-127
+                I = u_zero_I[t].to(Quu.dtype)
+                notI = 1 - I
+                qu_ = qu * notI
+                Quu_ = Quu * _outer(notI, notI)
+                Quu_ = Quu_ + torch.diag_embed(I) * 1e-8
+                Qux_ = Qux * notI.unsqueeze(2)
+                if n_ctrl == 1:
+                    K = -(1.0 / Quu_) * Qux_
+                    k = -(1.0 / Quu.squeeze(2)) * qu_  # unmasked Quu (lqr_step.py:123)
+                else:
+                    K = -torch.linalg.solve(Quu_, Qux_)
+                    k = -torch.linalg.solve(Quu_, qu_.unsqueeze(2)).squeeze(2)
+        else:                                          # lqr_step.py:128-148
+            lb = _bound(u_lower, t) - u[t]
+            ub = _bound(u_upper, t) - u[t]
+            out = pnqp(Quu, qu, lb, ub, x_init=prev_k, n_iter=20)
+            k = out.x
+            n_qp += 1 + out.n_iter
+            prev_k = k
+            Qux_ = Qux * out.If.unsqueeze(2)
+            if n_ctrl == 1:
+                K = -((1.0 / out.Hfree) * Qux_)
+            else:
+                K = -torch.linalg.solve(out.Hfree, Qux_)
+        KT = K.transpose(1, 2)
+        Ks.append(K)
+        ks.append(k)
+        V = Qxx + Qxu.bmm(K) + KT.bmm(Qux) + KT.bmm(Quu).bmm(K)   # lqr_step.py:155
+        v = qx + _mv(Qxu, k) + _mv(KT, qu) + _mv(KT.bmm(Quu), k)  # lqr_step.py:156-158
+    return Ks, ks, n_qp
+
+
+# --------------------------------------------------------------------------
+# rollout, cost, line search  (util.py:104-153, lqr_step.py:164-261)
+# --------------------------------------------------------------------------
+def step_dynamics(dynamics, t, x, u):
+    if isinstance(dynamics, LinDx):                    # util.py:117-121
+        nx = _mv(dynamics.F[t], torch.cat((x, u), 1))
+        if dynamics.f is not None and dynamics.f.nelement() > 0:
+            nx = nx + dynamics.f[t]
+        return nx
+    return dynamics(x, u)
+
+
+def get_traj(T, u, x_init, dynamics):                  # util.py:104-127
+    x = [x_init]
+    for t in range(T - 1):
+        x.append(step_dynamics(dynamics, t, x[t], u[t]))
+    return torch.stack(x, 0)
+
+
+def get_cost(T, u, cost, x):                           # util.py:130-153
+    objs = []
+    for t in range(T):
+        xut = torch.cat((x[t], u[t]), 1)
+        objs.append(0.5 * _quad(xut, cost.C[t]) + _dot(xut, cost.c[t]))
+    return torch.sum(torch.stack(objs, 0), dim=0)
+
+
+LqrFwdOut = namedtuple("LqrFwdOut", "x u costs full_du_norm mean_alphas alphas n_ls")
+
+
+def lqr_forward(x_init, cost, dynamics, Ks, ks, x, u, n_state, n_ctrl,
+                u_lower=None, u_upper=None, u_zero_I=None,
+                linesearch_decay=0.2, max_linesearch_iter=10):
+    """lqr_step.py:164-261.  Line search over the *true* dynamics."""
+    T, B = u.shape[0], u.shape[1]
+    old_cost = get_cost(T, u, cost, x)                 # lqr_step.py:169
+    alphas = torch.ones(B, dtype=u.dtype)
+    cur = None
+    full_du = None
+    i = 0
+    while (cur is None or bool(torch.any(cur > old_cost))) and \
+            i < max_linesearch_iter:
+        new_u, new_x = [], [x_init]
+        dx = torch.zeros_like(x_init)
+        objs = []
+        for t in range(T):
+            K, k = Ks[T - 1 - t], ks[T - 1 - t]
+            nxt = new_x[t]
+            nu = _mv(K, dx) + u[t] + alphas.unsqueeze(1) * k   # lqr_step.py:192
+            if u_zero_I is not None:
+                nu = nu.clone()
+                nu[u_zero_I[t]] = 0.0                  # lqr_step.py:197-198
+            if u_lower is not None:
+                nu = _clamp(nu, _bound(u_lower, t), _bound(u_upper, t))
+            new_u.append(nu)
+            xut = torch.cat((nxt, nu), 1)
+            if t < T - 1:
+                nx1 = step_dynamics(dynamics, t, nxt, nu)
+                new_x.append(nx1)
+                dx = nx1 - x[t + 1]                    # lqr_step.py:228
+            objs.append(0.5 * _quad(xut, cost.C[t]) + _dot(xut, cost.c[t]))
+        cur = torch.sum(torch.stack(objs), dim=0)
+        new_u = torch.stack(new_u)
+        new_x = torch.stack(new_x)
+        if full_du is None:                            # lqr_step.py:243-245
+            full_du = (u - new_u).transpose(1, 2).reshape(B, -1).norm(2, 1)
+        alphas[cur > old_cost] *= linesearch_decay     # lqr_step.py:247
+        i += 1
+    alphas[cur > old_cost] /= linesearch_decay         # lqr_step.py:252
+    return LqrFwdOut(new_x, new_u, cur, full_du, alphas.mean(), alphas, i)
+
+
+def c_back(C, c, x, u):                                # lqr_step.py:289-295
+    tau = torch.cat((x, u), 2)
+    return torch.einsum("tbij,tbj->tbi", C, tau) + c
+
+
+LqrStepOut = namedtuple(
+    "LqrStepOut", "x u n_total_qp_iter costs full_du_norm mean_alphas Ks ks alphas")
+
+
+def lqr_step(x_init, C, c, F, x, u, cost, dynamics, n_state, n_ctrl,
+             u_lower=None, u_upper=None, u_zero_I=None, linesearch_decay=0.2,
+             max_linesearch_iter=10, gain_solve="pinv"):
+    """LQRStepFn.forward, lqr_step.py:277-309 (delta-space Taylor expansion,
+    f_back=None)."""
+    T = C.shape[0]
+    cb = torch.stack([_mv(C[t], torch.cat((x[t], u[t]), 1)) + c[t]
+                      for t in range(T)])
+    Ks, ks, nqp = lqr_backward(C, cb, F, None, u, n_state, n_ctrl, u_lower,
+                               u_upper, u_zero_I, gain_solve)
+    o = lqr_forward(x_init, cost, dynamics, Ks, ks, x, u, n_state, n_ctrl,
+                    u_lower, u_upper, u_zero_I, linesearch_decay,
+                    max_linesearch_iter)
+    return LqrStepOut(o.x, o.u, nqp, o.costs, o.full_du_norm, o.mean_alphas,
+                      Ks, ks, o.alphas)
+
+
+# --------------------------------------------------------------------------
+# env_dx dynamics: forward + analytic first-order Jacobian
+# --------------------------------------------------------------------------
+class PendulumDx:
+    """env_dx/pendulum.py:28-95 (simple=True) and get_linear_dyn 444-475."""
+    n_state, n_ctrl = 3, 1
+    dt = 0.05
+    max_torque = 2.0
+    lower, upper = -2.0, 2.0
+    mpc_eps, linesearch_decay, max_linesearch_iter = 1e-3, 0.2, 5
+
+    def __init__(self, params=None, dtype=torch.float32):
+        self.params = (torch.tensor((10., 1., 1.), dtype=dtype)
+                       if params is None else params)
+
+    def get_true_obj(self):                            # pendulum.py:117-125
+        dt = self.params.dtype
+        gw = torch.tensor([1., 1., 0.1], dtype=dt)
+        gs = torch.tensor([1., 0., 0.], dtype=dt)
+        q = torch.cat((gw, 0.001 * torch.ones(1, dtype=dt)))
+        p = torch.cat((-torch.sqrt(gw) * gs, torch.zeros(1, dtype=dt)))
+        return q, p
+
+    def __call__(self, x, u):                          # pendulum.py:60-95
+        g, m, l = torch.unbind(self.params.detach())
+        uc = torch.clamp(u, -self.max_torque, self.max_torque)[:, 0]
+        c, s, w = torch.unbind(x, dim=1)
+        th = torch.atan2(s, c)
+        nw = w + self.dt * (-3. * g / (2. * l) * (-s) + 3. * uc / (m * l ** 2))
+        nth = th + nw * self.dt
+        return torch.stack((torch.cos(nth), torch.sin(nth), nw), dim=1)
+
+    def get_linear_dyn(self, x, u):                    # pendulum.py:444-475
+        g, m, l = torch.unbind(self.params.detach())
+        dt = self.dt
+        c, s, w = x[:, 0], x[:, 1], x[:, 2]
+        uu = u[:, 0]
+        phi = dt * (dt * (3 * g * s / (2 * l) + 3 * uu / (l ** 2 * m)) + w) \
+            + torch.atan2(s, c)
+        sp, cp = torch.sin(phi), torch.cos(phi)
+        r2 = c ** 2 + s ** 2
+        a = 3 * dt ** 2 * g / (2 * l)
+        b = 3 * dt ** 2 / (l ** 2 * m)
+        z, o = torch.zeros_like(c), torch.ones_like(c)
+        rows = [
+            [s * sp / r2, -(c / r2 + a) * sp, -dt * sp, -b * sp],
+            [-s * cp / r2, (c / r2 + a) * cp, dt * cp, b * cp],
+            [z, o * (3 * dt * g / (2 * l)), o, o * (3 * dt / (l ** 2 * m))],
+        ]
+        return torch.stack([torch.stack(r, 1) for r in rows], 1)
+
+
+class CartpoleDx:
+    """env_dx/cartpole.py:29-97 and get_linear_dyn 790-839."""
+    n_state, n_ctrl = 5, 1
+    dt = 0.05
+    force_mag = 100.0
+    lower, upper = -100.0, 100.0
+    mpc_eps, linesearch_decay, max_linesearch_iter = 1e-4, 0.5, 2
+
+    def __init__(self, params=None, dtype=torch.float32):
+        self.params = (torch.tensor((9.8, 1.0, 0.1, 0.5), dtype=dtype)
+                       if params is None else params)
+
+    def get_true_obj(self):                            # cartpole.py:859-867
+        dt = self.params.dtype
+        gw = torch.tensor([0.1, 0.1, 1., 1., 0.1], dtype=dt)
+        gs = torch.tensor([0., 0., 1., 0., 0.], dtype=dt)
+        q = torch.cat((gw, 0.001 * torch.ones(1, dtype=dt)))
+        p = torch.cat((-torch.sqrt(gw) * gs, torch.zeros(1, dtype=dt)))
+        return q, p
+
+    def __call__(self, state, u):                      # cartpole.py:64-97
+        g, mc, mp, l = torch.unbind(self.params.detach())
+        M = mp + mc
+        pml = mp * l
+        uc = torch.clamp(u[:, 0], -self.force_mag, self.force_mag)
+        x, dx, c, s, w = torch.unbind(state, dim=1)
+        th = torch.atan2(s, c)
+        cart_in = (uc + pml * w ** 2 * s) / M
+        th_acc = (g * s - c * cart_in) / (l * (4. / 3. - mp * c ** 2 / M))
+        xacc = cart_in - pml * th_acc * c / M
+        nx = x + self.dt * dx
+        ndx = dx + self.dt * xacc
+        nth = th + self.dt * w
+        nw = w + self.dt * th_acc
+        return torch.stack((nx, ndx, torch.cos(nth), torch.sin(nth), nw), 1)
+
+    def get_linear_dyn(self, x, u):                    # cartpole.py:790-839
+        """Closed-form Jacobian of the Euler step wrt (x, dx, cos, sin, dth, u),
+        ignoring the input clamp (the reference does the same)."""
+        g, mc, mp, l = torch.unbind(self.params.detach())
+        dt = self.dt
+        M = mc + mp
+        c, s, w = x[:, 2], x[:, 3], x[:, 4]
+        uu = u[:, 0]
+        z, o = torch.zeros_like(c), torch.ones_like(c)
+        A = w ** 2 * l * mp * s + uu                   # cart force numerator
+        G = -c * A / M + g * s                         # th_acc numerator
+        den = -c ** 2 * mp / M + 4. / 3.               # 4/3 - mp c^2 / M
+        den2 = (-3 * c ** 2 * mp / (4 * M) + 1) ** 2   # (3/4 den)^2
+        phi = dt * w + torch.atan2(s, c)
+        sp, cp = torch.sin(phi), torch.cos(phi)
+        r2 = c ** 2 + s ** 2
+        # d(xacc)/d(c,s,w,u)
+        xa_c = (-9 * c ** 2 * mp ** 2 * G / (8 * M ** 2 * den2)
+                + c * mp * A / (M ** 2 * den) - mp * G / (M * den))
+        xa_s = -c * mp * (-c * w ** 2 * l * mp / M + g) / (M * den) \
+            + w ** 2 * l * mp / M
+        xa_w = 2 * c ** 2 * w * l * mp ** 2 * s / (M ** 2 * den) \
+            + 2 * w * l * mp * s / M
+        xa_u = c ** 2 * mp / (M ** 2 * den) + 1 / M
+        # dt * d(th_acc)/d(c,s,w,u)
+        ta_c = 9 * c * dt * mp * G / (8 * l * M * den2) - dt * A / (l * M * den)
+        ta_s = dt * (-c * w ** 2 * l * mp / M + g) / (l * den)
+        ta_w = -2 * c * dt * w * mp * s / (M * den) + 1
+        ta_u = -c * dt / (l * M * den)
+        rows = [
+            [o, o * dt, z, z, z, z],
+            [z, o, dt * xa_c, dt * xa_s, dt * xa_w, dt * xa_u],
+            [z, z, s * sp / r2, -c * sp / r2, -dt * sp, z],
+            [z, z, -s * cp / r2, c * cp / r2, dt * cp, z],
+            [z, z, ta_c, ta_s, ta_w, ta_u],
+        ]
+        return torch.stack([torch.stack(r, 1) for r in rows], 1)
+
+
+def linearize_dynamics(x, u, dynamics):
+    """mpc_explicit.py:516-546 (ANALYTIC): F_t = D(x_t,u_t), f_t = f(x_t,u_t)
+    - D tau_t for t < T-1."""
+    T, B, ns = x.shape
+    nc = u.shape[2]
+    _x = x[:-1].reshape(-1, ns)
+    _u = u[:-1].reshape(-1, nc)
+    new_x = dynamics(_x, _u)
+    D = dynamics.get_linear_dyn(_x, _u)
+    d = new_x - torch.einsum("bnm,bm->bn", D, torch.cat((_x, _u), -1))
+    return D.reshape(T - 1, B, ns, ns + nc), d.reshape(T - 1, B, ns)
+
+
+# --------------------------------------------------------------------------
+# iLQR outer loop  (mpc.py:184-337 / mpc_explicit.py:182-358)
+# --------------------------------------------------------------------------
+MpcOut = namedtuple(
+    "MpcOut", "x u costs full_du_norm n_iters F f Ks qp_iters converged log")
+
+
+def mpc_forward(x_init, cost, dynamics, n_state, n_ctrl, T, u_lower=None,
+                u_upper=None, u_zero_I=None, u_init=None, lqr_iter=10,
+                eps=1e-7, linesearch_decay=0.2, max_linesearch_iter=10,
+                not_improved_lim=5, best_cost_eps=1e-4, gain_solve="pinv",
+                final_pass=True):
+    """MPC.forward (mpc.py:184-337).  ``cost`` is a QuadCost with dense
+    C[T,B,n,n], c[T,B,n]; ``dynamics`` a LinDx or an env object with
+    __call__/get_linear_dyn.  Returns best iterate, costs, and (for the
+    backward passes) the final linearisation F, f and the gains of the final
+    no-op LQR step (lqr_step_explicit.py:604-623)."""
+    B = x_init.shape[0]
+    dtype = x_init.dtype
+    if u_init is None:
+        u = torch.zeros(T, B, n_ctrl, dtype=dtype)     # mpc.py:230-231
+    else:
+        u = u_init.clone()
+        if u.ndimension() == 2:
+            u = u.unsqueeze(1).expand(T, B, -1).clone()
+    best = None
+    n_not_improved = 0
+    log = []
+    it = 0
+    for it in range(lqr_iter):                         # mpc.py:248
+        x = get_traj(T, u, x_init, dynamics)           # mpc.py:251
+        if isinstance(dynamics, LinDx):
+            F = dynamics.F
+        else:
+            F, _ = linearize_dynamics(x, u, dynamics)
+        o = lqr_step(x_init, cost.C, cost.c, F, x, u, cost, dynamics, n_state,
+                     n_ctrl, u_lower, u_upper, u_zero_I, linesearch_decay,
+                     max_linesearch_iter, gain_solve)
+        x, u = o.x, o.u
+        n_not_improved += 1                            # mpc.py:266
+        if best is None:                               # mpc.py:271-277
+            best = {"x": x.clone(), "u": u.clone(), "costs": o.costs.clone(),
+                    "du": o.full_du_norm.clone()}
+        else:                                          # mpc.py:278-285
+            imp = o.costs <= best["costs"] + best_cost_eps
+            if bool(imp.any()):
+                n_not_improved = 0
+            best["x"][:, imp] = x[:, imp]
+            best["u"][:, imp] = u[:, imp]
+            best["costs"][imp] = o.costs[imp]
+            best["du"][imp] = o.full_du_norm[imp]
+        log.append((o.n_total_qp_iter, float(o.full_du_norm.max()),
+                    float(o.mean_alphas), float(best["costs"].mean())))
+        if float(o.full_du_norm.max()) < eps or \
+                n_not_improved > not_improved_lim:     # mpc.py:299-301
+            break
+    x, u = best["x"], best["u"]
+    F = f = Ks = None
+    if final_pass:
+        if isinstance(dynamics, LinDx):
+            F, f = dynamics.F, dynamics.f
+        else:
+            F, f = linearize_dynamics(x, u, dynamics)  # mpc.py:310 (diff=True)
+        cb = c_back(cost.C, cost.c, x, u)
+        Ks, _, _ = lqr_backward(cost.C, cb, F, None, u, n_state, n_ctrl,
+                                u_lower, u_upper, u_zero_I, gain_solve)
+        Ks = torch.stack(Ks, 0)     # reverse time order, lqr_step_explicit.py:617-618
+    conv = bool(best["du"].max() <= eps)
+    return MpcOut(x, u, best["costs"], best["du"], it + 1, F, f, Ks,
+                  [l[0] for l in log], conv, log)
+
+
+# --------------------------------------------------------------------------
+# KKT / adjoint-LQR backward  (lqr_step.py:312-407)
+# --------------------------------------------------------------------------
+KktOut = namedtuple("KktOut", "dx_init dC dc dF df dx du")
+
+
+def kkt_backward(dl_dx, dl_du, x_init, C, c, F, f, x, u, n_state, n_ctrl,
+                 u_lower=None, u_upper=None, gain_solve="pinv",
+                 want_df=True):
+    """Gradients of a loss wrt (x_init, C, c, F, f) given dl/dx*, dl/du* at an
+    LQR solution (x*, u*) = argmin of the box-constrained LQR (C,c,F,f).
+    Restates LQRStepFn.backward, lqr_step.py:312-407: one adjoint LQR solve
+    (``MPC(lqr_iter=1, u_zero_I=active set)`` on cost (C,-r), dynamics
+    LinDx(F,None), x_init=0) followed by the two costate recursions."""
+    T, B = x.shape[0], x.shape[1]
+    ns = n_state
+    r = torch.cat((dl_dx, dl_du), 2)                   # lqr_step.py:316-320
+    if u_lower is None:
+        I = None
+    else:                                              # lqr_step.py:325-326
+        I = (torch.abs(u - u_lower) <= 1e-8) | (torch.abs(u - u_upper) <= 1e-8)
+    zero = torch.zeros_like(x_init)
+    o = mpc_forward(zero, QuadCost(C, -r), LinDx(F, None), n_state, n_ctrl, T,
+                    u_zero_I=I, lqr_iter=1, gain_solve=gain_solve,
+                    final_pass=False)                  # lqr_step.py:328-340
+    dx, du = o.x, o.u
+    dxu = torch.cat((dx, du), 2)
+    xu = torch.cat((x, u), 2)
+    dC = -0.5 * (torch.einsum("tbi,tbj->tbij", dxu, xu)
+                 + torch.einsum("tbi,tbj->tbij", xu, dxu))   # lqr_step.py:346-351
+    dc = -dxu                                          # lqr_step.py:353
+    lams = [None] * T
+    dlams = [None] * T
+    prev = dprev = None
+    for t in range(T - 1, -1, -1):                     # lqr_step.py:355-385
+        Cxx, Cxu = C[t, :, :ns, :ns], C[t, :, :ns, ns:]
+        lam = _mv(Cxx, x[t]) + _mv(Cxu, u[t]) + c[t, :, :ns]
+        dlam = _mv(Cxx, dx[t]) + _mv(Cxu, du[t]) - r[t, :, :ns]
+        if prev is not None:
+            FxT = F[t, :, :, :ns].transpose(1, 2)
+            lam = lam + _mv(FxT, prev)
+            dlam = dlam + _mv(FxT, dprev)
+        lams[t], dlams[t] = lam, dlam
+        prev, dprev = lam, dlam
+    dF = torch.zeros_like(F)
+    for t in range(T - 1):                             # lqr_step.py:387-395
+        dF[t] = -(_outer(dlams[t + 1], xu[t]) + _outer(lams[t + 1], dxu[t]))
+    dlams = torch.stack(dlams)
+    df = -dlams[1:] if want_df else None               # lqr_step.py:397-402
+    dx_init = -dlams[0]                                # lqr_step.py:404
+    return KktOut(dx_init, dC, dc, dF, df, dx, du)
