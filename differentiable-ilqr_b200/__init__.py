@@ -1,0 +1,16 @@
+"""differentiable-ilqr_b200 -- B200-native (sm_100a) batched differentiable
+iLQR / MPC solver; drop-in for the hot path of josef-w/Differentiable-iLQR.
+
+The directory name is not a valid Python identifier; import it with
+``importlib.import_module("differentiable-ilqr_b200")`` or through the
+``dilqr_b200`` alias module at the repo root.
+"""
+from . import _lib
+from .definitions import QuadCost, LinDx
+from .mpc import MPC, GradMethods
+
+__all__ = ["MPC", "GradMethods", "QuadCost", "LinDx", "build"]
+
+
+def build(verbose=False):
+    return _lib.build(verbose=verbose)

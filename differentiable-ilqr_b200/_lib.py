@@ -1,0 +1,133 @@
+"""ctypes binding of libdilqr.so (the C ABI in include/dilqr.h).
+
+There is no CPU fallback: every op of this package goes through this library;
+if it is missing the import of the op fails loudly (``DilqrLibraryError``).
+"""
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdilqr.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+F32, F64 = 0, 1
+DYN_LINDX, DYN_PENDULUM, DYN_CARTPOLE, DYN_ROCKET = 0, 1, 2, 3
+GAIN_PLAIN, GAIN_CHOL_REG = 0, 1
+BOUNDS_NONE, BOUNDS_SCALAR, BOUNDS_TENSOR = 0, 1, 2
+PNQP_MAX_ITER = 20
+
+ERRORS = {0: "ok", -1: "invalid argument", -2: "unsupported (dtype, n_state, n_ctrl, dynamics)",
+          -3: "pointer not 16-byte aligned", -4: "workspace too small",
+          -5: "CUDA launch failure"}
+
+
+class DilqrLibraryError(RuntimeError):
+    pass
+
+
+class DilqrStatus(C.Structure):
+    _fields_ = [
+        ("trace_match", C.c_uint32),
+        ("any_improved", C.c_uint32),
+        ("n_total_qp_iter", C.c_uint32),
+        ("pnqp_unconverged", C.c_uint32),
+        ("max_full_du", C.c_double),
+        ("mean_alpha", C.c_double),
+        ("mean_best_cost", C.c_double),
+        ("first_mismatch", C.c_uint32),
+        ("reserved", C.c_uint32 * 5),
+    ]
+
+
+class DilqrSolve(C.Structure):
+    _fields_ = [
+        ("n_state", C.c_int32), ("n_ctrl", C.c_int32), ("T", C.c_int32),
+        ("n_batch", C.c_int32),
+        ("dtype", C.c_int32), ("dynamics", C.c_int32), ("gain_solve", C.c_int32),
+        ("bounds_kind", C.c_int32), ("solo", C.c_int32),
+        ("max_linesearch_iter", C.c_int32), ("first_iteration", C.c_int32),
+        ("has_f", C.c_int32),
+        ("linesearch_decay", C.c_double),
+        ("u_lower", C.c_double), ("u_upper", C.c_double),
+        ("best_cost_eps", C.c_double),
+        ("dyn_params", C.c_double * 8),
+        ("x_init", C.c_void_p), ("C", C.c_void_p), ("c", C.c_void_p),
+        ("F", C.c_void_p), ("f", C.c_void_p), ("u_init", C.c_void_p),
+        ("x_cur", C.c_void_p), ("u_lower_t", C.c_void_p), ("u_upper_t", C.c_void_p),
+        ("u_zero_I", C.c_void_p),
+        ("x_out", C.c_void_p), ("u_out", C.c_void_p), ("cost_out", C.c_void_p),
+        ("du_out", C.c_void_p), ("alpha_out", C.c_void_p), ("K_out", C.c_void_p),
+        ("k_out", C.c_void_p),
+        ("status", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
+class DilqrKkt(C.Structure):
+    _fields_ = [
+        ("n_state", C.c_int32), ("n_ctrl", C.c_int32), ("T", C.c_int32),
+        ("n_batch", C.c_int32), ("dtype", C.c_int32), ("reserved", C.c_int32),
+        ("C", C.c_void_p), ("c", C.c_void_p), ("F", C.c_void_p),
+        ("x", C.c_void_p), ("u", C.c_void_p), ("dx", C.c_void_p), ("du", C.c_void_p),
+        ("r", C.c_void_p),
+        ("dC", C.c_void_p), ("dc", C.c_void_p), ("dF", C.c_void_p), ("df", C.c_void_p),
+        ("dx_init", C.c_void_p),
+    ]
+
+
+# every symbol include/dilqr.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "dilqr_version": (C.c_char_p, []),
+    "dilqr_supported": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "dilqr_workspace_bytes": (C.c_size_t, [C.POINTER(DilqrSolve)]),
+    "dilqr_mpc_begin": (C.c_int, [C.POINTER(DilqrSolve), C.c_void_p]),
+    "dilqr_mpc_iterate": (C.c_int, [C.POINTER(DilqrSolve), C.c_void_p]),
+    "dilqr_mpc_commit": (C.c_int, [C.POINTER(DilqrSolve), C.c_void_p]),
+    "dilqr_mpc_finish": (C.c_int, [C.POINTER(DilqrSolve), C.c_void_p]),
+    "dilqr_kkt_grads": (C.c_int, [C.POINTER(DilqrKkt), C.c_void_p]),
+    "dilqr_linearize": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dilqr_rollout": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+
+
+def build(verbose=False, extra=""):
+    """Compile libdilqr.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", CSRC, "-j", str(min(8, os.cpu_count() or 1))]
+    if extra:
+        cmd.append("EXTRA=" + extra)
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if verbose or r.returncode:
+        print(r.stdout)
+    if r.returncode:
+        raise DilqrLibraryError("building libdilqr.so failed")
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise DilqrLibraryError(
+            "libdilqr.so not found at %s -- run `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (there is no CPU fallback)" % LIB_PATH)
+    try:
+        L = C.CDLL(LIB_PATH)
+    except OSError as e:  # pragma: no cover
+        raise DilqrLibraryError("cannot load %s: %s" % (LIB_PATH, e))
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def check(code, what):
+    if code != 0:
+        raise DilqrLibraryError("%s failed: %s (%d)" % (what, ERRORS.get(code, "?"), code))

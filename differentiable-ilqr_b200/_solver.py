@@ -1,0 +1,274 @@
+"""Host driver of the fused iLQR kernels: owns the workspace, drives the
+iLQR outer loop of ``MPC.forward`` (reference mpc.py:184-337) over the C ABI,
+and assembles the KKT gradients (reference lqr_step.py:312-407).
+
+Nothing here computes on the CPU; torch is used for device memory, streams and
+autograd plumbing only.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+_DT = {torch.float32: _lib.F32, torch.float64: _lib.F64}
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class DynSpec:
+    """What the rollouts integrate: LinDx tensors or an env_dx model id + theta."""
+
+    def __init__(self, kind, params=None, F=None, f=None):
+        self.kind = kind
+        self.params = list(params) if params is not None else []
+        self.F = F
+        self.f = f
+
+
+class SolveInfo:
+    def __init__(self):
+        self.n_iters = 0
+        self.retries = 0
+        self.qp_iters = []
+        self.log = []
+        self.pnqp_unconverged = 0
+        self.converged = False
+        self.full_du_norm = None
+
+
+class Workspace:
+    """Device scratch + status block for one (shape, dtype) family; reused."""
+
+    def __init__(self, nbytes, device):
+        self.buf = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=device)
+        self.status_dev = torch.zeros(64, dtype=torch.uint8, device=device)
+        self.status_host = torch.zeros(64, dtype=torch.uint8).pin_memory()
+
+
+_ws_cache = {}
+
+
+def _require_cuda(t, name):
+    if not t.is_cuda:
+        raise _lib.DilqrLibraryError(
+            "%s must be a CUDA tensor: this package has no CPU path" % name)
+
+
+def _contig(t):
+    return t if t is None or t.is_contiguous() else t.contiguous()
+
+
+def _make_problem(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower, u_upper, u_zero_I,
+                  linesearch_decay, max_linesearch_iter, best_cost_eps, gain_solve,
+                  solo):
+    L = _lib.lib()
+    _require_cuda(x_init, "x_init")
+    dtype = x_init.dtype
+    if dtype not in _DT:
+        raise _lib.DilqrLibraryError("dtype %s unsupported (float32/float64 only)" % dtype)
+    B = x_init.shape[0]
+    s = _lib.DilqrSolve()
+    s.n_state, s.n_ctrl, s.T, s.n_batch = n_state, n_ctrl, T, B
+    s.dtype = _DT[dtype]
+    s.dynamics = dyn.kind
+    s.gain_solve = gain_solve
+    s.solo = 1 if solo else 0
+    s.max_linesearch_iter = max_linesearch_iter
+    s.linesearch_decay = float(linesearch_decay)
+    s.best_cost_eps = float(best_cost_eps)
+    for i, v in enumerate(dyn.params):
+        s.dyn_params[i] = float(v)
+    keep = []  # keep tensors alive while kernels run
+
+    def dev(t, name, dt=dtype):
+        if t is None:
+            return None
+        _require_cuda(t, name)
+        t = _contig(t.detach().to(dt))
+        keep.append(t)
+        return t
+
+    xi = dev(x_init, "x_init")
+    Cd, cd = dev(C_, "C"), dev(c_, "c")
+    s.x_init, s.C, s.c = _ptr(xi), _ptr(Cd), _ptr(cd)
+    if dyn.kind == _lib.DYN_LINDX:
+        Fd = dev(dyn.F, "F")
+        fd = dev(dyn.f, "f") if (dyn.f is not None and dyn.f.nelement() > 0) else None
+        s.F, s.f = _ptr(Fd), _ptr(fd)
+        s.has_f = 1 if fd is not None else 0
+    if u_lower is None:
+        s.bounds_kind = _lib.BOUNDS_NONE
+    elif isinstance(u_lower, float) and isinstance(u_upper, float):
+        s.bounds_kind = _lib.BOUNDS_SCALAR
+        s.u_lower, s.u_upper = u_lower, u_upper
+    else:
+        s.bounds_kind = _lib.BOUNDS_TENSOR
+        lo = u_lower if torch.is_tensor(u_lower) else torch.full(
+            (T, B, n_ctrl), float(u_lower), dtype=dtype, device=x_init.device)
+        hi = u_upper if torch.is_tensor(u_upper) else torch.full(
+            (T, B, n_ctrl), float(u_upper), dtype=dtype, device=x_init.device)
+        lo = dev(lo.expand(T, B, n_ctrl), "u_lower")
+        hi = dev(hi.expand(T, B, n_ctrl), "u_upper")
+        s.u_lower_t, s.u_upper_t = _ptr(lo), _ptr(hi)
+    if u_zero_I is not None:
+        zi = dev(u_zero_I.expand(T, B, n_ctrl), "u_zero_I", torch.uint8)
+        s.u_zero_I = _ptr(zi)
+    if not L.dilqr_supported(s.dtype, n_state, n_ctrl, dyn.kind):
+        raise _lib.DilqrLibraryError(
+            "no kernel compiled for dtype=%s n_state=%d n_ctrl=%d dynamics=%d "
+            "(add it to DILQR_CONFIGS in csrc/api.cu)" % (dtype, n_state, n_ctrl, dyn.kind))
+    need = L.dilqr_workspace_bytes(C.byref(s))
+    key = (x_init.device.index, need)
+    ws = _ws_cache.get(key)
+    if ws is None:
+        _ws_cache.clear()  # one live workspace per device is enough
+        ws = Workspace(need, x_init.device)
+        _ws_cache[key] = ws
+    s.workspace = _ptr(ws.buf)
+    s.workspace_bytes = ws.buf.numel()
+    s.status = _ptr(ws.status_dev)
+    return L, s, ws, keep
+
+
+def _read_status(ws):
+    ws.status_host.copy_(ws.status_dev, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return _lib.DilqrStatus.from_buffer_copy(ws.status_host.numpy().tobytes())
+
+
+MAX_TRACE_RETRIES = 64
+
+
+def _iterate_committed(L, s, ws, info):
+    """One iLQR iteration including the trace-verification retry loop."""
+    st = _stream()
+    for _ in range(MAX_TRACE_RETRIES):
+        _lib.check(L.dilqr_mpc_iterate(C.byref(s), st), "dilqr_mpc_iterate")
+        _lib.check(L.dilqr_mpc_commit(C.byref(s), st), "dilqr_mpc_commit")
+        status = _read_status(ws)
+        if status.trace_match:
+            return status
+        info.retries += 1
+    raise _lib.DilqrLibraryError("pnqp control-flow trace did not stabilise")
+
+
+def solve_mpc(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower=None, u_upper=None,
+              u_zero_I=None, u_init=None, lqr_iter=10, eps=1e-7, linesearch_decay=0.2,
+              max_linesearch_iter=10, not_improved_lim=5, best_cost_eps=1e-4,
+              gain_solve=_lib.GAIN_PLAIN, solo=False, verbose=0, x_cur=None,
+              want_gains=False):
+    """MPC.forward (mpc.py:184-306): returns (x, u, costs, info).  With ``x_cur``
+    given this is a single LQRStep around (x_cur, u_init) (lqr_step.py:277-309)
+    and returns the *new* iterate."""
+    L, s, ws, keep = _make_problem(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower,
+                                   u_upper, u_zero_I, linesearch_decay,
+                                   max_linesearch_iter, best_cost_eps, gain_solve, solo)
+    dtype, dev = x_init.dtype, x_init.device
+    B = x_init.shape[0]
+    if u_init is not None:
+        u0 = u_init.detach()
+        if u0.ndimension() == 2:
+            u0 = u0.unsqueeze(1).expand(T, B, -1)
+        u0 = u0.to(dtype).contiguous()
+        keep.append(u0)
+        s.u_init = _ptr(u0)
+    if x_cur is not None:
+        xc = x_cur.detach().to(dtype).contiguous()
+        keep.append(xc)
+        s.x_cur = _ptr(xc)
+    st = _stream()
+    info = SolveInfo()
+    _lib.check(L.dilqr_mpc_begin(C.byref(s), st), "dilqr_mpc_begin")
+    # python float eps is compared in the data dtype by torch (mpc.py:299)
+    eps_cmp = float(torch.tensor(eps, dtype=dtype))
+    n_not_improved = 0
+    n_loops = 1 if x_cur is not None else lqr_iter
+    for i in range(n_loops):
+        s.first_iteration = 1 if i == 0 else 0
+        status = _iterate_committed(L, s, ws, info)
+        info.n_iters = i + 1
+        info.qp_iters.append(status.n_total_qp_iter)
+        info.pnqp_unconverged += status.pnqp_unconverged
+        info.log.append((status.n_total_qp_iter, status.max_full_du, status.mean_alpha,
+                         status.mean_best_cost))
+        if status.pnqp_unconverged and verbose >= 0:
+            for _ in range(status.pnqp_unconverged):
+                print("[WARNING] pnqp warning: Did not converge")   # pnqp.py:81
+        n_not_improved += 1                                          # mpc.py:266
+        if i > 0 and status.any_improved:
+            n_not_improved = 0                                       # mpc.py:281
+        if verbose > 0:
+            print("| %d | %.4e | %.2e | %.2e | %d |" % (
+                i, status.mean_best_cost, status.max_full_du, status.mean_alpha,
+                status.n_total_qp_iter))
+        info.max_full_du = status.max_full_du
+        info.mean_alpha = status.mean_alpha
+        info.mean_best_cost = status.mean_best_cost
+        if status.max_full_du < eps_cmp or n_not_improved > not_improved_lim:
+            break                                                    # mpc.py:299-301
+    x = torch.empty(T, B, n_state, dtype=dtype, device=dev)
+    u = torch.empty(T, B, n_ctrl, dtype=dtype, device=dev)
+    costs = torch.empty(B, dtype=dtype, device=dev)
+    du = torch.empty(B, dtype=dtype, device=dev)
+    s.x_out, s.u_out, s.cost_out, s.du_out = _ptr(x), _ptr(u), _ptr(costs), _ptr(du)
+    extra = {}
+    if x_cur is not None:
+        al = torch.empty(B, dtype=dtype, device=dev)
+        s.alpha_out = _ptr(al)
+        extra["alphas"] = al
+    if want_gains:
+        K = torch.empty(T, B, n_ctrl, n_state, dtype=dtype, device=dev)
+        k = torch.empty(T, B, n_ctrl, dtype=dtype, device=dev)
+        s.K_out, s.k_out = _ptr(K), _ptr(k)
+        extra["K"], extra["k"] = K, k
+    _lib.check(L.dilqr_mpc_finish(C.byref(s), st), "dilqr_mpc_finish")
+    info.full_du_norm = du
+    info.converged = None
+    for k_, v_ in extra.items():
+        setattr(info, k_, v_)
+    return x, u, costs, info
+
+
+def kkt_grads(C_, c_, F, x, u, dx, du, r, n_state, n_ctrl, want_df=True):
+    """Costate recursions + outer products (lqr_step.py:343-404)."""
+    L = _lib.lib()
+    T, B = x.shape[0], x.shape[1]
+    dtype, dev = x.dtype, x.device
+    k = _lib.DilqrKkt()
+    k.n_state, k.n_ctrl, k.T, k.n_batch, k.dtype = n_state, n_ctrl, T, B, _DT[dtype]
+    ten = [_contig(t.detach()) for t in (C_, c_, F, x, u, dx, du, r)]
+    k.C, k.c, k.F, k.x, k.u, k.dx, k.du, k.r = [_ptr(t) for t in ten]
+    n = n_state + n_ctrl
+    dC = torch.empty(T, B, n, n, dtype=dtype, device=dev)
+    dc = torch.empty(T, B, n, dtype=dtype, device=dev)
+    dF = torch.empty(max(T - 1, 0), B, n_state, n, dtype=dtype, device=dev)
+    df = torch.empty(max(T - 1, 0), B, n_state, dtype=dtype, device=dev) if want_df else None
+    dx0 = torch.empty(B, n_state, dtype=dtype, device=dev)
+    k.dC, k.dc, k.dF, k.df, k.dx_init = _ptr(dC), _ptr(dc), _ptr(dF), _ptr(df), _ptr(dx0)
+    _lib.check(L.dilqr_kkt_grads(C.byref(k), _stream()), "dilqr_kkt_grads")
+    return dx0, dC, dc, dF, df
+
+
+def kkt_backward(dl_dx, dl_du, x_init, C_, c_, F, f, x, u, n_state, n_ctrl, u_lower=None,
+                 u_upper=None, gain_solve=_lib.GAIN_PLAIN, back_eps=1e-7):
+    """LQRStepFn.backward (lqr_step.py:312-407): adjoint LQR solve with the
+    active controls pinned to zero, then the gradient assembly."""
+    T, B = x.shape[0], x.shape[1]
+    r = torch.cat((dl_dx, dl_du), 2).contiguous()
+    if u_lower is None:
+        I = None
+    else:                                                   # lqr_step.py:325-326
+        I = (torch.abs(u - u_lower) <= 1e-8) | (torch.abs(u - u_upper) <= 1e-8)
+    zero = torch.zeros_like(x_init)
+    dyn = DynSpec(_lib.DYN_LINDX, F=F, f=None)
+    dx, du, _, _ = solve_mpc(zero, C_, -r, dyn, n_state, n_ctrl, T, u_zero_I=I, lqr_iter=1,
+                             eps=back_eps, gain_solve=gain_solve, verbose=-1)
+    want_df = f is not None and f.nelement() > 0
+    return kkt_grads(C_, c_, F, x, u, dx, du, r, n_state, n_ctrl, want_df)

@@ -1,0 +1,348 @@
+// api.cu -- extern "C" entry points of libdilqr (see include/dilqr.h).
+// Compiled once per scalar type (-DDILQR_SCALAR_F64=0/1) into separate objects;
+// dispatch.cu routes on DilqrSolve::dtype.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/dilqr.h"
+#include "ilqr_kernels.cuh"
+#include "misc_kernels.cuh"
+
+namespace dilqr {
+
+#if DILQR_SCALAR_F64
+using Scalar = double;
+#define DILQR_SUFFIX(name) name##_f64
+#else
+using Scalar = float;
+#define DILQR_SUFFIX(name) name##_f32
+#endif
+
+// (n_state, n_ctrl, dynamics) combinations compiled in.
+#ifdef DILQR_FAST_BUILD   // developer builds: a handful of shapes, seconds to compile
+#define DILQR_CONFIGS(X)       \
+  X(4, 2, DYN_LINDX)           \
+  X(5, 1, DYN_LINDX)           \
+  X(3, 1, DYN_PENDULUM)        \
+  X(5, 1, DYN_CARTPOLE)
+#else
+#define DILQR_CONFIGS(X)       \
+  X(2, 1, DYN_LINDX)           \
+  X(3, 1, DYN_LINDX)           \
+  X(4, 1, DYN_LINDX)           \
+  X(4, 2, DYN_LINDX)           \
+  X(4, 4, DYN_LINDX)           \
+  X(5, 1, DYN_LINDX)           \
+  X(8, 1, DYN_LINDX)           \
+  X(8, 2, DYN_LINDX)           \
+  X(8, 4, DYN_LINDX)           \
+  X(13, 3, DYN_LINDX)          \
+  X(16, 1, DYN_LINDX)          \
+  X(16, 2, DYN_LINDX)          \
+  X(16, 4, DYN_LINDX)          \
+  X(3, 1, DYN_PENDULUM)        \
+  X(5, 1, DYN_CARTPOLE)
+#endif
+
+constexpr size_t kStageBudget = 56 * 1024;  // per-warp staging budget (>= 4 warps / SM)
+
+template <class S, int NS, int NC, int DYN>
+constexpr bool staged_v() {
+  constexpr int N = NS + NC;
+  constexpr bool env = DYN != DYN_LINDX;
+  size_t per = (size_t)kWarp * sizeof(S) * (N * N + N + (env ? 0 : NS * N + NS));
+  return per * kStages <= kStageBudget;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct WsLayout {
+  size_t traj, Kk, cost_cur, cost_new, cost_best, du_new, du_best, alpha_new, sel, guess, votes,
+      total;
+  int Bp;
+};
+
+static WsLayout ws_layout(const DilqrSolve* s, size_t esz) {
+  WsLayout w;
+  const int N = s->n_state + s->n_ctrl;
+  const int NK = s->n_ctrl * s->n_state + s->n_ctrl;
+  w.Bp = (int)align_up((size_t)s->n_batch, 32);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  };
+  w.traj = take((size_t)3 * s->T * N * w.Bp * esz);
+  w.Kk = take((size_t)s->T * NK * w.Bp * esz);
+  w.cost_cur = take((size_t)w.Bp * esz);
+  w.cost_new = take((size_t)w.Bp * esz);
+  w.cost_best = take((size_t)w.Bp * esz);
+  w.du_new = take((size_t)w.Bp * esz);
+  w.du_best = take((size_t)w.Bp * esz);
+  w.alpha_new = take((size_t)w.Bp * esz);
+  w.sel = take((size_t)w.Bp * sizeof(int));
+  w.guess = take((size_t)s->T * kPnqpMaxIter * sizeof(uint32_t));
+  w.votes = take((size_t)s->T * kPnqpMaxIter * sizeof(uint32_t));
+  w.total = off;
+  return w;
+}
+
+static IterParams<Scalar> make_params(const DilqrSolve* s) {
+  using S = Scalar;
+  IterParams<S> p;
+  memset(&p, 0, sizeof(p));
+  const WsLayout w = ws_layout(s, sizeof(S));
+  char* ws = static_cast<char*>(s->workspace);
+  p.T = s->T;
+  p.B = s->n_batch;
+  p.Bp = w.Bp;
+  p.bounds_kind = s->bounds_kind;
+  p.solo = s->solo;
+  p.gain_solve = s->gain_solve;
+  p.max_ls = s->max_linesearch_iter;
+  p.has_f = s->has_f && s->f != nullptr;
+  p.first_iteration = s->first_iteration;
+  p.lo = (S)s->u_lower;
+  p.hi = (S)s->u_upper;
+  p.decay = (S)s->linesearch_decay;
+  p.best_cost_eps = (S)s->best_cost_eps;
+  p.lo_t = static_cast<const S*>(s->u_lower_t);
+  p.hi_t = static_cast<const S*>(s->u_upper_t);
+  p.zeroI = s->u_zero_I;
+  p.x_init = static_cast<const S*>(s->x_init);
+  p.C = static_cast<const S*>(s->C);
+  p.c = static_cast<const S*>(s->c);
+  p.F = static_cast<const S*>(s->F);
+  p.f = static_cast<const S*>(s->f);
+  p.u_init = static_cast<const S*>(s->u_init);
+  p.x_cur = static_cast<const S*>(s->x_cur);
+  p.traj = reinterpret_cast<S*>(ws + w.traj);
+  p.Kk = reinterpret_cast<S*>(ws + w.Kk);
+  p.cost_cur = reinterpret_cast<S*>(ws + w.cost_cur);
+  p.cost_new = reinterpret_cast<S*>(ws + w.cost_new);
+  p.cost_best = reinterpret_cast<S*>(ws + w.cost_best);
+  p.du_new = reinterpret_cast<S*>(ws + w.du_new);
+  p.du_best = reinterpret_cast<S*>(ws + w.du_best);
+  p.alpha_new = reinterpret_cast<S*>(ws + w.alpha_new);
+  p.sel = reinterpret_cast<int*>(ws + w.sel);
+  p.guess = reinterpret_cast<uint32_t*>(ws + w.guess);
+  p.votes = reinterpret_cast<uint32_t*>(ws + w.votes);
+  p.status = s->status;
+  p.x_out = static_cast<S*>(s->x_out);
+  p.u_out = static_cast<S*>(s->u_out);
+  p.cost_out = static_cast<S*>(s->cost_out);
+  p.du_out = static_cast<S*>(s->du_out);
+  p.alpha_out = static_cast<S*>(s->alpha_out);
+  p.K_out = static_cast<S*>(s->K_out);
+  p.k_out = static_cast<S*>(s->k_out);
+  for (int i = 0; i < 8; ++i) p.dyn.p[i] = (S)s->dyn_params[i];
+  return p;
+}
+
+static int check(const DilqrSolve* s, bool need_ws) {
+  if (!s || s->n_state <= 0 || s->n_ctrl <= 0 || s->T <= 0 || s->n_batch <= 0) return DILQR_EINVAL;
+  if (!s->x_init || !s->C || !s->c) return DILQR_EINVAL;
+  if (s->dynamics == DILQR_DYN_LINDX && s->T > 1 && !s->F) return DILQR_EINVAL;
+  if (s->bounds_kind == DILQR_BOUNDS_TENSOR && (!s->u_lower_t || !s->u_upper_t)) return DILQR_EINVAL;
+  if (s->bounds_kind < 0 || s->bounds_kind > 2) return DILQR_EINVAL;
+  auto mis = [](const void* p) { return p && (reinterpret_cast<uintptr_t>(p) & 15u); };
+  if (mis(s->C) || mis(s->c) || mis(s->F) || mis(s->f) || mis(s->workspace)) return DILQR_EALIGN;
+  if (need_ws) {
+    if (!s->workspace || !s->status) return DILQR_EINVAL;
+    if (s->workspace_bytes < ws_layout(s, sizeof(Scalar)).total) return DILQR_EWORKSPACE;
+  }
+  return DILQR_OK;
+}
+
+// launch geometry for the warp-per-32-problems kernels
+template <class S, int NS, int NC, int DYN>
+struct Geometry {
+  static constexpr bool STAGED = staged_v<S, NS, NC, DYN>();
+  using IK = IterKernel<S, NS, NC, DYN, STAGED>;
+  static int warps_per_block() {
+    if (!STAGED) return 4;
+    const size_t per = IK::smem_per_warp();
+    int w = (int)((100 * 1024) / per);  // <= ~100 KB / block so two blocks fit one SM
+    if (w > 4) w = 4;
+    if (w < 1) w = 1;
+    return w;
+  }
+  static size_t smem(int wpb) { return STAGED ? IK::smem_per_warp() * wpb : 0; }
+};
+
+template <int NS, int NC, int DYN>
+static int launch_begin(const DilqrSolve* s, cudaStream_t st) {
+  using S = Scalar;
+  using G = Geometry<S, NS, NC, DYN>;
+  IterParams<S> p = make_params(s);
+  const int wpb = G::warps_per_block();
+  const int warps = (p.B + kWarp - 1) / kWarp;
+  const int blocks = (warps + wpb - 1) / wpb;
+  const size_t smem = G::smem(wpb);
+  auto kern = ilqr_begin_kernel<S, NS, NC, DYN, G::STAGED>;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // default pnqp trace guess: at t = T-1 nothing moves (x_init=None is the exact
+  // minimiser); at t < T-1 one Newton step then convergence (SURVEY a-5).
+  const WsLayout w = ws_layout(s, sizeof(S));
+  static_assert(kPnqpMaxIter == DILQR_PNQP_MAX_ITER, "trace width");
+  cudaMemsetAsync(p.guess, 0, (size_t)p.T * kPnqpMaxIter * sizeof(uint32_t), st);
+  if (p.T > 1)
+    cudaMemset2DAsync(p.guess, kPnqpMaxIter * sizeof(uint32_t), 3, 1, p.T - 1, st);
+  (void)w;
+  kern<<<blocks, wpb * kWarp, smem, st>>>(p);
+  return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
+}
+
+template <int NS, int NC, int DYN>
+static int launch_iterate(const DilqrSolve* s, cudaStream_t st) {
+  using S = Scalar;
+  using G = Geometry<S, NS, NC, DYN>;
+  IterParams<S> p = make_params(s);
+  const int wpb = G::warps_per_block();
+  const int warps = (p.B + kWarp - 1) / kWarp;
+  const int blocks = (warps + wpb - 1) / wpb;
+  const size_t smem = G::smem(wpb);
+  auto kern = ilqr_iter_kernel<S, NS, NC, DYN, G::STAGED>;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (p.bounds_kind && !p.solo)
+    cudaMemsetAsync(p.votes, 0, (size_t)p.T * kPnqpMaxIter * sizeof(uint32_t), st);
+  kern<<<blocks, wpb * kWarp, smem, st>>>(p);
+  return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
+}
+
+static int launch_commit(const DilqrSolve* s, cudaStream_t st) {
+  using S = Scalar;
+  IterParams<S> p = make_params(s);
+  trace_verify_kernel<<<1, 256, 0, st>>>(p.guess, p.votes, p.T, p.bounds_kind != 0, p.solo,
+                                         s->status);
+  commit_kernel<S><<<(p.B + 127) / 128, 128, 0, st>>>(p);
+  return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
+}
+
+template <int NS, int NC>
+static int launch_finish(const DilqrSolve* s, cudaStream_t st) {
+  using S = Scalar;
+  IterParams<S> p = make_params(s);
+  dim3 grid((p.B + 127) / 128, p.T);
+  finish_kernel<S, NS, NC><<<grid, 128, 0, st>>>(p);
+  return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
+}
+
+template <int NS, int NC>
+static int launch_kkt(const DilqrKkt* k, cudaStream_t st) {
+  using S = Scalar;
+  kkt_grads_kernel<S, NS, NC><<<(k->n_batch + 127) / 128, 128, 0, st>>>(*k);
+  return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
+}
+
+// ------------------------------------------------------------------ dispatch
+enum Op { OP_BEGIN, OP_ITERATE, OP_FINISH };
+
+static int dispatch(const DilqrSolve* s, Op op, cudaStream_t st) {
+#define X(NS_, NC_, DYN_)                                                            \
+  if (s->n_state == NS_ && s->n_ctrl == NC_ && s->dynamics == DYN_) {                \
+    switch (op) {                                                                    \
+      case OP_BEGIN: return launch_begin<NS_, NC_, DYN_>(s, st);                     \
+      case OP_ITERATE: return launch_iterate<NS_, NC_, DYN_>(s, st);                 \
+      case OP_FINISH: return launch_finish<NS_, NC_>(s, st);                         \
+    }                                                                                \
+  }
+  DILQR_CONFIGS(X)
+#undef X
+  return DILQR_EUNSUPPORTED;
+}
+
+int DILQR_SUFFIX(supported)(int n_state, int n_ctrl, int dynamics) {
+#define X(NS_, NC_, DYN_) \
+  if (n_state == NS_ && n_ctrl == NC_ && dynamics == DYN_) return 1;
+  DILQR_CONFIGS(X)
+#undef X
+  return 0;
+}
+
+size_t DILQR_SUFFIX(workspace_bytes)(const DilqrSolve* s) {
+  return ws_layout(s, sizeof(Scalar)).total;
+}
+
+int DILQR_SUFFIX(mpc_begin)(const DilqrSolve* s, void* stream) {
+  int e = check(s, true);
+  if (e) return e;
+  return dispatch(s, OP_BEGIN, static_cast<cudaStream_t>(stream));
+}
+int DILQR_SUFFIX(mpc_iterate)(const DilqrSolve* s, void* stream) {
+  int e = check(s, true);
+  if (e) return e;
+  return dispatch(s, OP_ITERATE, static_cast<cudaStream_t>(stream));
+}
+int DILQR_SUFFIX(mpc_commit)(const DilqrSolve* s, void* stream) {
+  int e = check(s, true);
+  if (e) return e;
+  if (!DILQR_SUFFIX(supported)(s->n_state, s->n_ctrl, s->dynamics)) return DILQR_EUNSUPPORTED;
+  return launch_commit(s, static_cast<cudaStream_t>(stream));
+}
+int DILQR_SUFFIX(mpc_finish)(const DilqrSolve* s, void* stream) {
+  int e = check(s, true);
+  if (e) return e;
+  return dispatch(s, OP_FINISH, static_cast<cudaStream_t>(stream));
+}
+
+int DILQR_SUFFIX(kkt_grads)(const DilqrKkt* k, void* stream) {
+  if (!k || !k->C || !k->c || !k->x || !k->u || !k->dx || !k->du || !k->r) return DILQR_EINVAL;
+  if (k->T > 1 && !k->F) return DILQR_EINVAL;
+#define X(NS_, NC_, DYN_)                                            \
+  if (DYN_ == DYN_LINDX && k->n_state == NS_ && k->n_ctrl == NC_)    \
+    return launch_kkt<NS_, NC_>(k, static_cast<cudaStream_t>(stream));
+  DILQR_CONFIGS(X)
+#undef X
+  return DILQR_EUNSUPPORTED;
+}
+
+template <int DYN>
+static int launch_linearize(const double* dp, int T, int B, const void* x, const void* u, void* F,
+                            void* f, cudaStream_t st) {
+  using S = Scalar;
+  DynParams<S> P;
+  for (int i = 0; i < 8; ++i) P.p[i] = (S)dp[i];
+  if (T < 2) return DILQR_OK;
+  dim3 grid((B + 127) / 128, T - 1);
+  linearize_kernel<S, DYN><<<grid, 128, 0, st>>>(P, T, B, static_cast<const S*>(x),
+                                                  static_cast<const S*>(u), static_cast<S*>(F),
+                                                  static_cast<S*>(f));
+  return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
+}
+
+int DILQR_SUFFIX(linearize)(int dynamics, const double* dp, int T, int B, const void* x,
+                            const void* u, void* F, void* f, void* stream) {
+  if (!dp || !x || !u || !F || T <= 0 || B <= 0) return DILQR_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dynamics == DYN_PENDULUM) return launch_linearize<DYN_PENDULUM>(dp, T, B, x, u, F, f, st);
+  if (dynamics == DYN_CARTPOLE) return launch_linearize<DYN_CARTPOLE>(dp, T, B, x, u, F, f, st);
+  return DILQR_EUNSUPPORTED;
+}
+
+template <int DYN>
+static int launch_rollout(const double* dp, int T, int B, const void* x0, const void* u, void* x,
+                          cudaStream_t st) {
+  using S = Scalar;
+  DynParams<S> P;
+  for (int i = 0; i < 8; ++i) P.p[i] = (S)dp[i];
+  rollout_kernel<S, DYN><<<(B + 127) / 128, 128, 0, st>>>(P, T, B, static_cast<const S*>(x0),
+                                                           static_cast<const S*>(u),
+                                                           static_cast<S*>(x));
+  return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
+}
+
+int DILQR_SUFFIX(rollout)(int dynamics, const double* dp, int T, int B, const void* x0,
+                          const void* u, void* x, void* stream) {
+  if (!dp || !x0 || !u || !x || T <= 0 || B <= 0) return DILQR_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dynamics == DYN_PENDULUM) return launch_rollout<DYN_PENDULUM>(dp, T, B, x0, u, x, st);
+  if (dynamics == DYN_CARTPOLE) return launch_rollout<DYN_CARTPOLE>(dp, T, B, x0, u, x, st);
+  return DILQR_EUNSUPPORTED;
+}
+
+}  // namespace dilqr

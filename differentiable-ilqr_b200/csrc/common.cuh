@@ -1,0 +1,202 @@
+// common.cuh -- shared device helpers for the dilqr sm_100a kernels.
+//
+// Build note: every translation unit is compiled with -fmad=false and all
+// contractions are written as explicit fma() calls.  The line search compares
+// the cost of a new trajectory with the cost recorded for the current one
+// (lqr_step.py:169,176-179); the two values are produced by different kernels /
+// inlining contexts, and they must be bit-identical when the trajectories are
+// identical (fixed point).  Disabling implicit contraction makes the rounding
+// sequence a property of the source, not of the surrounding code.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dilqr {
+
+#define DILQR_DEVICE __device__ __forceinline__
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kPnqpMaxIter = 20;   // pnqp.py:5
+constexpr int kArmijoMax = 10;     // pnqp.py:65
+
+template <class S> DILQR_DEVICE S fmaS(S a, S b, S c);
+template <> DILQR_DEVICE float fmaS<float>(float a, float b, float c) { return fmaf(a, b, c); }
+template <> DILQR_DEVICE double fmaS<double>(double a, double b, double c) { return fma(a, b, c); }
+
+template <class S> DILQR_DEVICE S sqrtS(S a);
+template <> DILQR_DEVICE float sqrtS<float>(float a) { return sqrtf(a); }
+template <> DILQR_DEVICE double sqrtS<double>(double a) { return sqrt(a); }
+
+template <class S> DILQR_DEVICE S absS(S a);
+template <> DILQR_DEVICE float absS<float>(float a) { return fabsf(a); }
+template <> DILQR_DEVICE double absS<double>(double a) { return fabs(a); }
+
+template <class S> DILQR_DEVICE S atan2S(S y, S x);
+template <> DILQR_DEVICE float atan2S<float>(float y, float x) { return atan2f(y, x); }
+template <> DILQR_DEVICE double atan2S<double>(double y, double x) { return atan2(y, x); }
+
+template <class S> DILQR_DEVICE void sincosS(S a, S* s, S* c);
+template <> DILQR_DEVICE void sincosS<float>(float a, float* s, float* c) { sincosf(a, s, c); }
+template <> DILQR_DEVICE void sincosS<double>(double a, double* s, double* c) { sincos(a, s, c); }
+
+// eclamp (util.py:58-72): two masked assignments, NaN passes through.
+template <class S> DILQR_DEVICE S eclamp(S x, S lo, S hi) {
+  if (x < lo) x = lo;
+  if (x > hi) x = hi;
+  return x;
+}
+
+// ---------------------------------------------------------------------------
+// mbarrier + 1-D bulk async copy (TMA, SASS: UBLKCP) helpers
+// ---------------------------------------------------------------------------
+DILQR_DEVICE uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+DILQR_DEVICE void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+DILQR_DEVICE void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+DILQR_DEVICE void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+DILQR_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+DILQR_DEVICE void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// Per-warp double-buffered slab stager.
+//
+// The API tensors are time-major AoS: for a fixed t the data of the 32
+// consecutive problems a warp owns is ONE contiguous slab
+// (C[t, b0:b0+32] = 32*n*n scalars).  One elected lane moves each slab into
+// shared memory with a single cp.async.bulk (TMA) tracked by an mbarrier; every
+// lane then reads its own problem's block.  Two stages per warp, so the slab of
+// the next timestep is in flight while the current one is consumed.  Warps never
+// synchronise with each other.  Partial / unaligned slabs (tail warp) fall back
+// to a lane-strided copy.
+// ---------------------------------------------------------------------------
+constexpr int kStages = 2;
+constexpr int kMaxSeg = 4;
+
+template <class S>
+struct WarpStager {
+  char* base;        // this warp's staging area (kStages * stage_bytes)
+  uint64_t* bar;     // kStages barriers
+  uint32_t stage_bytes;
+  uint32_t seg_off[kMaxSeg];    // byte offset of each segment in a stage
+  uint32_t seg_elems[kMaxSeg];  // scalars per problem in each segment
+  uint32_t parity;   // bit s = parity to wait for on stage s
+  uint32_t via_tma;  // bit s = stage s was filled by a bulk copy (else lane copies)
+  int nvalid;        // problems this warp really has (<= 32)
+  bool tma;          // slabs are 16B-aligned/sized -> bulk copies
+  int lane;
+
+  DILQR_DEVICE void init(char* smem_base, uint64_t* bars, int lane_, int nvalid_, int nseg,
+                         const uint32_t* elems) {
+    base = smem_base;
+    bar = bars;
+    lane = lane_;
+    nvalid = nvalid_;
+    parity = 0;
+    via_tma = 0;
+    uint32_t off = 0;
+    tma = true;
+#pragma unroll
+    for (int i = 0; i < kMaxSeg; ++i) {
+      seg_off[i] = off;
+      seg_elems[i] = i < nseg ? elems[i] : 0;
+      uint32_t full = seg_elems[i] * kWarp * sizeof(S);
+      uint32_t now = seg_elems[i] * nvalid * sizeof(S);
+      if (now % 16u) tma = false;
+      off += (full + 15u) & ~15u;
+    }
+    stage_bytes = off;
+    if (lane == 0) {
+#pragma unroll
+      for (int s = 0; s < kStages; ++s) mbar_init(&bar[s], 1);
+      mbar_fence_init();
+    }
+    __syncwarp();
+  }
+
+  static __host__ __device__ uint32_t bytes_per_warp(int nseg, const uint32_t* elems) {
+    uint32_t off = 0;
+    for (int i = 0; i < nseg; ++i) off += (elems[i] * kWarp * (uint32_t)sizeof(S) + 15u) & ~15u;
+    return off * kStages;
+  }
+
+  // Start copying the slabs for one timestep into `stage`.  src[i] points at the
+  // first scalar of this warp's slab of segment i (or nullptr to skip).
+  DILQR_DEVICE void issue(int stage, const S* const* src, int nseg) {
+    char* dst = base + stage * stage_bytes;
+    __syncwarp();  // all lanes are done reading this stage (WAR)
+    bool bulk = tma;   // sizes are fine; sources must be 16-byte aligned too
+#pragma unroll
+    for (int i = 0; i < kMaxSeg; ++i)
+      if (i < nseg && src[i] && (reinterpret_cast<uintptr_t>(src[i]) & 15u)) bulk = false;
+    via_tma = bulk ? (via_tma | (1u << stage)) : (via_tma & ~(1u << stage));
+    if (bulk) {
+      if (lane == 0) {
+        uint32_t total = 0;
+#pragma unroll
+        for (int i = 0; i < kMaxSeg; ++i)
+          if (i < nseg && src[i]) total += seg_elems[i] * nvalid * sizeof(S);
+        mbar_expect_tx(&bar[stage], total);
+#pragma unroll
+        for (int i = 0; i < kMaxSeg; ++i)
+          if (i < nseg && src[i])
+            bulk_g2s(dst + seg_off[i], src[i], seg_elems[i] * nvalid * sizeof(S), &bar[stage]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < kMaxSeg; ++i) {
+        if (i < nseg && src[i]) {
+          S* d = reinterpret_cast<S*>(dst + seg_off[i]);
+          const int cnt = seg_elems[i] * nvalid;
+          for (int e = lane; e < cnt; e += kWarp) d[e] = __ldg(src[i] + e);
+        }
+      }
+    }
+  }
+
+  DILQR_DEVICE void wait(int stage) {
+    if ((via_tma >> stage) & 1u) {
+      mbar_wait(&bar[stage], (parity >> stage) & 1u);
+      parity ^= (1u << stage);
+    } else {
+      __syncwarp();
+    }
+  }
+
+  // Pointer to this lane's block of segment i in `stage`.
+  DILQR_DEVICE const S* lane_ptr(int stage, int seg) const {
+    return reinterpret_cast<const S*>(base + stage * stage_bytes + seg_off[seg]) +
+           lane * seg_elems[seg];
+  }
+};
+
+// ordered-uint encoding of non-negative doubles for atomicMax
+DILQR_DEVICE unsigned long long dbits(double v) { return (unsigned long long)__double_as_longlong(v); }
+
+}  // namespace dilqr

@@ -1,0 +1,71 @@
+// dispatch.cu -- the extern "C" surface declared in include/dilqr.h; routes on
+// dtype to the per-scalar objects built from api.cu.
+#include "../../include/dilqr.h"
+
+namespace dilqr {
+#define DECL(sfx)                                                                         \
+  int supported_##sfx(int, int, int);                                                     \
+  size_t workspace_bytes_##sfx(const DilqrSolve*);                                        \
+  int mpc_begin_##sfx(const DilqrSolve*, void*);                                          \
+  int mpc_iterate_##sfx(const DilqrSolve*, void*);                                        \
+  int mpc_commit_##sfx(const DilqrSolve*, void*);                                         \
+  int mpc_finish_##sfx(const DilqrSolve*, void*);                                         \
+  int kkt_grads_##sfx(const DilqrKkt*, void*);                                            \
+  int linearize_##sfx(int, const double*, int, int, const void*, const void*, void*, void*, \
+                      void*);                                                             \
+  int rollout_##sfx(int, const double*, int, int, const void*, const void*, void*, void*);
+DECL(f32)
+DECL(f64)
+#undef DECL
+}  // namespace dilqr
+
+#define ROUTE(dtype, call32, call64)                   \
+  ((dtype) == DILQR_F32 ? (call32) : ((dtype) == DILQR_F64 ? (call64) : DILQR_EINVAL))
+
+extern "C" {
+
+const char* dilqr_version(void) { return "dilqr-b200 0.1 (sm_100a)"; }
+
+int dilqr_supported(int dtype, int ns, int nc, int dyn) {
+  if (dtype == DILQR_F32) return dilqr::supported_f32(ns, nc, dyn);
+  if (dtype == DILQR_F64) return dilqr::supported_f64(ns, nc, dyn);
+  return 0;
+}
+
+size_t dilqr_workspace_bytes(const DilqrSolve* s) {
+  if (!s) return 0;
+  return s->dtype == DILQR_F32 ? dilqr::workspace_bytes_f32(s) : dilqr::workspace_bytes_f64(s);
+}
+
+int dilqr_mpc_begin(const DilqrSolve* s, void* st) {
+  if (!s) return DILQR_EINVAL;
+  return ROUTE(s->dtype, dilqr::mpc_begin_f32(s, st), dilqr::mpc_begin_f64(s, st));
+}
+int dilqr_mpc_iterate(const DilqrSolve* s, void* st) {
+  if (!s) return DILQR_EINVAL;
+  return ROUTE(s->dtype, dilqr::mpc_iterate_f32(s, st), dilqr::mpc_iterate_f64(s, st));
+}
+int dilqr_mpc_commit(const DilqrSolve* s, void* st) {
+  if (!s) return DILQR_EINVAL;
+  return ROUTE(s->dtype, dilqr::mpc_commit_f32(s, st), dilqr::mpc_commit_f64(s, st));
+}
+int dilqr_mpc_finish(const DilqrSolve* s, void* st) {
+  if (!s) return DILQR_EINVAL;
+  return ROUTE(s->dtype, dilqr::mpc_finish_f32(s, st), dilqr::mpc_finish_f64(s, st));
+}
+int dilqr_kkt_grads(const DilqrKkt* k, void* st) {
+  if (!k) return DILQR_EINVAL;
+  return ROUTE(k->dtype, dilqr::kkt_grads_f32(k, st), dilqr::kkt_grads_f64(k, st));
+}
+int dilqr_linearize(int dtype, int dyn, const double* dp, int T, int B, const void* x,
+                    const void* u, void* F, void* f, void* st) {
+  return ROUTE(dtype, dilqr::linearize_f32(dyn, dp, T, B, x, u, F, f, st),
+               dilqr::linearize_f64(dyn, dp, T, B, x, u, F, f, st));
+}
+int dilqr_rollout(int dtype, int dyn, const double* dp, int T, int B, const void* x0,
+                  const void* u, void* x, void* st) {
+  return ROUTE(dtype, dilqr::rollout_f32(dyn, dp, T, B, x0, u, x, st),
+               dilqr::rollout_f64(dyn, dp, T, B, x0, u, x, st));
+}
+
+}  // extern "C"

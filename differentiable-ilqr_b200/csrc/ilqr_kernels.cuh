@@ -1,0 +1,762 @@
+// ilqr_kernels.cuh -- the batched box-constrained iLQR iteration for sm_100a.
+//
+// Mapping: ONE THREAD PER MPC PROBLEM (n_tau <= ~10: the whole Riccati state of
+// a problem -- V, v, Q, q, K, k -- lives in that thread's registers), warps are
+// fully independent (no block-level synchronisation), and each warp streams the
+// API's time-major AoS tensors (C, c, F, f) one timestep at a time through a
+// double-buffered shared-memory stage filled by 1-D bulk TMA copies
+// (cp.async.bulk + mbarrier, see WarpStager).  Everything private to the solver
+// (trajectories, gains, per-problem bookkeeping) is kept in an SoA workspace
+// [T][component][B] so that per-thread accesses are perfectly coalesced.
+//
+// Tensor cores are deliberately not used: the per-problem matrices are at most
+// ~16x16, strictly sequential in t, and every problem has different operands.
+//
+// Reference semantics implemented here (file:line relative to the reference):
+//   LQRStepFn.forward            lqr_step.py:277-309
+//   lqr_backward (Riccati)       lqr_step.py:52-160, lqr_step_backup.py:163-259
+//   pnqp                         pnqp.py:5-82
+//   lqr_forward (line search)    lqr_step.py:164-261
+//   get_traj / get_cost          util.py:104-153
+//   ANALYTIC linearisation       mpc_explicit.py:516-546
+//   best-iterate bookkeeping     mpc.py:271-285
+//
+// Batch-global control flow.  pnqp terminates, and runs its Armijo loop, on
+// batch-wide reductions (pnqp.py:56-59,65,75).  Threads cannot see the batch, so
+// the kernel REPLAYS a guessed control-flow trace (one 32-bit word per
+// (timestep, pnqp iteration): bit0 = "some problem still moving", bit 1+c =
+// "Armijo loop exits after pass c") and every warp ORs what it actually observed
+// into a vote array.  The commit step compares votes with the guess; they are
+// equal up to the first wrong guess, so after at most a few re-runs (normally
+// zero: the trace of the previous iLQR iteration is the next guess) the result
+// is exactly what the reference computes on the whole batch.
+#pragma once
+#include "common.cuh"
+#include "dynamics.cuh"
+#include "smallmat.cuh"
+
+namespace dilqr {
+
+template <class S>
+struct IterParams {
+  int T, B, Bp;
+  int bounds_kind;   // 0 none, 1 scalar, 2 tensor
+  int solo;
+  int gain_solve;
+  int max_ls;
+  int has_f;
+  int first_iteration;
+  S lo, hi;
+  S decay;
+  S best_cost_eps;
+  const S* lo_t;
+  const S* hi_t;
+  const uint8_t* zeroI;
+  const S* x_init;
+  const S* C;
+  const S* c;
+  const S* F;
+  const S* f;
+  const S* u_init;
+  const S* x_cur;
+  S* traj;        // [3][T][N][Bp]
+  S* Kk;          // [T][NC*NS+NC][Bp]
+  S* cost_cur;    // [Bp]
+  S* cost_new;
+  S* cost_best;
+  S* du_new;
+  S* du_best;
+  S* alpha_new;
+  int* sel;       // [Bp]  bits 0-1: current buffer, bits 2-3: best buffer
+  uint32_t* guess;  // [T][kPnqpMaxIter]
+  uint32_t* votes;  // [T][kPnqpMaxIter]
+  void* status;     // DilqrStatus*
+  S* x_out;
+  S* u_out;
+  S* cost_out;
+  S* du_out;
+  S* alpha_out;
+  S* K_out;
+  S* k_out;
+  DynParams<S> dyn;
+};
+
+DILQR_DEVICE int sel_cur(int s) { return s & 3; }
+DILQR_DEVICE int sel_best(int s) { return (s >> 2) & 3; }
+DILQR_DEVICE int sel_free(int s) {
+  const int a = sel_cur(s), b = sel_best(s);
+  return (a != 0 && b != 0) ? 0 : ((a != 1 && b != 1) ? 1 : 2);
+}
+
+// ---------------------------------------------------------------------------
+// stage cost  0.5 tau' C tau + c' tau   (util.py:145-147: bquad then bdot)
+// C, c are this lane's blocks in shared memory (row-major).
+// ---------------------------------------------------------------------------
+template <class S, int N>
+DILQR_DEVICE S stage_cost(const S* __restrict__ Cs, const S* __restrict__ cs, const S* tau) {
+  S quad = S(0);
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    S row = S(0);
+#pragma unroll
+    for (int i = 0; i < N; ++i) row = fmaS<S>(tau[i], Cs[i * N + j], row);
+    quad = fmaS<S>(row, tau[j], quad);
+  }
+  S dot = S(0);
+#pragma unroll
+  for (int i = 0; i < N; ++i) dot = fmaS<S>(tau[i], cs[i], dot);
+  return S(0.5) * quad + dot;
+}
+
+// LinDx step  x' = F tau (+ f)    (util.py:117-121)
+template <class S, int NS, int N>
+DILQR_DEVICE void lin_step(const S* __restrict__ Fs, const S* __restrict__ fs, bool has_f,
+                           const S* tau, S* xn) {
+#pragma unroll
+  for (int i = 0; i < NS; ++i) {
+    S acc = S(0);
+#pragma unroll
+    for (int j = 0; j < N; ++j) acc = fmaS<S>(Fs[i * N + j], tau[j], acc);
+    if (has_f) acc = acc + fs[i];
+    xn[i] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// pnqp for one problem, replaying / voting the batch-global control flow.
+// (pnqp.py:5-82).  On return x is the solution, If the free-set mask and lu the
+// LU factors (N>1) or scalar (N==1, lu.a[0][0]) of the masked Hessian of the
+// last evaluated iteration -- exactly what lqr_backward consumes
+// (lqr_step.py:135-148).
+// ---------------------------------------------------------------------------
+template <class S, int N>
+DILQR_DEVICE void pnqp_thread(const S (&H)[N][N], const S (&q)[N], const S (&lo)[N],
+                              const S (&hi)[N], bool have_init, S (&x)[N], bool (&If)[N],
+                              LUpp<S, N>& lu, const uint32_t* __restrict__ guess,
+                              uint32_t* __restrict__ votes, bool solo, bool active, int lane) {
+  const S GAMMA = S(0.1);
+  if (!have_init) {  // pnqp.py:14-19
+    if (N == 1) {
+      x[0] = -(S(1) / H[0][0]) * q[0];
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) lu.a[i][j] = H[i][j];
+        x[i] = q[i];
+      }
+      lu.factor();
+      lu.solve(x);
+#pragma unroll
+      for (int i = 0; i < N; ++i) x[i] = -x[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) x[i] = eclamp<S>(x[i], lo[i], hi[i]);  // pnqp.py:23
+
+  for (int it = 0; it < kPnqpMaxIter; ++it) {
+    S g[N], dx[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {  // g = H x + q   (pnqp.py:29)
+      S acc = S(0);
+#pragma unroll
+      for (int j = 0; j < N; ++j) acc = fmaS<S>(H[i][j], x[j], acc);
+      g[i] = acc + q[i];
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {  // pnqp.py:32-33
+      const bool Ic = ((x[i] == lo[i]) && (g[i] > S(0))) || ((x[i] == hi[i]) && (g[i] < S(0)));
+      If[i] = !Ic;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {  // pnqp.py:44-48
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        S h = (If[i] && If[j]) ? H[i][j] : S(0);
+        if (i == j) h = h + S(1e-11);
+        lu.a[i][j] = h;
+      }
+      dx[i] = If[i] ? g[i] : S(0);
+    }
+    if (N == 1) {  // pnqp.py:50-51
+      dx[0] = -(S(1) / lu.a[0][0]) * dx[0];
+    } else {
+      lu.factor();
+      lu.solve(dx);
+#pragma unroll
+      for (int i = 0; i < N; ++i) dx[i] = -dx[i];
+    }
+    S nrm2 = S(0);
+#pragma unroll
+    for (int i = 0; i < N; ++i) nrm2 = fmaS<S>(dx[i], dx[i], nrm2);
+    const bool J = sqrtS<S>(nrm2) >= S(1e-4);  // pnqp.py:56
+    uint32_t vote = 0;
+    bool any_moving;
+    if (solo) {
+      any_moving = J;
+    } else {
+      if (__ballot_sync(kFull, active && J)) vote |= 1u;
+      any_moving = (__ldg(&guess[it]) & 1u) != 0;
+    }
+    if (!any_moving) {  // pnqp.py:57-59
+      if (!solo && vote && lane == 0) atomicOr(&votes[it], vote);
+      return;
+    }
+    // Armijo backtracking with a batch-global exit test (pnqp.py:61-76).
+    S fx = S(0);
+    {
+      S quad = S(0), dot = S(0);
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        S row = S(0);
+#pragma unroll
+        for (int i = 0; i < N; ++i) row = fmaS<S>(x[i], H[i][j], row);
+        quad = fmaS<S>(row, x[j], quad);
+      }
+#pragma unroll
+      for (int i = 0; i < N; ++i) dot = fmaS<S>(q[i], x[i], dot);
+      fx = S(0.5) * quad + dot;
+    }
+    S alpha = S(1);
+    S mx[N];
+    const uint32_t gword = solo ? 0u : __ldg(&guess[it]);
+    for (int cnt = 0; cnt < kArmijoMax; ++cnt) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) mx[i] = eclamp<S>(x[i] + alpha * dx[i], lo[i], hi[i]);
+      S arm = GAMMA + S(1e-6);
+      if (J) {
+        S quad = S(0), dot = S(0), gd = S(0);
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          S row = S(0);
+#pragma unroll
+          for (int i = 0; i < N; ++i) row = fmaS<S>(mx[i], H[i][j], row);
+          quad = fmaS<S>(row, mx[j], quad);
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) dot = fmaS<S>(q[i], mx[i], dot);
+#pragma unroll
+        for (int i = 0; i < N; ++i) gd = fmaS<S>(g[i], x[i] - mx[i], gd);
+        arm = (fx - (S(0.5) * quad + dot)) / gd;
+      }
+      const bool small = arm <= GAMMA;   // pnqp.py:73
+      if (small) alpha = alpha * S(0.1);
+      bool exit_loop;
+      if (solo) {
+        exit_loop = !small;
+      } else {
+        // max_armijo > GAMMA  <=>  some problem has !(arm <= GAMMA)
+        if (__ballot_sync(kFull, active && !small)) vote |= (2u << cnt);
+        exit_loop = (gword >> (1 + cnt)) & 1u;
+      }
+      if (exit_loop) break;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = mx[i];  // pnqp.py:78
+    if (!solo && vote && lane == 0) atomicOr(&votes[it], vote);
+  }
+  // fell through n_iter iterations: the reference returns the factors / If of the
+  // last iteration together with the stepped x (pnqp.py:81-82).
+}
+
+// ---------------------------------------------------------------------------
+// The fused iLQR iteration.
+// ---------------------------------------------------------------------------
+template <class S, int NS, int NC, int DYN, bool STAGED>
+struct IterKernel {
+  static constexpr int N = NS + NC;
+  static constexpr int NK = NC * NS + NC;
+  static constexpr bool kEnv = (DYN != DYN_LINDX);
+  using D = Dyn<S, DYN>;
+
+  static __host__ __device__ int nseg() { return kEnv ? 2 : 4; }
+  static __host__ __device__ void seg_elems(uint32_t* e) {
+    e[0] = N * N;
+    e[1] = N;
+    e[2] = NS * N;
+    e[3] = NS;
+  }
+  static __host__ __device__ size_t smem_per_warp() {
+    if (!STAGED) return 0;
+    uint32_t e[4];
+    seg_elems(e);
+    return WarpStager<S>::bytes_per_warp(nseg(), e) + kStages * sizeof(uint64_t);
+  }
+
+  // Per-lane pointers to the (C, c, F, f) blocks of timestep t: the staged copy
+  // in shared memory, or (shapes too large to stage) straight global memory.
+  struct Blk {
+    const S* C;
+    const S* c;
+    const S* F;
+    const S* f;
+  };
+  DILQR_DEVICE static Blk blocks(const IterParams<S>& p, const WarpStager<S>& st, int sg, int t,
+                                 int b) {
+    Blk k;
+    if (STAGED) {
+      k.C = st.lane_ptr(sg, 0);
+      k.c = st.lane_ptr(sg, 1);
+      k.F = kEnv ? nullptr : st.lane_ptr(sg, 2);
+      k.f = kEnv ? nullptr : st.lane_ptr(sg, 3);
+    } else {
+      k.C = p.C + ((size_t)t * p.B + b) * (N * N);
+      k.c = p.c + ((size_t)t * p.B + b) * N;
+      k.F = (kEnv || t >= p.T - 1) ? nullptr : p.F + ((size_t)t * p.B + b) * (NS * N);
+      k.f = (kEnv || !p.has_f || t >= p.T - 1) ? nullptr : p.f + ((size_t)t * p.B + b) * NS;
+    }
+    return k;
+  }
+
+  DILQR_DEVICE static const S* traj_ptr(const IterParams<S>& p, int buf, int t, int comp, int b) {
+    return p.traj + ((size_t)(buf * p.T + t) * N + comp) * p.Bp + b;
+  }
+  DILQR_DEVICE static S* traj_ptr_w(const IterParams<S>& p, int buf, int t, int comp, int b) {
+    return p.traj + ((size_t)(buf * p.T + t) * N + comp) * p.Bp + b;
+  }
+
+  DILQR_DEVICE static void bounds_at(const IterParams<S>& p, int t, int b, S* lo, S* hi) {
+    if (p.bounds_kind == 2) {
+#pragma unroll
+      for (int a = 0; a < NC; ++a) {
+        lo[a] = __ldg(p.lo_t + ((size_t)t * p.B + b) * NC + a);
+        hi[a] = __ldg(p.hi_t + ((size_t)t * p.B + b) * NC + a);
+      }
+    } else {
+#pragma unroll
+      for (int a = 0; a < NC; ++a) {
+        lo[a] = p.lo;
+        hi[a] = p.hi;
+      }
+    }
+  }
+
+  // issue the slabs of timestep t for this warp into `stage`
+  DILQR_DEVICE static void issue_t(WarpStager<S>& st, const IterParams<S>& p, int stage, int t,
+                                   int b0, bool want_F, bool want_f) {
+    if (!STAGED) return;
+    const S* src[4];
+    src[0] = p.C + ((size_t)t * p.B + b0) * (N * N);
+    src[1] = p.c + ((size_t)t * p.B + b0) * N;
+    src[2] = nullptr;
+    src[3] = nullptr;
+    if (!kEnv) {
+      if (want_F && t < p.T - 1) src[2] = p.F + ((size_t)t * p.B + b0) * (NS * N);
+      if (want_f && p.has_f && t < p.T - 1) src[3] = p.f + ((size_t)t * p.B + b0) * NS;
+    }
+    st.issue(stage, src, nseg());
+  }
+
+  // ======================================================================
+  // Phase A: c_back + Riccati backward sweep with gains (and pnqp).
+  // ======================================================================
+  DILQR_DEVICE static void backward_sweep(const IterParams<S>& p, WarpStager<S>& st, int b0,
+                                          int b, bool active, int lane, int cur) {
+    S V[NS][NS], v[NS];
+    S kprev[NC];
+    S xnext[NS];  // x_{t+1} of the nominal trajectory (trig reuse for env Jacobians)
+    bool have_prev = false;
+    const int T = p.T;
+    issue_t(st, p, 0, T - 1, b0, true, false);
+    for (int t = T - 1; t >= 0; --t) {
+      const int sg = (T - 1 - t) & 1;
+      if (t > 0) issue_t(st, p, sg ^ 1, t - 1, b0, true, false);
+      S tau[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) tau[i] = *traj_ptr(p, cur, t, i, b);
+      if (STAGED) st.wait(sg);
+      const Blk blk = blocks(p, st, sg, t, b);
+      const S* Cs = blk.C;
+      const S* cs = blk.c;
+
+      S Q[N][N], qv[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) {  // c_back = C tau + c   (lqr_step.py:294)
+        S acc = S(0);
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          const S cij = Cs[i * N + j];
+          Q[i][j] = cij;
+          acc = fmaS<S>(cij, tau[j], acc);
+        }
+        qv[i] = acc + cs[i];
+      }
+      if (t < T - 1) {
+        S Fm[NS][N];
+        if constexpr (kEnv) {
+          S sp, cp;
+          if (D::kTrigFromNext && D::trig_reusable(&tau[NS])) {
+            sp = xnext[DYN == DYN_PENDULUM ? 1 : 3];
+            cp = xnext[DYN == DYN_PENDULUM ? 0 : 2];
+          } else {
+            D::trig(p.dyn, tau, &tau[NS], &sp, &cp);
+          }
+          D::jac(p.dyn, tau, &tau[NS], sp, cp, Fm);
+        } else {
+          const S* Fs = blk.F;
+#pragma unroll
+          for (int i = 0; i < NS; ++i)
+#pragma unroll
+            for (int j = 0; j < N; ++j) Fm[i][j] = Fs[i * N + j];
+        }
+        // Q = C + (F' V) F ; q = c~ + F' v     (lqr_step.py:66-70)
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          S M[NS];
+#pragma unroll
+          for (int k = 0; k < NS; ++k) {
+            S acc = S(0);
+#pragma unroll
+            for (int l = 0; l < NS; ++l) acc = fmaS<S>(Fm[l][i], V[l][k], acc);
+            M[k] = acc;
+          }
+#pragma unroll
+          for (int j = 0; j < N; ++j) {
+            S acc = S(0);
+#pragma unroll
+            for (int k = 0; k < NS; ++k) acc = fmaS<S>(M[k], Fm[k][j], acc);
+            Q[i][j] = Q[i][j] + acc;
+          }
+          S acc = S(0);
+#pragma unroll
+          for (int l = 0; l < NS; ++l) acc = fmaS<S>(Fm[l][i], v[l], acc);
+          qv[i] = qv[i] + acc;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NS; ++i) xnext[i] = tau[i];
+
+      // ------------------------------------------------------------ gains
+      S K[NC][NS], k[NC];
+      if (p.bounds_kind == 0) {
+        bool mask[NC];
+        bool any_mask = false;
+#pragma unroll
+        for (int a = 0; a < NC; ++a) {
+          mask[a] = p.zeroI ? (p.zeroI[((size_t)t * p.B + b) * NC + a] != 0) : false;
+          any_mask |= mask[a];
+        }
+        if (NC == 1) {
+          if (!p.zeroI) {  // lqr_step.py:84-86
+            const S r = S(1) / Q[NS][NS];
+#pragma unroll
+            for (int j = 0; j < NS; ++j) K[0][j] = -(r * Q[NS][j]);
+            k[0] = -(r * qv[NS]);
+          } else {         // lqr_step.py:101-123
+            const S quu_m = mask[0] ? S(1e-8) : Q[NS][NS];
+            const S r = S(1) / quu_m;
+#pragma unroll
+            for (int j = 0; j < NS; ++j) K[0][j] = -(r * (mask[0] ? S(0) : Q[NS][j]));
+            k[0] = -((S(1) / Q[NS][NS]) * (mask[0] ? S(0) : qv[NS]));
+          }
+        } else if (!p.zeroI && p.gain_solve == 1) {  // lqr_step_backup.py:202-205
+          Chol<S, NC> ch;
+#pragma unroll
+          for (int a = 0; a < NC; ++a)
+#pragma unroll
+            for (int c2 = 0; c2 < NC; ++c2)
+              ch.l[a][c2] = Q[NS + a][NS + c2] + (a == c2 ? S(1e-6) : S(0));
+          ch.factor();
+#pragma unroll
+          for (int j = 0; j <= NS; ++j) {
+            S rhs[NC];
+#pragma unroll
+            for (int a = 0; a < NC; ++a) rhs[a] = (j < NS) ? Q[NS + a][j] : qv[NS + a];
+            ch.solve(rhs);
+#pragma unroll
+            for (int a = 0; a < NC; ++a) {
+              if (j < NS) K[a][j] = -rhs[a];
+              else k[a] = -rhs[a];
+            }
+          }
+        } else {  // plain solve / u_zero_I-masked LU solve (lqr_step.py:88-94,101-127)
+          LUpp<S, NC> lu;
+#pragma unroll
+          for (int a = 0; a < NC; ++a)
+#pragma unroll
+            for (int c2 = 0; c2 < NC; ++c2) {
+              S h = (mask[a] || mask[c2]) ? S(0) : Q[NS + a][NS + c2];
+              if (a == c2 && mask[a]) h = h + S(1e-8);
+              lu.a[a][c2] = h;
+            }
+          lu.factor();
+#pragma unroll
+          for (int j = 0; j <= NS; ++j) {
+            S rhs[NC];
+#pragma unroll
+            for (int a = 0; a < NC; ++a)
+              rhs[a] = mask[a] ? S(0) : ((j < NS) ? Q[NS + a][j] : qv[NS + a]);
+            lu.solve(rhs);
+#pragma unroll
+            for (int a = 0; a < NC; ++a) {
+              if (j < NS) K[a][j] = -rhs[a];
+              else k[a] = -rhs[a];
+            }
+          }
+        }
+      } else {  // box constraints: pnqp   (lqr_step.py:128-148)
+        S lo[NC], hi[NC], H[NC][NC], qu[NC];
+        bounds_at(p, t, b, lo, hi);
+#pragma unroll
+        for (int a = 0; a < NC; ++a) {
+          lo[a] = lo[a] - tau[NS + a];
+          hi[a] = hi[a] - tau[NS + a];
+          qu[a] = qv[NS + a];
+#pragma unroll
+          for (int c2 = 0; c2 < NC; ++c2) H[a][c2] = Q[NS + a][NS + c2];
+          k[a] = have_prev ? kprev[a] : S(0);
+        }
+        bool If[NC];
+        LUpp<S, NC> lu;
+        pnqp_thread<S, NC>(H, qu, lo, hi, have_prev, k, If, lu,
+                           p.guess + (size_t)t * kPnqpMaxIter,
+                           p.votes + (size_t)t * kPnqpMaxIter, p.solo != 0, active, lane);
+        have_prev = true;
+#pragma unroll
+        for (int a = 0; a < NC; ++a) kprev[a] = k[a];
+        if (NC == 1) {  // lqr_step.py:144-146
+          const S r = S(1) / lu.a[0][0];
+#pragma unroll
+          for (int j = 0; j < NS; ++j) K[0][j] = -(r * (If[0] ? Q[NS][j] : S(0)));
+        } else {        // lqr_step.py:148
+#pragma unroll
+          for (int j = 0; j < NS; ++j) {
+            S rhs[NC];
+#pragma unroll
+            for (int a = 0; a < NC; ++a) rhs[a] = If[a] ? Q[NS + a][j] : S(0);
+            lu.solve(rhs);
+#pragma unroll
+            for (int a = 0; a < NC; ++a) K[a][j] = -rhs[a];
+          }
+        }
+      }
+      if (active) {
+#pragma unroll
+        for (int a = 0; a < NC; ++a) {
+#pragma unroll
+          for (int j = 0; j < NS; ++j)
+            p.Kk[((size_t)t * NK + a * NS + j) * p.Bp + b] = K[a][j];
+          p.Kk[((size_t)t * NK + NC * NS + a) * p.Bp + b] = k[a];
+        }
+      }
+      // -------------------------------------------- value function update
+      // V = Qxx + Qxu K + K' Qux + (K' Quu) K      (lqr_step.py:155)
+      // v = qx + Qxu k + K' qu + (K' Quu) k        (lqr_step.py:156-158)
+      S KQ[NS][NC];  // K' Quu
+#pragma unroll
+      for (int i = 0; i < NS; ++i)
+#pragma unroll
+        for (int a = 0; a < NC; ++a) {
+          S acc = S(0);
+#pragma unroll
+          for (int c2 = 0; c2 < NC; ++c2) acc = fmaS<S>(K[c2][i], Q[NS + c2][NS + a], acc);
+          KQ[i][a] = acc;
+        }
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+          S t1 = S(0), t2 = S(0), t3 = S(0);
+#pragma unroll
+          for (int a = 0; a < NC; ++a) {
+            t1 = fmaS<S>(Q[i][NS + a], K[a][j], t1);
+            t2 = fmaS<S>(K[a][i], Q[NS + a][j], t2);
+            t3 = fmaS<S>(KQ[i][a], K[a][j], t3);
+          }
+          V[i][j] = ((Q[i][j] + t1) + t2) + t3;
+        }
+        S t1 = S(0), t2 = S(0), t3 = S(0);
+#pragma unroll
+        for (int a = 0; a < NC; ++a) {
+          t1 = fmaS<S>(Q[i][NS + a], k[a], t1);
+          t2 = fmaS<S>(K[a][i], qv[NS + a], t2);
+          t3 = fmaS<S>(KQ[i][a], k[a], t3);
+        }
+        v[i] = ((qv[i] + t1) + t2) + t3;
+      }
+    }
+  }
+
+  // ======================================================================
+  // Phase B: forward rollout with the affine control law + line search over
+  // the true dynamics (lqr_step.py:164-261).
+  // ======================================================================
+  DILQR_DEVICE static void forward_linesearch(const IterParams<S>& p, WarpStager<S>& st, int b0,
+                                              int b, bool active, int lane, int cur, int nw) {
+    const int T = p.T;
+    const S old_cost = p.cost_cur[b];
+    S alpha = S(1);
+    bool accepted = false;
+    S res_cost = S(0), res_alpha = S(1), full_du = S(0);
+    S x0[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) x0[i] = __ldg(p.x_init + (size_t)b * NS + i);
+
+    for (int tr = 0; tr < p.max_ls; ++tr) {
+      if (!__any_sync(kFull, active && !accepted)) break;
+      const bool run = active && !accepted;
+      S xh[NS];
+#pragma unroll
+      for (int i = 0; i < NS; ++i) xh[i] = x0[i];
+      S cost = S(0), du2 = S(0);
+      issue_t(st, p, 0, 0, b0, true, true);
+      for (int t = 0; t < T; ++t) {
+        const int sg = t & 1;
+        if (t + 1 < T) issue_t(st, p, sg ^ 1, t + 1, b0, true, true);
+        S tau[N];   // nominal (x_t, u_t)
+#pragma unroll
+        for (int i = 0; i < N; ++i) tau[i] = *traj_ptr(p, cur, t, i, b);
+        S th[N];    // new (x^_t, u^_t)
+#pragma unroll
+        for (int i = 0; i < NS; ++i) th[i] = xh[i];
+        S lo[NC], hi[NC];
+        if (p.bounds_kind) bounds_at(p, t, b, lo, hi);
+#pragma unroll
+        for (int a = 0; a < NC; ++a) {  // lqr_step.py:192
+          S acc = S(0);
+          if (t > 0) {
+#pragma unroll
+            for (int j = 0; j < NS; ++j)
+              acc = fmaS<S>(p.Kk[((size_t)t * NK + a * NS + j) * p.Bp + b], xh[j] - tau[j], acc);
+          }
+          S un = (acc + tau[NS + a]) + alpha * p.Kk[((size_t)t * NK + NC * NS + a) * p.Bp + b];
+          if (p.zeroI && p.zeroI[((size_t)t * p.B + b) * NC + a]) un = S(0);  // :197-198
+          if (p.bounds_kind) un = eclamp<S>(un, lo[a], hi[a]);                  // :213
+          th[NS + a] = un;
+          const S d = tau[NS + a] - un;
+          du2 = fmaS<S>(d, d, du2);
+        }
+        if (run) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) *traj_ptr_w(p, nw, t, i, b) = th[i];
+        }
+        if (STAGED) st.wait(sg);
+        const Blk blk = blocks(p, st, sg, t, b);
+        cost = cost + stage_cost<S, N>(blk.C, blk.c, th);
+        if (t < T - 1) {
+          if constexpr (kEnv) {
+            D::step(p.dyn, th, &th[NS], xh);
+          } else {
+            lin_step<S, NS, N>(blk.F, blk.f, p.has_f != 0, th, xh);
+          }
+        }
+      }
+      if (tr == 0) full_du = sqrtS<S>(du2);
+      if (run) {
+        res_cost = cost;
+        res_alpha = alpha;
+        accepted = !(cost > old_cost);      // lqr_step.py:176-179,247
+        if (!accepted) alpha = alpha * p.decay;
+      }
+    }
+    if (active) {
+      p.cost_new[b] = res_cost;
+      p.alpha_new[b] = res_alpha;
+      p.du_new[b] = full_du;
+    }
+  }
+};
+
+template <class S, int NS, int NC, int DYN, bool STAGED>
+__global__ void __launch_bounds__(128)
+ilqr_iter_kernel(const __grid_constant__ IterParams<S> p) {
+  using IK = IterKernel<S, NS, NC, DYN, STAGED>;
+  extern __shared__ __align__(128) char smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int wpb = blockDim.x >> 5;
+  const int b0 = (blockIdx.x * wpb + warp) * kWarp;
+  if (b0 >= p.B) return;
+  const int nvalid = min(kWarp, p.B - b0);
+  const bool active = lane < nvalid;
+  const int b = active ? b0 + lane : b0;
+
+  const size_t per_warp = IK::smem_per_warp();
+  char* wbase = smem + warp * per_warp;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wbase);
+  WarpStager<S> st;
+  if (STAGED) {
+    uint32_t e[4];
+    IK::seg_elems(e);
+    st.init(wbase + kStages * sizeof(uint64_t), bars, lane, nvalid, IK::nseg(), e);
+  }
+
+  const int s = p.sel[b];
+  const int cur = sel_cur(s);
+  const int nw = sel_free(s);
+  IK::backward_sweep(p, st, b0, b, active, lane, cur);
+  IK::forward_linesearch(p, st, b0, b, active, lane, cur, nw);
+}
+
+// ---------------------------------------------------------------------------
+// begin: nominal rollout of u_init (util.get_traj) + its cost (util.get_cost)
+// into trajectory buffer 0.  With p.x_cur != nullptr the given trajectory is
+// loaded instead of rolled out (standalone LQRStep, lqr_step.py:164-169).
+// ---------------------------------------------------------------------------
+template <class S, int NS, int NC, int DYN, bool STAGED>
+__global__ void __launch_bounds__(128)
+ilqr_begin_kernel(const __grid_constant__ IterParams<S> p) {
+  using IK = IterKernel<S, NS, NC, DYN, STAGED>;
+  using D = Dyn<S, DYN>;
+  constexpr int N = NS + NC;
+  constexpr bool kEnv = (DYN != DYN_LINDX);
+  extern __shared__ __align__(128) char smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int wpb = blockDim.x >> 5;
+  const int b0 = (blockIdx.x * wpb + warp) * kWarp;
+  if (b0 >= p.B) return;
+  const int nvalid = min(kWarp, p.B - b0);
+  const bool active = lane < nvalid;
+  const int b = active ? b0 + lane : b0;
+  const size_t per_warp = IK::smem_per_warp();
+  char* wbase = smem + warp * per_warp;
+  WarpStager<S> st;
+  if (STAGED) {
+    uint32_t e[4];
+    IK::seg_elems(e);
+    st.init(wbase + kStages * sizeof(uint64_t), reinterpret_cast<uint64_t*>(wbase), lane, nvalid,
+            IK::nseg(), e);
+  }
+  const int T = p.T;
+  S xh[NS];
+#pragma unroll
+  for (int i = 0; i < NS; ++i) xh[i] = __ldg(p.x_init + (size_t)b * NS + i);
+  S cost = S(0);
+  IK::issue_t(st, p, 0, 0, b0, true, true);
+  for (int t = 0; t < T; ++t) {
+    const int sg = t & 1;
+    if (t + 1 < T) IK::issue_t(st, p, sg ^ 1, t + 1, b0, true, true);
+    S th[N];
+    if (p.x_cur) {
+#pragma unroll
+      for (int i = 0; i < NS; ++i) th[i] = __ldg(p.x_cur + ((size_t)t * p.B + b) * NS + i);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NS; ++i) th[i] = xh[i];
+    }
+#pragma unroll
+    for (int a = 0; a < NC; ++a)
+      th[NS + a] = p.u_init ? __ldg(p.u_init + ((size_t)t * p.B + b) * NC + a) : S(0);
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) *IK::traj_ptr_w(p, 0, t, i, b) = th[i];
+    }
+    if (STAGED) st.wait(sg);
+    const typename IK::Blk blk = IK::blocks(p, st, sg, t, b);
+    cost = cost + stage_cost<S, N>(blk.C, blk.c, th);
+    if (t < T - 1 && !p.x_cur) {
+      if constexpr (kEnv) {
+        D::step(p.dyn, th, &th[NS], xh);
+      } else {
+        lin_step<S, NS, N>(blk.F, blk.f, p.has_f != 0, th, xh);
+      }
+    }
+  }
+  if (active) {
+    p.cost_cur[b] = cost;
+    p.sel[b] = 0;
+  }
+}
+
+}  // namespace dilqr

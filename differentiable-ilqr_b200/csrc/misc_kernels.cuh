@@ -1,0 +1,333 @@
+// misc_kernels.cuh -- bookkeeping kernels around the fused iLQR iteration:
+// trace verification, best-iterate commit, gather to the API layout, analytic
+// linearisation, nominal rollout, and the KKT gradient assembly.
+#pragma once
+#include "../../include/dilqr.h"
+#include "ilqr_kernels.cuh"
+
+namespace dilqr {
+
+// ---------------------------------------------------------------------------
+// Verify the replayed pnqp control-flow trace (one block).  votes == guess up
+// to the first wrong guess; on mismatch the votes become the next guess.
+// Also derives n_total_qp_iter = sum_t (1 + n_qp_iter_t)  (lqr_step.py:140) and
+// resets the reduction fields of the status block.
+// ---------------------------------------------------------------------------
+static __global__ void trace_verify_kernel(uint32_t* __restrict__ guess, const uint32_t* __restrict__ votes,
+                                    int T, int boxed, int solo, DilqrStatus* status) {
+  __shared__ int s_first;
+  __shared__ unsigned s_nqp, s_unconv;
+  const int n = T * kPnqpMaxIter;
+  if (threadIdx.x == 0) {
+    s_first = n;
+    s_nqp = 0;
+    s_unconv = 0;
+  }
+  __syncthreads();
+  if (boxed && !solo) {
+    // Normalised vote of a slot: if nobody was moving the sweep left the slot
+    // right there, so Armijo bits voted under a wrong "moving" guess are void.
+    // Processing order of the sweep is t = T-1 .. 0, it = 0 .. 19.
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int t = T - 1 - i / kPnqpMaxIter, it = i % kPnqpMaxIter;
+      const int slot = t * kPnqpMaxIter + it;
+      uint32_t v = votes[slot];
+      if (!(v & 1u)) v = 0;
+      if (guess[slot] != v) atomicMin(&s_first, i);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+      int it = 0;
+      while (it < kPnqpMaxIter && (votes[t * kPnqpMaxIter + it] & 1u)) ++it;
+      if (it == kPnqpMaxIter) {
+        atomicAdd(&s_unconv, 1u);
+        it = kPnqpMaxIter - 1;   // pnqp.py:82 returns i = n_iter-1
+      }
+      atomicAdd(&s_nqp, 1u + (unsigned)it);
+    }
+    __syncthreads();
+    if (s_first < n) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        uint32_t v = votes[i];
+        if (!(v & 1u)) v = 0;
+        // moving, but the sweep exited here on a wrong guess so no Armijo pass was
+        // observed: guess the overwhelmingly common "exit after the first pass".
+        else if (!(guess[i] & 1u)) v = 3u;
+        guess[i] = v;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    status->trace_match = (s_first >= n) ? 1u : 0u;
+    status->first_mismatch = (uint32_t)s_first;
+    status->any_improved = 0;
+    status->n_total_qp_iter = s_nqp;
+    status->pnqp_unconverged = s_unconv;
+    status->max_full_du = 0.0;
+    status->mean_alpha = 0.0;
+    status->mean_best_cost = 0.0;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Per-problem commit: best-iterate bookkeeping (mpc.py:271-285) + the batch
+// reductions the host needs for the stop rule (mpc.py:299-301).
+// ---------------------------------------------------------------------------
+template <class S>
+__global__ void commit_kernel(const __grid_constant__ IterParams<S> p) {
+  DilqrStatus* status = reinterpret_cast<DilqrStatus*>(p.status);
+  if (status->trace_match == 0) return;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  double du = 0.0, al = 0.0, bc = 0.0;
+  bool improved = false;
+  if (b < p.B) {
+    const int s = p.sel[b];
+    const int nw = sel_free(s);
+    int best = sel_best(s);
+    const S cn = p.cost_new[b];
+    if (p.first_iteration) {
+      best = nw;
+      p.cost_best[b] = cn;
+      p.du_best[b] = p.du_new[b];
+    } else if (cn <= p.cost_best[b] + p.best_cost_eps) {  // mpc.py:280
+      best = nw;
+      p.cost_best[b] = cn;
+      p.du_best[b] = p.du_new[b];
+      improved = true;
+    }
+    p.cost_cur[b] = cn;
+    p.sel[b] = nw | (best << 2);
+    du = (double)p.du_new[b];
+    al = (double)p.alpha_new[b];
+    bc = (double)p.cost_best[b];
+  }
+  // warp reductions, then one atomic per warp
+  bool nan_du = du != du;
+  for (int o = 16; o > 0; o >>= 1) {
+    du = fmax(du, __shfl_xor_sync(kFull, du, o));
+    al += __shfl_xor_sync(kFull, al, o);
+    bc += __shfl_xor_sync(kFull, bc, o);
+  }
+  const unsigned imp = __ballot_sync(kFull, improved);
+  const unsigned nn = __ballot_sync(kFull, nan_du);
+  if ((threadIdx.x & 31) == 0) {
+    if (nn) du = __longlong_as_double(0x7ff8000000000000LL);  // propagate NaN like python max()
+    atomicMax(reinterpret_cast<unsigned long long*>(&status->max_full_du), dbits(du));
+    atomicAdd(&status->mean_alpha, al / p.B);
+    atomicAdd(&status->mean_best_cost, bc / p.B);
+    if (imp) atomicOr(&status->any_improved, 1u);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Gather the best iterate into the API (AoS) layout  (mpc.py:304-306).
+// One thread per (t, b); the SoA reads are coalesced, the AoS writes are
+// contiguous per warp (consecutive b).
+// ---------------------------------------------------------------------------
+template <class S, int NS, int NC>
+__global__ void finish_kernel(const __grid_constant__ IterParams<S> p) {
+  constexpr int N = NS + NC;
+  constexpr int NK = NC * NS + NC;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.y;
+  if (b >= p.B) return;
+  const int best = sel_best(p.sel[b]);
+  const S* src = p.traj + ((size_t)(best * p.T + t) * N) * p.Bp + b;
+  if (p.x_out) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) p.x_out[((size_t)t * p.B + b) * NS + i] = src[(size_t)i * p.Bp];
+  }
+  if (p.u_out) {
+#pragma unroll
+    for (int a = 0; a < NC; ++a)
+      p.u_out[((size_t)t * p.B + b) * NC + a] = src[(size_t)(NS + a) * p.Bp];
+  }
+  if (p.K_out) {
+#pragma unroll
+    for (int e = 0; e < NC * NS; ++e)
+      p.K_out[((size_t)t * p.B + b) * (NC * NS) + e] = p.Kk[((size_t)t * NK + e) * p.Bp + b];
+  }
+  if (p.k_out) {
+#pragma unroll
+    for (int a = 0; a < NC; ++a)
+      p.k_out[((size_t)t * p.B + b) * NC + a] = p.Kk[((size_t)t * NK + NC * NS + a) * p.Bp + b];
+  }
+  if (t == 0) {
+    if (p.cost_out) p.cost_out[b] = p.cost_best[b];
+    if (p.du_out) p.du_out[b] = p.du_best[b];
+    if (p.alpha_out) p.alpha_out[b] = p.alpha_new[b];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Analytic linearisation F_t = D(x_t,u_t), f_t = step(x_t,u_t) - D tau_t
+// (mpc_explicit.py:516-546) for t < T-1.  One thread per (t, b).
+// ---------------------------------------------------------------------------
+template <class S, int DYN>
+__global__ void linearize_kernel(DynParams<S> P, int T, int B, const S* __restrict__ x,
+                                 const S* __restrict__ u, S* __restrict__ F, S* __restrict__ f) {
+  using D = Dyn<S, DYN>;
+  constexpr int NS = D::NS, NC = D::NC, N = D::N;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.y;
+  if (b >= B || t >= T - 1) return;
+  S tau[N], xn[NS], Fm[NS][N];
+#pragma unroll
+  for (int i = 0; i < NS; ++i) tau[i] = x[((size_t)t * B + b) * NS + i];
+#pragma unroll
+  for (int a = 0; a < NC; ++a) tau[NS + a] = u[((size_t)t * B + b) * NC + a];
+  D::step(P, tau, &tau[NS], xn);
+  S sp, cp;
+  D::trig(P, tau, &tau[NS], &sp, &cp);
+  D::jac(P, tau, &tau[NS], sp, cp, Fm);
+  S* Fo = F + ((size_t)t * B + b) * (NS * N);
+#pragma unroll
+  for (int i = 0; i < NS; ++i) {
+    S acc = S(0);
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      Fo[i * N + j] = Fm[i][j];
+      acc = fmaS<S>(Fm[i][j], tau[j], acc);
+    }
+    if (f) f[((size_t)t * B + b) * NS + i] = xn[i] - acc;
+  }
+}
+
+// nominal rollout (util.py:104-127), one thread per problem
+template <class S, int DYN>
+__global__ void rollout_kernel(DynParams<S> P, int T, int B, const S* __restrict__ x_init,
+                               const S* __restrict__ u, S* __restrict__ x) {
+  using D = Dyn<S, DYN>;
+  constexpr int NS = D::NS, NC = D::NC;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  S xc[NS], uc[NC], xn[NS];
+#pragma unroll
+  for (int i = 0; i < NS; ++i) xc[i] = x_init[(size_t)b * NS + i];
+  for (int t = 0; t < T; ++t) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) x[((size_t)t * B + b) * NS + i] = xc[i];
+    if (t < T - 1) {
+#pragma unroll
+      for (int a = 0; a < NC; ++a) uc[a] = u[((size_t)t * B + b) * NC + a];
+      D::step(P, xc, uc, xn);
+#pragma unroll
+      for (int i = 0; i < NS; ++i) xc[i] = xn[i];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// KKT gradient assembly (lqr_step.py:343-404): costates lambda / dlambda by a
+// reverse sweep, then
+//   dC_t = -1/2 (dtau tau' + tau dtau')   dc_t = -dtau
+//   dF_t = -(dlam_{t+1} tau_t' + lam_{t+1} dtau_t')   df_t = -dlam_{t+1}
+//   dx_init = -dlam_0.
+// One thread per problem.
+// ---------------------------------------------------------------------------
+template <class S, int NS, int NC>
+__global__ void __launch_bounds__(128) kkt_grads_kernel(const __grid_constant__ DilqrKkt k) {
+  constexpr int N = NS + NC;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int T = k.T, B = k.n_batch;
+  if (b >= B) return;
+  const S* C = static_cast<const S*>(k.C);
+  const S* c = static_cast<const S*>(k.c);
+  const S* F = static_cast<const S*>(k.F);
+  const S* x = static_cast<const S*>(k.x);
+  const S* u = static_cast<const S*>(k.u);
+  const S* dx = static_cast<const S*>(k.dx);
+  const S* du = static_cast<const S*>(k.du);
+  const S* r = static_cast<const S*>(k.r);
+  S* dC = static_cast<S*>(k.dC);
+  S* dc = static_cast<S*>(k.dc);
+  S* dF = static_cast<S*>(k.dF);
+  S* df = static_cast<S*>(k.df);
+  S* dx0 = static_cast<S*>(k.dx_init);
+  S lam[NS], dlam[NS];
+  for (int t = T - 1; t >= 0; --t) {
+    const size_t tb = (size_t)t * B + b;
+    S tau[N], dtau[N];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      tau[i] = x[tb * NS + i];
+      dtau[i] = dx[tb * NS + i];
+    }
+#pragma unroll
+    for (int a = 0; a < NC; ++a) {
+      tau[NS + a] = u[tb * NC + a];
+      dtau[NS + a] = du[tb * NC + a];
+    }
+    // gradients that pair step t with the costates of t+1 (held in lam/dlam)
+    if (t < T - 1) {
+      if (dF) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i)
+#pragma unroll
+          for (int j = 0; j < N; ++j)
+            dF[tb * (NS * N) + i * N + j] = -(dlam[i] * tau[j] + lam[i] * dtau[j]);
+      }
+      if (df) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) df[tb * NS + i] = -dlam[i];
+      }
+    }
+    if (dC) {
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+          dC[tb * (N * N) + i * N + j] = S(-0.5) * (dtau[i] * tau[j] + tau[i] * dtau[j]);
+    }
+    if (dc) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) dc[tb * N + i] = -dtau[i];
+    }
+    // lam_t = Cxx x + Cxu u + c_x + Fx' lam_{t+1}   (lqr_step.py:355-369)
+    S nl[NS], ndl[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      S a1 = S(0), a2 = S(0), d1 = S(0), d2 = S(0);
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        const S cij = C[tb * (N * N) + i * N + j];
+        a1 = fmaS<S>(cij, tau[j], a1);
+        d1 = fmaS<S>(cij, dtau[j], d1);
+      }
+#pragma unroll
+      for (int a = 0; a < NC; ++a) {
+        const S cij = C[tb * (N * N) + i * N + NS + a];
+        a2 = fmaS<S>(cij, tau[NS + a], a2);
+        d2 = fmaS<S>(cij, dtau[NS + a], d2);
+      }
+      nl[i] = (a1 + a2) + c[tb * N + i];
+      ndl[i] = (d1 + d2) - r[tb * N + i];
+    }
+    if (t < T - 1) {
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+        S a1 = S(0), d1 = S(0);
+#pragma unroll
+        for (int l = 0; l < NS; ++l) {
+          const S fli = F[tb * (NS * N) + l * N + i];
+          a1 = fmaS<S>(fli, lam[l], a1);
+          d1 = fmaS<S>(fli, dlam[l], d1);
+        }
+        nl[i] = nl[i] + a1;
+        ndl[i] = ndl[i] + d1;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      lam[i] = nl[i];
+      dlam[i] = ndl[i];
+    }
+  }
+  if (dx0) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) dx0[(size_t)b * NS + i] = -dlam[i];
+  }
+}
+
+}  // namespace dilqr

@@ -1,0 +1,165 @@
+"""``MPC`` -- drop-in for the reference's ``mpc.MPC`` (mpc.py:58-337): same
+constructor, same ``forward(x_init, cost, dx) -> (x, u, costs)``, gradients by
+the KKT / adjoint-LQR backward of ``LQRStepFn.backward`` (lqr_step.py:312-407).
+
+All arithmetic runs in the sm_100a kernels behind ``libdilqr.so``; this module
+is the host-side mirror of the reference interface (argument handling, the
+stop rule, warnings, unconverged masking).
+"""
+import sys
+from enum import Enum
+
+import torch
+from torch import nn
+from torch.autograd import Function
+
+from . import _lib, _solver
+from .definitions import QuadCost, LinDx
+
+
+class GradMethods(Enum):          # mpc.py:29-33
+    AUTO_DIFF = 1
+    FINITE_DIFF = 2
+    ANALYTIC = 3
+    ANALYTIC_CHECK = 4
+
+
+def _dyn_spec(dx):
+    if isinstance(dx, LinDx):
+        return _solver.DynSpec(_lib.DYN_LINDX, F=dx.F, f=dx.f)
+    kind = getattr(dx, "_dilqr_kind", None)
+    if kind is None:
+        raise NotImplementedError(
+            "dynamics of type %s: only LinDx and the env_dx models of this package "
+            "(analytic linearisation) are supported" % type(dx).__name__)
+    return _solver.DynSpec(kind, params=dx.params.detach().double().cpu().tolist())
+
+
+class _MPCFn(Function):
+    """Forward: fused iLQR solve.  Backward: KKT adjoint (lqr_step.py:312-407)."""
+
+    @staticmethod
+    def forward(ctx, mod, dx, x_init, C, c, F, f):
+        dyn = _dyn_spec(dx)
+        x, u, costs, info = _solver.solve_mpc(
+            x_init, C, c, dyn, mod.n_state, mod.n_ctrl, mod.T,
+            u_lower=mod.u_lower, u_upper=mod.u_upper, u_zero_I=mod.u_zero_I,
+            u_init=mod.u_init, lqr_iter=mod.lqr_iter, eps=mod.eps,
+            linesearch_decay=mod.linesearch_decay,
+            max_linesearch_iter=mod.max_linesearch_iter,
+            not_improved_lim=mod.not_improved_lim, best_cost_eps=mod.best_cost_eps,
+            gain_solve=mod._gain_solve, solo=mod.solo, verbose=mod.verbose)
+        mod.last_info = info
+        ctx.mod = mod
+        ctx.dyn_kind = dyn.kind
+        ctx.mask = None
+        eps_cmp = float(torch.tensor(mod.eps, dtype=x.dtype))
+        if mod.detach_unconverged:                       # mpc.py:321-334
+            # full_du_norm of the best iterates decides convergence
+            if float(info.full_du_norm.max()) > eps_cmp:
+                if mod.exit_unconverged:
+                    assert False
+                if mod.verbose >= 0:
+                    print("LQR Warning: All examples did not converge to a fixed point.")
+                    print("Detaching and *not* backpropping through the bad examples.")
+                ctx.mask = (info.full_du_norm < eps_cmp).to(x.dtype)
+        ctx.save_for_backward(x_init, C, c, F if F is not None else x.new_empty(0),
+                              f if f is not None else x.new_empty(0), x, u)
+        ctx.mark_non_differentiable(costs)
+        return x, u, costs
+
+    @staticmethod
+    def backward(ctx, dl_dx, dl_du, _dcosts):
+        mod = ctx.mod
+        x_init, C, c, F, f, x, u = ctx.saved_tensors
+        if ctx.dyn_kind != _lib.DYN_LINDX:
+            raise NotImplementedError(
+                "mpc.MPC differentiates LinDx problems (KKT gradients); use "
+                "mpc_explicit.MPC for env_dx dynamics")
+        if ctx.mask is not None:
+            dl_dx = dl_dx * ctx.mask.view(1, -1, 1)
+            dl_du = dl_du * ctx.mask.view(1, -1, 1)
+        dx0, dC, dc, dF, df = _solver.kkt_backward(
+            dl_dx.contiguous(), dl_du.contiguous(), x_init, C, c, F, f, x, u,
+            mod.n_state, mod.n_ctrl, mod.u_lower, mod.u_upper,
+            gain_solve=mod._gain_solve, back_eps=mod.back_eps)
+        if f.nelement() == 0:
+            df = None
+        return None, None, dx0, dC, dc, dF, df
+
+
+class MPC(nn.Module):
+    """See the reference docstring (mpc.py:59-121); arguments are identical."""
+
+    _gain_solve = _lib.GAIN_PLAIN     # lqr_step.py:88-94
+    _Fn = _MPCFn
+
+    def __init__(self, n_state, n_ctrl, T, u_lower=None, u_upper=None, u_zero_I=None,
+                 u_init=None, lqr_iter=10, grad_method=GradMethods.ANALYTIC, delta_u=None,
+                 verbose=0, eps=1e-7, back_eps=1e-7, n_batch=None, linesearch_decay=0.2,
+                 max_linesearch_iter=10, exit_unconverged=True, detach_unconverged=True,
+                 backprop=True, slew_rate_penalty=None, prev_ctrl=None,
+                 not_improved_lim=5, best_cost_eps=1e-4, solo=False):
+        super().__init__()
+        assert (u_lower is None) == (u_upper is None)      # mpc.py:146
+        assert max_linesearch_iter > 0                     # mpc.py:147
+        if delta_u is not None or slew_rate_penalty is not None:
+            raise NotImplementedError("delta_u / slew_rate_penalty are out of scope (SURVEY 8a-13)")
+        self.n_state, self.n_ctrl, self.T = n_state, n_ctrl, T
+        det = lambda v: v if (v is None or isinstance(v, float)) else v.detach()
+        self.u_lower, self.u_upper = det(u_lower), det(u_upper)
+        self.u_zero_I = None if u_zero_I is None else u_zero_I.detach()
+        self.u_init = None if u_init is None else u_init.detach()
+        self.lqr_iter = lqr_iter
+        self.grad_method = grad_method
+        self.delta_u = delta_u
+        self.verbose = verbose
+        self.eps, self.back_eps = eps, back_eps
+        self.n_batch = n_batch
+        self.linesearch_decay = linesearch_decay
+        self.max_linesearch_iter = max_linesearch_iter
+        self.exit_unconverged = exit_unconverged
+        self.detach_unconverged = detach_unconverged
+        self.backprop = backprop
+        self.not_improved_lim = not_improved_lim
+        self.best_cost_eps = best_cost_eps
+        self.slew_rate_penalty = slew_rate_penalty
+        self.prev_ctrl = prev_ctrl
+        self.solo = solo
+        self.last_info = None
+
+    def _expand_cost(self, cost, n_batch):
+        """mpc.py:205-226: accept C[n,n] / C[T,n,n] / C[T,B,n,n] and c likewise."""
+        n = self.n_state + self.n_ctrl
+        C, c = cost
+        if C.ndimension() == 2:
+            C = C.unsqueeze(0).unsqueeze(0).expand(self.T, n_batch, n, -1)
+        elif C.ndimension() == 3:
+            C = C.unsqueeze(1).expand(self.T, n_batch, n, -1)
+        if c.ndimension() == 1:
+            c = c.unsqueeze(0).unsqueeze(0).expand(self.T, n_batch, -1)
+        elif c.ndimension() == 2:
+            c = c.unsqueeze(1).expand(self.T, n_batch, -1)
+        if C.ndimension() != 4 or c.ndimension() != 3:
+            print('MPC Error: Unexpected QuadCost shape.')
+            sys.exit(-1)
+        return C, c
+
+    def forward(self, x_init, cost, dx):
+        if not isinstance(cost, QuadCost):
+            raise NotImplementedError("only QuadCost is supported (SURVEY 8a-2)")
+        if self.n_batch is not None:
+            n_batch = self.n_batch
+        elif cost.C.ndimension() == 4:
+            n_batch = cost.C.size(1)
+        else:
+            print('MPC Error: Could not infer batch size, pass in as n_batch')
+            sys.exit(-1)
+        C, c = self._expand_cost(cost, n_batch)
+        assert x_init.ndimension() == 2 and x_init.size(0) == n_batch
+        if isinstance(dx, LinDx):
+            F, f = dx.F, dx.f
+        else:
+            F = f = None
+        x, u, costs = self._Fn.apply(self, dx, x_init, C, c, F, f)
+        return x, u, costs

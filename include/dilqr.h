@@ -1,0 +1,195 @@
+/* dilqr.h -- C ABI of libdilqr (B200 / sm_100a batched differentiable iLQR-MPC).
+ *
+ * This is the drop-in boundary for the hot path of josef-w/Differentiable-iLQR
+ * (a pure PyTorch reference; it has no FFI of its own, so each entry point
+ * below names the *Python* function it replaces, file:line relative to the
+ * reference root).  Plain pointers and sizes only: no torch types.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated otherwise; tensors are
+ *     contiguous, time-major, batch-second exactly as in the reference
+ *     (mpc.py:185-186): C[T,B,n,n] c[T,B,n] F[T-1,B,ns,n] f[T-1,B,ns]
+ *     x[T,B,ns] u[T,B,nc] x_init[B,ns], n = ns + nc;
+ *   - `dtype` selects float (DILQR_F32) or double (DILQR_F64) for ALL float
+ *     tensors of a call;
+ *   - the caller owns every buffer including the workspace; the library never
+ *     allocates, frees or synchronises; all work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*);
+ *   - return value: 0 on success, negative DILQR_E* on error (nothing enqueued);
+ *     numerical non-convergence is data (status block), never an error.
+ */
+#ifndef DILQR_H_
+#define DILQR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { DILQR_F32 = 0, DILQR_F64 = 1 };
+
+/* Where F_t comes from / what the rollouts integrate. */
+enum {
+  DILQR_DYN_LINDX    = 0, /* definitions.py:4  LinDx(F,f): x' = F_t [x;u] (+ f_t)      */
+  DILQR_DYN_PENDULUM = 1, /* env_dx/pendulum.py:60-95, Jacobian 444-475             */
+  DILQR_DYN_CARTPOLE = 2, /* env_dx/cartpole.py:64-97, Jacobian 790-839             */
+  DILQR_DYN_ROCKET   = 3  /* env_dx/rocket.py:82-164,  Jacobian 324-426             */
+};
+
+/* How unconstrained multi-input gains are solved (the reference copies differ). */
+enum {
+  DILQR_GAIN_PLAIN    = 0, /* lqr_step.py:88-94 (pinverse of an SPD Quu == inverse)  */
+  DILQR_GAIN_CHOL_REG = 1  /* lqr_step_backup.py:202-205 (Cholesky of Quu + 1e-6 I)  */
+};
+
+enum { DILQR_BOUNDS_NONE = 0, DILQR_BOUNDS_SCALAR = 1, DILQR_BOUNDS_TENSOR = 2 };
+
+enum {
+  DILQR_OK = 0,
+  DILQR_EINVAL = -1,       /* bad dims / null pointer / bad enum                   */
+  DILQR_EUNSUPPORTED = -2, /* (dtype, n_state, n_ctrl, dynamics) not instantiated  */
+  DILQR_EALIGN = -3,       /* a pointer is not 16-byte aligned                      */
+  DILQR_EWORKSPACE = -4,   /* workspace too small                                   */
+  DILQR_ECUDA = -5         /* kernel launch failed (cudaGetLastError != success)    */
+};
+
+#define DILQR_PNQP_MAX_ITER 20   /* pnqp.py:5  n_iter=20 (lqr_step.py:137)           */
+
+/* Host-visible solver status, written by dilqr_mpc_commit into DEVICE memory
+ * (`status` below); the host copies it back once per iLQR iteration to apply
+ * the stop rule of mpc.py:299-301. */
+typedef struct DilqrStatus {
+  uint32_t trace_match;     /* 1: pnqp control-flow guess == votes (iteration valid) */
+  uint32_t any_improved;    /* any problem improved its best cost (mpc.py:280-281)   */
+  uint32_t n_total_qp_iter; /* sum_t (1 + n_qp_iter_t)            (lqr_step.py:140)  */
+  uint32_t pnqp_unconverged;/* #timesteps where pnqp hit n_iter   (pnqp.py:81)       */
+  double   max_full_du;     /* max_b ||u - u_new||_2              (mpc.py:299)       */
+  double   mean_alpha;      /* mean_b alpha_b                     (lqr_step.py:259)  */
+  double   mean_best_cost;  /* mean_b best cost (verbose table,   mpc.py:288)        */
+  uint32_t first_mismatch;  /* slot index of first trace mismatch (debug)            */
+  uint32_t reserved[5];
+} DilqrStatus;
+
+/* One batched MPC / LQR problem instance.  Unused pointers may be NULL. */
+typedef struct DilqrSolve {
+  int32_t n_state, n_ctrl, T, n_batch;
+  int32_t dtype;            /* DILQR_F32 / DILQR_F64                                */
+  int32_t dynamics;         /* DILQR_DYN_*                                          */
+  int32_t gain_solve;       /* DILQR_GAIN_*                                         */
+  int32_t bounds_kind;      /* DILQR_BOUNDS_*                                       */
+  int32_t solo;             /* 0: batch-global pnqp control flow (== reference on
+                               the same batch); 1: per-problem (== reference B=1)   */
+  int32_t max_linesearch_iter; /* mpc.py:135                                        */
+  int32_t first_iteration;  /* commit: 1 on the first iLQR iteration (mpc.py:271)   */
+  int32_t has_f;            /* LinDx: f present (util.py:121)                        */
+  double  linesearch_decay; /* mpc.py:134                                           */
+  double  u_lower, u_upper; /* scalar bounds (mpc.py:81-82)                         */
+  double  best_cost_eps;    /* mpc.py:142                                           */
+  double  dyn_params[8];    /* env parameters theta (pendulum g,m,l; cartpole
+                               g,m_c,m_p,l; rocket Jx,Jy,Jz,mass,l), host copy      */
+  /* inputs */
+  const void* x_init;       /* [B,ns]                                               */
+  const void* C;            /* [T,B,n,n]                                            */
+  const void* c;            /* [T,B,n]                                              */
+  const void* F;            /* [T-1,B,ns,n]  (LinDx)                                */
+  const void* f;            /* [T-1,B,ns]    (LinDx, optional)                      */
+  const void* u_init;       /* [T,B,nc] or NULL (zeros, mpc.py:230-231)             */
+  const void* x_cur;        /* [T,B,ns] current trajectory (dilqr_lqr_step only)    */
+  const void* u_lower_t;    /* [T,B,nc] tensor bounds (lqr_step.py:264-272)         */
+  const void* u_upper_t;
+  const uint8_t* u_zero_I;  /* [T,B,nc] bool mask or NULL (lqr_step.py:99-127)      */
+  /* outputs */
+  void* x_out;              /* [T,B,ns]                                             */
+  void* u_out;              /* [T,B,nc]                                             */
+  void* cost_out;           /* [B]                                                  */
+  void* du_out;             /* [B]  full_du_norm                                    */
+  void* alpha_out;          /* [B]  accepted line-search step (lqr_step only)       */
+  void* K_out;              /* [T,B,nc,ns] gains, FORWARD time order (optional)     */
+  void* k_out;              /* [T,B,nc]    (optional)                               */
+  DilqrStatus* status;      /* device                                               */
+  /* scratch */
+  void*  workspace;
+  size_t workspace_bytes;
+} DilqrSolve;
+
+const char* dilqr_version(void);
+
+/* 1 if kernels for this combination are compiled in, else 0. */
+int dilqr_supported(int dtype, int n_state, int n_ctrl, int dynamics);
+
+/* Bytes of workspace the dilqr_mpc_* / dilqr_lqr_step calls need. */
+size_t dilqr_workspace_bytes(const DilqrSolve* s);
+
+/* ---- iLQR outer loop, MPC.forward (mpc.py:184-337, mpc_explicit.py:182-358) -- */
+
+/* Initial nominal rollout x = get_traj(u_init) (util.py:104-127) and its cost
+ * (util.py:130-153); resets the best-iterate record and the pnqp trace guess. */
+int dilqr_mpc_begin(const DilqrSolve* s, void* stream);
+
+/* One fused iLQR iteration = LQRStepFn.forward (lqr_step.py:277-309):
+ * c_back (289-295) + analytic linearisation (mpc_explicit.py:516-546) +
+ * Riccati backward with pnqp (lqr_step.py:52-160, pnqp.py:5-82) + line-search
+ * rollout over the true dynamics (lqr_step.py:164-261).  Results are staged;
+ * nothing is committed until dilqr_mpc_commit. */
+int dilqr_mpc_iterate(const DilqrSolve* s, void* stream);
+
+/* Verify the pnqp control-flow trace, then per problem the best-iterate
+ * bookkeeping of mpc.py:271-285 and the batch reductions of mpc.py:299-301;
+ * writes *s->status.  If status.trace_match == 0 nothing was committed: call
+ * dilqr_mpc_iterate + dilqr_mpc_commit again (the guess has been corrected). */
+int dilqr_mpc_commit(const DilqrSolve* s, void* stream);
+
+/* Gather the best iterate into x_out,u_out,cost_out,du_out (mpc.py:304-306). */
+int dilqr_mpc_finish(const DilqrSolve* s, void* stream);
+
+/* ---- single LQR step, LQRStep(...)(x_init,C,c,F,f) (lqr_step.py:22-38,277-309)
+ * around (x_cur,u_init); writes x_out,u_out,cost_out,du_out,alpha_out and, if
+ * non-NULL, K_out,k_out; status gets n_total_qp_iter / mean_alpha.  Runs the
+ * trace-verification loop on the device side up to `max_retries` times; returns
+ * 0 and sets status.trace_match accordingly (host re-calls if it is 0). */
+int dilqr_lqr_step(const DilqrSolve* s, void* stream);
+
+/* ---- standalone pnqp (pnqp.py:5-82) -------------------------------------
+ * H[B,n,n] q[B,n] lower[B,n] upper[B,n] x_init[B,n] or NULL -> x[B,n],
+ * Hfree[B,n,n] (masked Hessian + 1e-11 I of the last iteration), If[B,n]
+ * (float 0/1), n_iter (device int32[2]: {i, converged}).  Batch-global control
+ * flow is resolved with a cooperative grid (n_batch limited to resident
+ * threads) -- see DESIGN.md. */
+int dilqr_pnqp(int dtype, int n, int n_batch, const void* H, const void* q,
+               const void* lower, const void* upper, const void* x_init,
+               void* x, void* Hfree, void* If, int32_t* n_iter, int solo,
+               void* stream);
+
+/* ---- analytic linearisation (mpc_explicit.py:516-546) --------------------
+ * x[T,B,ns], u[T,B,nc] -> F[T-1,B,ns,n], f[T-1,B,ns] (f may be NULL). */
+int dilqr_linearize(int dtype, int dynamics, const double* dyn_params, int T,
+                    int n_batch, const void* x, const void* u, void* F, void* f,
+                    void* stream);
+
+/* ---- nominal rollout, util.get_traj (util.py:104-127) for env dynamics ---- */
+int dilqr_rollout(int dtype, int dynamics, const double* dyn_params, int T,
+                  int n_batch, const void* x_init, const void* u, void* x,
+                  void* stream);
+
+/* ---- KKT / adjoint-LQR backward, LQRStepFn.backward (lqr_step.py:312-407) --
+ * Given the adjoint solution (dx,du) of the masked LQR (computed with
+ * dilqr_mpc_* on cost (C,-r), LinDx(F,None), x_init=0, u_zero_I=active set),
+ * the two costate recursions and outer products:
+ *   dC[T,B,n,n] dc[T,B,n] dF[T-1,B,ns,n] df[T-1,B,ns] dx_init[B,ns].
+ * Any output pointer may be NULL to skip it. */
+typedef struct DilqrKkt {
+  int32_t n_state, n_ctrl, T, n_batch, dtype, reserved;
+  const void *C, *c, *F;        /* problem data                               */
+  const void *x, *u;            /* solution  x*[T,B,ns], u*[T,B,nc]           */
+  const void *dx, *du;          /* adjoint solution                           */
+  const void *r;                /* [T,B,n] = cat(dl_dx, dl_du)                 */
+  void *dC, *dc, *dF, *df, *dx_init;
+} DilqrKkt;
+int dilqr_kkt_grads(const DilqrKkt* k, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DILQR_H_ */
