@@ -131,3 +131,31 @@ def lib():
 def check(code, what):
     if code != 0:
         raise DilqrLibraryError("%s failed: %s (%d)" % (what, ERRORS.get(code, "?"), code))
+
+
+# kernels enqueued per C-ABI call (memsets not counted)
+KERNELS_PER_CALL = {
+    "dilqr_mpc_begin": 1, "dilqr_mpc_iterate": 1, "dilqr_mpc_commit": 2,
+    "dilqr_mpc_finish": 1, "dilqr_kkt_grads": 1, "dilqr_linearize": 1, "dilqr_rollout": 1,
+}
+launch_count = 0     # running total of kernels launched through this binding
+profile = None       # set to a dict {name: [(start_event, end_event), ...]} to time calls
+
+
+def call(name, *args):
+    """Invoke a C-ABI entry point; counts launches and (optionally) brackets the
+    call with CUDA events on the current stream for per-kernel timing."""
+    global launch_count
+    fn = getattr(lib(), name)
+    if profile is not None:
+        import torch
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        profile.setdefault(name, []).append((e0, e1))
+    else:
+        rc = fn(*args)
+    check(rc, name)
+    launch_count += KERNELS_PER_CALL.get(name, 0)

@@ -150,8 +150,8 @@ def _iterate_committed(L, s, ws, info):
     """One iLQR iteration including the trace-verification retry loop."""
     st = _stream()
     for _ in range(MAX_TRACE_RETRIES):
-        _lib.check(L.dilqr_mpc_iterate(C.byref(s), st), "dilqr_mpc_iterate")
-        _lib.check(L.dilqr_mpc_commit(C.byref(s), st), "dilqr_mpc_commit")
+        _lib.call("dilqr_mpc_iterate", C.byref(s), st)
+        _lib.call("dilqr_mpc_commit", C.byref(s), st)
         status = _read_status(ws)
         if status.trace_match:
             return status
@@ -185,7 +185,7 @@ def solve_mpc(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower=None, u_upper=Non
         s.x_cur = _ptr(xc)
     st = _stream()
     info = SolveInfo()
-    _lib.check(L.dilqr_mpc_begin(C.byref(s), st), "dilqr_mpc_begin")
+    _lib.call("dilqr_mpc_begin", C.byref(s), st)
     # python float eps is compared in the data dtype by torch (mpc.py:299)
     eps_cmp = float(torch.tensor(eps, dtype=dtype))
     n_not_improved = 0
@@ -228,7 +228,7 @@ def solve_mpc(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower=None, u_upper=Non
         k = torch.empty(T, B, n_ctrl, dtype=dtype, device=dev)
         s.K_out, s.k_out = _ptr(K), _ptr(k)
         extra["K"], extra["k"] = K, k
-    _lib.check(L.dilqr_mpc_finish(C.byref(s), st), "dilqr_mpc_finish")
+    _lib.call("dilqr_mpc_finish", C.byref(s), st)
     info.full_du_norm = du
     info.converged = None
     for k_, v_ in extra.items():
@@ -252,7 +252,7 @@ def kkt_grads(C_, c_, F, x, u, dx, du, r, n_state, n_ctrl, want_df=True):
     df = torch.empty(max(T - 1, 0), B, n_state, dtype=dtype, device=dev) if want_df else None
     dx0 = torch.empty(B, n_state, dtype=dtype, device=dev)
     k.dC, k.dc, k.dF, k.df, k.dx_init = _ptr(dC), _ptr(dc), _ptr(dF), _ptr(df), _ptr(dx0)
-    _lib.check(L.dilqr_kkt_grads(C.byref(k), _stream()), "dilqr_kkt_grads")
+    _lib.call("dilqr_kkt_grads", C.byref(k), _stream())
     return dx0, dC, dc, dF, df
 
 

@@ -33,9 +33,8 @@ class EnvDx(nn.Module):
         uu = torch.cat((u.detach().to(x.dtype).reshape(1, N, self.n_ctrl),
                         torch.zeros(1, N, self.n_ctrl, dtype=x.dtype, device=x.device)), 0)
         out = torch.empty(2, N, self.n_state, dtype=x.dtype, device=x.device)
-        _lib.check(_lib.lib().dilqr_rollout(_DT[x.dtype], self._dilqr_kind, self._theta(), 2, N,
-                                            _ptr(x0), _ptr(uu), _ptr(out), _stream()),
-                   "dilqr_rollout")
+        _lib.call("dilqr_rollout", _DT[x.dtype], self._dilqr_kind, self._theta(), 2, N,
+                                            _ptr(x0), _ptr(uu), _ptr(out), _stream())
         y = out[1]
         return y.squeeze(0) if squeeze else y
 
@@ -46,9 +45,8 @@ class EnvDx(nn.Module):
         xx = torch.stack((x.detach(), x.detach()), 0).contiguous()
         uu = torch.stack((u.detach(), u.detach()), 0).to(x.dtype).contiguous()
         D = torch.empty(1, N, self.n_state, n, dtype=x.dtype, device=x.device)
-        _lib.check(_lib.lib().dilqr_linearize(_DT[x.dtype], self._dilqr_kind, self._theta(), 2, N,
-                                              _ptr(xx), _ptr(uu), _ptr(D), None, _stream()),
-                   "dilqr_linearize")
+        _lib.call("dilqr_linearize", _DT[x.dtype], self._dilqr_kind, self._theta(), 2, N,
+                                              _ptr(xx), _ptr(uu), _ptr(D), None, _stream())
         return D[0]
 
     def linearize_traj(self, x, u):
@@ -57,10 +55,10 @@ class EnvDx(nn.Module):
         n = self.n_state + self.n_ctrl
         F = torch.empty(T - 1, B, self.n_state, n, dtype=x.dtype, device=x.device)
         f = torch.empty(T - 1, B, self.n_state, dtype=x.dtype, device=x.device)
-        _lib.check(_lib.lib().dilqr_linearize(_DT[x.dtype], self._dilqr_kind, self._theta(), T, B,
+        _lib.call("dilqr_linearize", _DT[x.dtype], self._dilqr_kind, self._theta(), T, B,
                                               _ptr(x.detach().contiguous()),
                                               _ptr(u.detach().contiguous()), _ptr(F), _ptr(f),
-                                              _stream()), "dilqr_linearize")
+                                              _stream())
         return F, f
 
     def get_true_obj(self):

@@ -558,3 +558,101 @@ def kkt_backward(dl_dx, dl_du, x_init, C, c, F, f, x, u, n_state, n_ctrl,
     df = -dlams[1:] if want_df else None               # lqr_step.py:397-402
     dx_init = -dlams[0]                                # lqr_step.py:404
     return KktOut(dx_init, dC, dc, dF, df, dx, du)
+
+
+# --------------------------------------------------------------------------
+# DiLQR implicit gradient (lqr_step_explicit.py:652-712 + fix_point_equ 458-598)
+# in its algebraically identical matrix-free form
+# --------------------------------------------------------------------------
+def env_tables(dynamics, x, u):
+    """get_matrices (cartpole.py:105-716 / pendulum.py:152-382), generated."""
+    import env_tables_gen as G
+    fn = G.cartpole_tables if isinstance(dynamics, CartpoleDx) else G.pendulum_tables
+    return fn(x, u, dynamics.params.detach())
+
+
+def grad_input(dynamics, X, U, K):
+    """Closed-loop parameter-sensitivity rollout, cartpole.py:717-788 /
+    pendulum.py:383-443.  ``K`` is indexed exactly like the reference does
+    (K[t] of the *reverse-time* stack)."""
+    T, B, ns = X.shape
+    nc = U.shape[2]
+    n = ns + nc
+    D, Dth, Dx, Du, xth, xx, xu = env_tables(dynamics, X.reshape(T * B, ns), U.reshape(T * B, nc))
+    nth = Dth.shape[-1]
+    D = D.reshape(T, B, ns, n)
+    Dth = Dth.reshape(T, B, ns, n, nth)
+    Dx = Dx.reshape(T, B, ns, n, ns)
+    Du = Du.reshape(T, B, ns, n, nc)
+    xth = xth.reshape(T, B, ns, nth)
+    xx = xx.reshape(T, B, ns, ns)
+    xu = xu.reshape(T, B, ns, nc)
+    XU = torch.cat((X, U), -1)
+    d_x = torch.einsum("tbnmk,tbm->tbnk", -Dx, XU)       # cartpole.py:752
+    d_u = torch.einsum("tbnmk,tbm->tbnk", -Du, XU)       # cartpole.py:753
+    G = torch.zeros(B, ns, nth, dtype=X.dtype)
+    grad_D, grad_d = [], []
+    Gm1 = None
+    for t in range(T):
+        Kt = K[t]
+        if t > 0:
+            Ktm1 = K[t - 1]
+            Gm1 = G
+            G = xth[t] + torch.matmul(xx[t] + torch.matmul(xu[t], Ktm1), G)   # :768
+        if t < T - 1:                                                         # :773-775
+            gD = Dth[t] + torch.matmul(Dx[t] + torch.matmul(Du[t], Kt.unsqueeze(1)),
+                                       G.unsqueeze(1))
+            grad_D.append(gD)
+        if t > 0:                                                             # :778-782
+            Z = torch.cat((Gm1, torch.matmul(Ktm1, Gm1)), 1)
+            gd = G - torch.einsum("bnmk,bm->bnk", grad_D[t - 1], XU[t - 1]) \
+                - torch.matmul(D[t - 1], Z)
+            grad_d.append(gd)
+    return (torch.stack(grad_D), torch.stack(grad_d), Dx[:T - 1], Du[:T - 1], D[:T - 1],
+            d_x[:T - 1], d_u[:T - 1])
+
+
+DilqrOut = namedtuple("DilqrOut", "dC dc dtheta w n_passes resid")
+
+
+def dilqr_backward(dl_dx, dl_du, x_init, C, c, x, u, dynamics, n_state, n_ctrl,
+                   u_lower=None, u_upper=None, n_passes=8, tol=None):
+    """Implicit (fixed-point) gradient of lqr_step_explicit.LQRStepFn.backward:
+       solve A' w = g with A = I - (J_F dD/dtau + J_f dd/dtau) by Richardson
+       iteration w <- g + M' w, where M' w needs one KKT adjoint pass; then one
+       more KKT pass with r = w gives dC, dc and (dF_w, df_w), and
+       dtheta_b = <dF_w, dD/dtheta> + <df_w, dd/dtheta>.
+    The adjoint solves use mpc_backup/lqr_step_backup (Cholesky + 1e-6 I when
+    unconstrained, lqr_step_explicit.py:277-290)."""
+    T, B = x.shape[0], x.shape[1]
+    F, f = linearize_dynamics(x, u, dynamics)
+    cb = c_back(C, c, x, u)
+    Ks, _, _ = lqr_backward(C, cb, F, None, u, n_state, n_ctrl, u_lower, u_upper)
+    Ks = torch.stack(Ks, 0)                                   # reverse-time stack (:617-618)
+    grad_D, grad_d, Dx, Du, D, d_x, d_u = grad_input(dynamics, x, u, Ks)
+    g = torch.cat((dl_dx, dl_du), 2)
+    w = g.clone()
+    resid = None
+    k = None
+    passes = 0
+    for it in range(n_passes + 1):
+        k = kkt_backward(w[:, :, :n_state], w[:, :, n_state:], x_init, C, c, F, f, x, u,
+                         n_state, n_ctrl, u_lower, u_upper, gain_solve="chol_reg")
+        if it == n_passes:
+            break
+        Mw = torch.zeros_like(g)
+        Mw[:T - 1, :, :n_state] = torch.einsum("tbnm,tbnmk->tbk", k.dF, Dx) + \
+            torch.einsum("tbn,tbnk->tbk", k.df, d_x)
+        Mw[:T - 1, :, n_state:] = torch.einsum("tbnm,tbnmk->tbk", k.dF, Du) + \
+            torch.einsum("tbn,tbnk->tbk", k.df, d_u)
+        w_new = g + Mw
+        resid = float((w_new - w).abs().max() / (w_new.abs().max() + 1e-300))
+        w = w_new
+        passes = it + 1
+        if tol is not None and resid < tol:
+            k = kkt_backward(w[:, :, :n_state], w[:, :, n_state:], x_init, C, c, F, f, x, u,
+                             n_state, n_ctrl, u_lower, u_upper, gain_solve="chol_reg")
+            break
+    dtheta = torch.einsum("tbnm,tbnmk->bk", k.dF, grad_D) + \
+        torch.einsum("tbn,tbnk->bk", k.df, grad_d)
+    return DilqrOut(k.dC, k.dc, dtheta, w, passes, resid)
