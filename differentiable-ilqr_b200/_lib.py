@@ -90,6 +90,11 @@ SYMBOLS = {
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dilqr_rollout": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dilqr_costate_tables": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int]
+                             + [C.c_void_p] * 7),
+    "dilqr_richardson_update": (C.c_int, [C.c_int] * 5 + [C.c_void_p] * 8),
+    "dilqr_sens_theta": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int]
+                         + [C.c_void_p] * 9),
 }
 
 _lib = None
@@ -137,6 +142,7 @@ def check(code, what):
 KERNELS_PER_CALL = {
     "dilqr_mpc_begin": 1, "dilqr_mpc_iterate": 1, "dilqr_mpc_commit": 2,
     "dilqr_mpc_finish": 1, "dilqr_kkt_grads": 1, "dilqr_linearize": 1, "dilqr_rollout": 1,
+    "dilqr_costate_tables": 1, "dilqr_richardson_update": 1, "dilqr_sens_theta": 1,
 }
 launch_count = 0     # running total of kernels launched through this binding
 profile = None       # set to a dict {name: [(start_event, end_event), ...]} to time calls

@@ -146,12 +146,16 @@ def _read_status(ws):
 MAX_TRACE_RETRIES = 64
 
 
-def _iterate_committed(L, s, ws, info):
-    """One iLQR iteration including the trace-verification retry loop."""
+def _iterate_committed(L, s, ws, info, sync=True):
+    """One iLQR iteration including the trace-verification retry loop.  With
+    ``sync=False`` (no box constraints => no pnqp trace, and nothing on the host
+    depends on the status) the call is fire-and-forget: no host sync."""
     st = _stream()
     for _ in range(MAX_TRACE_RETRIES):
         _lib.call("dilqr_mpc_iterate", C.byref(s), st)
         _lib.call("dilqr_mpc_commit", C.byref(s), st)
+        if not sync:
+            return None
         status = _read_status(ws)
         if status.trace_match:
             return status
@@ -163,7 +167,7 @@ def solve_mpc(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower=None, u_upper=Non
               u_zero_I=None, u_init=None, lqr_iter=10, eps=1e-7, linesearch_decay=0.2,
               max_linesearch_iter=10, not_improved_lim=5, best_cost_eps=1e-4,
               gain_solve=_lib.GAIN_PLAIN, solo=False, verbose=0, x_cur=None,
-              want_gains=False):
+              want_gains=False, sync=True):
     """MPC.forward (mpc.py:184-306): returns (x, u, costs, info).  With ``x_cur``
     given this is a single LQRStep around (x_cur, u_init) (lqr_step.py:277-309)
     and returns the *new* iterate."""
@@ -190,10 +194,13 @@ def solve_mpc(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower=None, u_upper=Non
     eps_cmp = float(torch.tensor(eps, dtype=dtype))
     n_not_improved = 0
     n_loops = 1 if x_cur is not None else lqr_iter
+    nosync = (not sync) and n_loops == 1 and (s.bounds_kind == _lib.BOUNDS_NONE or solo)
     for i in range(n_loops):
         s.first_iteration = 1 if i == 0 else 0
-        status = _iterate_committed(L, s, ws, info)
+        status = _iterate_committed(L, s, ws, info, sync=not nosync)
         info.n_iters = i + 1
+        if status is None:
+            break
         info.qp_iters.append(status.n_total_qp_iter)
         info.pnqp_unconverged += status.pnqp_unconverged
         info.log.append((status.n_total_qp_iter, status.max_full_du, status.mean_alpha,
@@ -236,7 +243,7 @@ def solve_mpc(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower=None, u_upper=Non
     return x, u, costs, info
 
 
-def kkt_grads(C_, c_, F, x, u, dx, du, r, n_state, n_ctrl, want_df=True):
+def kkt_grads(C_, c_, F, x, u, dx, du, r, n_state, n_ctrl, want_df=True, want_dF=True):
     """Costate recursions + outer products (lqr_step.py:343-404)."""
     L = _lib.lib()
     T, B = x.shape[0], x.shape[1]
@@ -248,7 +255,7 @@ def kkt_grads(C_, c_, F, x, u, dx, du, r, n_state, n_ctrl, want_df=True):
     n = n_state + n_ctrl
     dC = torch.empty(T, B, n, n, dtype=dtype, device=dev)
     dc = torch.empty(T, B, n, dtype=dtype, device=dev)
-    dF = torch.empty(max(T - 1, 0), B, n_state, n, dtype=dtype, device=dev)
+    dF = torch.empty(max(T - 1, 0), B, n_state, n, dtype=dtype, device=dev) if want_dF else None
     df = torch.empty(max(T - 1, 0), B, n_state, dtype=dtype, device=dev) if want_df else None
     dx0 = torch.empty(B, n_state, dtype=dtype, device=dev)
     k.dC, k.dc, k.dF, k.df, k.dx_init = _ptr(dC), _ptr(dc), _ptr(dF), _ptr(df), _ptr(dx0)
@@ -269,6 +276,83 @@ def kkt_backward(dl_dx, dl_du, x_init, C_, c_, F, f, x, u, n_state, n_ctrl, u_lo
     zero = torch.zeros_like(x_init)
     dyn = DynSpec(_lib.DYN_LINDX, F=F, f=None)
     dx, du, _, _ = solve_mpc(zero, C_, -r, dyn, n_state, n_ctrl, T, u_zero_I=I, lqr_iter=1,
-                             eps=back_eps, gain_solve=gain_solve, verbose=-1)
+                             eps=back_eps, gain_solve=gain_solve, verbose=-1, sync=False)
     want_df = f is not None and f.nelement() > 0
     return kkt_grads(C_, c_, F, x, u, dx, du, r, n_state, n_ctrl, want_df)
+
+
+def dilqr_backward(dl_dx, dl_du, x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u_lower=None,
+                   u_upper=None, n_passes=8, tol=None, back_eps=1e-7, solo=False, stats=None):
+    """DiLQR implicit gradient (lqr_step_explicit.py:652-712 + fix_point_equ
+    458-598) in matrix-free form (derivation in
+    csrc/dilqr_backward.cuh).  Returns (dC, dc, dtheta[B, n_theta]).
+
+    n_passes Richardson passes solve A' w = g (each = one adjoint LQR solve); with
+    ``tol`` the loop stops early once max|dw| <= tol * max|w| (one host sync per
+    pass).  The adjoint solves follow mpc_backup / lqr_step_backup (Cholesky +
+    1e-6 I for unconstrained multi-input problems, lqr_step_backup.py:202-205)."""
+    T, B = x.shape[0], x.shape[1]
+    dtype, dev = x.dtype, x.device
+    n = n_state + n_ctrl
+    kind = dxmod._dilqr_kind
+    theta = dxmod._theta()
+    x = x.detach().contiguous()
+    u = u.detach().contiguous()
+    C_ = _contig(C_.detach())
+    c_ = _contig(c_.detach())
+    # (1) final linearisation F = D(tau*)  (mpc_explicit.py:310) -- f is not needed
+    F = torch.empty(T - 1, B, n_state, n, dtype=dtype, device=dev)
+    _lib.call("dilqr_linearize", _DT[dtype], kind, theta, T, B, _ptr(x), _ptr(u), _ptr(F), None,
+              _stream())
+    # (2) gains of the final no-op LQR pass at tau* (lqr_step_explicit.py:604-618)
+    dyn = DynSpec(kind, params=list(theta))
+    _, _, _, info = solve_mpc(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower=u_lower,
+                              u_upper=u_upper, u_init=u, x_cur=x, lqr_iter=1, max_linesearch_iter=1,
+                              solo=solo, verbose=-1, want_gains=True)
+    K = info.K
+    # (3) primal costates + contracted second-order tables
+    lam = torch.empty(T, B, n_state, dtype=dtype, device=dev)
+    Lam = torch.empty(T - 1, B, n, n, dtype=dtype, device=dev)
+    _lib.call("dilqr_costate_tables", _DT[dtype], kind, theta, T, B, _ptr(C_), _ptr(c_), _ptr(x),
+              _ptr(u), _ptr(lam), _ptr(Lam), _stream())
+    # (4) Richardson iteration on A' w = g
+    g = torch.cat((dl_dx, dl_du), 2).contiguous()
+    if u_lower is None:
+        I = None
+    else:                                                   # lqr_step_explicit.py:690-691
+        I = (torch.abs(u - u_lower) <= 1e-8) | (torch.abs(u - u_upper) <= 1e-8)
+    w = g.clone()
+    negw = -g
+    zero = torch.zeros_like(x_init)
+    lin = DynSpec(_lib.DYN_LINDX, F=F, f=None)
+    resid = torch.zeros(2, dtype=torch.float64, device=dev)
+
+    def adjoint():
+        return solve_mpc(zero, C_, negw, lin, n_state, n_ctrl, T, u_zero_I=I, lqr_iter=1,
+                         eps=back_eps, gain_solve=_lib.GAIN_CHOL_REG, verbose=-1, sync=False)[:2]
+
+    passes = 0
+    rel = None
+    for _ in range(n_passes):
+        dxa, dua = adjoint()
+        _lib.call("dilqr_richardson_update", _DT[dtype], n_state, n_ctrl, T, B, _ptr(g), _ptr(Lam),
+                  _ptr(dxa), _ptr(dua), _ptr(w), _ptr(negw), _ptr(resid), _stream())
+        passes += 1
+        if tol is not None:
+            r = resid.cpu()
+            rel = float(r[0]) / (float(r[1]) + 1e-300)
+            if rel <= tol:
+                break
+    # (5) one more KKT pass with r = w: dC, dc and df_w = -dlam
+    dxa, dua = adjoint()
+    _, dC, dc, _, df = kkt_grads(C_, c_, F, x, u, dxa, dua, w, n_state, n_ctrl, want_df=True,
+                                 want_dF=False)
+    # (6) dtheta through the closed-loop sensitivity rollout
+    nth = len(dxmod.params)
+    dtheta = torch.empty(B, nth, dtype=dtype, device=dev)
+    _lib.call("dilqr_sens_theta", _DT[dtype], kind, theta, T, B, _ptr(x), _ptr(u), _ptr(K),
+              _ptr(lam), _ptr(dxa), _ptr(dua), _ptr(df), _ptr(dtheta), _stream())
+    if stats is not None:
+        stats["passes"] = passes
+        stats["resid"] = rel
+    return dC, dc, dtheta

@@ -8,6 +8,7 @@
 #include "../../include/dilqr.h"
 #include "ilqr_kernels.cuh"
 #include "misc_kernels.cuh"
+#include "dilqr_backward.cuh"
 
 namespace dilqr {
 
@@ -22,6 +23,7 @@ using Scalar = float;
 // (n_state, n_ctrl, dynamics) combinations compiled in.
 #ifdef DILQR_FAST_BUILD   // developer builds: a handful of shapes, seconds to compile
 #define DILQR_CONFIGS(X)       \
+  X(3, 1, DYN_LINDX)           \
   X(4, 2, DYN_LINDX)           \
   X(5, 1, DYN_LINDX)           \
   X(3, 1, DYN_PENDULUM)        \
@@ -342,6 +344,75 @@ int DILQR_SUFFIX(rollout)(int dynamics, const double* dp, int T, int B, const vo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dynamics == DYN_PENDULUM) return launch_rollout<DYN_PENDULUM>(dp, T, B, x0, u, x, st);
   if (dynamics == DYN_CARTPOLE) return launch_rollout<DYN_CARTPOLE>(dp, T, B, x0, u, x, st);
+  return DILQR_EUNSUPPORTED;
+}
+
+// ------------------------------------------------- DiLQR implicit backward
+template <int DYN>
+static int launch_costate(const double* dp, int T, int B, const void* C, const void* c,
+                          const void* x, const void* u, void* lam, void* Lam, cudaStream_t st) {
+  using S = Scalar;
+  DynParams<S> P;
+  for (int i = 0; i < 8; ++i) P.p[i] = (S)dp[i];
+  costate_tables_kernel<S, DYN><<<(B + 63) / 64, 64, 0, st>>>(
+      P, T, B, static_cast<const S*>(C), static_cast<const S*>(c), static_cast<const S*>(x),
+      static_cast<const S*>(u), static_cast<S*>(lam), static_cast<S*>(Lam));
+  return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
+}
+
+int DILQR_SUFFIX(costate_tables)(int dynamics, const double* dp, int T, int B, const void* C,
+                                 const void* c, const void* x, const void* u, void* lam,
+                                 void* Lam, void* stream) {
+  if (!dp || !C || !c || !x || !u || !lam || !Lam || T <= 0 || B <= 0) return DILQR_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dynamics == DYN_PENDULUM) return launch_costate<DYN_PENDULUM>(dp, T, B, C, c, x, u, lam, Lam, st);
+  if (dynamics == DYN_CARTPOLE) return launch_costate<DYN_CARTPOLE>(dp, T, B, C, c, x, u, lam, Lam, st);
+  return DILQR_EUNSUPPORTED;
+}
+
+template <int DYN>
+static int launch_sens(const double* dp, int T, int B, const void* x, const void* u,
+                       const void* K, const void* lam, const void* dx, const void* du,
+                       const void* df, void* dtheta, cudaStream_t st) {
+  using S = Scalar;
+  DynParams<S> P;
+  for (int i = 0; i < 8; ++i) P.p[i] = (S)dp[i];
+  sens_theta_kernel<S, DYN><<<(B + 63) / 64, 64, 0, st>>>(
+      P, T, B, static_cast<const S*>(x), static_cast<const S*>(u), static_cast<const S*>(K),
+      static_cast<const S*>(lam), static_cast<const S*>(dx), static_cast<const S*>(du),
+      static_cast<const S*>(df), static_cast<S*>(dtheta));
+  return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
+}
+
+int DILQR_SUFFIX(sens_theta)(int dynamics, const double* dp, int T, int B, const void* x,
+                             const void* u, const void* K, const void* lam, const void* dx,
+                             const void* du, const void* df, void* dtheta, void* stream) {
+  if (!dp || !x || !u || !K || !lam || !dx || !du || !df || !dtheta || T <= 1 || B <= 0)
+    return DILQR_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dynamics == DYN_PENDULUM) return launch_sens<DYN_PENDULUM>(dp, T, B, x, u, K, lam, dx, du, df, dtheta, st);
+  if (dynamics == DYN_CARTPOLE) return launch_sens<DYN_CARTPOLE>(dp, T, B, x, u, K, lam, dx, du, df, dtheta, st);
+  return DILQR_EUNSUPPORTED;
+}
+
+int DILQR_SUFFIX(richardson_update)(int ns, int nc, int T, int B, const void* g, const void* Lam,
+                                    const void* dx, const void* du, void* w, void* negw,
+                                    void* resid, void* stream) {
+  using S = Scalar;
+  if (!g || !Lam || !dx || !du || !w || !negw || !resid || T <= 0 || B <= 0) return DILQR_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid((B + 127) / 128, T);
+  cudaMemsetAsync(resid, 0, 16, st);
+#define X(NS_, NC_, DYN_)                                                                   \
+  if (DYN_ == DYN_LINDX && ns == NS_ && nc == NC_) {                                        \
+    richardson_update_kernel<S, NS_, NC_><<<grid, 128, 0, st>>>(                            \
+        T, B, static_cast<const S*>(g), static_cast<const S*>(Lam), static_cast<const S*>(dx), \
+        static_cast<const S*>(du), static_cast<S*>(w), static_cast<S*>(negw),               \
+        static_cast<unsigned long long*>(resid));                                           \
+    return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;                      \
+  }
+  DILQR_CONFIGS(X)
+#undef X
   return DILQR_EUNSUPPORTED;
 }
 

@@ -1,0 +1,291 @@
+// dilqr_backward.cuh -- kernels of the DiLQR implicit-differentiation backward
+// pass (lqr_step_explicit.py:652-712 + fix_point_equ 458-598) in its matrix-free
+// form.
+//
+// With tau* the converged trajectory, the reference solves
+//     A X = B,   A = I - (J_F dD/dtau + J_f dd/dtau)           (dense, (T n)^3)
+// where J_F, J_f are Jacobians of the LQR solution wrt (F, f) obtained from T*n
+// KKT adjoint solves.  Equivalent and matrix-free:  solve A' w = g by the
+// Richardson iteration  w <- g + M' w;  M' w needs ONE adjoint LQR solve with
+// r = w:  with dtau the adjoint solution and lambda the costates of the primal
+// solution (lqr_step.py:355-369),
+//     dF_w = -(dlam_{t+1} tau' + lam_{t+1} dtau'),  df_w = -dlam_{t+1}
+//     (M' w)_t[k] = sum_ij (dF_w - df_w tau')[i,j] dD_t[i,j]/dtau_k
+//                 = - sum_j Lam_t[k][j] dtau_t[j],
+//     Lam_t[k][j] = sum_i lam_{t+1}[i] dD_t[i,j]/dtau_k          (independent of w).
+// Finally dC, dc come from one more KKT pass with r = w (kkt_grads_kernel) and
+//     dtheta_b = sum_t <dF_w, dD_t/dtheta> + <df_w, dd_t/dtheta>
+// with the total derivatives dD/dtheta, dd/dtheta of the closed-loop
+// sensitivity rollout grad_input (cartpole.py:717-788), contracted on the fly.
+#pragma once
+#include "common.cuh"
+#include "dynamics.cuh"
+#include "env_tables_gen.cuh"
+
+namespace dilqr {
+
+// ---------------------------------------------------------------------------
+// Primal costates lambda_t (lqr_step.py:355-369) and the contracted second-order
+// tables Lam_t.  One thread per problem, reverse sweep.
+//   lam  [T,B,ns]      Lam [T-1,B,n,n]  (row k = d/dtau_k, col j)
+// ---------------------------------------------------------------------------
+template <class S, int DYN>
+__global__ void __launch_bounds__(128)
+costate_tables_kernel(DynParams<S> P, int T, int B, const S* __restrict__ C,
+                      const S* __restrict__ c, const S* __restrict__ x, const S* __restrict__ u,
+                      S* __restrict__ lam_out, S* __restrict__ Lam_out) {
+  using D = Dyn<S, DYN>;
+  using TB = EnvTables<S, DYN>;
+  constexpr int NS = D::NS, NC = D::NC, N = D::N, NTH = TB::NTH;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  S lam[NS];
+  for (int t = T - 1; t >= 0; --t) {
+    const size_t tb = (size_t)t * B + b;
+    S tau[N];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) tau[i] = x[tb * NS + i];
+#pragma unroll
+    for (int a = 0; a < NC; ++a) tau[NS + a] = u[tb * NC + a];
+    S Dm[NS][N];
+    if (t < T - 1) {
+      S Dth[NS][N][NTH], Dx[NS][N][NS], Du[NS][N][NC], xth[NS][NTH], xx[NS][NS], xu[NS][NC];
+      TB::eval(P, tau, &tau[NS], Dm, Dth, Dx, Du, xth, xx, xu);
+      // Lam_t[k][j] = sum_i lam_{t+1}[i] dD[i][j]/dtau_k
+      S* Lo = Lam_out + tb * (N * N);
+#pragma unroll
+      for (int k = 0; k < N; ++k)
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          S acc = S(0);
+#pragma unroll
+          for (int i = 0; i < NS; ++i)
+            acc = fmaS<S>(lam[i], k < NS ? Dx[i][j][k < NS ? k : 0] : Du[i][j][k < NS ? 0 : k - NS],
+                          acc);
+          Lo[k * N + j] = acc;
+        }
+    }
+    S nl[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      S a1 = S(0), a2 = S(0);
+#pragma unroll
+      for (int j = 0; j < NS; ++j) a1 = fmaS<S>(C[tb * (N * N) + i * N + j], tau[j], a1);
+#pragma unroll
+      for (int a = 0; a < NC; ++a)
+        a2 = fmaS<S>(C[tb * (N * N) + i * N + NS + a], tau[NS + a], a2);
+      nl[i] = (a1 + a2) + c[tb * N + i];
+    }
+    if (t < T - 1) {
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+        S a1 = S(0);
+#pragma unroll
+        for (int l = 0; l < NS; ++l) a1 = fmaS<S>(Dm[l][i], lam[l], a1);
+        nl[i] = nl[i] + a1;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      lam[i] = nl[i];
+      lam_out[tb * NS + i] = nl[i];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Richardson update  w_t = g_t - Lam_t dtau_t  (t < T-1),  w_{T-1} = g_{T-1};
+// also writes -w (the linear cost of the next adjoint solve) and reduces
+// max|w_new - w_old| and max|w_new| into resid[0], resid[1] (ordered-uint max).
+// One thread per (t, b).
+// ---------------------------------------------------------------------------
+template <class S, int NS, int NC>
+__global__ void richardson_update_kernel(int T, int B, const S* __restrict__ g,
+                                         const S* __restrict__ Lam, const S* __restrict__ dx,
+                                         const S* __restrict__ du, S* __restrict__ w,
+                                         S* __restrict__ negw,
+                                         unsigned long long* __restrict__ resid) {
+  constexpr int N = NS + NC;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.y;
+  double dmax = 0.0, wmax = 0.0;
+  if (b < B) {
+    const size_t tb = (size_t)t * B + b;
+    S dt[N];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) dt[i] = dx[tb * NS + i];
+#pragma unroll
+    for (int a = 0; a < NC; ++a) dt[NS + a] = du[tb * NC + a];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      S acc = S(0);
+      if (t < T - 1) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) acc = fmaS<S>(Lam[tb * (N * N) + k * N + j], dt[j], acc);
+      }
+      const S wn = g[tb * N + k] - acc;
+      const S wo = w[tb * N + k];
+      dmax = fmax(dmax, fabs((double)wn - (double)wo));
+      wmax = fmax(wmax, fabs((double)wn));
+      w[tb * N + k] = wn;
+      negw[tb * N + k] = -wn;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    dmax = fmax(dmax, __shfl_xor_sync(kFull, dmax, o));
+    wmax = fmax(wmax, __shfl_xor_sync(kFull, wmax, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(&resid[0], dbits(dmax));
+    atomicMax(&resid[1], dbits(wmax));
+  }
+}
+
+// ---------------------------------------------------------------------------
+// dtheta: closed-loop sensitivity rollout (cartpole.py:755-782) contracted on
+// the fly with the adjoint quantities.  One thread per problem, forward sweep.
+//   K      [T,B,nc,ns]  gains of the final LQR pass in FORWARD time order; the
+//                       reference indexes its reverse-time stack with t
+//                       (SURVEY 8a-10 quirk), i.e. uses K_{T-1-t} at step t.
+//   lam    [T,B,ns]     primal costates           dx,du: adjoint solution (r = w)
+//   df     [T-1,B,ns]   = -dlam_{t+1}             dtheta [B,nth]
+// ---------------------------------------------------------------------------
+template <class S, int DYN>
+__global__ void __launch_bounds__(128)
+sens_theta_kernel(DynParams<S> P, int T, int B, const S* __restrict__ x,
+                  const S* __restrict__ u, const S* __restrict__ K, const S* __restrict__ lam,
+                  const S* __restrict__ dx, const S* __restrict__ du, const S* __restrict__ df,
+                  S* __restrict__ dtheta) {
+  using D = Dyn<S, DYN>;
+  using TB = EnvTables<S, DYN>;
+  constexpr int NS = D::NS, NC = D::NC, N = D::N, NTH = TB::NTH;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  S G[NS][NTH], Gp[NS][NTH], Dprev[NS][N], Kp[NC][NS];
+  S acc[NTH];
+#pragma unroll
+  for (int q = 0; q < NTH; ++q) acc[q] = S(0);
+#pragma unroll
+  for (int i = 0; i < NS; ++i)
+#pragma unroll
+    for (int q = 0; q < NTH; ++q) G[i][q] = S(0);
+  for (int t = 0; t < T; ++t) {
+    const size_t tb = (size_t)t * B + b;
+    S tau[N], dtau[N];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      tau[i] = x[tb * NS + i];
+      dtau[i] = dx[tb * NS + i];
+    }
+#pragma unroll
+    for (int a = 0; a < NC; ++a) {
+      tau[NS + a] = u[tb * NC + a];
+      dtau[NS + a] = du[tb * NC + a];
+    }
+    S Dm[NS][N], Dth[NS][N][NTH], Dx[NS][N][NS], Du[NS][N][NC], xth[NS][NTH], xx[NS][NS],
+        xu[NS][NC];
+    TB::eval(P, tau, &tau[NS], Dm, Dth, Dx, Du, xth, xx, xu);
+    S Kt[NC][NS];   // K_ref[t] = K_{T-1-t}
+    {
+      const size_t kb = ((size_t)(T - 1 - t) * B + b) * (NC * NS);
+#pragma unroll
+      for (int a = 0; a < NC; ++a)
+#pragma unroll
+        for (int j = 0; j < NS; ++j) Kt[a][j] = K[kb + a * NS + j];
+    }
+    if (t > 0) {
+      // G_t = xth + (xx + xu K_ref[t-1]) G_{t-1}                 (cartpole.py:768)
+      S A[NS][NS];
+#pragma unroll
+      for (int i = 0; i < NS; ++i)
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+          S s = S(0);
+#pragma unroll
+          for (int a = 0; a < NC; ++a) s = fmaS<S>(xu[i][a], Kp[a][j], s);
+          A[i][j] = xx[i][j] + s;
+        }
+#pragma unroll
+      for (int i = 0; i < NS; ++i)
+#pragma unroll
+        for (int q = 0; q < NTH; ++q) Gp[i][q] = G[i][q];
+#pragma unroll
+      for (int i = 0; i < NS; ++i)
+#pragma unroll
+        for (int q = 0; q < NTH; ++q) {
+          S s = S(0);
+#pragma unroll
+          for (int j = 0; j < NS; ++j) s = fmaS<S>(A[i][j], Gp[j][q], s);
+          G[i][q] = xth[i][q] + s;
+        }
+      // <df_{t-1}, G_t - D_{t-1} [G_{t-1}; K_ref[t-1] G_{t-1}]>   (cartpole.py:778-782)
+      S Z[N][NTH];
+#pragma unroll
+      for (int q = 0; q < NTH; ++q) {
+#pragma unroll
+        for (int j = 0; j < NS; ++j) Z[j][q] = Gp[j][q];
+#pragma unroll
+        for (int a = 0; a < NC; ++a) {
+          S s = S(0);
+#pragma unroll
+          for (int j = 0; j < NS; ++j) s = fmaS<S>(Kp[a][j], Gp[j][q], s);
+          Z[NS + a][q] = s;
+        }
+      }
+      const size_t pb = (size_t)(t - 1) * B + b;
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+        const S dfi = df[pb * NS + i];
+#pragma unroll
+        for (int q = 0; q < NTH; ++q) {
+          S s = S(0);
+#pragma unroll
+          for (int m = 0; m < N; ++m) s = fmaS<S>(Dprev[i][m], Z[m][q], s);
+          acc[q] = fmaS<S>(dfi, G[i][q] - s, acc[q]);
+        }
+      }
+    }
+    if (t < T - 1) {
+      // sum_ij W[i][j] gradD_t[i][j][:],  W = -lam_{t+1} dtau_t'
+      // gradD = Dth + (Dx + Du K_ref[t]) G_t                      (cartpole.py:773-775)
+      const size_t nb = (size_t)(t + 1) * B + b;
+      S lm[NS];
+#pragma unroll
+      for (int i = 0; i < NS; ++i) lm[i] = lam[nb * NS + i];
+      S om[NS];   // om[k] = sum_ij W_ij (Dx[i][j][k] + sum_a Du[i][j][a] K[a][k])
+#pragma unroll
+      for (int k = 0; k < NS; ++k) om[k] = S(0);
+#pragma unroll
+      for (int i = 0; i < NS; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          const S wij = -(lm[i] * dtau[j]);
+#pragma unroll
+          for (int q = 0; q < NTH; ++q) acc[q] = fmaS<S>(wij, Dth[i][j][q], acc[q]);
+#pragma unroll
+          for (int k = 0; k < NS; ++k) {
+            S e = Dx[i][j][k];
+#pragma unroll
+            for (int a = 0; a < NC; ++a) e = fmaS<S>(Du[i][j][a], Kt[a][k], e);
+            om[k] = fmaS<S>(wij, e, om[k]);
+          }
+        }
+#pragma unroll
+      for (int k = 0; k < NS; ++k)
+#pragma unroll
+        for (int q = 0; q < NTH; ++q) acc[q] = fmaS<S>(om[k], G[k][q], acc[q]);
+    }
+#pragma unroll
+    for (int i = 0; i < NS; ++i)
+#pragma unroll
+      for (int j = 0; j < N; ++j) Dprev[i][j] = Dm[i][j];
+#pragma unroll
+    for (int a = 0; a < NC; ++a)
+#pragma unroll
+      for (int j = 0; j < NS; ++j) Kp[a][j] = Kt[a][j];
+  }
+#pragma unroll
+  for (int q = 0; q < NTH; ++q) dtheta[(size_t)b * NTH + q] = acc[q];
+}
+
+}  // namespace dilqr

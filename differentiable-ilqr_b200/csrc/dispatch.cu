@@ -13,7 +13,13 @@ namespace dilqr {
   int kkt_grads_##sfx(const DilqrKkt*, void*);                                            \
   int linearize_##sfx(int, const double*, int, int, const void*, const void*, void*, void*, \
                       void*);                                                             \
-  int rollout_##sfx(int, const double*, int, int, const void*, const void*, void*, void*);
+  int rollout_##sfx(int, const double*, int, int, const void*, const void*, void*, void*);     \
+  int costate_tables_##sfx(int, const double*, int, int, const void*, const void*, const void*, \
+                           const void*, void*, void*, void*);                               \
+  int sens_theta_##sfx(int, const double*, int, int, const void*, const void*, const void*,   \
+                       const void*, const void*, const void*, const void*, void*, void*);   \
+  int richardson_update_##sfx(int, int, int, int, const void*, const void*, const void*,      \
+                              const void*, void*, void*, void*, void*);
 DECL(f32)
 DECL(f64)
 #undef DECL
@@ -66,6 +72,25 @@ int dilqr_rollout(int dtype, int dyn, const double* dp, int T, int B, const void
                   const void* u, void* x, void* st) {
   return ROUTE(dtype, dilqr::rollout_f32(dyn, dp, T, B, x0, u, x, st),
                dilqr::rollout_f64(dyn, dp, T, B, x0, u, x, st));
+}
+
+int dilqr_costate_tables(int dtype, int dyn, const double* dp, int T, int B, const void* C,
+                         const void* c, const void* x, const void* u, void* lam, void* Lam,
+                         void* st) {
+  return ROUTE(dtype, dilqr::costate_tables_f32(dyn, dp, T, B, C, c, x, u, lam, Lam, st),
+               dilqr::costate_tables_f64(dyn, dp, T, B, C, c, x, u, lam, Lam, st));
+}
+int dilqr_sens_theta(int dtype, int dyn, const double* dp, int T, int B, const void* x,
+                     const void* u, const void* K, const void* lam, const void* dx,
+                     const void* du, const void* df, void* dtheta, void* st) {
+  return ROUTE(dtype, dilqr::sens_theta_f32(dyn, dp, T, B, x, u, K, lam, dx, du, df, dtheta, st),
+               dilqr::sens_theta_f64(dyn, dp, T, B, x, u, K, lam, dx, du, df, dtheta, st));
+}
+int dilqr_richardson_update(int dtype, int ns, int nc, int T, int B, const void* g,
+                            const void* Lam, const void* dx, const void* du, void* w, void* negw,
+                            void* resid, void* st) {
+  return ROUTE(dtype, dilqr::richardson_update_f32(ns, nc, T, B, g, Lam, dx, du, w, negw, resid, st),
+               dilqr::richardson_update_f64(ns, nc, T, B, g, Lam, dx, du, w, negw, resid, st));
 }
 
 }  // extern "C"

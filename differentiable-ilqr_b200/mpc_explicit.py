@@ -1,0 +1,84 @@
+"""``mpc_explicit.MPC`` -- drop-in for the reference's DiLQR variant
+(mpc_explicit.py:58-358 + lqr_step_explicit.py): same forward as ``mpc.MPC``
+with the analytic env_dx linearisation (mpc_explicit.py:516-546), and the
+implicit fixed-point gradient wrt the cost (C, c) and the dynamics parameters
+``dx.params`` in the backward pass (lqr_step_explicit.py:652-712)."""
+import torch
+from torch.autograd import Function
+
+from . import _lib, _solver
+from .definitions import QuadCost, LinDx  # noqa: F401
+from .mpc import MPC as _BaseMPC, GradMethods, _dyn_spec  # noqa: F401
+
+
+class _MPCExplicitFn(Function):
+    @staticmethod
+    def forward(ctx, mod, dx, x_init, C, c, theta):
+        dyn = _dyn_spec(dx)
+        x, u, costs, info = _solver.solve_mpc(
+            x_init, C, c, dyn, mod.n_state, mod.n_ctrl, mod.T,
+            u_lower=mod.u_lower, u_upper=mod.u_upper, u_zero_I=mod.u_zero_I,
+            u_init=mod.u_init, lqr_iter=mod.lqr_iter, eps=mod.eps,
+            linesearch_decay=mod.linesearch_decay,
+            max_linesearch_iter=mod.max_linesearch_iter,
+            not_improved_lim=mod.not_improved_lim, best_cost_eps=mod.best_cost_eps,
+            gain_solve=_lib.GAIN_PLAIN, solo=mod.solo, verbose=mod.verbose)
+        mod.last_info = info
+        ctx.mod, ctx.dx = mod, dx
+        ctx.mask = None
+        eps_cmp = float(torch.tensor(mod.eps, dtype=x.dtype))
+        if mod.detach_unconverged:                       # mpc_explicit.py:343-356
+            if float(info.full_du_norm.max()) > eps_cmp:
+                if mod.exit_unconverged:
+                    assert False
+                if mod.verbose >= 0:
+                    print("LQR Warning: All examples did not converge to a fixed point.")
+                    print("Detaching and *not* backpropping through the bad examples.")
+                ctx.mask = (info.full_du_norm < eps_cmp).to(x.dtype)
+        ctx.save_for_backward(x_init, C, c, x, u)
+        ctx.mark_non_differentiable(costs)
+        return x, u, costs
+
+    @staticmethod
+    def backward(ctx, dl_dx, dl_du, _dcosts):
+        mod, dx = ctx.mod, ctx.dx
+        x_init, C, c, x, u = ctx.saved_tensors
+        if ctx.mask is not None:
+            dl_dx = dl_dx * ctx.mask.view(1, -1, 1)
+            dl_du = dl_du * ctx.mask.view(1, -1, 1)
+        stats = {}
+        dC, dc, dtheta = _solver.dilqr_backward(
+            dl_dx.contiguous(), dl_du.contiguous(), x_init, C, c, x, u, dx, mod.n_state,
+            mod.n_ctrl, mod.u_lower, mod.u_upper, n_passes=mod.richardson_passes,
+            tol=mod.richardson_tol, back_eps=mod.back_eps, solo=mod.solo, stats=stats)
+        mod.last_backward = stats
+        # the reference returns dtheta[B, n_theta]; autograd sums it to theta's shape
+        return None, None, None, dC, dc, dtheta.sum(0)
+
+
+class MPC(_BaseMPC):
+    """Arguments as the reference (mpc_explicit.py:122-143) plus two knobs of the
+    matrix-free fixed-point solve: ``richardson_passes`` (max adjoint-LQR passes)
+    and ``richardson_tol`` (relative stop tolerance; None = fixed pass count)."""
+
+    def __init__(self, *args, richardson_passes=30, richardson_tol=1e-14, **kw):
+        super().__init__(*args, **kw)
+        self.richardson_passes = richardson_passes
+        self.richardson_tol = richardson_tol
+        self.last_backward = None
+
+    def forward(self, x_init, cost, dx):
+        if isinstance(dx, LinDx):
+            # the reference's explicit variant rejects LinDx (mpc_explicit.py:325)
+            raise AttributeError("'LinDx' object has no attribute 'params'")
+        if not isinstance(cost, QuadCost):
+            raise NotImplementedError("only QuadCost is supported (SURVEY 8a-2)")
+        n_batch = self.n_batch if self.n_batch is not None else (
+            cost.C.size(1) if cost.C.ndimension() == 4 else None)
+        if n_batch is None:
+            print('MPC Error: Could not infer batch size, pass in as n_batch')
+            import sys
+            sys.exit(-1)
+        C, c = self._expand_cost(cost, n_batch)
+        assert x_init.ndimension() == 2 and x_init.size(0) == n_batch
+        return _MPCExplicitFn.apply(self, dx, x_init, C, c, dx.params)

@@ -96,7 +96,7 @@ typedef struct DilqrSolve {
   const void* F;            /* [T-1,B,ns,n]  (LinDx)                                */
   const void* f;            /* [T-1,B,ns]    (LinDx, optional)                      */
   const void* u_init;       /* [T,B,nc] or NULL (zeros, mpc.py:230-231)             */
-  const void* x_cur;        /* [T,B,ns] current trajectory (dilqr_lqr_step only)    */
+  const void* x_cur;        /* [T,B,ns] current trajectory (single LQR step only)    */
   const void* u_lower_t;    /* [T,B,nc] tensor bounds (lqr_step.py:264-272)         */
   const void* u_upper_t;
   const uint8_t* u_zero_I;  /* [T,B,nc] bool mask or NULL (lqr_step.py:99-127)      */
@@ -119,7 +119,7 @@ const char* dilqr_version(void);
 /* 1 if kernels for this combination are compiled in, else 0. */
 int dilqr_supported(int dtype, int n_state, int n_ctrl, int dynamics);
 
-/* Bytes of workspace the dilqr_mpc_* / dilqr_lqr_step calls need. */
+/* Bytes of workspace the dilqr_mpc_* calls need. */
 size_t dilqr_workspace_bytes(const DilqrSolve* s);
 
 /* ---- iLQR outer loop, MPC.forward (mpc.py:184-337, mpc_explicit.py:182-358) -- */
@@ -144,23 +144,12 @@ int dilqr_mpc_commit(const DilqrSolve* s, void* stream);
 /* Gather the best iterate into x_out,u_out,cost_out,du_out (mpc.py:304-306). */
 int dilqr_mpc_finish(const DilqrSolve* s, void* stream);
 
-/* ---- single LQR step, LQRStep(...)(x_init,C,c,F,f) (lqr_step.py:22-38,277-309)
- * around (x_cur,u_init); writes x_out,u_out,cost_out,du_out,alpha_out and, if
- * non-NULL, K_out,k_out; status gets n_total_qp_iter / mean_alpha.  Runs the
- * trace-verification loop on the device side up to `max_retries` times; returns
- * 0 and sets status.trace_match accordingly (host re-calls if it is 0). */
-int dilqr_lqr_step(const DilqrSolve* s, void* stream);
-
-/* ---- standalone pnqp (pnqp.py:5-82) -------------------------------------
- * H[B,n,n] q[B,n] lower[B,n] upper[B,n] x_init[B,n] or NULL -> x[B,n],
- * Hfree[B,n,n] (masked Hessian + 1e-11 I of the last iteration), If[B,n]
- * (float 0/1), n_iter (device int32[2]: {i, converged}).  Batch-global control
- * flow is resolved with a cooperative grid (n_batch limited to resident
- * threads) -- see DESIGN.md. */
-int dilqr_pnqp(int dtype, int n, int n_batch, const void* H, const void* q,
-               const void* lower, const void* upper, const void* x_init,
-               void* x, void* Hfree, void* If, int32_t* n_iter, int solo,
-               void* stream);
+/* A single LQR step, LQRStep(...)(x_init,C,c,F,f) (lqr_step.py:22-38,277-309), is
+ * the same call sequence with `x_cur` (and `u_init` = current u) set: dilqr_mpc_begin
+ * then loads the given trajectory instead of rolling it out, one
+ * dilqr_mpc_iterate + dilqr_mpc_commit(first_iteration=1) runs the step, and
+ * dilqr_mpc_finish returns the new iterate (x_out,u_out,cost_out,du_out,
+ * alpha_out) and, if requested, the gains K_out,k_out of lqr_backward. */
 
 /* ---- analytic linearisation (mpc_explicit.py:516-546) --------------------
  * x[T,B,ns], u[T,B,nc] -> F[T-1,B,ns,n], f[T-1,B,ns] (f may be NULL). */
@@ -188,6 +177,33 @@ typedef struct DilqrKkt {
   void *dC, *dc, *dF, *df, *dx_init;
 } DilqrKkt;
 int dilqr_kkt_grads(const DilqrKkt* k, void* stream);
+
+/* ---- DiLQR implicit (fixed-point) gradient, LQRStepFn.backward +
+ * fix_point_equ (lqr_step_explicit.py:652-712, 458-598), matrix-free -------- */
+
+/* Primal costates lam[T,B,ns] (lqr_step_explicit.py:305-319) and contracted
+ * second-order tables Lam[T-1,B,n,n], Lam_t[k][j] = sum_i lam_{t+1}[i]
+ * dD_t[i][j]/dtau_k with dD/dtau from get_matrices (cartpole.py:425-613,
+ * pendulum.py:152-382). */
+int dilqr_costate_tables(int dtype, int dynamics, const double* dyn_params, int T, int n_batch,
+                         const void* C, const void* c, const void* x, const void* u, void* lam,
+                         void* Lam, void* stream);
+
+/* One Richardson update of A' w = g:  w_t = g_t - Lam_t dtau_t (t < T-1),
+ * w_{T-1} = g_{T-1}; writes w and -w, and resid[0] = max|w_new - w_old|,
+ * resid[1] = max|w_new| (two doubles, device).  (dx,du) is the adjoint LQR
+ * solution for r = w_old (lqr_step_explicit.py:276-303). */
+int dilqr_richardson_update(int dtype, int n_state, int n_ctrl, int T, int n_batch, const void* g,
+                            const void* Lam, const void* dx, const void* du, void* w, void* negw,
+                            void* resid, void* stream);
+
+/* dtheta[B,n_theta] = sum_t <dF_w, dD_t/dtheta> + <df_w, dd_t/dtheta> with the
+ * closed-loop sensitivity rollout grad_input (cartpole.py:717-788, pendulum.py:
+ * 383-443) contracted on the fly.  K[T,B,nc,ns]: gains of the final LQR pass in
+ * forward time order; df[T-1,B,ns] = -dlam_{t+1} from dilqr_kkt_grads. */
+int dilqr_sens_theta(int dtype, int dynamics, const double* dyn_params, int T, int n_batch,
+                     const void* x, const void* u, const void* K, const void* lam, const void* dx,
+                     const void* du, const void* df, void* dtheta, void* stream);
 
 #ifdef __cplusplus
 }

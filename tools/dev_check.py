@@ -95,7 +95,7 @@ def run_env(name, T, B, dtype, lqr_iter, sigma=0.5, seed=0):
           f"cost {rel(costs, o.costs):.2e} | cpu {t_cpu:.2f}s gpu {t_gpu:.3f}s")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and os.environ.get("BASIC", "1") == "1":
     print(torch.cuda.get_device_name(0))
     for dtype in (torch.float64, torch.float32):
         run_lindx(4, 2, 12, 16, dtype, False)
@@ -107,3 +107,48 @@ if __name__ == "__main__":
         run_env("cartpole", 20, 64, dtype, 1)
         run_env("cartpole", 50, 128, dtype, 10)
     run_env("cartpole", 50, 65536, torch.float64, 10) if os.environ.get("BIG") else None
+
+
+def run_dilqr(name, T, B, dtype, lqr_iter, sigma=0.05, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    if name == "cartpole":
+        pdx = port.CartpoleDx(dtype=dtype)
+        th0 = torch.tensor((9.8, 1.0, 0.1, 0.5), dtype=dtype)
+        gdx = env.CartpoleDx(th0.to(dev).requires_grad_())
+        r = (torch.rand(B, 4, generator=g, dtype=torch.float64) * 2 - 1) * sigma
+        x0 = torch.stack((r[:, 0], r[:, 1], torch.cos(r[:, 2]), torch.sin(r[:, 2]), r[:, 3]), 1)
+    else:
+        pdx = port.PendulumDx(dtype=dtype)
+        gdx = env.PendulumDx(torch.tensor((10., 1., 1.), dtype=dtype, device=dev).requires_grad_())
+        th = (torch.rand(B, generator=g, dtype=torch.float64) - 0.5) * 3.14159
+        w = torch.rand(B, generator=g, dtype=torch.float64) * 2 - 1
+        x0 = torch.stack((torch.cos(th), torch.sin(th), w), 1)
+    x0 = x0.to(dtype)
+    ns, nc = pdx.n_state, pdx.n_ctrl
+    q, p = pdx.get_true_obj()
+    C = torch.diag(q)[None, None].repeat(T, B, 1, 1)
+    c = p[None, None].repeat(T, B, 1)
+    kw = dict(u_lower=pdx.lower, u_upper=pdx.upper, lqr_iter=lqr_iter, eps=1e-9,
+              linesearch_decay=pdx.linesearch_decay,
+              max_linesearch_iter=pdx.max_linesearch_iter)
+    o = port.mpc_forward(x0, port.QuadCost(C, c), pdx, ns, nc, T, final_pass=False, **kw)
+    gg = torch.Generator().manual_seed(7)
+    gx = torch.randn(o.x.shape, generator=gg, dtype=torch.float64).to(dtype)
+    gu = torch.randn(o.u.shape, generator=gg, dtype=torch.float64).to(dtype)
+    ref = port.dilqr_backward(gx, gu, x0, C, c, o.x, o.u, pdx, ns, nc, pdx.lower, pdx.upper,
+                              n_passes=30, tol=1e-15)
+    m = d.mpc_explicit.MPC(ns, nc, T, verbose=-1, exit_unconverged=False,
+                           detach_unconverged=False, **kw)
+    Cg, cg = C.to(dev).requires_grad_(), c.to(dev).requires_grad_()
+    x, u, costs = m(x0.to(dev), d.QuadCost(Cg, cg), gdx)
+    ((x * gx.to(dev)).sum() + (u * gu.to(dev)).sum()).backward()
+    print(f"dilqr {name} T={T} B={B} {dtype}: fwd iters {m.last_info.n_iters}/{o.n_iters} x {rel(x, o.x):.2e} "
+          f"passes {m.last_backward} (cpu {ref.n_passes}) dtheta {rel(gdx.params.grad, ref.dtheta.sum(0)):.2e} "
+          f"dC {rel(Cg.grad, ref.dC):.2e} dc {rel(cg.grad, ref.dc):.2e}")
+
+
+if __name__ == "__main__" and os.environ.get("DILQR", "1") == "1":
+    for dtype in (torch.float64, torch.float32):
+        run_dilqr("pendulum", 20, 8, dtype, 60)
+        run_dilqr("cartpole", 12, 8, dtype, 80)
+        run_dilqr("cartpole", 30, 40, dtype, 80, sigma=0.3)
