@@ -8,7 +8,7 @@ The directory name is not a valid Python identifier; import it with
 from . import _lib
 from .definitions import QuadCost, LinDx
 from .mpc import MPC, GradMethods
-from . import mpc, mpc_explicit, env_dx  # noqa: F401
+from . import mpc, mpc_explicit, env_dx, il, parallel  # noqa: F401
 
 __all__ = ["MPC", "GradMethods", "QuadCost", "LinDx", "build"]
 

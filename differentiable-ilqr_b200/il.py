@@ -1,0 +1,77 @@
+"""Imitation-learning step in the shape of the reference's ``il_exp`` loop
+(il_exp.py:326-409) and ``IL_Env.mpc`` (il_env.py:153-188): tile the diagonal
+cost, solve the batched MPC, imitation loss against expert controls, implicit
+backward to (theta, q, p).  Problems are sharded across ranks by batch index;
+the only collective is one all-reduce of the (n_theta + 2 n) gradient scalars.
+"""
+import torch
+
+from . import mpc_explicit, parallel
+from .definitions import QuadCost
+
+
+class ImitationStep:
+    def __init__(self, dx_cls, T, lqr_iter, dtype, device, n_richardson=4, richardson_tol=None,
+                 group=None):
+        self.dx_cls = dx_cls
+        self.T = T
+        self.dtype, self.device = dtype, device
+        proto = dx_cls()
+        self.ns, self.nc = proto.n_state, proto.n_ctrl
+        self.mpc = mpc_explicit.MPC(
+            self.ns, self.nc, T, u_lower=proto.lower, u_upper=proto.upper, lqr_iter=lqr_iter,
+            verbose=-1, exit_unconverged=False, detach_unconverged=False,
+            linesearch_decay=proto.linesearch_decay,
+            max_linesearch_iter=proto.max_linesearch_iter, eps=proto.mpc_eps,
+            richardson_passes=n_richardson, richardson_tol=richardson_tol)
+        self.group = group
+        self.retries = 0
+        self.backward_name = "DiLQR implicit (%d Richardson passes)" % n_richardson
+        self.d2h_bytes = 0
+
+    # -- pieces -----------------------------------------------------------
+    def tile_cost(self, q, p, B):
+        """il_env.py:159-162: Q = diag(q) tiled to [T,B,n,n], p tiled to [T,B,n]."""
+        C = torch.diag(q).unsqueeze(0).unsqueeze(0).repeat(self.T, B, 1, 1)
+        c = p.unsqueeze(0).repeat(self.T, B, 1)
+        return C, c
+
+    def prepare(self, x0, q, p, theta):
+        return {"x0": x0, "q": q.clone().requires_grad_(), "p": p.clone().requires_grad_(),
+                "theta": theta.clone().requires_grad_()}
+
+    def _step(self, x0, uexp, q, p, theta, world_frac=1.0):
+        for t in (q, p, theta):
+            t.grad = None
+        B = x0.shape[0]
+        C, c = self.tile_cost(q, p, B)
+        dx = self.dx_cls(theta)
+        x, u, _ = self.mpc(x0, QuadCost(C, c), dx)
+        loss = (u - uexp).pow(2).mean() * world_frac      # il_exp.py:346
+        loss.backward()                                    # il_exp.py:373
+        self.retries += self.mpc.last_info.retries
+        flat = torch.cat((theta.grad, q.grad, p.grad, loss.detach().reshape(1)))
+        return parallel.allreduce_sum_(flat, self.group)
+
+    # -- resident inputs (device timing) -----------------------------------
+    def run_resident(self, res, uexp):
+        w = 1.0
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            w = 1.0 / torch.distributed.get_world_size()
+        return self._step(res["x0"], uexp, res["q"], res["p"], res["theta"], w)
+
+    # -- host inputs (end to end) -------------------------------------------
+    def run_host(self, x0_h, uexp_h, q_h, p_h, theta_h):
+        dev = self.device
+        x0 = x0_h.to(dev, non_blocking=True)
+        uexp = uexp_h.to(dev, non_blocking=True)
+        q = q_h.to(dev, non_blocking=True).requires_grad_()
+        p = p_h.to(dev, non_blocking=True).requires_grad_()
+        theta = theta_h.to(dev, non_blocking=True).requires_grad_()
+        w = 1.0
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            w = 1.0 / torch.distributed.get_world_size()
+        flat = self._step(x0, uexp, q, p, theta, w)
+        out = flat.cpu()                                   # loss + gradients back to the host
+        self.d2h_bytes = out.numel() * out.element_size()
+        return out

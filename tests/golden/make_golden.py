@@ -1,0 +1,157 @@
+#!/usr/bin/env python
+"""Generate the golden vectors in tests/golden/*.npz by running the UNMODIFIED
+reference (/root/reference, imported through oracle/ref_harness.py).
+
+Build-container only (the reference does not travel to the GPU box); the
+resulting small .npz files are committed and are what the tests read.
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+"""
+import os
+import pickle
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import ref_harness  # noqa: E402
+
+R = ref_harness.load()
+
+
+def npz(name, **kw):
+    out = {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v))
+           for k, v in kw.items()}
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print("wrote", name, {k: v.shape for k, v in out.items()})
+
+
+def fixtures():
+    """The reference's own data/*.pkl expert trajectories."""
+    for env in ("cartpole", "pendulum"):
+        e = pickle.load(open(os.path.join(ref_harness.REF_ROOT, "data", env + ".pkl"), "rb"))
+        tau = torch.cat((e.train_data, e.val_data, e.test_data), 0).detach()
+        npz("fixture_%s.npz" % env, tau=tau, mpc_T=e.mpc_T, lqr_iter=e.lqr_iter)
+
+
+def lindx(boxed):
+    torch.manual_seed(0)
+    torch.set_default_dtype(torch.float64)
+    ns, nc, T, B = 4, 2, 12, 16
+    n = ns + nc
+    A = torch.randn(T, B, n, n)
+    C = A.transpose(2, 3) @ A + torch.eye(n)
+    c = torch.randn(T, B, n)
+    F = torch.cat((torch.eye(ns).expand(T - 1, B, ns, ns) + 0.2 * torch.randn(T - 1, B, ns, ns) / ns ** 0.5,
+                   torch.randn(T - 1, B, ns, nc) / ns ** 0.5), 3)
+    f = 0.1 * torch.randn(T - 1, B, ns)
+    x0 = torch.randn(B, ns)
+    kw = dict(u_lower=-1.0, u_upper=1.0) if boxed else {}
+    Cg, cg, Fg, fg, x0g = [t.clone().requires_grad_() for t in (C, c, F, f, x0)]
+    m = R.mpc.MPC(ns, nc, T, lqr_iter=20, verbose=-1, exit_unconverged=False, **kw)
+    x, u, costs = m(x0g, R.mpc.QuadCost(Cg, cg), R.mpc.LinDx(Fg, fg))
+    g = torch.Generator().manual_seed(7)
+    gx = torch.randn(x.shape, generator=g)
+    gu = torch.randn(u.shape, generator=g)
+    ((x * gx).sum() + (u * gu).sum()).backward()
+    npz("ref_lindx_%s.npz" % ("boxed" if boxed else "free"), C=C, c=c, F=F, f=f, x0=x0, x=x, u=u,
+        costs=costs, gx=gx, gu=gu, dx0=x0g.grad, dC=Cg.grad, dc=cg.grad, dF=Fg.grad, df=fg.grad)
+
+
+def dilqr(env, T, B, lqr_iter, sigma):
+    torch.manual_seed(0)
+    torch.set_default_dtype(torch.float64)
+    dt = torch.float64
+    if env == "pendulum":
+        theta = torch.tensor((10., 1., 1.), dtype=dt, requires_grad=True)
+        dx = R.pendulum.PendulumDx(theta)
+        th = (torch.rand(B) - 0.5) * 3.14159
+        w = torch.rand(B) * 2 - 1
+        x0 = torch.stack((torch.cos(th), torch.sin(th), w), 1)
+    else:
+        theta = torch.tensor((9.8, 1.0, 0.1, 0.5), dtype=dt, requires_grad=True)
+        dx = R.cartpole.CartpoleDx(theta)
+        r = (torch.rand(B, 4) * 2 - 1) * sigma
+        x0 = torch.stack((r[:, 0], r[:, 1], torch.cos(r[:, 2]), torch.sin(r[:, 2]), r[:, 3]), 1)
+    q, p = dx.get_true_obj()
+    q, p = q.to(dt), p.to(dt)
+    C = torch.diag(q)[None, None].repeat(T, B, 1, 1).requires_grad_()
+    c = p[None, None].repeat(T, B, 1).requires_grad_()
+    m = R.mpc_explicit.MPC(dx.n_state, dx.n_ctrl, T, u_lower=dx.lower, u_upper=dx.upper,
+                           lqr_iter=lqr_iter, verbose=-1, exit_unconverged=False,
+                           detach_unconverged=False, linesearch_decay=dx.linesearch_decay,
+                           max_linesearch_iter=dx.max_linesearch_iter, eps=1e-9,
+                           grad_method=R.mpc_explicit.GradMethods.ANALYTIC)
+    x, u, costs = m(x0, R.mpc_explicit.QuadCost(C, c), dx)
+    g = torch.Generator().manual_seed(7)
+    gx = torch.randn(x.shape, generator=g)
+    gu = torch.randn(u.shape, generator=g)
+    ((x * gx).sum() + (u * gu).sum()).backward()
+    npz("ref_dilqr_%s.npz" % env, x0=x0, q=q, p=p, theta=theta.detach(), x=x, u=u, costs=costs,
+        gx=gx, gu=gu, dC=C.grad, dc=c.grad, dtheta=theta.grad, T=T, lqr_iter=lqr_iter)
+
+
+def tables():
+    torch.manual_seed(1)
+    torch.set_default_dtype(torch.float64)
+    out = {}
+    for env, cls, ns, nth in (("cartpole", R.cartpole.CartpoleDx, 5, 4),
+                              ("pendulum", R.pendulum.PendulumDx, 3, 3)):
+        theta = torch.rand(nth) * 2 + 0.3
+        dx = cls(theta.clone())
+        x = torch.randn(6, ns)
+        u = torch.randn(6, 1)
+        names = ["D", "D_theta", "D_x", "D_u", "x_theta", "x_x", "x_u"]
+        res = dx.get_matrices(x, u)
+        out.update({env + "_theta": theta, env + "_x": x, env + "_u": u})
+        out.update({env + "_" + n: t for n, t in zip(names, res)})
+        out[env + "_step"] = dx(x, u)
+        out[env + "_lin"] = dx.get_linear_dyn(x, u)
+    npz("ref_tables.npz", **out)
+
+
+def env_forward(env, T, B, lqr_iter, dtype):
+    """Forward-only env solve incl. per-iteration qp counts (control-flow parity)."""
+    torch.manual_seed(3)
+    torch.set_default_dtype(dtype)
+    if env == "pendulum":
+        dx = R.pendulum.PendulumDx(torch.tensor((10., 1., 1.), dtype=dtype))
+        th = (torch.rand(B) - 0.5) * 3.14159
+        w = torch.rand(B) * 2 - 1
+        x0 = torch.stack((torch.cos(th), torch.sin(th), w), 1)
+    else:
+        dx = R.cartpole.CartpoleDx(torch.tensor((9.8, 1.0, 0.1, 0.5), dtype=dtype))
+        r = (torch.rand(B, 4) * 2 - 1) * 0.5
+        x0 = torch.stack((r[:, 0], r[:, 1], torch.cos(r[:, 2]), torch.sin(r[:, 2]), r[:, 3]), 1)
+    q, p = dx.get_true_obj()
+    C = torch.diag(q.to(dtype))[None, None].repeat(T, B, 1, 1)
+    c = p.to(dtype)[None, None].repeat(T, B, 1)
+    m = R.mpc_explicit.MPC(dx.n_state, dx.n_ctrl, T, u_lower=dx.lower, u_upper=dx.upper,
+                           lqr_iter=lqr_iter, verbose=-1, exit_unconverged=False,
+                           detach_unconverged=False, linesearch_decay=dx.linesearch_decay,
+                           max_linesearch_iter=dx.max_linesearch_iter, eps=dx.mpc_eps,
+                           grad_method=R.mpc_explicit.GradMethods.ANALYTIC)
+    with torch.no_grad():
+        try:
+            x, u, costs = m(x0, R.mpc_explicit.QuadCost(C, c), dx)
+        except RuntimeError:
+            raise
+    tag = "f64" if dtype == torch.float64 else "f32"
+    npz("ref_fwd_%s_%s.npz" % (env, tag), x0=x0, q=q.to(dtype), p=p.to(dtype), x=x, u=u,
+        costs=costs, T=T, lqr_iter=lqr_iter)
+    torch.set_default_dtype(torch.float32)
+
+
+if __name__ == "__main__":
+    fixtures()
+    lindx(False)
+    lindx(True)
+    dilqr("pendulum", 20, 4, 60, None)
+    dilqr("cartpole", 12, 8, 80, 0.05)
+    tables()
+    env_forward("cartpole", 25, 16, 6, torch.float64)
+    env_forward("pendulum", 20, 16, 8, torch.float64)
+    env_forward("cartpole", 25, 16, 6, torch.float32)

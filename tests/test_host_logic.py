@@ -1,0 +1,78 @@
+"""Host-side mirror of the reference interface: argument handling that needs no GPU."""
+import importlib
+
+import pytest
+import torch
+
+
+def test_constructor_defaults_match_reference(dilqr):
+    m = dilqr.MPC(3, 1, 20)
+    ref = dict(u_lower=None, u_upper=None, u_zero_I=None, u_init=None, lqr_iter=10, delta_u=None,
+               verbose=0, eps=1e-7, back_eps=1e-7, n_batch=None, linesearch_decay=0.2,
+               max_linesearch_iter=10, exit_unconverged=True, detach_unconverged=True,
+               backprop=True, slew_rate_penalty=None, prev_ctrl=None, not_improved_lim=5,
+               best_cost_eps=1e-4)                        # mpc.py:123-144
+    for k, v in ref.items():
+        assert getattr(m, k) == v, k
+    assert m.grad_method == dilqr.GradMethods.ANALYTIC
+
+
+def test_bounds_must_come_in_pairs(dilqr):
+    with pytest.raises(AssertionError):
+        dilqr.MPC(3, 1, 20, u_lower=-1.0)                # mpc.py:146
+    with pytest.raises(AssertionError):
+        dilqr.MPC(3, 1, 20, max_linesearch_iter=0)       # mpc.py:147
+
+
+def test_cost_expansion_shapes(dilqr):
+    m = dilqr.MPC(3, 1, 5)
+    C, c = m._expand_cost(dilqr.QuadCost(torch.eye(4), torch.zeros(4)), 7)     # mpc.py:205-226
+    assert tuple(C.shape) == (5, 7, 4, 4) and tuple(c.shape) == (5, 7, 4)
+    C, c = m._expand_cost(dilqr.QuadCost(torch.eye(4).repeat(5, 1, 1), torch.zeros(5, 4)), 7)
+    assert tuple(C.shape) == (5, 7, 4, 4) and tuple(c.shape) == (5, 7, 4)
+    with pytest.raises(SystemExit):
+        m._expand_cost(dilqr.QuadCost(torch.zeros(4), torch.zeros(4)), 7)
+
+
+def test_batch_size_inference_error(dilqr):
+    m = dilqr.MPC(3, 1, 5)
+    with pytest.raises(SystemExit):                      # mpc.py:198-199
+        m(torch.zeros(2, 3), dilqr.QuadCost(torch.eye(4), torch.zeros(4)),
+          dilqr.LinDx(torch.zeros(4, 2, 3, 4), None))
+
+
+def test_explicit_rejects_lindx_like_reference(dilqr):
+    m = dilqr.mpc_explicit.MPC(3, 1, 5, n_batch=2)
+    with pytest.raises(AttributeError):                  # mpc_explicit.py:325
+        m(torch.zeros(2, 3), dilqr.QuadCost(torch.eye(4), torch.zeros(4)),
+          dilqr.LinDx(torch.zeros(4, 2, 3, 4), None))
+
+
+def test_env_models_expose_reference_attributes():
+    env = importlib.import_module("differentiable-ilqr_b200.env_dx")
+    cp, pd = env.CartpoleDx(), env.PendulumDx()
+    assert (cp.n_state, cp.n_ctrl, cp.lower, cp.upper) == (5, 1, -100.0, 100.0)
+    assert (cp.mpc_eps, cp.linesearch_decay, cp.max_linesearch_iter, cp.dt) == (1e-4, 0.5, 2, 0.05)
+    assert (pd.n_state, pd.n_ctrl, pd.lower, pd.upper) == (3, 1, -2.0, 2.0)
+    assert (pd.mpc_eps, pd.linesearch_decay, pd.max_linesearch_iter, pd.dt) == (1e-3, 0.2, 5, 0.05)
+    q, p = cp.get_true_obj()                             # cartpole.py:859-867
+    assert torch.allclose(q, torch.tensor([0.1, 0.1, 1., 1., 0.1, 0.001]))
+    assert torch.allclose(p, torch.tensor([0., 0., -1., 0., 0., 0.]))
+    q, p = pd.get_true_obj()                             # pendulum.py:117-125
+    assert torch.allclose(q, torch.tensor([1., 1., 0.1, 0.001]))
+    assert torch.allclose(p, torch.tensor([-1., 0., 0., 0.]))
+
+
+def test_unsupported_features_fail_loudly(dilqr):
+    with pytest.raises(NotImplementedError):
+        dilqr.MPC(3, 1, 5, slew_rate_penalty=1.0)
+    with pytest.raises(NotImplementedError):
+        dilqr.MPC(3, 1, 5, u_lower=-1.0, u_upper=1.0, delta_u=0.1)
+
+
+def test_bytes_per_solve_model():
+    """cartpole T=50 L=10 -> 235.0 KB (fp64) / 117.5 KB (fp32)."""
+    import bench
+    it, bwd, tot = bench.bytes_per_solve(8)
+    assert it == 2457 * 8 and bwd == 4809 * 8 and tot == 235032
+    assert bench.bytes_per_solve(4)[2] == 117516
