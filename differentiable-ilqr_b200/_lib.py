@@ -76,6 +76,19 @@ class DilqrKkt(C.Structure):
     ]
 
 
+class DilqrAdjoint(C.Structure):
+    _fields_ = [
+        ("n_state", C.c_int32), ("n_ctrl", C.c_int32), ("T", C.c_int32), ("n_batch", C.c_int32),
+        ("dtype", C.c_int32), ("dynamics", C.c_int32), ("bounds_kind", C.c_int32),
+        ("gain_solve", C.c_int32),
+        ("u_lower", C.c_double), ("u_upper", C.c_double), ("dyn_params", C.c_double * 8),
+        ("C", C.c_void_p), ("x", C.c_void_p), ("u", C.c_void_p), ("g", C.c_void_p),
+        ("Lam", C.c_void_p), ("w", C.c_void_p), ("dC", C.c_void_p), ("dc", C.c_void_p),
+        ("df", C.c_void_p), ("dx_out", C.c_void_p), ("du_out", C.c_void_p),
+        ("resid", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
 # every symbol include/dilqr.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "dilqr_version": (C.c_char_p, []),
@@ -95,6 +108,10 @@ SYMBOLS = {
     "dilqr_richardson_update": (C.c_int, [C.c_int] * 5 + [C.c_void_p] * 8),
     "dilqr_sens_theta": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int]
                          + [C.c_void_p] * 9),
+    "dilqr_adjoint_workspace_bytes": (C.c_size_t, [C.POINTER(DilqrAdjoint)]),
+    "dilqr_adjoint_factor": (C.c_int, [C.POINTER(DilqrAdjoint), C.c_void_p]),
+    "dilqr_adjoint_pass": (C.c_int, [C.POINTER(DilqrAdjoint), C.c_void_p]),
+    "dilqr_adjoint_final": (C.c_int, [C.POINTER(DilqrAdjoint), C.c_void_p]),
 }
 
 _lib = None
@@ -143,6 +160,7 @@ KERNELS_PER_CALL = {
     "dilqr_mpc_begin": 1, "dilqr_mpc_iterate": 1, "dilqr_mpc_commit": 2,
     "dilqr_mpc_finish": 1, "dilqr_kkt_grads": 1, "dilqr_linearize": 1, "dilqr_rollout": 1,
     "dilqr_costate_tables": 1, "dilqr_richardson_update": 1, "dilqr_sens_theta": 1,
+    "dilqr_adjoint_factor": 1, "dilqr_adjoint_pass": 1, "dilqr_adjoint_final": 1,
 }
 launch_count = 0     # running total of kernels launched through this binding
 profile = None       # set to a dict {name: [(start_event, end_event), ...]} to time calls

@@ -282,7 +282,8 @@ def kkt_backward(dl_dx, dl_du, x_init, C_, c_, F, f, x, u, n_state, n_ctrl, u_lo
 
 
 def dilqr_backward(dl_dx, dl_du, x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u_lower=None,
-                   u_upper=None, n_passes=8, tol=None, back_eps=1e-7, solo=False, stats=None):
+                   u_upper=None, n_passes=8, tol=None, back_eps=1e-7, solo=False, stats=None,
+                   factored=True):
     """DiLQR implicit gradient (lqr_step_explicit.py:652-712 + fix_point_equ
     458-598) in matrix-free form (derivation in
     csrc/dilqr_backward.cuh).  Returns (dC, dc, dtheta[B, n_theta]).
@@ -290,7 +291,12 @@ def dilqr_backward(dl_dx, dl_du, x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u
     n_passes Richardson passes solve A' w = g (each = one adjoint LQR solve); with
     ``tol`` the loop stops early once max|dw| <= tol * max|w| (one host sync per
     pass).  The adjoint solves follow mpc_backup / lqr_step_backup (Cholesky +
-    1e-6 I for unconstrained multi-input problems, lqr_step_backup.py:202-205)."""
+    1e-6 I for unconstrained multi-input problems, lqr_step_backup.py:202-205).
+
+    ``factored=True`` runs the adjoint solves with the factor-once / affine-pass
+    kernels (csrc/adjoint_kernels.cuh); if any problem's adjoint step would have been
+    rejected by the reference's line search (non-convex model), the whole backward is
+    recomputed with the generic line-searching kernels (``factored=False``)."""
     T, B = x.shape[0], x.shape[1]
     dtype, dev = x.dtype, x.device
     n = n_state + n_ctrl
@@ -300,59 +306,104 @@ def dilqr_backward(dl_dx, dl_du, x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u
     u = u.detach().contiguous()
     C_ = _contig(C_.detach())
     c_ = _contig(c_.detach())
-    # (1) final linearisation F = D(tau*)  (mpc_explicit.py:310) -- f is not needed
-    F = torch.empty(T - 1, B, n_state, n, dtype=dtype, device=dev)
-    _lib.call("dilqr_linearize", _DT[dtype], kind, theta, T, B, _ptr(x), _ptr(u), _ptr(F), None,
-              _stream())
-    # (2) gains of the final no-op LQR pass at tau* (lqr_step_explicit.py:604-618)
+    scalar_bounds = u_lower is None or (isinstance(u_lower, float) and isinstance(u_upper, float))
+    if not scalar_bounds:
+        factored = False
+    # (1) gains of the final no-op LQR pass at tau* (lqr_step_explicit.py:604-618)
     dyn = DynSpec(kind, params=list(theta))
     _, _, _, info = solve_mpc(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower=u_lower,
                               u_upper=u_upper, u_init=u, x_cur=x, lqr_iter=1, max_linesearch_iter=1,
                               solo=solo, verbose=-1, want_gains=True)
     K = info.K
-    # (3) primal costates + contracted second-order tables
+    # (2) primal costates + contracted second-order tables
     lam = torch.empty(T, B, n_state, dtype=dtype, device=dev)
     Lam = torch.empty(T - 1, B, n, n, dtype=dtype, device=dev)
     _lib.call("dilqr_costate_tables", _DT[dtype], kind, theta, T, B, _ptr(C_), _ptr(c_), _ptr(x),
               _ptr(u), _ptr(lam), _ptr(Lam), _stream())
-    # (4) Richardson iteration on A' w = g
     g = torch.cat((dl_dx, dl_du), 2).contiguous()
-    if u_lower is None:
-        I = None
-    else:                                                   # lqr_step_explicit.py:690-691
-        I = (torch.abs(u - u_lower) <= 1e-8) | (torch.abs(u - u_upper) <= 1e-8)
     w = g.clone()
-    negw = -g
-    zero = torch.zeros_like(x_init)
-    lin = DynSpec(_lib.DYN_LINDX, F=F, f=None)
-    resid = torch.zeros(2, dtype=torch.float64, device=dev)
-
-    def adjoint():
-        return solve_mpc(zero, C_, negw, lin, n_state, n_ctrl, T, u_zero_I=I, lqr_iter=1,
-                         eps=back_eps, gain_solve=_lib.GAIN_CHOL_REG, verbose=-1, sync=False)[:2]
-
+    resid = torch.zeros(3, dtype=torch.float64, device=dev)
     passes = 0
     rel = None
-    for _ in range(n_passes):
-        dxa, dua = adjoint()
-        _lib.call("dilqr_richardson_update", _DT[dtype], n_state, n_ctrl, T, B, _ptr(g), _ptr(Lam),
-                  _ptr(dxa), _ptr(dua), _ptr(w), _ptr(negw), _ptr(resid), _stream())
-        passes += 1
-        if tol is not None:
-            r = resid.cpu()
-            rel = float(r[0]) / (float(r[1]) + 1e-300)
-            if rel <= tol:
-                break
-    # (5) one more KKT pass with r = w: dC, dc and df_w = -dlam
-    dxa, dua = adjoint()
-    _, dC, dc, _, df = kkt_grads(C_, c_, F, x, u, dxa, dua, w, n_state, n_ctrl, want_df=True,
-                                 want_dF=False)
-    # (6) dtheta through the closed-loop sensitivity rollout
     nth = len(dxmod.params)
+    dC = torch.empty(T, B, n, n, dtype=dtype, device=dev)
+    dc = torch.empty(T, B, n, dtype=dtype, device=dev)
+    df = torch.empty(T - 1, B, n_state, dtype=dtype, device=dev)
+
+    def converged():
+        r = resid.cpu()
+        return float(r[0]) / (float(r[1]) + 1e-300)
+
+    if factored:
+        a = _lib.DilqrAdjoint()
+        a.n_state, a.n_ctrl, a.T, a.n_batch, a.dtype, a.dynamics = n_state, n_ctrl, T, B, _DT[dtype], kind
+        a.bounds_kind = _lib.BOUNDS_NONE if u_lower is None else _lib.BOUNDS_SCALAR
+        a.gain_solve = _lib.GAIN_CHOL_REG
+        if u_lower is not None:
+            a.u_lower, a.u_upper = u_lower, u_upper
+        for i in range(8):
+            a.dyn_params[i] = theta[i]
+        dxa = torch.empty(T, B, n_state, dtype=dtype, device=dev)
+        dua = torch.empty(T, B, n_ctrl, dtype=dtype, device=dev)
+        a.C, a.x, a.u, a.g, a.Lam, a.w = _ptr(C_), _ptr(x), _ptr(u), _ptr(g), _ptr(Lam), _ptr(w)
+        a.dC, a.dc, a.df, a.dx_out, a.du_out = _ptr(dC), _ptr(dc), _ptr(df), _ptr(dxa), _ptr(dua)
+        a.resid = _ptr(resid)
+        need = _lib.lib().dilqr_adjoint_workspace_bytes(C.byref(a))
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        a.workspace, a.workspace_bytes = _ptr(ws), need
+        st = _stream()
+        _lib.call("dilqr_adjoint_factor", C.byref(a), st)
+        for _ in range(n_passes):
+            _lib.call("dilqr_adjoint_pass", C.byref(a), st)
+            passes += 1
+            if tol is not None:
+                rel = converged()
+                if rel <= tol:
+                    break
+        _lib.call("dilqr_adjoint_final", C.byref(a), st)
+    else:
+        # generic path: every adjoint solve is a full (line-searching) LQR step
+        F = torch.empty(T - 1, B, n_state, n, dtype=dtype, device=dev)
+        _lib.call("dilqr_linearize", _DT[dtype], kind, theta, T, B, _ptr(x), _ptr(u), _ptr(F), None,
+                  _stream())
+        if u_lower is None:
+            I = None
+        else:                                               # lqr_step_explicit.py:690-691
+            I = (torch.abs(u - u_lower) <= 1e-8) | (torch.abs(u - u_upper) <= 1e-8)
+        negw = -g
+        zero = torch.zeros_like(x_init)
+        lin = DynSpec(_lib.DYN_LINDX, F=F, f=None)
+
+        def adjoint():
+            return solve_mpc(zero, C_, negw, lin, n_state, n_ctrl, T, u_zero_I=I, lqr_iter=1,
+                             eps=back_eps, gain_solve=_lib.GAIN_CHOL_REG, verbose=-1,
+                             sync=False)[:2]
+
+        for _ in range(n_passes):
+            dxa, dua = adjoint()
+            _lib.call("dilqr_richardson_update", _DT[dtype], n_state, n_ctrl, T, B, _ptr(g),
+                      _ptr(Lam), _ptr(dxa), _ptr(dua), _ptr(w), _ptr(negw), _ptr(resid), _stream())
+            passes += 1
+            if tol is not None:
+                rel = converged()
+                if rel <= tol:
+                    break
+        dxa, dua = adjoint()
+        _, dC, dc, _, df = kkt_grads(C_, c_, F, x, u, dxa, dua, w, n_state, n_ctrl, want_df=True,
+                                     want_dF=False)
+    # (3) dtheta through the closed-loop sensitivity rollout
     dtheta = torch.empty(B, nth, dtype=dtype, device=dev)
     _lib.call("dilqr_sens_theta", _DT[dtype], kind, theta, T, B, _ptr(x), _ptr(u), _ptr(K),
               _ptr(lam), _ptr(dxa), _ptr(dua), _ptr(df), _ptr(dtheta), _stream())
+    if factored:
+        # one sync at the end: did the reference's line search reject any adjoint step?
+        n_rej = int(resid[2:3].view(torch.int64).item())
+        if n_rej:
+            return dilqr_backward(dl_dx, dl_du, x_init, C_, c_, x, u, dxmod, n_state, n_ctrl,
+                                  u_lower, u_upper, n_passes, tol, back_eps, solo, stats,
+                                  factored=False)
     if stats is not None:
         stats["passes"] = passes
         stats["resid"] = rel
+        stats["factored"] = factored
     return dC, dc, dtheta

@@ -9,6 +9,7 @@
 #include "ilqr_kernels.cuh"
 #include "misc_kernels.cuh"
 #include "dilqr_backward.cuh"
+#include "adjoint_kernels.cuh"
 
 namespace dilqr {
 
@@ -344,6 +345,120 @@ int DILQR_SUFFIX(rollout)(int dynamics, const double* dp, int T, int B, const vo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dynamics == DYN_PENDULUM) return launch_rollout<DYN_PENDULUM>(dp, T, B, x0, u, x, st);
   if (dynamics == DYN_CARTPOLE) return launch_rollout<DYN_CARTPOLE>(dp, T, B, x0, u, x, st);
+  return DILQR_EUNSUPPORTED;
+}
+
+// ------------------------------------------------- factored adjoint solves
+struct AdjLayout {
+  size_t fac, kvec, dtau, total;
+  int Bp;
+};
+template <int DYN>
+static AdjLayout adj_layout(const DilqrAdjoint* a) {
+  using A = Adj<Scalar, DYN>;
+  AdjLayout w;
+  w.Bp = (int)align_up((size_t)a->n_batch, 32);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  };
+  w.fac = take((size_t)a->T * A::NFAC * w.Bp * sizeof(Scalar));
+  w.kvec = take((size_t)a->T * A::NC * w.Bp * sizeof(Scalar));
+  w.dtau = take((size_t)a->T * A::N * w.Bp * sizeof(Scalar));
+  w.total = off;
+  return w;
+}
+
+template <int DYN>
+static int adj_run(const DilqrAdjoint* a, int what, cudaStream_t st) {
+  using S = Scalar;
+  using A = Adj<S, DYN>;
+  if (a->n_state != A::NS || a->n_ctrl != A::NC) return DILQR_EINVAL;
+  const AdjLayout w = adj_layout<DYN>(a);
+  if (!a->workspace || a->workspace_bytes < w.total) return DILQR_EWORKSPACE;
+  AdjParams<S> p;
+  memset(&p, 0, sizeof(p));
+  char* ws = static_cast<char*>(a->workspace);
+  p.T = a->T;
+  p.B = a->n_batch;
+  p.Bp = w.Bp;
+  p.bounds_kind = a->bounds_kind;
+  p.gain_solve = a->gain_solve;
+  p.final_pass = what == 2;
+  p.lo = (S)a->u_lower;
+  p.hi = (S)a->u_upper;
+  p.C = static_cast<const S*>(a->C);
+  p.x = static_cast<const S*>(a->x);
+  p.u = static_cast<const S*>(a->u);
+  p.g = static_cast<const S*>(a->g);
+  p.Lam = static_cast<const S*>(a->Lam);
+  p.w = static_cast<S*>(a->w);
+  p.fac = reinterpret_cast<S*>(ws + w.fac);
+  p.kvec = reinterpret_cast<S*>(ws + w.kvec);
+  p.dtau = reinterpret_cast<S*>(ws + w.dtau);
+  p.dC = static_cast<S*>(a->dC);
+  p.dc = static_cast<S*>(a->dc);
+  p.df = static_cast<S*>(a->df);
+  p.dx_out = static_cast<S*>(a->dx_out);
+  p.du_out = static_cast<S*>(a->du_out);
+  p.resid = static_cast<unsigned long long*>(a->resid);
+  for (int i = 0; i < 8; ++i) p.dyn.p[i] = (S)a->dyn_params[i];
+  const int warps = (p.B + kWarp - 1) / kWarp;
+  constexpr int N = A::N;
+  const uint32_t e1[1] = {N * N};
+  const uint32_t e2[2] = {N * N, N};
+  if (what == 0) {
+    const int wpb = 4;
+    const size_t smem = (WarpStager<S>::bytes_per_warp(1, e1) + kStages * sizeof(uint64_t)) * wpb;
+    auto kern = adjoint_factor_kernel<S, DYN>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<(warps + wpb - 1) / wpb, wpb * kWarp, smem, st>>>(p);
+  } else if (what == 1) {
+    const int wpb = 2;
+    const size_t smem = (WarpStager<S>::bytes_per_warp(2, e2) + kStages * sizeof(uint64_t)) * wpb;
+    auto kern = adjoint_pass_kernel<S, DYN, false>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaMemsetAsync(p.resid, 0, 16, st);   // max|dw|, max|w|; the reject counter accumulates
+    kern<<<(warps + wpb - 1) / wpb, wpb * kWarp, smem, st>>>(p);
+  } else {
+    const int wpb = 2;
+    const size_t out = (((size_t)kWarp * (N * N + N) * sizeof(S)) + 15) & ~(size_t)15;
+    const size_t smem =
+        (WarpStager<S>::bytes_per_warp(2, e2) + kStages * sizeof(uint64_t) + out) * wpb;
+    auto kern = adjoint_pass_kernel<S, DYN, true>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<(warps + wpb - 1) / wpb, wpb * kWarp, smem, st>>>(p);
+  }
+  return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
+}
+
+static int adj_check(const DilqrAdjoint* a, int what) {
+  if (!a || a->T < 2 || a->n_batch <= 0 || !a->C || !a->x || !a->u || !a->w || !a->resid)
+    return DILQR_EINVAL;
+  if (what == 1 && (!a->g || !a->Lam)) return DILQR_EINVAL;
+  if (a->bounds_kind != DILQR_BOUNDS_NONE && a->bounds_kind != DILQR_BOUNDS_SCALAR)
+    return DILQR_EINVAL;
+  auto mis = [](const void* p) { return p && (reinterpret_cast<uintptr_t>(p) & 15u); };
+  if (mis(a->C) || mis(a->g) || mis(a->Lam) || mis(a->dC) || mis(a->dc) || mis(a->workspace))
+    return DILQR_EALIGN;
+  return DILQR_OK;
+}
+
+size_t DILQR_SUFFIX(adjoint_workspace_bytes)(const DilqrAdjoint* a) {
+  if (!a) return 0;
+  if (a->dynamics == DYN_PENDULUM) return adj_layout<DYN_PENDULUM>(a).total;
+  if (a->dynamics == DYN_CARTPOLE) return adj_layout<DYN_CARTPOLE>(a).total;
+  return 0;
+}
+
+int DILQR_SUFFIX(adjoint_run)(const DilqrAdjoint* a, int what, void* stream) {
+  int e = adj_check(a, what);
+  if (e) return e;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (a->dynamics == DYN_PENDULUM) return adj_run<DYN_PENDULUM>(a, what, st);
+  if (a->dynamics == DYN_CARTPOLE) return adj_run<DYN_CARTPOLE>(a, what, st);
   return DILQR_EUNSUPPORTED;
 }
 

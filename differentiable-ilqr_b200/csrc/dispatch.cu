@@ -19,7 +19,9 @@ namespace dilqr {
   int sens_theta_##sfx(int, const double*, int, int, const void*, const void*, const void*,   \
                        const void*, const void*, const void*, const void*, void*, void*);   \
   int richardson_update_##sfx(int, int, int, int, const void*, const void*, const void*,      \
-                              const void*, void*, void*, void*, void*);
+                              const void*, void*, void*, void*, void*);                     \
+  size_t adjoint_workspace_bytes_##sfx(const DilqrAdjoint*);                                 \
+  int adjoint_run_##sfx(const DilqrAdjoint*, int, void*);
 DECL(f32)
 DECL(f64)
 #undef DECL
@@ -91,6 +93,24 @@ int dilqr_richardson_update(int dtype, int ns, int nc, int T, int B, const void*
                             void* resid, void* st) {
   return ROUTE(dtype, dilqr::richardson_update_f32(ns, nc, T, B, g, Lam, dx, du, w, negw, resid, st),
                dilqr::richardson_update_f64(ns, nc, T, B, g, Lam, dx, du, w, negw, resid, st));
+}
+
+size_t dilqr_adjoint_workspace_bytes(const DilqrAdjoint* a) {
+  if (!a) return 0;
+  return a->dtype == DILQR_F32 ? dilqr::adjoint_workspace_bytes_f32(a)
+                               : dilqr::adjoint_workspace_bytes_f64(a);
+}
+int dilqr_adjoint_factor(const DilqrAdjoint* a, void* st) {
+  if (!a) return DILQR_EINVAL;
+  return ROUTE(a->dtype, dilqr::adjoint_run_f32(a, 0, st), dilqr::adjoint_run_f64(a, 0, st));
+}
+int dilqr_adjoint_pass(const DilqrAdjoint* a, void* st) {
+  if (!a) return DILQR_EINVAL;
+  return ROUTE(a->dtype, dilqr::adjoint_run_f32(a, 1, st), dilqr::adjoint_run_f64(a, 1, st));
+}
+int dilqr_adjoint_final(const DilqrAdjoint* a, void* st) {
+  if (!a) return DILQR_EINVAL;
+  return ROUTE(a->dtype, dilqr::adjoint_run_f32(a, 2, st), dilqr::adjoint_run_f64(a, 2, st));
 }
 
 }  // extern "C"

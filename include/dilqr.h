@@ -197,6 +197,35 @@ int dilqr_richardson_update(int dtype, int n_state, int n_ctrl, int T, int n_bat
                             const void* Lam, const void* dx, const void* du, void* w, void* negw,
                             void* resid, void* stream);
 
+/* Adjoint (KKT) LQR solves of the DiLQR backward for env_dx dynamics, factored
+ * once and replayed per Richardson pass (lqr_step_explicit.py:276-303 restated;
+ * see csrc/adjoint_kernels.cuh).  F_t = D(x*_t,u*_t) is re-derived on the fly. */
+typedef struct DilqrAdjoint {
+  int32_t n_state, n_ctrl, T, n_batch, dtype, dynamics;
+  int32_t bounds_kind;   /* NONE: no active set; SCALAR: I = |u*-bound| <= 1e-8 (:690-691) */
+  int32_t gain_solve;    /* DILQR_GAIN_CHOL_REG for the explicit variant (mpc_backup)      */
+  double u_lower, u_upper;
+  double dyn_params[8];
+  const void *C;         /* [T,B,n,n]                                                  */
+  const void *x, *u;     /* solution tau* [T,B,ns], [T,B,nc]                           */
+  const void *g;         /* [T,B,n]  cat(dl_dx, dl_du)                                 */
+  const void *Lam;       /* [T-1,B,n,n] from dilqr_costate_tables                      */
+  void *w;               /* [T,B,n]  Richardson iterate, in/out (initialise to g)      */
+  void *dC, *dc, *df;    /* final pass outputs: [T,B,n,n], [T,B,n], [T-1,B,ns]         */
+  void *dx_out, *du_out; /* final pass: adjoint solution (optional)                    */
+  void *resid;           /* device, 3 x 8 bytes: max|dw|, max|w| (doubles), #problems
+                            whose adjoint step the reference's line search would reject */
+  void *workspace;
+  size_t workspace_bytes;
+} DilqrAdjoint;
+size_t dilqr_adjoint_workspace_bytes(const DilqrAdjoint* a);
+/* Masked Riccati sweep at tau*: gains and the r-independent blocks. */
+int dilqr_adjoint_factor(const DilqrAdjoint* a, void* stream);
+/* One Richardson pass: adjoint solve with r = w fused with w <- g - Lam dtau. */
+int dilqr_adjoint_pass(const DilqrAdjoint* a, void* stream);
+/* Adjoint solve with r = w, then costates and dC, dc, df (lqr_step.py:346-402). */
+int dilqr_adjoint_final(const DilqrAdjoint* a, void* stream);
+
 /* dtheta[B,n_theta] = sum_t <dF_w, dD_t/dtheta> + <df_w, dd_t/dtheta> with the
  * closed-loop sensitivity rollout grad_input (cartpole.py:717-788, pendulum.py:
  * 383-443) contracted on the fly.  K[T,B,nc,ns]: gains of the final LQR pass in
