@@ -46,8 +46,8 @@ class DilqrSolve(C.Structure):
         ("n_batch", C.c_int32),
         ("dtype", C.c_int32), ("dynamics", C.c_int32), ("gain_solve", C.c_int32),
         ("bounds_kind", C.c_int32), ("solo", C.c_int32),
-        ("max_linesearch_iter", C.c_int32), ("first_iteration", C.c_int32),
-        ("has_f", C.c_int32),
+        ("max_linesearch_iter", C.c_int32), ("iteration", C.c_int32),
+        ("has_f", C.c_int32), ("gains_only", C.c_int32), ("reserved0", C.c_int32),
         ("linesearch_decay", C.c_double),
         ("u_lower", C.c_double), ("u_upper", C.c_double),
         ("best_cost_eps", C.c_double),

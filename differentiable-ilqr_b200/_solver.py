@@ -167,7 +167,7 @@ def solve_mpc(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower=None, u_upper=Non
               u_zero_I=None, u_init=None, lqr_iter=10, eps=1e-7, linesearch_decay=0.2,
               max_linesearch_iter=10, not_improved_lim=5, best_cost_eps=1e-4,
               gain_solve=_lib.GAIN_PLAIN, solo=False, verbose=0, x_cur=None,
-              want_gains=False, sync=True):
+              want_gains=False, sync=True, gains_only=False):
     """MPC.forward (mpc.py:184-306): returns (x, u, costs, info).  With ``x_cur``
     given this is a single LQRStep around (x_cur, u_init) (lqr_step.py:277-309)
     and returns the *new* iterate."""
@@ -189,6 +189,9 @@ def solve_mpc(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower=None, u_upper=Non
         s.x_cur = _ptr(xc)
     st = _stream()
     info = SolveInfo()
+    if gains_only:
+        s.gains_only = 1
+        want_gains = True
     _lib.call("dilqr_mpc_begin", C.byref(s), st)
     # python float eps is compared in the data dtype by torch (mpc.py:299)
     eps_cmp = float(torch.tensor(eps, dtype=dtype))
@@ -196,7 +199,7 @@ def solve_mpc(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower=None, u_upper=Non
     n_loops = 1 if x_cur is not None else lqr_iter
     nosync = (not sync) and n_loops == 1 and (s.bounds_kind == _lib.BOUNDS_NONE or solo)
     for i in range(n_loops):
-        s.first_iteration = 1 if i == 0 else 0
+        s.iteration = i
         status = _iterate_committed(L, s, ws, info, sync=not nosync)
         info.n_iters = i + 1
         if status is None:
@@ -220,13 +223,15 @@ def solve_mpc(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower=None, u_upper=Non
         info.mean_best_cost = status.mean_best_cost
         if status.max_full_du < eps_cmp or n_not_improved > not_improved_lim:
             break                                                    # mpc.py:299-301
-    x = torch.empty(T, B, n_state, dtype=dtype, device=dev)
-    u = torch.empty(T, B, n_ctrl, dtype=dtype, device=dev)
-    costs = torch.empty(B, dtype=dtype, device=dev)
-    du = torch.empty(B, dtype=dtype, device=dev)
-    s.x_out, s.u_out, s.cost_out, s.du_out = _ptr(x), _ptr(u), _ptr(costs), _ptr(du)
+    x = u = costs = du = None
+    if not gains_only:
+        x = torch.empty(T, B, n_state, dtype=dtype, device=dev)
+        u = torch.empty(T, B, n_ctrl, dtype=dtype, device=dev)
+        costs = torch.empty(B, dtype=dtype, device=dev)
+        du = torch.empty(B, dtype=dtype, device=dev)
+        s.x_out, s.u_out, s.cost_out, s.du_out = _ptr(x), _ptr(u), _ptr(costs), _ptr(du)
     extra = {}
-    if x_cur is not None:
+    if x_cur is not None and not gains_only:
         al = torch.empty(B, dtype=dtype, device=dev)
         s.alpha_out = _ptr(al)
         extra["alphas"] = al
@@ -313,7 +318,7 @@ def dilqr_backward(dl_dx, dl_du, x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u
     dyn = DynSpec(kind, params=list(theta))
     _, _, _, info = solve_mpc(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower=u_lower,
                               u_upper=u_upper, u_init=u, x_cur=x, lqr_iter=1, max_linesearch_iter=1,
-                              solo=solo, verbose=-1, want_gains=True)
+                              solo=solo, verbose=-1, gains_only=True)
     K = info.K
     # (2) primal costates + contracted second-order tables
     lam = torch.empty(T, B, n_state, dtype=dtype, device=dev)

@@ -233,24 +233,23 @@ __global__ void __launch_bounds__(128) adjoint_factor_kernel(const __grid_consta
         for (int c2 = 0; c2 < NC; ++c2) acc = fmaS<S>(K[c2][i], Q[NS + c2][NS + a], acc);
         KQ[i][a] = acc;
       }
-    if (act) {
-      S* f = p.fac + (size_t)t * NFAC * p.Bp + b;
+    {
+      S* f = p.fac + bidx(t, 0, NFAC, b0 + lane, p.Bp / kWarp);   // own (padded) column
 #pragma unroll
       for (int a = 0; a < NC; ++a)
 #pragma unroll
-        for (int j = 0; j < NS; ++j) f[(size_t)(A::OFF_K + a * NS + j) * p.Bp] = K[a][j];
+        for (int j = 0; j < NS; ++j) f[(A::OFF_K + a * NS + j) * kWarp] = K[a][j];
 #pragma unroll
       for (int a = 0; a < NC; ++a)
 #pragma unroll
         for (int c2 = 0; c2 < NC; ++c2) {
-          f[(size_t)(A::OFF_G + a * NC + c2) * p.Bp] = G[a][c2];
-          f[(size_t)(A::OFF_Q + a * NC + c2) * p.Bp] = Q[NS + a][NS + c2];
+          f[(A::OFF_G + a * NC + c2) * kWarp] = G[a][c2];
+          f[(A::OFF_Q + a * NC + c2) * kWarp] = Q[NS + a][NS + c2];
         }
 #pragma unroll
       for (int i = 0; i < NS; ++i)
 #pragma unroll
-        for (int a = 0; a < NC; ++a)
-          f[(size_t)(A::OFF_M + i * NC + a) * p.Bp] = Q[i][NS + a] + KQ[i][a];
+        for (int a = 0; a < NC; ++a) f[(A::OFF_M + i * NC + a) * kWarp] = Q[i][NS + a] + KQ[i][a];
     }
 #pragma unroll
     for (int i = 0; i < NS; ++i)
@@ -270,13 +269,45 @@ __global__ void __launch_bounds__(128) adjoint_factor_kernel(const __grid_consta
 
 // ---------------------------------------------------------------------------
 // One adjoint solve with r = w (affine sweep + linear rollout).
-//   final_pass == 0: fused Richardson update  w_t <- g_t - Lam_t dtau_t.
-//   final_pass == 1: keeps dtau (SoA workspace + optional AoS dx_out/du_out), then a
-//                    costate sweep (lqr_step.py:371-385) writes dC, dc, df.
+//   FINAL == false: fused Richardson update  w_t <- g_t - Lam_t dtau_t.
+//   FINAL == true : keeps dtau (workspace + optional AoS dx_out/du_out), then a
+//                   costate sweep (lqr_step.py:371-385) writes dC, dc, df.
+// Every per-timestep operand (w, x*, u*, factor record, Lam, g, k, dtau, C) is
+// staged through shared memory by TMA one step ahead of its use.
 // ---------------------------------------------------------------------------
-template <class S, int DYN, bool FINAL>
-__global__ void __launch_bounds__(128) adjoint_pass_kernel(const __grid_constant__ AdjParams<S> p) {
+template <class S, int DYN>
+struct AdjStage {
   using A = Adj<S, DYN>;
+  static constexpr int NS = A::NS, NC = A::NC, N = A::N, NFAC = A::NFAC;
+  // segments: 0 big[N*N] (Lam_t or C_t)  1 vec[N] (w_t or g_t)  2 x[NS]  3 u[NC]
+  //           4 fac[NFAC] (blocked)      5 kv[N] (blocked: kvec_t[NC] or dtau_t[N])
+  static constexpr int kNSeg = 6;
+  static constexpr uint32_t kFullMask = (1u << 4) | (1u << 5);
+  static __host__ __device__ void seg_elems(uint32_t* e) {
+    e[0] = N * N;
+    e[1] = N;
+    e[2] = NS;
+    e[3] = NC;
+    e[4] = NFAC;
+    e[5] = N;
+  }
+  static __host__ __device__ size_t stage_bytes() {
+    uint32_t e[kNSeg];
+    seg_elems(e);
+    return WarpStager<S>::bytes_per_warp(kNSeg, e);
+  }
+  static __host__ __device__ size_t out_bytes(bool fin) {
+    return fin ? (((size_t)kWarp * (N * N + N) * sizeof(S) + 15) & ~(size_t)15) : 0;
+  }
+  static __host__ __device__ size_t smem_per_warp(bool fin) {
+    return stage_bytes() + kStages * sizeof(uint64_t) + out_bytes(fin);
+  }
+};
+
+template <class S, int DYN, bool FINAL>
+__global__ void __launch_bounds__(64) adjoint_pass_kernel(const __grid_constant__ AdjParams<S> p) {
+  using A = Adj<S, DYN>;
+  using AS = AdjStage<S, DYN>;
   constexpr int NS = A::NS, NC = A::NC, N = A::N, NFAC = A::NFAC;
   extern __shared__ __align__(128) char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -284,30 +315,48 @@ __global__ void __launch_bounds__(128) adjoint_pass_kernel(const __grid_constant
   if (b0 >= p.B) return;
   const int nvalid = min(kWarp, p.B - b0);
   const bool act = lane < nvalid;
-  const int b = act ? b0 + lane : b0;
+  const int b = act ? b0 + lane : b0;     // API tensors
+  const int bw = b0 + lane;               // own workspace column
   const int T = p.T;
-  // stage: seg0 = n*n block (Lam_t or C_t), seg1 = n vector (g_t)
-  const uint32_t elems[2] = {N * N, N};
-  const size_t stage_bytes = WarpStager<S>::bytes_per_warp(2, elems);
-  const size_t out_bytes = FINAL ? (((size_t)kWarp * (N * N + N) * sizeof(S) + 15) & ~(size_t)15) : 0;
-  const size_t per_warp = stage_bytes + kStages * sizeof(uint64_t) + out_bytes;
+  const int nW = p.Bp / kWarp;
+  const size_t per_warp = AS::smem_per_warp(FINAL);
   char* wbase = smem + warp * per_warp;
   WarpStager<S> st;
-  st.init(wbase + kStages * sizeof(uint64_t), reinterpret_cast<uint64_t*>(wbase), lane, nvalid, 2,
-          elems);
-  S* outC = reinterpret_cast<S*>(wbase + kStages * sizeof(uint64_t) + stage_bytes);
+  {
+    uint32_t e[AS::kNSeg];
+    AS::seg_elems(e);
+    st.init(wbase + kStages * sizeof(uint64_t), reinterpret_cast<uint64_t*>(wbase), lane, nvalid,
+            AS::kNSeg, e, AS::kFullMask);
+  }
+  S* outC = reinterpret_cast<S*>(wbase + kStages * sizeof(uint64_t) + AS::stage_bytes());
   S* outc = outC + kWarp * N * N;
 
+  auto slab = [&](const S* base, int t, int elems) { return base + ((size_t)t * p.B + b0) * elems; };
+
   // ---------------- affine backward sweep
+  auto issue_a = [&](int stage, int t) {
+    const S* src[AS::kNSeg] = {nullptr, slab(p.w, t, N), slab(p.x, t, NS), slab(p.u, t, NC),
+                               p.fac + bidx(t, 0, NFAC, b0, nW), nullptr};
+    st.issue(stage, src, AS::kNSeg);
+  };
   S v[NS], xnext[NS];
   S pred = S(0);
+  issue_a(0, T - 1);
   for (int t = T - 1; t >= 0; --t) {
-    S tau[N];
-    A::load_tau(p, t, b, tau);
-    S q[N];
-    const size_t tb = (size_t)t * p.B + b;
+    const int sg = (T - 1 - t) & 1;
+    if (t > 0) issue_a(sg ^ 1, t - 1);
+    st.wait(sg);
+    const S* ws_ = st.lane_ptr(sg, 1);
+    const S* xs_ = st.lane_ptr(sg, 2);
+    const S* us_ = st.lane_ptr(sg, 3);
+    const S* f = st.seg_ptr(sg, 4) + lane;
+    S tau[N], q[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) q[i] = -p.w[tb * N + i];
+    for (int i = 0; i < NS; ++i) tau[i] = xs_[i];
+#pragma unroll
+    for (int a = 0; a < NC; ++a) tau[NS + a] = us_[a];
+#pragma unroll
+    for (int i = 0; i < N; ++i) q[i] = -ws_[i];
     if (t < T - 1) {
       S Fm[NS][N];
       A::jac_at(p, tau, xnext, Fm);
@@ -321,7 +370,6 @@ __global__ void __launch_bounds__(128) adjoint_pass_kernel(const __grid_constant
     }
 #pragma unroll
     for (int i = 0; i < NS; ++i) xnext[i] = tau[i];
-    const S* f = p.fac + (size_t)t * NFAC * p.Bp + b;
     S qm[NC], k[NC];
 #pragma unroll
     for (int a = 0; a < NC; ++a) qm[a] = A::active(p, tau[NS + a]) ? S(0) : q[NS + a];
@@ -329,7 +377,7 @@ __global__ void __launch_bounds__(128) adjoint_pass_kernel(const __grid_constant
     for (int a = 0; a < NC; ++a) {
       S acc = S(0);
 #pragma unroll
-      for (int c2 = 0; c2 < NC; ++c2) acc = fmaS<S>(f[(size_t)(A::OFF_G + a * NC + c2) * p.Bp], qm[c2], acc);
+      for (int c2 = 0; c2 < NC; ++c2) acc = fmaS<S>(f[(A::OFF_G + a * NC + c2) * kWarp], qm[c2], acc);
       k[a] = -acc;
     }
     // optimal value of the masked QP: sum_t q_u'k + 1/2 k'Q_uu k
@@ -337,7 +385,7 @@ __global__ void __launch_bounds__(128) adjoint_pass_kernel(const __grid_constant
     for (int a = 0; a < NC; ++a) {
       S hk = S(0);
 #pragma unroll
-      for (int c2 = 0; c2 < NC; ++c2) hk = fmaS<S>(f[(size_t)(A::OFF_Q + a * NC + c2) * p.Bp], k[c2], hk);
+      for (int c2 = 0; c2 < NC; ++c2) hk = fmaS<S>(f[(A::OFF_Q + a * NC + c2) * kWarp], k[c2], hk);
       pred = fmaS<S>(k[a], q[NS + a] + S(0.5) * hk, pred);
     }
 #pragma unroll
@@ -345,39 +393,63 @@ __global__ void __launch_bounds__(128) adjoint_pass_kernel(const __grid_constant
       S t1 = S(0), t2 = S(0);
 #pragma unroll
       for (int a = 0; a < NC; ++a) {
-        t1 = fmaS<S>(f[(size_t)(A::OFF_M + i * NC + a) * p.Bp], k[a], t1);
-        t2 = fmaS<S>(f[(size_t)(A::OFF_K + a * NS + i) * p.Bp], q[NS + a], t2);
+        t1 = fmaS<S>(f[(A::OFF_M + i * NC + a) * kWarp], k[a], t1);
+        t2 = fmaS<S>(f[(A::OFF_K + a * NS + i) * kWarp], q[NS + a], t2);
       }
       v[i] = (q[i] + t1) + t2;
     }
-    if (act) {
+    {
+      S* ko = p.kvec + bidx(t, 0, NC, bw, nW);
 #pragma unroll
-      for (int a = 0; a < NC; ++a) p.kvec[((size_t)t * NC + a) * p.Bp + b] = k[a];
+      for (int a = 0; a < NC; ++a) ko[a * kWarp] = k[a];
     }
   }
   if (act && !(pred <= S(0))) atomicAdd(&p.resid[2], 1ull);
+  // kvec (generic-proxy stores) is read back through TMA below
+  __threadfence();
+  asm volatile("fence.proxy.async;" ::: "memory");
+  __syncwarp();
 
   // ---------------- linear rollout (+ Richardson update)
-  S dx[NS];
-#pragma unroll
-  for (int i = 0; i < NS; ++i) dx[i] = S(0);
-  double dmax = 0.0, wmax = 0.0;
-  auto issue_fwd = [&](int stage, int t) {
-    const S* src[2];
-    src[0] = (t < T - 1) ? p.Lam + ((size_t)t * p.B + b0) * (N * N) : nullptr;
-    src[1] = p.g + ((size_t)t * p.B + b0) * N;
-    st.issue(stage, src, 2);
+  auto issue_f = [&](int stage, int t) {
+    const S* src[AS::kNSeg] = {(!FINAL && t < T - 1) ? slab(p.Lam, t, N * N) : nullptr,
+                               FINAL ? nullptr : slab(p.g, t, N), slab(p.x, t, NS),
+                               slab(p.u, t, NC), p.fac + bidx(t, 0, NFAC, b0, nW),
+                               p.kvec + bidx(t, 0, NC, b0, nW)};
+    st.issue(stage, src, AS::kNSeg);
   };
-  if (!FINAL) issue_fwd(0, 0);
-  S tau[N];
-  A::load_tau(p, 0, b, tau);
+  S dt[N], tprev[N];
+  double dmax = 0.0, wmax = 0.0;
+  issue_f(0, 0);
   for (int t = 0; t < T; ++t) {
     const int sg = t & 1;
-    if (!FINAL && t + 1 < T) issue_fwd(sg ^ 1, t + 1);
-    S taun[N];
-    if (t + 1 < T) A::load_tau(p, t + 1, b, taun);
-    const S* f = p.fac + (size_t)t * NFAC * p.Bp + b;
-    S dt[N];
+    if (t + 1 < T) issue_f(sg ^ 1, t + 1);
+    st.wait(sg);
+    const S* xs_ = st.lane_ptr(sg, 2);
+    const S* us_ = st.lane_ptr(sg, 3);
+    const S* f = st.seg_ptr(sg, 4) + lane;
+    const S* kv = st.seg_ptr(sg, 5) + lane;
+    S tau[N];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) tau[i] = xs_[i];
+#pragma unroll
+    for (int a = 0; a < NC; ++a) tau[NS + a] = us_[a];
+    // dx_t = F_{t-1} dtau_{t-1}; the trig of F_{t-1} is part of x_t (just arrived)
+    S dx[NS];
+    if (t > 0) {
+      S Fm[NS][N];
+      A::jac_at(p, tprev, tau, Fm);
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+        S acc = S(0);
+#pragma unroll
+        for (int j = 0; j < N; ++j) acc = fmaS<S>(Fm[i][j], dt[j], acc);
+        dx[i] = acc;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NS; ++i) dx[i] = S(0);
+    }
 #pragma unroll
     for (int i = 0; i < NS; ++i) dt[i] = dx[i];
 #pragma unroll
@@ -385,16 +457,19 @@ __global__ void __launch_bounds__(128) adjoint_pass_kernel(const __grid_constant
       S acc = S(0);
       if (t > 0) {
 #pragma unroll
-        for (int j = 0; j < NS; ++j) acc = fmaS<S>(f[(size_t)(A::OFF_K + a * NS + j) * p.Bp], dx[j], acc);
+        for (int j = 0; j < NS; ++j) acc = fmaS<S>(f[(A::OFF_K + a * NS + j) * kWarp], dx[j], acc);
       }
-      S un = acc + p.kvec[((size_t)t * NC + a) * p.Bp + b];
+      S un = acc + kv[a * kWarp];
       if (A::active(p, tau[NS + a])) un = S(0);          // lqr_step.py:197-198
       dt[NS + a] = un;
     }
-    if (FINAL) {
-      if (act) {
 #pragma unroll
-        for (int i = 0; i < N; ++i) p.dtau[((size_t)t * N + i) * p.Bp + b] = dt[i];
+    for (int i = 0; i < N; ++i) tprev[i] = tau[i];
+    if (FINAL) {
+      S* dto = p.dtau + bidx(t, 0, N, bw, nW);
+#pragma unroll
+      for (int i = 0; i < N; ++i) dto[i * kWarp] = dt[i];
+      if (act) {
         const size_t tb = (size_t)t * p.B + b;
         if (p.dx_out) {
 #pragma unroll
@@ -406,7 +481,6 @@ __global__ void __launch_bounds__(128) adjoint_pass_kernel(const __grid_constant
         }
       }
     } else {
-      st.wait(sg);
       const S* Ls = st.lane_ptr(sg, 0);
       const S* gs = st.lane_ptr(sg, 1);
       const size_t tb = (size_t)t * p.B + b;
@@ -426,19 +500,6 @@ __global__ void __launch_bounds__(128) adjoint_pass_kernel(const __grid_constant
         }
       }
     }
-    if (t < T - 1) {
-      S Fm[NS][N];
-      A::jac_at(p, tau, taun, Fm);
-#pragma unroll
-      for (int i = 0; i < NS; ++i) {
-        S acc = S(0);
-#pragma unroll
-        for (int j = 0; j < N; ++j) acc = fmaS<S>(Fm[i][j], dt[j], acc);
-        dx[i] = acc;
-      }
-#pragma unroll
-      for (int i = 0; i < N; ++i) tau[i] = taun[i];
-    }
   }
   if (!FINAL) {
     for (int o = 16; o > 0; o >>= 1) {
@@ -455,21 +516,34 @@ __global__ void __launch_bounds__(128) adjoint_pass_kernel(const __grid_constant
   // ---------------- final pass: costate sweep + gradient assembly
   //   dlam_t = Cxx dx + Cxu du - r_x + Fx' dlam_{t+1}          (lqr_step.py:371-385)
   //   dC_t = -1/2 (dtau tau' + tau dtau'), dc_t = -dtau, df_t = -dlam_{t+1}
-  auto issue_bwd = [&](int stage, int t) {
-    const S* src[2] = {p.C + ((size_t)t * p.B + b0) * (N * N), nullptr};
-    st.issue(stage, src, 2);
+  __threadfence();
+  asm volatile("fence.proxy.async;" ::: "memory");
+  __syncwarp();
+  auto issue_b = [&](int stage, int t) {
+    const S* src[AS::kNSeg] = {slab(p.C, t, N * N), slab(p.w, t, N), slab(p.x, t, NS),
+                               slab(p.u, t, NC), nullptr, p.dtau + bidx(t, 0, N, b0, nW)};
+    st.issue(stage, src, AS::kNSeg);
   };
   const bool bulk_out = (nvalid == kWarp) && ((((size_t)N * N * sizeof(S) * kWarp) & 15) == 0) &&
                         ((((size_t)N * sizeof(S) * kWarp) & 15) == 0);
   S dlam[NS];
-  issue_bwd(0, T - 1);
+  issue_b(0, T - 1);
   for (int t = T - 1; t >= 0; --t) {
     const int sg = (T - 1 - t) & 1;
-    if (t > 0) issue_bwd(sg ^ 1, t - 1);
-    S tt[N], dt[N];
-    A::load_tau(p, t, b, tt);
+    if (t > 0) issue_b(sg ^ 1, t - 1);
+    st.wait(sg);
+    const S* Cs = st.lane_ptr(sg, 0);
+    const S* ws_ = st.lane_ptr(sg, 1);
+    const S* xs_ = st.lane_ptr(sg, 2);
+    const S* us_ = st.lane_ptr(sg, 3);
+    const S* ds_ = st.seg_ptr(sg, 5) + lane;
+    S tt[N], dtv[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) dt[i] = p.dtau[((size_t)t * N + i) * p.Bp + b];
+    for (int i = 0; i < NS; ++i) tt[i] = xs_[i];
+#pragma unroll
+    for (int a = 0; a < NC; ++a) tt[NS + a] = us_[a];
+#pragma unroll
+    for (int i = 0; i < N; ++i) dtv[i] = ds_[i * kWarp];
     const size_t tb = (size_t)t * p.B + b;
     if (t < T - 1 && p.df && act) {
 #pragma unroll
@@ -487,11 +561,11 @@ __global__ void __launch_bounds__(128) adjoint_pass_kernel(const __grid_constant
 #pragma unroll
         for (int i = 0; i < N; ++i)
 #pragma unroll
-          for (int j = 0; j < N; ++j) oC[i * N + j] = S(-0.5) * (dt[i] * tt[j] + tt[i] * dt[j]);
+          for (int j = 0; j < N; ++j) oC[i * N + j] = S(-0.5) * (dtv[i] * tt[j] + tt[i] * dtv[j]);
       }
       if (p.dc) {
 #pragma unroll
-        for (int i = 0; i < N; ++i) oc[i] = -dt[i];
+        for (int i = 0; i < N; ++i) oc[i] = -dtv[i];
       }
     }
     if (bulk_out) {
@@ -503,27 +577,19 @@ __global__ void __launch_bounds__(128) adjoint_pass_kernel(const __grid_constant
         bulk_commit();
       }
     }
-    st.wait(sg);
-    const S* Cs = st.lane_ptr(sg, 0);
     S nd[NS];
 #pragma unroll
     for (int i = 0; i < NS; ++i) {
       S d1 = S(0), d2 = S(0);
 #pragma unroll
-      for (int j = 0; j < NS; ++j) d1 = fmaS<S>(Cs[i * N + j], dt[j], d1);
+      for (int j = 0; j < NS; ++j) d1 = fmaS<S>(Cs[i * N + j], dtv[j], d1);
 #pragma unroll
-      for (int a = 0; a < NC; ++a) d2 = fmaS<S>(Cs[i * N + NS + a], dt[NS + a], d2);
-      nd[i] = (d1 + d2) - p.w[tb * N + i];
+      for (int a = 0; a < NC; ++a) d2 = fmaS<S>(Cs[i * N + NS + a], dtv[NS + a], d2);
+      nd[i] = (d1 + d2) - ws_[i];
     }
     if (t < T - 1) {
-      S xn[NS];
-      {
-        const size_t nb = (size_t)(t + 1) * p.B + b;
-#pragma unroll
-        for (int i = 0; i < NS; ++i) xn[i] = __ldg(p.x + nb * NS + i);
-      }
       S Fm[NS][N];
-      A::jac_at(p, tt, xn, Fm);
+      A::jac_at(p, tt, xnext, Fm);
 #pragma unroll
       for (int i = 0; i < NS; ++i) {
         S d1 = S(0);
@@ -533,7 +599,10 @@ __global__ void __launch_bounds__(128) adjoint_pass_kernel(const __grid_constant
       }
     }
 #pragma unroll
-    for (int i = 0; i < NS; ++i) dlam[i] = nd[i];
+    for (int i = 0; i < NS; ++i) {
+      dlam[i] = nd[i];
+      xnext[i] = tt[i];
+    }
   }
   if (bulk_out) bulk_wait0();
 }

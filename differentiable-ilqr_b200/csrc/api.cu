@@ -61,8 +61,8 @@ constexpr bool staged_v() {
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
-  size_t traj, Kk, cost_cur, cost_new, cost_best, du_new, du_best, alpha_new, sel, guess, votes,
-      total;
+  size_t traj[2], best, Kk, cost_cur, cost_new, cost_best, du_new, du_best, alpha_new, take, guess,
+      votes, total;
   int Bp;
 };
 
@@ -77,7 +77,9 @@ static WsLayout ws_layout(const DilqrSolve* s, size_t esz) {
     off = align_up(off + bytes, 256);
     return o;
   };
-  w.traj = take((size_t)3 * s->T * N * w.Bp * esz);
+  w.traj[0] = take((size_t)s->T * N * w.Bp * esz);
+  w.traj[1] = take((size_t)s->T * N * w.Bp * esz);
+  w.best = take((size_t)s->T * N * w.Bp * esz);
   w.Kk = take((size_t)s->T * NK * w.Bp * esz);
   w.cost_cur = take((size_t)w.Bp * esz);
   w.cost_new = take((size_t)w.Bp * esz);
@@ -85,14 +87,16 @@ static WsLayout ws_layout(const DilqrSolve* s, size_t esz) {
   w.du_new = take((size_t)w.Bp * esz);
   w.du_best = take((size_t)w.Bp * esz);
   w.alpha_new = take((size_t)w.Bp * esz);
-  w.sel = take((size_t)w.Bp * sizeof(int));
+  w.take = take((size_t)w.Bp * sizeof(int));
   w.guess = take((size_t)s->T * kPnqpMaxIter * sizeof(uint32_t));
   w.votes = take((size_t)s->T * kPnqpMaxIter * sizeof(uint32_t));
   w.total = off;
   return w;
 }
 
-static IterParams<Scalar> make_params(const DilqrSolve* s) {
+// `role`: 0 = begin (writes the current iterate), 1 = iterate / commit / finish of
+// iLQR iteration s->iteration (reads buffer it&1, writes buffer (it+1)&1).
+static IterParams<Scalar> make_params(const DilqrSolve* s, int role = 1) {
   using S = Scalar;
   IterParams<S> p;
   memset(&p, 0, sizeof(p));
@@ -106,7 +110,8 @@ static IterParams<Scalar> make_params(const DilqrSolve* s) {
   p.gain_solve = s->gain_solve;
   p.max_ls = s->max_linesearch_iter;
   p.has_f = s->has_f && s->f != nullptr;
-  p.first_iteration = s->first_iteration;
+  p.first_iteration = s->iteration == 0;
+  p.nW = w.Bp / 32;
   p.lo = (S)s->u_lower;
   p.hi = (S)s->u_upper;
   p.decay = (S)s->linesearch_decay;
@@ -121,7 +126,12 @@ static IterParams<Scalar> make_params(const DilqrSolve* s) {
   p.f = static_cast<const S*>(s->f);
   p.u_init = static_cast<const S*>(s->u_init);
   p.x_cur = static_cast<const S*>(s->x_cur);
-  p.traj = reinterpret_cast<S*>(ws + w.traj);
+  {
+    const int cur = role == 0 ? 1 : (s->iteration & 1);   // begin "writes new" = buffer 0
+    p.traj_cur = reinterpret_cast<const S*>(ws + w.traj[cur]);
+    p.traj_new = reinterpret_cast<S*>(ws + w.traj[cur ^ 1]);
+    p.traj_best = reinterpret_cast<S*>(ws + w.best);
+  }
   p.Kk = reinterpret_cast<S*>(ws + w.Kk);
   p.cost_cur = reinterpret_cast<S*>(ws + w.cost_cur);
   p.cost_new = reinterpret_cast<S*>(ws + w.cost_new);
@@ -129,7 +139,8 @@ static IterParams<Scalar> make_params(const DilqrSolve* s) {
   p.du_new = reinterpret_cast<S*>(ws + w.du_new);
   p.du_best = reinterpret_cast<S*>(ws + w.du_best);
   p.alpha_new = reinterpret_cast<S*>(ws + w.alpha_new);
-  p.sel = reinterpret_cast<int*>(ws + w.sel);
+  p.take = reinterpret_cast<int*>(ws + w.take);
+  p.gains_only = s->gains_only;
   p.guess = reinterpret_cast<uint32_t*>(ws + w.guess);
   p.votes = reinterpret_cast<uint32_t*>(ws + w.votes);
   p.status = s->status;
@@ -167,7 +178,7 @@ struct Geometry {
   static int warps_per_block() {
     if (!STAGED) return 4;
     const size_t per = IK::smem_per_warp();
-    int w = (int)((100 * 1024) / per);  // <= ~100 KB / block so two blocks fit one SM
+    int w = (int)((112 * 1024) / per);  // <= ~112 KB / block so two blocks fit one SM
     if (w > 4) w = 4;
     if (w < 1) w = 1;
     return w;
@@ -179,7 +190,7 @@ template <int NS, int NC, int DYN>
 static int launch_begin(const DilqrSolve* s, cudaStream_t st) {
   using S = Scalar;
   using G = Geometry<S, NS, NC, DYN>;
-  IterParams<S> p = make_params(s);
+  IterParams<S> p = make_params(s, 0);
   const int wpb = G::warps_per_block();
   const int warps = (p.B + kWarp - 1) / kWarp;
   const int blocks = (warps + wpb - 1) / wpb;
@@ -217,12 +228,13 @@ static int launch_iterate(const DilqrSolve* s, cudaStream_t st) {
   return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
 }
 
+template <int NS, int NC>
 static int launch_commit(const DilqrSolve* s, cudaStream_t st) {
   using S = Scalar;
   IterParams<S> p = make_params(s);
   trace_verify_kernel<<<1, 256, 0, st>>>(p.guess, p.votes, p.T, p.bounds_kind != 0, p.solo,
                                          s->status);
-  commit_kernel<S><<<(p.B + 127) / 128, 128, 0, st>>>(p);
+  commit_kernel<S, NS + NC><<<(p.B + 127) / 128, 128, 0, st>>>(p);
   return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
 }
 
@@ -243,7 +255,7 @@ static int launch_kkt(const DilqrKkt* k, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------ dispatch
-enum Op { OP_BEGIN, OP_ITERATE, OP_FINISH };
+enum Op { OP_BEGIN, OP_ITERATE, OP_COMMIT, OP_FINISH };
 
 static int dispatch(const DilqrSolve* s, Op op, cudaStream_t st) {
 #define X(NS_, NC_, DYN_)                                                            \
@@ -251,6 +263,7 @@ static int dispatch(const DilqrSolve* s, Op op, cudaStream_t st) {
     switch (op) {                                                                    \
       case OP_BEGIN: return launch_begin<NS_, NC_, DYN_>(s, st);                     \
       case OP_ITERATE: return launch_iterate<NS_, NC_, DYN_>(s, st);                 \
+      case OP_COMMIT: return launch_commit<NS_, NC_>(s, st);                         \
       case OP_FINISH: return launch_finish<NS_, NC_>(s, st);                         \
     }                                                                                \
   }
@@ -284,8 +297,7 @@ int DILQR_SUFFIX(mpc_iterate)(const DilqrSolve* s, void* stream) {
 int DILQR_SUFFIX(mpc_commit)(const DilqrSolve* s, void* stream) {
   int e = check(s, true);
   if (e) return e;
-  if (!DILQR_SUFFIX(supported)(s->n_state, s->n_ctrl, s->dynamics)) return DILQR_EUNSUPPORTED;
-  return launch_commit(s, static_cast<cudaStream_t>(stream));
+  return dispatch(s, OP_COMMIT, static_cast<cudaStream_t>(stream));
 }
 int DILQR_SUFFIX(mpc_finish)(const DilqrSolve* s, void* stream) {
   int e = check(s, true);
@@ -408,7 +420,6 @@ static int adj_run(const DilqrAdjoint* a, int what, cudaStream_t st) {
   const int warps = (p.B + kWarp - 1) / kWarp;
   constexpr int N = A::N;
   const uint32_t e1[1] = {N * N};
-  const uint32_t e2[2] = {N * N, N};
   if (what == 0) {
     const int wpb = 4;
     const size_t smem = (WarpStager<S>::bytes_per_warp(1, e1) + kStages * sizeof(uint64_t)) * wpb;
@@ -416,17 +427,15 @@ static int adj_run(const DilqrAdjoint* a, int what, cudaStream_t st) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<(warps + wpb - 1) / wpb, wpb * kWarp, smem, st>>>(p);
   } else if (what == 1) {
-    const int wpb = 2;
-    const size_t smem = (WarpStager<S>::bytes_per_warp(2, e2) + kStages * sizeof(uint64_t)) * wpb;
+    const int wpb = 1;
+    const size_t smem = AdjStage<S, DYN>::smem_per_warp(false) * wpb;
     auto kern = adjoint_pass_kernel<S, DYN, false>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaMemsetAsync(p.resid, 0, 16, st);   // max|dw|, max|w|; the reject counter accumulates
     kern<<<(warps + wpb - 1) / wpb, wpb * kWarp, smem, st>>>(p);
   } else {
-    const int wpb = 2;
-    const size_t out = (((size_t)kWarp * (N * N + N) * sizeof(S)) + 15) & ~(size_t)15;
-    const size_t smem =
-        (WarpStager<S>::bytes_per_warp(2, e2) + kStages * sizeof(uint64_t) + out) * wpb;
+    const int wpb = 1;
+    const size_t smem = AdjStage<S, DYN>::smem_per_warp(true) * wpb;
     auto kern = adjoint_pass_kernel<S, DYN, true>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<(warps + wpb - 1) / wpb, wpb * kWarp, smem, st>>>(p);

@@ -97,7 +97,7 @@ DILQR_DEVICE void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t*
 // to a lane-strided copy.
 // ---------------------------------------------------------------------------
 constexpr int kStages = 2;
-constexpr int kMaxSeg = 4;
+constexpr int kMaxSeg = 6;
 
 template <class S>
 struct WarpStager {
@@ -106,15 +106,23 @@ struct WarpStager {
   uint32_t stage_bytes;
   uint32_t seg_off[kMaxSeg];    // byte offset of each segment in a stage
   uint32_t seg_elems[kMaxSeg];  // scalars per problem in each segment
+  uint32_t seg_full;            // bit i: segment i always holds 32 problems (workspace chunks)
   uint32_t parity;   // bit s = parity to wait for on stage s
   uint32_t via_tma;  // bit s = stage s was filled by a bulk copy (else lane copies)
   int nvalid;        // problems this warp really has (<= 32)
   bool tma;          // slabs are 16B-aligned/sized -> bulk copies
   int lane;
 
+  DILQR_DEVICE uint32_t seg_bytes(int i) const {
+    return seg_elems[i] * (((seg_full >> i) & 1u) ? kWarp : nvalid) * (uint32_t)sizeof(S);
+  }
+
+  // `full_mask` bit i = segment i is a warp-blocked workspace chunk [elems][32]
+  // (always complete, lane-interleaved) rather than an API slab [nvalid][elems].
   DILQR_DEVICE void init(char* smem_base, uint64_t* bars, int lane_, int nvalid_, int nseg,
-                         const uint32_t* elems) {
+                         const uint32_t* elems, uint32_t full_mask = 0) {
     base = smem_base;
+    seg_full = full_mask;
     bar = bars;
     lane = lane_;
     nvalid = nvalid_;
@@ -127,7 +135,7 @@ struct WarpStager {
       seg_off[i] = off;
       seg_elems[i] = i < nseg ? elems[i] : 0;
       uint32_t full = seg_elems[i] * kWarp * sizeof(S);
-      uint32_t now = seg_elems[i] * nvalid * sizeof(S);
+      uint32_t now = seg_bytes(i);
       if (now % 16u) tma = false;
       off += (full + 15u) & ~15u;
     }
@@ -161,19 +169,19 @@ struct WarpStager {
         uint32_t total = 0;
 #pragma unroll
         for (int i = 0; i < kMaxSeg; ++i)
-          if (i < nseg && src[i]) total += seg_elems[i] * nvalid * sizeof(S);
+          if (i < nseg && src[i]) total += seg_bytes(i);
         mbar_expect_tx(&bar[stage], total);
 #pragma unroll
         for (int i = 0; i < kMaxSeg; ++i)
           if (i < nseg && src[i])
-            bulk_g2s(dst + seg_off[i], src[i], seg_elems[i] * nvalid * sizeof(S), &bar[stage]);
+            bulk_g2s(dst + seg_off[i], src[i], seg_bytes(i), &bar[stage]);
       }
     } else {
 #pragma unroll
       for (int i = 0; i < kMaxSeg; ++i) {
         if (i < nseg && src[i]) {
           S* d = reinterpret_cast<S*>(dst + seg_off[i]);
-          const int cnt = seg_elems[i] * nvalid;
+          const int cnt = seg_bytes(i) / sizeof(S);
           for (int e = lane; e < cnt; e += kWarp) d[e] = __ldg(src[i] + e);
         }
       }
@@ -189,12 +197,22 @@ struct WarpStager {
     }
   }
 
+  // Base of segment i in `stage` (blocked chunks: element e of this lane is [e*32+lane]).
+  DILQR_DEVICE const S* seg_ptr(int stage, int seg) const {
+    return reinterpret_cast<const S*>(base + stage * stage_bytes + seg_off[seg]);
+  }
+
   // Pointer to this lane's block of segment i in `stage`.
   DILQR_DEVICE const S* lane_ptr(int stage, int seg) const {
     return reinterpret_cast<const S*>(base + stage * stage_bytes + seg_off[seg]) +
            lane * seg_elems[seg];
   }
 };
+
+// warp-blocked SoA index of workspace arrays [T][B/32][ncomp][32]
+DILQR_DEVICE size_t bidx(int t, int comp, int ncomp, int b, int nW) {
+  return (((size_t)t * nW + (b >> 5)) * ncomp + comp) * kWarp + (b & 31);
+}
 
 // ordered-uint encoding of non-negative doubles for atomicMax
 DILQR_DEVICE unsigned long long dbits(double v) { return (unsigned long long)__double_as_longlong(v); }

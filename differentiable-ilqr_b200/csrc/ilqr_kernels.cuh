@@ -6,8 +6,11 @@
 // API's time-major AoS tensors (C, c, F, f) one timestep at a time through a
 // double-buffered shared-memory stage filled by 1-D bulk TMA copies
 // (cp.async.bulk + mbarrier, see WarpStager).  Everything private to the solver
-// (trajectories, gains, per-problem bookkeeping) is kept in an SoA workspace
-// [T][component][B] so that per-thread accesses are perfectly coalesced.
+// (trajectories, gains, per-problem bookkeeping) is kept in a warp-blocked SoA
+// workspace [T][B/32][component][32]: per-thread accesses are perfectly coalesced
+// AND the chunk a warp needs for one timestep is contiguous, so it rides the same
+// TMA stage as the API slabs -- every per-timestep operand of the sweep arrives in
+// shared memory one step ahead of its use.
 //
 // Tensor cores are deliberately not used: the per-problem matrices are at most
 // ~16x16, strictly sequential in t, and every problem has different operands.
@@ -59,15 +62,20 @@ struct IterParams {
   const S* f;
   const S* u_init;
   const S* x_cur;
-  S* traj;        // [3][T][N][Bp]
-  S* Kk;          // [T][NC*NS+NC][Bp]
+  const S* traj_cur;  // [T][Bp/32][N][32]  current iterate (read)
+  S* traj_new;        // [T][Bp/32][N][32]  new iterate (written)
+  S* traj_best;       // [T][Bp/32][N][32]  best iterate so far
+  S* Kk;              // [T][Bp/32][NC*NS+NC][32]
+  int nW;             // Bp / 32
+  int* take;          // [Bp] 1: the problem's best iterate is the CURRENT trajectory and
+                      //         has not been copied to traj_best yet (lazy best tracking)
+  int gains_only;     // skip the line-search rollout (only K,k are wanted)
   S* cost_cur;    // [Bp]
   S* cost_new;
   S* cost_best;
   S* du_new;
   S* du_best;
   S* alpha_new;
-  int* sel;       // [Bp]  bits 0-1: current buffer, bits 2-3: best buffer
   uint32_t* guess;  // [T][kPnqpMaxIter]
   uint32_t* votes;  // [T][kPnqpMaxIter]
   void* status;     // DilqrStatus*
@@ -80,13 +88,6 @@ struct IterParams {
   S* k_out;
   DynParams<S> dyn;
 };
-
-DILQR_DEVICE int sel_cur(int s) { return s & 3; }
-DILQR_DEVICE int sel_best(int s) { return (s >> 2) & 3; }
-DILQR_DEVICE int sel_free(int s) {
-  const int a = sel_cur(s), b = sel_best(s);
-  return (a != 0 && b != 0) ? 0 : ((a != 1 && b != 1) ? 1 : 2);
-}
 
 // ---------------------------------------------------------------------------
 // stage cost  0.5 tau' C tau + c' tau   (util.py:145-147: bquad then bdot)
@@ -268,51 +269,58 @@ struct IterKernel {
   static constexpr int NK = NC * NS + NC;
   static constexpr bool kEnv = (DYN != DYN_LINDX);
   using D = Dyn<S, DYN>;
+  // stage segments: 0 C[n*n]  1 c[n]  2 F[ns*n]  3 f[ns]  (API slabs)
+  //                 4 traj_cur[t] chunk [N][32]   5 Kk[t] chunk [NK][32]   (workspace)
+  static constexpr int kNSeg = 6;
+  static constexpr uint32_t kFullMask = (1u << 4) | (1u << 5);
 
-  static __host__ __device__ int nseg() { return kEnv ? 2 : 4; }
   static __host__ __device__ void seg_elems(uint32_t* e) {
     e[0] = N * N;
     e[1] = N;
-    e[2] = NS * N;
-    e[3] = NS;
+    e[2] = kEnv ? 0 : NS * N;
+    e[3] = kEnv ? 0 : NS;
+    e[4] = N;
+    e[5] = NK;
   }
   static __host__ __device__ size_t smem_per_warp() {
     if (!STAGED) return 0;
-    uint32_t e[4];
+    uint32_t e[kNSeg];
     seg_elems(e);
-    return WarpStager<S>::bytes_per_warp(nseg(), e) + kStages * sizeof(uint64_t);
+    return WarpStager<S>::bytes_per_warp(kNSeg, e) + kStages * sizeof(uint64_t);
   }
 
-  // Per-lane pointers to the (C, c, F, f) blocks of timestep t: the staged copy
-  // in shared memory, or (shapes too large to stage) straight global memory.
+  // Per-lane view of the operands of timestep t: staged copies in shared memory, or
+  // (shapes too large to stage) straight global memory.  C,c,F,f are this lane's
+  // row-major blocks; tau / Kk are lane-interleaved (element e at [e * tstride]).
   struct Blk {
     const S* C;
     const S* c;
     const S* F;
     const S* f;
+    const S* tau;
+    const S* Kk;
+    int tstride;
   };
   DILQR_DEVICE static Blk blocks(const IterParams<S>& p, const WarpStager<S>& st, int sg, int t,
-                                 int b) {
+                                 int b, int bw, int lane) {
     Blk k;
     if (STAGED) {
       k.C = st.lane_ptr(sg, 0);
       k.c = st.lane_ptr(sg, 1);
       k.F = kEnv ? nullptr : st.lane_ptr(sg, 2);
       k.f = kEnv ? nullptr : st.lane_ptr(sg, 3);
+      k.tau = st.seg_ptr(sg, 4) + lane;
+      k.Kk = st.seg_ptr(sg, 5) + lane;
     } else {
       k.C = p.C + ((size_t)t * p.B + b) * (N * N);
       k.c = p.c + ((size_t)t * p.B + b) * N;
       k.F = (kEnv || t >= p.T - 1) ? nullptr : p.F + ((size_t)t * p.B + b) * (NS * N);
       k.f = (kEnv || !p.has_f || t >= p.T - 1) ? nullptr : p.f + ((size_t)t * p.B + b) * NS;
+      k.tau = p.traj_cur + bidx(t, 0, N, bw, p.nW);
+      k.Kk = p.Kk + bidx(t, 0, NK, bw, p.nW);
     }
+    k.tstride = kWarp;
     return k;
-  }
-
-  DILQR_DEVICE static const S* traj_ptr(const IterParams<S>& p, int buf, int t, int comp, int b) {
-    return p.traj + ((size_t)(buf * p.T + t) * N + comp) * p.Bp + b;
-  }
-  DILQR_DEVICE static S* traj_ptr_w(const IterParams<S>& p, int buf, int t, int comp, int b) {
-    return p.traj + ((size_t)(buf * p.T + t) * N + comp) * p.Bp + b;
   }
 
   DILQR_DEVICE static void bounds_at(const IterParams<S>& p, int t, int b, S* lo, S* hi) {
@@ -331,43 +339,55 @@ struct IterKernel {
     }
   }
 
-  // issue the slabs of timestep t for this warp into `stage`
+  // issue the operands of timestep t for this warp into `stage`
   DILQR_DEVICE static void issue_t(WarpStager<S>& st, const IterParams<S>& p, int stage, int t,
-                                   int b0, bool want_F, bool want_f) {
+                                   int b0, bool want_f, bool want_traj, bool want_K) {
     if (!STAGED) return;
-    const S* src[4];
+    const S* src[kNSeg];
     src[0] = p.C + ((size_t)t * p.B + b0) * (N * N);
     src[1] = p.c + ((size_t)t * p.B + b0) * N;
     src[2] = nullptr;
     src[3] = nullptr;
     if (!kEnv) {
-      if (want_F && t < p.T - 1) src[2] = p.F + ((size_t)t * p.B + b0) * (NS * N);
+      if (t < p.T - 1) src[2] = p.F + ((size_t)t * p.B + b0) * (NS * N);
       if (want_f && p.has_f && t < p.T - 1) src[3] = p.f + ((size_t)t * p.B + b0) * NS;
     }
-    st.issue(stage, src, nseg());
+    src[4] = want_traj ? p.traj_cur + bidx(t, 0, N, b0, p.nW) : nullptr;
+    src[5] = want_K ? p.Kk + bidx(t, 0, NK, b0, p.nW) : nullptr;
+    st.issue(stage, src, kNSeg);
   }
 
   // ======================================================================
   // Phase A: c_back + Riccati backward sweep with gains (and pnqp).
   // ======================================================================
+  // b: problem index for the API tensors (clamped for padded lanes); bw: this
+  // lane's own column of the (padded) workspace.
   DILQR_DEVICE static void backward_sweep(const IterParams<S>& p, WarpStager<S>& st, int b0,
-                                          int b, bool active, int lane, int cur) {
+                                          int b, int bw, bool active, int lane) {
     S V[NS][NS], v[NS];
     S kprev[NC];
     S xnext[NS];  // x_{t+1} of the nominal trajectory (trig reuse for env Jacobians)
     bool have_prev = false;
     const int T = p.T;
-    issue_t(st, p, 0, T - 1, b0, true, false);
+    // lazy best-iterate tracking (mpc.py:272-285): if the previous iteration made the
+    // current trajectory this problem's best, park it in traj_best while it streams by.
+    const bool flush = p.take[bw] != 0;
+    issue_t(st, p, 0, T - 1, b0, false, true, false);
     for (int t = T - 1; t >= 0; --t) {
       const int sg = (T - 1 - t) & 1;
-      if (t > 0) issue_t(st, p, sg ^ 1, t - 1, b0, true, false);
-      S tau[N];
-#pragma unroll
-      for (int i = 0; i < N; ++i) tau[i] = *traj_ptr(p, cur, t, i, b);
+      if (t > 0) issue_t(st, p, sg ^ 1, t - 1, b0, false, true, false);
       if (STAGED) st.wait(sg);
-      const Blk blk = blocks(p, st, sg, t, b);
+      const Blk blk = blocks(p, st, sg, t, b, bw, lane);
       const S* Cs = blk.C;
       const S* cs = blk.c;
+      S tau[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) tau[i] = blk.tau[i * kWarp];
+      if (flush) {
+        S* bo = p.traj_best + bidx(t, 0, N, bw, p.nW);
+#pragma unroll
+        for (int i = 0; i < N; ++i) bo[i * kWarp] = tau[i];
+      }
 
       S Q[N][N], qv[N];
 #pragma unroll
@@ -430,12 +450,9 @@ struct IterKernel {
       S K[NC][NS], k[NC];
       if (p.bounds_kind == 0) {
         bool mask[NC];
-        bool any_mask = false;
 #pragma unroll
-        for (int a = 0; a < NC; ++a) {
+        for (int a = 0; a < NC; ++a)
           mask[a] = p.zeroI ? (p.zeroI[((size_t)t * p.B + b) * NC + a] != 0) : false;
-          any_mask |= mask[a];
-        }
         if (NC == 1) {
           if (!p.zeroI) {  // lqr_step.py:84-86
             const S r = S(1) / Q[NS][NS];
@@ -530,13 +547,13 @@ struct IterKernel {
           }
         }
       }
-      if (active) {
+      {
+        S* ko = p.Kk + bidx(t, 0, NK, bw, p.nW);   // padded lanes own their column: no guard
 #pragma unroll
         for (int a = 0; a < NC; ++a) {
 #pragma unroll
-          for (int j = 0; j < NS; ++j)
-            p.Kk[((size_t)t * NK + a * NS + j) * p.Bp + b] = K[a][j];
-          p.Kk[((size_t)t * NK + NC * NS + a) * p.Bp + b] = k[a];
+          for (int j = 0; j < NS; ++j) ko[(a * NS + j) * kWarp] = K[a][j];
+          ko[(NC * NS + a) * kWarp] = k[a];
         }
       }
       // -------------------------------------------- value function update
@@ -582,7 +599,7 @@ struct IterKernel {
   // the true dynamics (lqr_step.py:164-261).
   // ======================================================================
   DILQR_DEVICE static void forward_linesearch(const IterParams<S>& p, WarpStager<S>& st, int b0,
-                                              int b, bool active, int lane, int cur, int nw) {
+                                              int b, int bw, bool active, int lane) {
     const int T = p.T;
     const S old_cost = p.cost_cur[b];
     S alpha = S(1);
@@ -591,6 +608,11 @@ struct IterKernel {
     S x0[NS];
 #pragma unroll
     for (int i = 0; i < NS; ++i) x0[i] = __ldg(p.x_init + (size_t)b * NS + i);
+    // the gains written by phase A (generic-proxy stores) are read back through the
+    // async proxy (TMA) below
+    __threadfence();
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncwarp();
 
     for (int tr = 0; tr < p.max_ls; ++tr) {
       if (!__any_sync(kFull, active && !accepted)) break;
@@ -599,13 +621,15 @@ struct IterKernel {
 #pragma unroll
       for (int i = 0; i < NS; ++i) xh[i] = x0[i];
       S cost = S(0), du2 = S(0);
-      issue_t(st, p, 0, 0, b0, true, true);
+      issue_t(st, p, 0, 0, b0, true, true, true);
       for (int t = 0; t < T; ++t) {
         const int sg = t & 1;
-        if (t + 1 < T) issue_t(st, p, sg ^ 1, t + 1, b0, true, true);
+        if (t + 1 < T) issue_t(st, p, sg ^ 1, t + 1, b0, true, true, true);
+        if (STAGED) st.wait(sg);
+        const Blk blk = blocks(p, st, sg, t, b, bw, lane);
         S tau[N];   // nominal (x_t, u_t)
 #pragma unroll
-        for (int i = 0; i < N; ++i) tau[i] = *traj_ptr(p, cur, t, i, b);
+        for (int i = 0; i < N; ++i) tau[i] = blk.tau[i * kWarp];
         S th[N];    // new (x^_t, u^_t)
 #pragma unroll
         for (int i = 0; i < NS; ++i) th[i] = xh[i];
@@ -617,21 +641,20 @@ struct IterKernel {
           if (t > 0) {
 #pragma unroll
             for (int j = 0; j < NS; ++j)
-              acc = fmaS<S>(p.Kk[((size_t)t * NK + a * NS + j) * p.Bp + b], xh[j] - tau[j], acc);
+              acc = fmaS<S>(blk.Kk[(a * NS + j) * kWarp], xh[j] - tau[j], acc);
           }
-          S un = (acc + tau[NS + a]) + alpha * p.Kk[((size_t)t * NK + NC * NS + a) * p.Bp + b];
+          S un = (acc + tau[NS + a]) + alpha * blk.Kk[(NC * NS + a) * kWarp];
           if (p.zeroI && p.zeroI[((size_t)t * p.B + b) * NC + a]) un = S(0);  // :197-198
           if (p.bounds_kind) un = eclamp<S>(un, lo[a], hi[a]);                  // :213
           th[NS + a] = un;
           const S d = tau[NS + a] - un;
           du2 = fmaS<S>(d, d, du2);
         }
-        if (run) {
+        if (!accepted) {   // padded lanes keep their own columns defined as well
+          S* to = p.traj_new + bidx(t, 0, N, bw, p.nW);
 #pragma unroll
-          for (int i = 0; i < N; ++i) *traj_ptr_w(p, nw, t, i, b) = th[i];
+          for (int i = 0; i < N; ++i) to[i * kWarp] = th[i];
         }
-        if (STAGED) st.wait(sg);
-        const Blk blk = blocks(p, st, sg, t, b);
         cost = cost + stage_cost<S, N>(blk.C, blk.c, th);
         if (t < T - 1) {
           if constexpr (kEnv) {
@@ -669,29 +692,28 @@ ilqr_iter_kernel(const __grid_constant__ IterParams<S> p) {
   if (b0 >= p.B) return;
   const int nvalid = min(kWarp, p.B - b0);
   const bool active = lane < nvalid;
-  const int b = active ? b0 + lane : b0;
+  const int b = b0 + lane;   // padded lanes index their own (padded) workspace column
 
   const size_t per_warp = IK::smem_per_warp();
   char* wbase = smem + warp * per_warp;
   uint64_t* bars = reinterpret_cast<uint64_t*>(wbase);
   WarpStager<S> st;
   if (STAGED) {
-    uint32_t e[4];
+    uint32_t e[IK::kNSeg];
     IK::seg_elems(e);
-    st.init(wbase + kStages * sizeof(uint64_t), bars, lane, nvalid, IK::nseg(), e);
+    st.init(wbase + kStages * sizeof(uint64_t), bars, lane, nvalid, IK::kNSeg, e, IK::kFullMask);
   }
-
-  const int s = p.sel[b];
-  const int cur = sel_cur(s);
-  const int nw = sel_free(s);
-  IK::backward_sweep(p, st, b0, b, active, lane, cur);
-  IK::forward_linesearch(p, st, b0, b, active, lane, cur, nw);
+  // padded lanes (tail warp) read the API tensors of the warp's first problem
+  const int bsafe = active ? b : b0;
+  IK::backward_sweep(p, st, b0, bsafe, b, active, lane);
+  if (!p.gains_only) IK::forward_linesearch(p, st, b0, bsafe, b, active, lane);
 }
 
 // ---------------------------------------------------------------------------
 // begin: nominal rollout of u_init (util.get_traj) + its cost (util.get_cost)
-// into trajectory buffer 0.  With p.x_cur != nullptr the given trajectory is
-// loaded instead of rolled out (standalone LQRStep, lqr_step.py:164-169).
+// into the current-trajectory buffer.  With p.x_cur != nullptr the given
+// trajectory is loaded instead of rolled out (standalone LQRStep,
+// lqr_step.py:164-169).
 // ---------------------------------------------------------------------------
 template <class S, int NS, int NC, int DYN, bool STAGED>
 __global__ void __launch_bounds__(128)
@@ -713,20 +735,20 @@ ilqr_begin_kernel(const __grid_constant__ IterParams<S> p) {
   char* wbase = smem + warp * per_warp;
   WarpStager<S> st;
   if (STAGED) {
-    uint32_t e[4];
+    uint32_t e[IK::kNSeg];
     IK::seg_elems(e);
     st.init(wbase + kStages * sizeof(uint64_t), reinterpret_cast<uint64_t*>(wbase), lane, nvalid,
-            IK::nseg(), e);
+            IK::kNSeg, e, IK::kFullMask);
   }
   const int T = p.T;
   S xh[NS];
 #pragma unroll
   for (int i = 0; i < NS; ++i) xh[i] = __ldg(p.x_init + (size_t)b * NS + i);
   S cost = S(0);
-  IK::issue_t(st, p, 0, 0, b0, true, true);
+  IK::issue_t(st, p, 0, 0, b0, true, false, false);
   for (int t = 0; t < T; ++t) {
     const int sg = t & 1;
-    if (t + 1 < T) IK::issue_t(st, p, sg ^ 1, t + 1, b0, true, true);
+    if (t + 1 < T) IK::issue_t(st, p, sg ^ 1, t + 1, b0, true, false, false);
     S th[N];
     if (p.x_cur) {
 #pragma unroll
@@ -738,12 +760,13 @@ ilqr_begin_kernel(const __grid_constant__ IterParams<S> p) {
 #pragma unroll
     for (int a = 0; a < NC; ++a)
       th[NS + a] = p.u_init ? __ldg(p.u_init + ((size_t)t * p.B + b) * NC + a) : S(0);
-    if (active) {
+    {
+      S* to = p.traj_new + bidx(t, 0, N, b0 + lane, p.nW);
 #pragma unroll
-      for (int i = 0; i < N; ++i) *IK::traj_ptr_w(p, 0, t, i, b) = th[i];
+      for (int i = 0; i < N; ++i) to[i * kWarp] = th[i];
     }
     if (STAGED) st.wait(sg);
-    const typename IK::Blk blk = IK::blocks(p, st, sg, t, b);
+    const typename IK::Blk blk = IK::blocks(p, st, sg, t, b, b0 + lane, lane);
     cost = cost + stage_cost<S, N>(blk.C, blk.c, th);
     if (t < T - 1 && !p.x_cur) {
       if constexpr (kEnv) {
@@ -753,10 +776,8 @@ ilqr_begin_kernel(const __grid_constant__ IterParams<S> p) {
       }
     }
   }
-  if (active) {
-    p.cost_cur[b] = cost;
-    p.sel[b] = 0;
-  }
+  if (active) p.cost_cur[b] = cost;
+  p.take[b0 + lane] = 0;
 }
 
 }  // namespace dilqr

@@ -74,7 +74,7 @@ static __global__ void trace_verify_kernel(uint32_t* __restrict__ guess, const u
 // Per-problem commit: best-iterate bookkeeping (mpc.py:271-285) + the batch
 // reductions the host needs for the stop rule (mpc.py:299-301).
 // ---------------------------------------------------------------------------
-template <class S>
+template <class S, int N>
 __global__ void commit_kernel(const __grid_constant__ IterParams<S> p) {
   DilqrStatus* status = reinterpret_cast<DilqrStatus*>(p.status);
   if (status->trace_match == 0) return;
@@ -82,22 +82,20 @@ __global__ void commit_kernel(const __grid_constant__ IterParams<S> p) {
   double du = 0.0, al = 0.0, bc = 0.0;
   bool improved = false;
   if (b < p.B) {
-    const int s = p.sel[b];
-    const int nw = sel_free(s);
-    int best = sel_best(s);
     const S cn = p.cost_new[b];
+    bool take = false;
     if (p.first_iteration) {
-      best = nw;
-      p.cost_best[b] = cn;
-      p.du_best[b] = p.du_new[b];
+      take = true;
     } else if (cn <= p.cost_best[b] + p.best_cost_eps) {  // mpc.py:280
-      best = nw;
-      p.cost_best[b] = cn;
-      p.du_best[b] = p.du_new[b];
+      take = true;
       improved = true;
     }
+    if (take) {   // best <- new   (mpc.py:272-285); the trajectory copy is deferred:
+      p.cost_best[b] = cn;   // the next sweep (or finish) moves it, see IterParams::take
+      p.du_best[b] = p.du_new[b];
+    }
+    p.take[b] = take ? 1 : 0;
     p.cost_cur[b] = cn;
-    p.sel[b] = nw | (best << 2);
     du = (double)p.du_new[b];
     al = (double)p.alpha_new[b];
     bc = (double)p.cost_best[b];
@@ -122,7 +120,7 @@ __global__ void commit_kernel(const __grid_constant__ IterParams<S> p) {
 
 // ---------------------------------------------------------------------------
 // Gather the best iterate into the API (AoS) layout  (mpc.py:304-306).
-// One thread per (t, b); the SoA reads are coalesced, the AoS writes are
+// One thread per (t, b); workspace reads are coalesced, the AoS writes are
 // contiguous per warp (consecutive b).
 // ---------------------------------------------------------------------------
 template <class S, int NS, int NC>
@@ -132,26 +130,25 @@ __global__ void finish_kernel(const __grid_constant__ IterParams<S> p) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   const int t = blockIdx.y;
   if (b >= p.B) return;
-  const int best = sel_best(p.sel[b]);
-  const S* src = p.traj + ((size_t)(best * p.T + t) * N) * p.Bp + b;
+  // best iterate: parked in traj_best, or still the latest trajectory (take flag)
+  const S* src = (p.take[b] ? p.traj_new : p.traj_best) + bidx(t, 0, N, b, p.nW);
   if (p.x_out) {
 #pragma unroll
-    for (int i = 0; i < NS; ++i) p.x_out[((size_t)t * p.B + b) * NS + i] = src[(size_t)i * p.Bp];
+    for (int i = 0; i < NS; ++i) p.x_out[((size_t)t * p.B + b) * NS + i] = src[i * kWarp];
   }
   if (p.u_out) {
 #pragma unroll
-    for (int a = 0; a < NC; ++a)
-      p.u_out[((size_t)t * p.B + b) * NC + a] = src[(size_t)(NS + a) * p.Bp];
+    for (int a = 0; a < NC; ++a) p.u_out[((size_t)t * p.B + b) * NC + a] = src[(NS + a) * kWarp];
   }
+  const S* ks = p.Kk + bidx(t, 0, NK, b, p.nW);
   if (p.K_out) {
 #pragma unroll
-    for (int e = 0; e < NC * NS; ++e)
-      p.K_out[((size_t)t * p.B + b) * (NC * NS) + e] = p.Kk[((size_t)t * NK + e) * p.Bp + b];
+    for (int e = 0; e < NC * NS; ++e) p.K_out[((size_t)t * p.B + b) * (NC * NS) + e] = ks[e * kWarp];
   }
   if (p.k_out) {
 #pragma unroll
     for (int a = 0; a < NC; ++a)
-      p.k_out[((size_t)t * p.B + b) * NC + a] = p.Kk[((size_t)t * NK + NC * NS + a) * p.Bp + b];
+      p.k_out[((size_t)t * p.B + b) * NC + a] = ks[(NC * NS + a) * kWarp];
   }
   if (t == 0) {
     if (p.cost_out) p.cost_out[b] = p.cost_best[b];

@@ -82,8 +82,13 @@ typedef struct DilqrSolve {
   int32_t solo;             /* 0: batch-global pnqp control flow (== reference on
                                the same batch); 1: per-problem (== reference B=1)   */
   int32_t max_linesearch_iter; /* mpc.py:135                                        */
-  int32_t first_iteration;  /* commit: 1 on the first iLQR iteration (mpc.py:271)   */
+  int32_t iteration;        /* 0-based iLQR iteration index of this iterate/commit call
+                               (0: first -> best := new, mpc.py:271; parity selects
+                               the ping-pong trajectory buffer)                      */
   int32_t has_f;            /* LinDx: f present (util.py:121)                        */
+  int32_t gains_only;       /* iterate: only lqr_backward (K_out,k_out), no rollout --
+                               the final no-op LQR pass of lqr_step_explicit.py:604-618 */
+  int32_t reserved0;
   double  linesearch_decay; /* mpc.py:134                                           */
   double  u_lower, u_upper; /* scalar bounds (mpc.py:81-82)                         */
   double  best_cost_eps;    /* mpc.py:142                                           */
@@ -147,7 +152,7 @@ int dilqr_mpc_finish(const DilqrSolve* s, void* stream);
 /* A single LQR step, LQRStep(...)(x_init,C,c,F,f) (lqr_step.py:22-38,277-309), is
  * the same call sequence with `x_cur` (and `u_init` = current u) set: dilqr_mpc_begin
  * then loads the given trajectory instead of rolling it out, one
- * dilqr_mpc_iterate + dilqr_mpc_commit(first_iteration=1) runs the step, and
+ * dilqr_mpc_iterate + dilqr_mpc_commit (iteration = 0) runs the step, and
  * dilqr_mpc_finish returns the new iterate (x_out,u_out,cost_out,du_out,
  * alpha_out) and, if requested, the gains K_out,k_out of lqr_backward. */
 
