@@ -478,7 +478,12 @@ static int launch_costate(const double* dp, int T, int B, const void* C, const v
   using S = Scalar;
   DynParams<S> P;
   for (int i = 0; i < 8; ++i) P.p[i] = (S)dp[i];
-  costate_tables_kernel<S, DYN><<<(B + 63) / 64, 64, 0, st>>>(
+  const int wpb = 2;
+  const size_t smem = CostateStage<S, DYN>::smem_per_warp() * wpb;
+  auto kern = costate_tables_kernel<S, DYN>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int warps = (B + kWarp - 1) / kWarp;
+  kern<<<(warps + wpb - 1) / wpb, wpb * kWarp, smem, st>>>(
       P, T, B, static_cast<const S*>(C), static_cast<const S*>(c), static_cast<const S*>(x),
       static_cast<const S*>(u), static_cast<S*>(lam), static_cast<S*>(Lam));
   return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;

@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "dynamics.cuh"
 #include "env_tables_gen.cuh"
+#include "adjoint_kernels.cuh"
 
 namespace dilqr {
 
@@ -30,67 +31,138 @@ namespace dilqr {
 //   lam  [T,B,ns]      Lam [T-1,B,n,n]  (row k = d/dtau_k, col j)
 // ---------------------------------------------------------------------------
 template <class S, int DYN>
-__global__ void __launch_bounds__(128)
+struct CostateStage {
+  using D = Dyn<S, DYN>;
+  static constexpr int NS = D::NS, NC = D::NC, N = D::N;
+  static constexpr int kNSeg = 4;   // C[N*N], c[N], x[NS], u[NC]
+  static __host__ __device__ void seg_elems(uint32_t* e) {
+    e[0] = N * N;
+    e[1] = N;
+    e[2] = NS;
+    e[3] = NC;
+  }
+  static __host__ __device__ size_t out_bytes() {
+    return ((size_t)kWarp * (N * N) * sizeof(S) + 15) & ~(size_t)15;
+  }
+  static __host__ __device__ size_t smem_per_warp() {
+    uint32_t e[kNSeg];
+    seg_elems(e);
+    return WarpStager<S>::bytes_per_warp(kNSeg, e) + kStages * sizeof(uint64_t) + out_bytes();
+  }
+};
+
+template <class S, int DYN>
+__global__ void __launch_bounds__(64)
 costate_tables_kernel(DynParams<S> P, int T, int B, const S* __restrict__ C,
                       const S* __restrict__ c, const S* __restrict__ x, const S* __restrict__ u,
                       S* __restrict__ lam_out, S* __restrict__ Lam_out) {
   using D = Dyn<S, DYN>;
   using TB = EnvTables<S, DYN>;
+  using CS = CostateStage<S, DYN>;
   constexpr int NS = D::NS, NC = D::NC, N = D::N, NTH = TB::NTH;
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
+  extern __shared__ __align__(128) char smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int b0 = (blockIdx.x * wpb + warp) * kWarp;
+  if (b0 >= B) return;
+  const int nvalid = min(kWarp, B - b0);
+  const bool act = lane < nvalid;
+  const int b = act ? b0 + lane : b0;
+  char* wbase = smem + warp * CS::smem_per_warp();
+  WarpStager<S> st;
+  {
+    uint32_t e[CS::kNSeg];
+    CS::seg_elems(e);
+    st.init(wbase + kStages * sizeof(uint64_t), reinterpret_cast<uint64_t*>(wbase), lane, nvalid,
+            CS::kNSeg, e);
+  }
+  S* outL = reinterpret_cast<S*>(wbase + CS::smem_per_warp() - CS::out_bytes());
+  auto issue = [&](int stage, int t) {
+    const size_t o = (size_t)t * B + b0;
+    const S* src[CS::kNSeg] = {C + o * (N * N), c + o * N, x + o * NS, u + o * NC};
+    st.issue(stage, src, CS::kNSeg);
+  };
+  const bool bulk_out = (nvalid == kWarp) && ((((size_t)N * N * sizeof(S) * kWarp) & 15) == 0);
   S lam[NS];
+  issue(0, T - 1);
   for (int t = T - 1; t >= 0; --t) {
+    const int sg = (T - 1 - t) & 1;
+    if (t > 0) issue(sg ^ 1, t - 1);
+    st.wait(sg);
+    const S* Cs = st.lane_ptr(sg, 0);
+    const S* cs = st.lane_ptr(sg, 1);
+    const S* xs_ = st.lane_ptr(sg, 2);
+    const S* us_ = st.lane_ptr(sg, 3);
     const size_t tb = (size_t)t * B + b;
     S tau[N];
 #pragma unroll
-    for (int i = 0; i < NS; ++i) tau[i] = x[tb * NS + i];
+    for (int i = 0; i < NS; ++i) tau[i] = xs_[i];
 #pragma unroll
-    for (int a = 0; a < NC; ++a) tau[NS + a] = u[tb * NC + a];
+    for (int a = 0; a < NC; ++a) tau[NS + a] = us_[a];
     S Dm[NS][N];
     if (t < T - 1) {
       S Dth[NS][N][NTH], Dx[NS][N][NS], Du[NS][N][NC], xth[NS][NTH], xx[NS][NS], xu[NS][NC];
       TB::eval(P, tau, &tau[NS], Dm, Dth, Dx, Du, xth, xx, xu);
       // Lam_t[k][j] = sum_i lam_{t+1}[i] dD[i][j]/dtau_k
-      S* Lo = Lam_out + tb * (N * N);
+      if (bulk_out) {
+        bulk_wait_read0();
+        __syncwarp();
+      }
+      S* Lo = bulk_out ? outL + lane * (N * N) : Lam_out + tb * (N * N);
+      if (act || bulk_out) {
 #pragma unroll
-      for (int k = 0; k < N; ++k)
+        for (int k = 0; k < N; ++k)
 #pragma unroll
-        for (int j = 0; j < N; ++j) {
-          S acc = S(0);
+          for (int j = 0; j < N; ++j) {
+            S acc = S(0);
 #pragma unroll
-          for (int i = 0; i < NS; ++i)
-            acc = fmaS<S>(lam[i], k < NS ? Dx[i][j][k < NS ? k : 0] : Du[i][j][k < NS ? 0 : k - NS],
-                          acc);
-          Lo[k * N + j] = acc;
+            for (int i = 0; i < NS; ++i) {
+              if (k < NS) {
+                if (TB::nz_Dx(i, j, k < NS ? k : 0))
+                  acc = fmaS<S>(lam[i], Dx[i][j][k < NS ? k : 0], acc);
+              } else {
+                if (TB::nz_Du(i, j, k < NS ? 0 : k - NS))
+                  acc = fmaS<S>(lam[i], Du[i][j][k < NS ? 0 : k - NS], acc);
+              }
+            }
+            Lo[k * N + j] = acc;
+          }
+      }
+      if (bulk_out) {
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          bulk_s2g(Lam_out + ((size_t)t * B + b0) * (N * N), outL, kWarp * N * N * sizeof(S));
+          bulk_commit();
         }
+      }
     }
     S nl[NS];
 #pragma unroll
     for (int i = 0; i < NS; ++i) {
       S a1 = S(0), a2 = S(0);
 #pragma unroll
-      for (int j = 0; j < NS; ++j) a1 = fmaS<S>(C[tb * (N * N) + i * N + j], tau[j], a1);
+      for (int j = 0; j < NS; ++j) a1 = fmaS<S>(Cs[i * N + j], tau[j], a1);
 #pragma unroll
-      for (int a = 0; a < NC; ++a)
-        a2 = fmaS<S>(C[tb * (N * N) + i * N + NS + a], tau[NS + a], a2);
-      nl[i] = (a1 + a2) + c[tb * N + i];
+      for (int a = 0; a < NC; ++a) a2 = fmaS<S>(Cs[i * N + NS + a], tau[NS + a], a2);
+      nl[i] = (a1 + a2) + cs[i];
     }
     if (t < T - 1) {
 #pragma unroll
       for (int i = 0; i < NS; ++i) {
         S a1 = S(0);
 #pragma unroll
-        for (int l = 0; l < NS; ++l) a1 = fmaS<S>(Dm[l][i], lam[l], a1);
+        for (int l = 0; l < NS; ++l)
+          if (TB::nz_D(l, i)) a1 = fmaS<S>(Dm[l][i], lam[l], a1);
         nl[i] = nl[i] + a1;
       }
     }
 #pragma unroll
     for (int i = 0; i < NS; ++i) {
       lam[i] = nl[i];
-      lam_out[tb * NS + i] = nl[i];
+      if (act) lam_out[tb * NS + i] = nl[i];
     }
   }
+  if (bulk_out) bulk_wait0();
 }
 
 // ---------------------------------------------------------------------------
@@ -202,8 +274,9 @@ sens_theta_kernel(DynParams<S> P, int T, int B, const S* __restrict__ x,
         for (int j = 0; j < NS; ++j) {
           S s = S(0);
 #pragma unroll
-          for (int a = 0; a < NC; ++a) s = fmaS<S>(xu[i][a], Kp[a][j], s);
-          A[i][j] = xx[i][j] + s;
+          for (int a = 0; a < NC; ++a)
+            if (TB::nz_xu(i, a)) s = fmaS<S>(xu[i][a], Kp[a][j], s);
+          A[i][j] = (TB::nz_xx(i, j) ? xx[i][j] : S(0)) + s;
         }
 #pragma unroll
       for (int i = 0; i < NS; ++i)
@@ -216,7 +289,7 @@ sens_theta_kernel(DynParams<S> P, int T, int B, const S* __restrict__ x,
           S s = S(0);
 #pragma unroll
           for (int j = 0; j < NS; ++j) s = fmaS<S>(A[i][j], Gp[j][q], s);
-          G[i][q] = xth[i][q] + s;
+          G[i][q] = (TB::nz_xth(i, q) ? xth[i][q] : S(0)) + s;
         }
       // <df_{t-1}, G_t - D_{t-1} [G_{t-1}; K_ref[t-1] G_{t-1}]>   (cartpole.py:778-782)
       S Z[N][NTH];
@@ -240,7 +313,8 @@ sens_theta_kernel(DynParams<S> P, int T, int B, const S* __restrict__ x,
         for (int q = 0; q < NTH; ++q) {
           S s = S(0);
 #pragma unroll
-          for (int m = 0; m < N; ++m) s = fmaS<S>(Dprev[i][m], Z[m][q], s);
+          for (int m = 0; m < N; ++m)
+            if (TB::nz_D(i, m)) s = fmaS<S>(Dprev[i][m], Z[m][q], s);
           acc[q] = fmaS<S>(dfi, G[i][q] - s, acc[q]);
         }
       }
@@ -261,13 +335,19 @@ sens_theta_kernel(DynParams<S> P, int T, int B, const S* __restrict__ x,
         for (int j = 0; j < N; ++j) {
           const S wij = -(lm[i] * dtau[j]);
 #pragma unroll
-          for (int q = 0; q < NTH; ++q) acc[q] = fmaS<S>(wij, Dth[i][j][q], acc[q]);
+          for (int q = 0; q < NTH; ++q)
+            if (TB::nz_Dth(i, j, q)) acc[q] = fmaS<S>(wij, Dth[i][j][q], acc[q]);
 #pragma unroll
           for (int k = 0; k < NS; ++k) {
-            S e = Dx[i][j][k];
+            bool any = TB::nz_Dx(i, j, k);
+            S e = any ? Dx[i][j][k] : S(0);
 #pragma unroll
-            for (int a = 0; a < NC; ++a) e = fmaS<S>(Du[i][j][a], Kt[a][k], e);
-            om[k] = fmaS<S>(wij, e, om[k]);
+            for (int a = 0; a < NC; ++a)
+              if (TB::nz_Du(i, j, a)) {
+                e = fmaS<S>(Du[i][j][a], Kt[a][k], e);
+                any = true;
+              }
+            if (any) om[k] = fmaS<S>(wij, e, om[k]);
           }
         }
 #pragma unroll

@@ -29,6 +29,8 @@ struct Dyn;
 template <class S>
 struct Dyn<S, DYN_LINDX> {
   static constexpr bool kEnv = false;
+  // structural non-zero pattern of F (dense for user-supplied LinDx)
+  __host__ __device__ static constexpr bool nz(int, int) { return true; }
 };
 
 // ------------------------------------------------------------------- pendulum
@@ -37,6 +39,8 @@ struct Dyn<S, DYN_PENDULUM> {
   static constexpr bool kEnv = true;
   static constexpr int NS = 3, NC = 1, N = 4;
   static constexpr bool kTrigFromNext = true;
+  // structural zeros of D (pendulum.py:450-474): only D[2][0]
+  __host__ __device__ static constexpr bool nz(int i, int j) { return !(i == 2 && j == 0); }
 
   // pendulum.py:81-91   x = (cos th, sin th, dth), params (g, m, l), dt = 0.05
   DILQR_DEVICE static void step(const DynParams<S>& P, const S* x, const S* u, S* xn) {
@@ -103,6 +107,12 @@ struct Dyn<S, DYN_CARTPOLE> {
   static constexpr bool kEnv = true;
   static constexpr int NS = 5, NC = 1, N = 6;
   static constexpr bool kTrigFromNext = true;
+  // structural non-zeros of D (cartpole.py:802-838): 16 of 30 entries.  Skipping a
+  // structurally zero term is exact: x*0 + acc == acc for finite x.
+  __host__ __device__ static constexpr bool nz(int i, int j) {
+    return (i == 0 && j <= 1) || (i == 1 && j >= 1) || ((i == 2 || i == 3) && j >= 2 && j <= 4) ||
+           (i == 4 && j >= 2);
+  }
 
   // cartpole.py:70-95  state (x, dx, cos th, sin th, dth), params (g, m_c, m_p, l)
   DILQR_DEVICE static void step(const DynParams<S>& P, const S* x, const S* u, S* xn) {

@@ -133,8 +133,15 @@ DILQR_DEVICE void lin_step(const S* __restrict__ Fs, const S* __restrict__ fs, b
 template <class S, int N>
 DILQR_DEVICE void pnqp_thread(const S (&H)[N][N], const S (&q)[N], const S (&lo)[N],
                               const S (&hi)[N], bool have_init, S (&x)[N], bool (&If)[N],
-                              LUpp<S, N>& lu, const uint32_t* __restrict__ guess,
+                              LUpp<S, N>& lu, const uint32_t* __restrict__ guess, uint4 gpre,
                               uint32_t* __restrict__ votes, bool solo, bool active, int lane) {
+  // gpre = guess[0..3], loaded by the caller long before this point (the common
+  // case never looks past the first two words; a global load here would sit on
+  // the critical path of the sweep).
+  auto gword_at = [&](int it) -> uint32_t {
+    return it == 0 ? gpre.x : it == 1 ? gpre.y : it == 2 ? gpre.z : it == 3 ? gpre.w
+                                                                            : __ldg(&guess[it]);
+  };
   const S GAMMA = S(0.1);
   if (!have_init) {  // pnqp.py:14-19
     if (N == 1) {
@@ -197,7 +204,7 @@ DILQR_DEVICE void pnqp_thread(const S (&H)[N][N], const S (&q)[N], const S (&lo)
       any_moving = J;
     } else {
       if (__ballot_sync(kFull, active && J)) vote |= 1u;
-      any_moving = (__ldg(&guess[it]) & 1u) != 0;
+      any_moving = (gword_at(it) & 1u) != 0;
     }
     if (!any_moving) {  // pnqp.py:57-59
       if (!solo && vote && lane == 0) atomicOr(&votes[it], vote);
@@ -220,7 +227,7 @@ DILQR_DEVICE void pnqp_thread(const S (&H)[N][N], const S (&q)[N], const S (&lo)
     }
     S alpha = S(1);
     S mx[N];
-    const uint32_t gword = solo ? 0u : __ldg(&guess[it]);
+    const uint32_t gword = solo ? 0u : gword_at(it);
     for (int cnt = 0; cnt < kArmijoMax; ++cnt) {
 #pragma unroll
       for (int i = 0; i < N; ++i) mx[i] = eclamp<S>(x[i] + alpha * dx[i], lo[i], hi[i]);
@@ -376,6 +383,9 @@ struct IterKernel {
     for (int t = T - 1; t >= 0; --t) {
       const int sg = (T - 1 - t) & 1;
       if (t > 0) issue_t(st, p, sg ^ 1, t - 1, b0, false, true, false);
+      uint4 gpre = make_uint4(0, 0, 0, 0);
+      if (p.bounds_kind && !p.solo)
+        gpre = __ldg(reinterpret_cast<const uint4*>(p.guess + (size_t)t * kPnqpMaxIter));
       if (STAGED) st.wait(sg);
       const Blk blk = blocks(p, st, sg, t, b, bw, lane);
       const S* Cs = blk.C;
@@ -419,7 +429,8 @@ struct IterKernel {
 #pragma unroll
             for (int j = 0; j < N; ++j) Fm[i][j] = Fs[i * N + j];
         }
-        // Q = C + (F' V) F ; q = c~ + F' v     (lqr_step.py:66-70)
+        // Q = C + (F' V) F ; q = c~ + F' v     (lqr_step.py:66-70).  Structurally
+        // zero entries of the env Jacobians are skipped at compile time (exact).
 #pragma unroll
         for (int i = 0; i < N; ++i) {
           S M[NS];
@@ -427,19 +438,22 @@ struct IterKernel {
           for (int k = 0; k < NS; ++k) {
             S acc = S(0);
 #pragma unroll
-            for (int l = 0; l < NS; ++l) acc = fmaS<S>(Fm[l][i], V[l][k], acc);
+            for (int l = 0; l < NS; ++l)
+              if (D::nz(l, i)) acc = fmaS<S>(Fm[l][i], V[l][k], acc);
             M[k] = acc;
           }
 #pragma unroll
           for (int j = 0; j < N; ++j) {
             S acc = S(0);
 #pragma unroll
-            for (int k = 0; k < NS; ++k) acc = fmaS<S>(M[k], Fm[k][j], acc);
+            for (int k = 0; k < NS; ++k)
+              if (D::nz(k, j)) acc = fmaS<S>(M[k], Fm[k][j], acc);
             Q[i][j] = Q[i][j] + acc;
           }
           S acc = S(0);
 #pragma unroll
-          for (int l = 0; l < NS; ++l) acc = fmaS<S>(Fm[l][i], v[l], acc);
+          for (int l = 0; l < NS; ++l)
+            if (D::nz(l, i)) acc = fmaS<S>(Fm[l][i], v[l], acc);
           qv[i] = qv[i] + acc;
         }
       }
@@ -526,7 +540,7 @@ struct IterKernel {
         bool If[NC];
         LUpp<S, NC> lu;
         pnqp_thread<S, NC>(H, qu, lo, hi, have_prev, k, If, lu,
-                           p.guess + (size_t)t * kPnqpMaxIter,
+                           p.guess + (size_t)t * kPnqpMaxIter, gpre,
                            p.votes + (size_t)t * kPnqpMaxIter, p.solo != 0, active, lane);
         have_prev = true;
 #pragma unroll

@@ -210,7 +210,18 @@ def emit(name, tables, state_syms, ctrl_syms, param_syms, ns, nc, nth, out):
              "x_x": "xx", "x_u": "xu"}
     for (nm, idx), e in zip(index, red):
         w("    %s%s = %s;\n" % (cname[nm], "".join("[%d]" % i for i in idx), pr.doprint(e)))
-    w("  }\n};\n\n")
+    w("  }\n")
+    # structural non-zero masks (compile-time pruning of the contractions)
+    for nm in ["D", "D_theta", "D_x", "D_u", "x_theta", "x_x", "x_u"]:
+        a = tables[nm]
+        args = ", ".join("int i%d" % d for d in range(a.ndim))
+        terms = []
+        for idx in np.ndindex(a.shape):
+            if sp.sympify(a[idx]) != 0:
+                terms.append("(" + " && ".join("i%d == %d" % (d, v) for d, v in enumerate(idx)) + ")")
+        w("  __host__ __device__ static constexpr bool nz_%s(%s) {\n    return %s;\n  }\n" % (
+            cname[nm], args, " ||\n           ".join(terms) if terms else "false"))
+    w("};\n\n")
 
 
 def emit_py(name, tables, state_syms, ctrl_syms, param_syms, out):
