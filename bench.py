@@ -197,7 +197,7 @@ def run_b200(args):
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {
                 "workload": "cartpole env_dx MPC T=50 B=%d/GPU forward(lqr_iter=10, cold start "
-                            "sigma=0.5)+%s backward on 1 B200" % (B, step.backward_name),
+                            "sigma=0.5)+%s backward, per B200" % (B, step.backward_name),
                 "batch_per_gpu": B, "T": T_H, "lqr_iter": LQR_ITER,
                 "l2": "inputs larger than L2 (C alone is %.2f GB)" % (T_H * B * N * N * s / 1e9),
                 "parallelism": "batch-sharded x%d, no data-path collective" % world,
@@ -217,14 +217,15 @@ def run_b200(args):
             "kernel_ms": {k: sum(v) / len(v) for k, v in prof.items()},
         }
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(dtype, sample_B=args.cpu_batch)
+            line["cpu_baseline"] = cpu_baseline(dtype, sample_B=args.cpu_batch,
+                                                n_passes=args.richardson)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
 # ------------------------------------------------------------- reference arm
-def cpu_solve_once(torch, port, dtype, B, seed=0):
+def cpu_solve_once(torch, port, dtype, B, seed=0, n_passes=4):
     """One step of the same workload with the oracle port (== the reference's
     algorithm, validated bit-exact against it) on the host CPU."""
     x0, uexp = make_inputs(torch, B, dtype, seed)
@@ -239,22 +240,23 @@ def cpu_solve_once(torch, port, dtype, B, seed=0):
                          max_linesearch_iter=dx.max_linesearch_iter, final_pass=True)
     gu = 2.0 * (o.u - uexp) / o.u.numel()
     gx = torch.zeros_like(o.x)
-    port.kkt_backward(gx, gu, x0, C, c, o.F, o.f, o.x, o.u, NS, NC, u_lower=dx.lower,
-                      u_upper=dx.upper, gain_solve="chol_reg")
+    port.dilqr_backward(gx, gu, x0, C, c, o.x, o.u, dx, NS, NC, dx.lower, dx.upper,
+                        n_passes=n_passes)
     return time.time() - t0
 
 
-def cpu_baseline(dtype, sample_B=512):
+def cpu_baseline(dtype, sample_B=2048, n_passes=4):
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import port
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     with torch.no_grad():
-        dt = cpu_solve_once(torch, port, dtype, sample_B)
+        dt = cpu_solve_once(torch, port, dtype, sample_B, n_passes=n_passes)
     return {"value": sample_B / dt, "unit": "solves/s", "cores": cores, "kind": "port",
-            "sample": "B=%d problems of the same workload (one forward+backward), %.1f s"
-                      % (sample_B, dt)}
+            "sample": "B=%d problems of the same workload (forward lqr_iter=10 + DiLQR backward, "
+                      "%d Richardson passes) with the oracle port of the reference, %.1f s"
+                      % (sample_B, n_passes, dt)}
 
 
 def run_reference(args):
@@ -270,8 +272,9 @@ def run_reference(args):
     Bs = args.cpu_batch
     with torch.no_grad():
         for _ in range(min(args.warmup, 1)):
-            cpu_solve_once(torch, port, dtype, min(Bs, 64))
-        t = [cpu_solve_once(torch, port, dtype, Bs, seed=i) for i in range(max(1, min(args.steps, 3)))]
+            cpu_solve_once(torch, port, dtype, min(Bs, 64), n_passes=args.richardson)
+        t = [cpu_solve_once(torch, port, dtype, Bs, seed=i, n_passes=args.richardson)
+             for i in range(max(1, min(args.steps, 3)))]
     ms = 1e3 * sum(t) / len(t)
     v = Bs / (ms * 1e-3)
     sample = "B=%d problems per step on %d host threads (reference is O(B^2); never extrapolated)" % (Bs, cores)
@@ -282,8 +285,9 @@ def run_reference(args):
         "steps": len(t), "warmup": min(args.warmup, 1), "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
         "data": "synthetic",
-        "config": {"workload": "cartpole env_dx MPC T=50 forward(lqr_iter=10)+backward, oracle port "
-                               "of the reference on host CPU", "batch": Bs},
+        "config": {"workload": "cartpole env_dx MPC T=50 forward(lqr_iter=10, cold start sigma=0.5)"
+                               "+DiLQR implicit (%d Richardson passes) backward, oracle port of "
+                               "the reference on host CPU" % args.richardson, "batch": Bs},
         "cpu_baseline": {"value": v, "unit": "solves/s", "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": v, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -298,7 +302,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--batch", type=int, default=65536)
-    ap.add_argument("--cpu-batch", type=int, default=512)
+    ap.add_argument("--cpu-batch", type=int, default=2048)
     ap.add_argument("--richardson", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
