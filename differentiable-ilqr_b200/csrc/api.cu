@@ -61,8 +61,8 @@ constexpr bool staged_v() {
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
-  size_t traj[2], best, Kk, cost_cur, cost_new, cost_best, du_new, du_best, alpha_new, take, guess,
-      votes, total;
+  size_t traj[2], best, Kk, cost_cur, cost_new, cost_best, du_new, du_best, alpha_new, dusq, take,
+      guess, votes, total;
   int Bp;
 };
 
@@ -87,6 +87,7 @@ static WsLayout ws_layout(const DilqrSolve* s, size_t esz) {
   w.du_new = take((size_t)w.Bp * esz);
   w.du_best = take((size_t)w.Bp * esz);
   w.alpha_new = take((size_t)w.Bp * esz);
+  w.dusq = take((size_t)s->T * s->n_ctrl * w.Bp * esz);
   w.take = take((size_t)w.Bp * sizeof(int));
   w.guess = take((size_t)s->T * kPnqpMaxIter * sizeof(uint32_t));
   w.votes = take((size_t)s->T * kPnqpMaxIter * sizeof(uint32_t));
@@ -139,6 +140,7 @@ static IterParams<Scalar> make_params(const DilqrSolve* s, int role = 1) {
   p.du_new = reinterpret_cast<S*>(ws + w.du_new);
   p.du_best = reinterpret_cast<S*>(ws + w.du_best);
   p.alpha_new = reinterpret_cast<S*>(ws + w.alpha_new);
+  p.dusq = reinterpret_cast<S*>(ws + w.dusq);
   p.take = reinterpret_cast<int*>(ws + w.take);
   p.gains_only = s->gains_only;
   p.guess = reinterpret_cast<uint32_t*>(ws + w.guess);
@@ -234,7 +236,7 @@ static int launch_commit(const DilqrSolve* s, cudaStream_t st) {
   IterParams<S> p = make_params(s);
   trace_verify_kernel<<<1, 256, 0, st>>>(p.guess, p.votes, p.T, p.bounds_kind != 0, p.solo,
                                          s->status);
-  commit_kernel<S, NS + NC><<<(p.B + 127) / 128, 128, 0, st>>>(p);
+  commit_kernel<S, NS + NC, NC><<<(p.B + 127) / 128, 128, 0, st>>>(p);
   return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
 }
 
@@ -358,6 +360,40 @@ int DILQR_SUFFIX(rollout)(int dynamics, const double* dp, int T, int B, const vo
   if (dynamics == DYN_PENDULUM) return launch_rollout<DYN_PENDULUM>(dp, T, B, x0, u, x, st);
   if (dynamics == DYN_CARTPOLE) return launch_rollout<DYN_CARTPOLE>(dp, T, B, x0, u, x, st);
   return DILQR_EUNSUPPORTED;
+}
+
+// ------------------------------------------------- standalone pnqp
+template <int N>
+static int launch_pnqp(int B, const void* H, const void* q, const void* lo, const void* hi,
+                       const void* x0, void* x, void* lu, int32_t* piv, void* If, uint32_t* trace,
+                       int solo, DilqrStatus* status, cudaStream_t st) {
+  using S = Scalar;
+  uint32_t* guess = trace;
+  uint32_t* votes = trace + kPnqpMaxIter;
+  cudaMemsetAsync(votes, 0, kPnqpMaxIter * sizeof(uint32_t), st);
+  pnqp_kernel<S, N><<<(B + 127) / 128, 128, 0, st>>>(
+      B, static_cast<const S*>(H), static_cast<const S*>(q), static_cast<const S*>(lo),
+      static_cast<const S*>(hi), static_cast<const S*>(x0), static_cast<S*>(x),
+      static_cast<S*>(lu), piv, static_cast<S*>(If), guess, votes, solo);
+  trace_verify_kernel<<<1, 32, 0, st>>>(guess, votes, 1, 1, solo, status);
+  return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
+}
+
+int DILQR_SUFFIX(pnqp)(int n, int B, const void* H, const void* q, const void* lo, const void* hi,
+                       const void* x0, void* x, void* lu, int32_t* piv, void* If, uint32_t* trace,
+                       int solo, DilqrStatus* status, void* stream) {
+  if (!H || !q || !lo || !hi || !x || !lu || !piv || !If || !trace || !status || B <= 0)
+    return DILQR_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (n) {
+    case 1: return launch_pnqp<1>(B, H, q, lo, hi, x0, x, lu, piv, If, trace, solo, status, st);
+    case 2: return launch_pnqp<2>(B, H, q, lo, hi, x0, x, lu, piv, If, trace, solo, status, st);
+    case 3: return launch_pnqp<3>(B, H, q, lo, hi, x0, x, lu, piv, If, trace, solo, status, st);
+    case 4: return launch_pnqp<4>(B, H, q, lo, hi, x0, x, lu, piv, If, trace, solo, status, st);
+    case 6: return launch_pnqp<6>(B, H, q, lo, hi, x0, x, lu, piv, If, trace, solo, status, st);
+    case 8: return launch_pnqp<8>(B, H, q, lo, hi, x0, x, lu, piv, If, trace, solo, status, st);
+    default: return DILQR_EUNSUPPORTED;
+  }
 }
 
 // ------------------------------------------------- factored adjoint solves

@@ -20,6 +20,8 @@ namespace dilqr {
                        const void*, const void*, const void*, const void*, void*, void*);   \
   int richardson_update_##sfx(int, int, int, int, const void*, const void*, const void*,      \
                               const void*, void*, void*, void*, void*);                     \
+  int pnqp_##sfx(int, int, const void*, const void*, const void*, const void*, const void*,    \
+                 void*, void*, int32_t*, void*, uint32_t*, int, DilqrStatus*, void*);         \
   size_t adjoint_workspace_bytes_##sfx(const DilqrAdjoint*);                                 \
   int adjoint_run_##sfx(const DilqrAdjoint*, int, void*);
 DECL(f32)
@@ -93,6 +95,14 @@ int dilqr_richardson_update(int dtype, int ns, int nc, int T, int B, const void*
                             void* resid, void* st) {
   return ROUTE(dtype, dilqr::richardson_update_f32(ns, nc, T, B, g, Lam, dx, du, w, negw, resid, st),
                dilqr::richardson_update_f64(ns, nc, T, B, g, Lam, dx, du, w, negw, resid, st));
+}
+
+int dilqr_pnqp(int dtype, int n, int B, const void* H, const void* q, const void* lower,
+               const void* upper, const void* x_init, void* x, void* lu, int32_t* pivots, void* If,
+               uint32_t* trace, int solo, DilqrStatus* status, void* st) {
+  return ROUTE(dtype,
+               dilqr::pnqp_f32(n, B, H, q, lower, upper, x_init, x, lu, pivots, If, trace, solo, status, st),
+               dilqr::pnqp_f64(n, B, H, q, lower, upper, x_init, x, lu, pivots, If, trace, solo, status, st));
 }
 
 size_t dilqr_adjoint_workspace_bytes(const DilqrAdjoint* a) {

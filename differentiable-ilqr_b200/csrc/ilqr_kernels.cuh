@@ -67,6 +67,7 @@ struct IterParams {
   S* traj_best;       // [T][Bp/32][N][32]  best iterate so far
   S* Kk;              // [T][Bp/32][NC*NS+NC][32]
   int nW;             // Bp / 32
+  S* dusq;            // [T][NC][B] squared control changes of the first line-search pass
   int* take;          // [Bp] 1: the problem's best iterate is the CURRENT trajectory and
                       //         has not been copied to traj_best yet (lazy best tracking)
   int gains_only;     // skip the line-search rollout (only K,k are wanted)
@@ -618,7 +619,7 @@ struct IterKernel {
     const S old_cost = p.cost_cur[b];
     S alpha = S(1);
     bool accepted = false;
-    S res_cost = S(0), res_alpha = S(1), full_du = S(0);
+    S res_cost = S(0), res_alpha = S(1);
     S x0[NS];
 #pragma unroll
     for (int i = 0; i < NS; ++i) x0[i] = __ldg(p.x_init + (size_t)b * NS + i);
@@ -634,7 +635,7 @@ struct IterKernel {
       S xh[NS];
 #pragma unroll
       for (int i = 0; i < NS; ++i) xh[i] = x0[i];
-      S cost = S(0), du2 = S(0);
+      S cost = S(0);
       issue_t(st, p, 0, 0, b0, true, true, true);
       for (int t = 0; t < T; ++t) {
         const int sg = t & 1;
@@ -661,8 +662,14 @@ struct IterKernel {
           if (p.zeroI && p.zeroI[((size_t)t * p.B + b) * NC + a]) un = S(0);  // :197-198
           if (p.bounds_kind) un = eclamp<S>(un, lo[a], hi[a]);                  // :213
           th[NS + a] = un;
-          const S d = tau[NS + a] - un;
-          du2 = fmaS<S>(d, d, du2);
+          // full_du_norm (lqr_step.py:243-245) is the row norm of
+          // (u - new_u).transpose(1,2).contiguous().view(n_batch, -1): the [T,nc,B]
+          // array re-read as [B, T*nc] -- rows mix problems and timesteps.  Mirror it:
+          // store the squares in [T,nc,B] order, the commit kernel sums the rows.
+          if (tr == 0 && active) {
+            const S d = tau[NS + a] - un;
+            p.dusq[((size_t)t * NC + a) * p.B + b] = d * d;
+          }
         }
         if (!accepted) {   // padded lanes keep their own columns defined as well
           S* to = p.traj_new + bidx(t, 0, N, bw, p.nW);
@@ -678,7 +685,6 @@ struct IterKernel {
           }
         }
       }
-      if (tr == 0) full_du = sqrtS<S>(du2);
       if (run) {
         res_cost = cost;
         res_alpha = alpha;
@@ -689,7 +695,6 @@ struct IterKernel {
     if (active) {
       p.cost_new[b] = res_cost;
       p.alpha_new[b] = res_alpha;
-      p.du_new[b] = full_du;
     }
   }
 };

@@ -74,7 +74,7 @@ static __global__ void trace_verify_kernel(uint32_t* __restrict__ guess, const u
 // Per-problem commit: best-iterate bookkeeping (mpc.py:271-285) + the batch
 // reductions the host needs for the stop rule (mpc.py:299-301).
 // ---------------------------------------------------------------------------
-template <class S, int N>
+template <class S, int N, int NCc>
 __global__ void commit_kernel(const __grid_constant__ IterParams<S> p) {
   DilqrStatus* status = reinterpret_cast<DilqrStatus*>(p.status);
   if (status->trace_match == 0) return;
@@ -82,6 +82,15 @@ __global__ void commit_kernel(const __grid_constant__ IterParams<S> p) {
   double du = 0.0, al = 0.0, bc = 0.0;
   bool improved = false;
   if (b < p.B) {
+    // full_du_norm[b]: norm of row b of the [T,nc,B] squares re-read as [B, T*nc]
+    // (lqr_step.py:243-245, see the note in forward_linesearch)
+    {
+      const int row = p.T * NCc;
+      const S* src = p.dusq + (size_t)b * row;
+      S acc = S(0);
+      for (int k = 0; k < row; ++k) acc = acc + src[k];
+      p.du_new[b] = sqrtS<S>(acc);
+    }
     const S cn = p.cost_new[b];
     bool take = false;
     if (p.first_iteration) {
@@ -324,6 +333,54 @@ __global__ void __launch_bounds__(128) kkt_grads_kernel(const __grid_constant__ 
   if (dx0) {
 #pragma unroll
     for (int i = 0; i < NS; ++i) dx0[(size_t)b * NS + i] = -dlam[i];
+  }
+}
+
+}  // namespace dilqr
+
+namespace dilqr {
+
+// ---------------------------------------------------------------------------
+// Standalone projected-Newton box QP (pnqp.py:5-82), one thread per problem,
+// batch-global control flow replayed from a 20-word trace exactly like the fused
+// sweep.  Outputs: x[B,n], LU[B,n,n] + pivots[B,n] (LAPACK getrf layout, 1-based
+// pivots == what Tensor.lu() returns; for n == 1 LU is the scalar H_), If[B,n].
+// ---------------------------------------------------------------------------
+template <class S, int N>
+__global__ void pnqp_kernel(int B, const S* __restrict__ H, const S* __restrict__ q,
+                            const S* __restrict__ lower, const S* __restrict__ upper,
+                            const S* __restrict__ x_init, S* __restrict__ x_out,
+                            S* __restrict__ lu_out, int32_t* __restrict__ piv_out,
+                            S* __restrict__ if_out, const uint32_t* __restrict__ guess,
+                            uint32_t* __restrict__ votes, int solo) {
+  const int lane = threadIdx.x & 31;
+  const int b0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane;
+  if (b0 >= B) return;
+  const bool active = b0 + lane < B;
+  const int b = active ? b0 + lane : b0;
+  S Hm[N][N], qv[N], lo[N], hi[N], x[N];
+  bool If[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) Hm[i][j] = H[((size_t)b * N + i) * N + j];
+    qv[i] = q[(size_t)b * N + i];
+    lo[i] = lower[(size_t)b * N + i];
+    hi[i] = upper[(size_t)b * N + i];
+    x[i] = x_init ? x_init[(size_t)b * N + i] : S(0);
+  }
+  LUpp<S, N> lu;
+  const uint4 gpre = solo ? make_uint4(0, 0, 0, 0) : __ldg(reinterpret_cast<const uint4*>(guess));
+  pnqp_thread<S, N>(Hm, qv, lo, hi, x_init != nullptr, x, If, lu, guess, gpre, votes, solo != 0,
+                    active, lane);
+  if (!active) return;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    x_out[(size_t)b * N + i] = x[i];
+    if_out[(size_t)b * N + i] = If[i] ? S(1) : S(0);
+    piv_out[(size_t)b * N + i] = (N == 1) ? 1 : lu.piv[i] + 1;
+#pragma unroll
+    for (int j = 0; j < N; ++j) lu_out[((size_t)b * N + i) * N + j] = lu.a[i][j];
   }
 }
 

@@ -156,6 +156,20 @@ int dilqr_mpc_finish(const DilqrSolve* s, void* stream);
  * dilqr_mpc_finish returns the new iterate (x_out,u_out,cost_out,du_out,
  * alpha_out) and, if requested, the gains K_out,k_out of lqr_backward. */
 
+/* ---- standalone pnqp (pnqp.py:5-82) --------------------------------------
+ * H[B,n,n] q[B,n] lower[B,n] upper[B,n] x_init[B,n] (or NULL: unconstrained
+ * minimiser, pnqp.py:14-19) -> x[B,n], lu[B,n,n] + pivots[B,n] (LAPACK getrf layout
+ * of the masked Hessian H_ + 1e-11 I of the last iteration, what Tensor.lu() returns;
+ * n == 1: the scalar H_), If[B,n] (float 0/1).  `trace`: 40 device words (20-word
+ * control-flow guess, zero-initialised by the caller before the first call, then
+ * 20 vote words).  After the call status->trace_match tells whether the replayed
+ * batch-global control flow was right; if 0, call again (the guess was corrected).
+ * status->n_total_qp_iter - 1 is the returned iteration count `i`,
+ * status->pnqp_unconverged != 0 the "[WARNING] pnqp warning" case (pnqp.py:81). */
+int dilqr_pnqp(int dtype, int n, int n_batch, const void* H, const void* q, const void* lower,
+               const void* upper, const void* x_init, void* x, void* lu, int32_t* pivots,
+               void* If, uint32_t* trace, int solo, DilqrStatus* status, void* stream);
+
 /* ---- analytic linearisation (mpc_explicit.py:516-546) --------------------
  * x[T,B,ns], u[T,B,nc] -> F[T-1,B,ns,n], f[T-1,B,ns] (f may be NULL). */
 int dilqr_linearize(int dtype, int dynamics, const double* dyn_params, int T,

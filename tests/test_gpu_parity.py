@@ -276,3 +276,71 @@ def test_full_size_properties(dilqr, env, dev):
     cost_chk = (0.5 * (tau * q.to(dtype).to(dev)) * tau + p.to(dtype).to(dev) * tau).sum((0, 2))
     assert rel(costs, cost_chk) < 1e-12
     assert bool(torch.isfinite(costs).all())
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4])
+@pytest.mark.parametrize("warm", [False, True])
+def test_pnqp_standalone(dilqr, port, dev, n, warm):
+    """pnqp(H, q, lower, upper, x_init) (pnqp.py:5-82): solution, free set, iteration
+    count and the returned factorisation, with the batch-global control flow."""
+    g = torch.Generator().manual_seed(n)
+    B = 70
+    A = torch.randn(B, n, n, generator=g, dtype=torch.float64)
+    H = A.transpose(1, 2) @ A + 0.5 * torch.eye(n, dtype=torch.float64)
+    q = 2 * torch.randn(B, n, generator=g, dtype=torch.float64)
+    lo = -torch.rand(B, n, generator=g, dtype=torch.float64)
+    hi = torch.rand(B, n, generator=g, dtype=torch.float64)
+    x0 = torch.randn(B, n, generator=g, dtype=torch.float64) if warm else None
+    o = port.pnqp(H, q, lo, hi, x_init=x0)
+    x, fac, If, i = dilqr.pnqp(H.to(dev), q.to(dev), lo.to(dev), hi.to(dev),
+                               x_init=None if x0 is None else x0.to(dev))
+    assert i == o.n_iter
+    assert torch.equal(If.cpu(), o.If)                       # active sets: exact
+    assert rel(x, o.x) < 1e-12
+    rhs = torch.randn(B, n, 1, generator=g, dtype=torch.float64)
+    want = torch.linalg.solve(o.Hfree, rhs)
+    if n == 1:
+        got = rhs.to(dev) / fac
+    else:
+        got = torch.linalg.lu_solve(fac[0], fac[1], rhs.to(dev))
+    assert rel(got, want) < 1e-10
+
+
+@pytest.mark.parametrize("boxed", [False, True])
+def test_lqr_step_api(dilqr, port, dev, boxed):
+    """LQRStep(...)(x_init, C, c, F, f) (lqr_step.py:22-38,277-309) + its KKT backward."""
+    ns, nc, T, B = 4, 2, 12, 16
+    C, c, F, f, x0 = lindx_problem(ns, nc, T, B, torch.float64, seed=3)
+    kw = dict(u_lower=-1.0, u_upper=1.0) if boxed else {}
+    u0 = 0.1 * torch.ones(T, B, nc, dtype=torch.float64)
+    xc = port.get_traj(T, u0, x0, port.LinDx(F, f))
+    o = port.lqr_step(x0, C, c, F, xc, u0, port.QuadCost(C, c), port.LinDx(F, f), ns, nc, **kw)
+    leaves = [t.to(dev).requires_grad_() for t in (x0, C, c, F, f)]
+    step = dilqr.LQRStep(ns, nc, T, true_cost=dilqr.QuadCost(leaves[1], leaves[2]),
+                         true_dynamics=dilqr.LinDx(leaves[3], leaves[4]), current_x=xc.to(dev),
+                         current_u=u0.to(dev), **kw)
+    x, u, n_qp, costs, du, mean_alpha = step(*leaves)
+    assert rel(x, o.x) < 1e-10 and rel(u, o.u) < 1e-10 and rel(costs, o.costs) < 1e-10
+    assert float(n_qp) == o.n_total_qp_iter and n_qp.dtype == torch.float32
+    assert rel(du, o.full_du_norm) < 1e-10
+    assert abs(float(mean_alpha) - float(o.mean_alphas)) < 1e-12
+    g = torch.Generator().manual_seed(11)
+    gx = torch.randn(x.shape, generator=g, dtype=torch.float64)
+    gu = torch.randn(u.shape, generator=g, dtype=torch.float64)
+    ((x * gx.to(dev)).sum() + (u * gu.to(dev)).sum()).backward()
+    k = port.kkt_backward(gx, gu, x0, C, c, F, f, o.x, o.u, ns, nc, **kw)
+    for leaf, ref_ in zip(leaves, (k.dx_init, k.dC, k.dc, k.dF, k.df)):
+        assert rel(leaf.grad, ref_) < 1e-9
+
+
+def test_util_helpers(dilqr, port, env, dev):
+    """get_traj / get_cost (util.py:104-153) on env dynamics."""
+    pdx, x0, C, c, kw = env_problem(port, "cartpole", 20, 9, torch.float64)
+    g = torch.Generator().manual_seed(5)
+    u = torch.randn(20, 9, 1, generator=g, dtype=torch.float64)
+    xr = port.get_traj(20, u, x0, pdx)
+    cr = port.get_cost(20, u, port.QuadCost(C, c), xr)
+    gdx = env.CartpoleDx(pdx.params.to(dev))
+    x = dilqr.util.get_traj(20, u.to(dev), x0.to(dev), gdx)
+    cost = dilqr.util.get_cost(20, u.to(dev), dilqr.QuadCost(C.to(dev), c.to(dev)), x=x)
+    assert rel(x, xr) < 1e-13 and rel(cost, cr) < 1e-13
