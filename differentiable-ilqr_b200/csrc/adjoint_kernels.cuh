@@ -79,14 +79,7 @@ struct Adj {
   // F_t = D(x_t, u_t); sin/cos of the new angle are components of x_{t+1}
   DILQR_DEVICE static void jac_at(const AdjParams<S>& p, const S* tau, const S* xnext,
                                   S (*F)[N]) {
-    S sp, cp;
-    if (D::trig_reusable(&tau[NS])) {
-      sp = xnext[DYN == DYN_PENDULUM ? 1 : 3];
-      cp = xnext[DYN == DYN_PENDULUM ? 0 : 2];
-    } else {
-      D::trig(p.dyn, tau, &tau[NS], &sp, &cp);
-    }
-    D::jac(p.dyn, tau, &tau[NS], sp, cp, F);
+    D::jacobian(p.dyn, tau, xnext, F);
   }
 
   DILQR_DEVICE static void load_tau(const AdjParams<S>& p, int t, int b, S* tau) {

@@ -27,8 +27,10 @@ using Scalar = float;
   X(3, 1, DYN_LINDX)           \
   X(4, 2, DYN_LINDX)           \
   X(5, 1, DYN_LINDX)           \
+  X(13, 3, DYN_LINDX)          \
   X(3, 1, DYN_PENDULUM)        \
-  X(5, 1, DYN_CARTPOLE)
+  X(5, 1, DYN_CARTPOLE)        \
+  X(13, 3, DYN_ROCKET)
 #else
 #define DILQR_CONFIGS(X)       \
   X(2, 1, DYN_LINDX)           \
@@ -45,7 +47,8 @@ using Scalar = float;
   X(16, 2, DYN_LINDX)          \
   X(16, 4, DYN_LINDX)          \
   X(3, 1, DYN_PENDULUM)        \
-  X(5, 1, DYN_CARTPOLE)
+  X(5, 1, DYN_CARTPOLE)        \
+  X(13, 3, DYN_ROCKET)
 #endif
 
 constexpr size_t kStageBudget = 56 * 1024;  // per-warp staging budget (>= 4 warps / SM)
@@ -338,6 +341,7 @@ int DILQR_SUFFIX(linearize)(int dynamics, const double* dp, int T, int B, const 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dynamics == DYN_PENDULUM) return launch_linearize<DYN_PENDULUM>(dp, T, B, x, u, F, f, st);
   if (dynamics == DYN_CARTPOLE) return launch_linearize<DYN_CARTPOLE>(dp, T, B, x, u, F, f, st);
+  if (dynamics == DYN_ROCKET) return launch_linearize<DYN_ROCKET>(dp, T, B, x, u, F, f, st);
   return DILQR_EUNSUPPORTED;
 }
 
@@ -359,6 +363,7 @@ int DILQR_SUFFIX(rollout)(int dynamics, const double* dp, int T, int B, const vo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dynamics == DYN_PENDULUM) return launch_rollout<DYN_PENDULUM>(dp, T, B, x0, u, x, st);
   if (dynamics == DYN_CARTPOLE) return launch_rollout<DYN_CARTPOLE>(dp, T, B, x0, u, x, st);
+  if (dynamics == DYN_ROCKET) return launch_rollout<DYN_ROCKET>(dp, T, B, x0, u, x, st);
   return DILQR_EUNSUPPORTED;
 }
 

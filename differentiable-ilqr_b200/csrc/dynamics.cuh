@@ -25,6 +25,9 @@ struct DynParams {
 template <class S, int DYN>
 struct Dyn;
 
+template <class S, int DYN>
+struct EnvTables;   // generated second-order tables (env_tables_gen.cuh)
+
 // ------------------------------------------------------------------ LinDx stub
 template <class S>
 struct Dyn<S, DYN_LINDX> {
@@ -74,6 +77,19 @@ struct Dyn<S, DYN_PENDULUM> {
     const S acc = (S(3.0) * g * s) / (S(2.0) * l) + (S(3.0) * u[0]) / (l * l * m);
     const S phi = dt * (dt * acc + w) + atan2S<S>(s, c);
     sincosS<S>(phi, sp, cp);
+  }
+
+  // F_t = D(x_t, u_t); `xnext` = x_{t+1} of the same rollout supplies sin/cos.
+  DILQR_DEVICE static void jacobian(const DynParams<S>& P, const S* tau, const S* xnext,
+                                    S (*F)[N]) {
+    S sp, cp;
+    if (trig_reusable(&tau[NS])) {
+      sp = xnext[1];
+      cp = xnext[0];
+    } else {
+      trig(P, tau, &tau[NS], &sp, &cp);
+    }
+    jac(P, tau, &tau[NS], sp, cp, F);
   }
 
   // pendulum.py:450-474.  F is row-major [NS][N], columns (cos, sin, dth, u).
@@ -146,6 +162,11 @@ struct Dyn<S, DYN_CARTPOLE> {
     sincosS<S>(phi, sp, cp);
   }
 
+  DILQR_DEVICE static void jacobian(const DynParams<S>& P, const S* tau, const S* xnext,
+                                    S (*F)[N]) {
+    jac(P, tau, &tau[NS], xnext[3], xnext[2], F);
+  }
+
   // cartpole.py:802-838, simplified: with M = m_c+m_p, A = dth^2 l m_p s + u,
   // G = g s - c A / M, den = 4/3 - m_p c^2 / M :
   //   th_acc = G/(l den),  xacc = A/M - m_p c G/(M den).
@@ -196,6 +217,78 @@ struct Dyn<S, DYN_CARTPOLE> {
     F[4][3] = dt * ta_s;
     F[4][4] = S(1.0) + dt * ta_w;
     F[4][5] = dt * ta_u;
+  }
+};
+
+// --------------------------------------------------------------------- rocket
+template <class S>
+struct Dyn<S, DYN_ROCKET> {
+  static constexpr bool kEnv = true;
+  static constexpr int NS = 13, NC = 3, N = 16;
+  static constexpr bool kTrigFromNext = false;
+  // structural non-zeros of D (rocket.py:340-424, 69 of 208): generated mask
+  __host__ __device__ static constexpr bool nz(int i, int j) {
+    return EnvTables<S, DYN_ROCKET>::nz_D(i, j);
+  }
+
+  // rocket.py:82-164.  state r(3) v(3) q(4) w(3); params (Jx, Jy, Jz, mass, l);
+  // dt = 0.1; returns the UN-normalised quaternion like the reference (:158-164).
+  DILQR_DEVICE static void step(const DynParams<S>& P, const S* x, const S* u, S* xn) {
+    const S Jx = P.p[0], Jy = P.p[1], Jz = P.p[2], mass = P.p[3], l = P.p[4];
+    const S dt = S(0.1);
+    S T[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      S v = u[a];
+      v = v < S(-400.0) ? S(-400.0) : v;      // torch.clamp (rocket.py:111)
+      v = v > S(400.0) ? S(400.0) : v;
+      T[a] = v;
+    }
+    const S q0 = x[6], q1 = x[7], q2 = x[8], q3 = x[9];
+    const S wx = x[10], wy = x[11], wz = x[12];
+    S Cb[3][3];                                 // C_B_I (rocket.py:119-123)
+    Cb[0][0] = S(1) - S(2) * (q2 * q2 + q3 * q3);
+    Cb[0][1] = S(2) * (q1 * q2 + q0 * q3);
+    Cb[0][2] = S(2) * (q1 * q3 - q0 * q2);
+    Cb[1][0] = S(2) * (q1 * q2 - q0 * q3);
+    Cb[1][1] = S(1) - S(2) * (q1 * q1 + q3 * q3);
+    Cb[1][2] = S(2) * (q2 * q3 + q0 * q1);
+    Cb[2][0] = S(2) * (q1 * q3 + q0 * q2);
+    Cb[2][1] = S(2) * (q2 * q3 - q0 * q1);
+    Cb[2][2] = S(1) - S(2) * (q1 * q1 + q2 * q2);
+    S d[13];
+    d[0] = x[3];
+    d[1] = x[4];
+    d[2] = x[5];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {               // thrust_global = C_I_B T_B (:131)
+      S acc = S(0);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) acc = fmaS<S>(Cb[j][i], T[j], acc);
+      d[3 + i] = acc / mass + (i == 0 ? S(-10.0) : S(0));
+    }
+    // dq = 0.5 * Omega(w) q   (rocket.py:133-144)
+    d[6] = S(0.5) * (((-wx) * q1 + (-wy) * q2) + (-wz) * q3);
+    d[7] = S(0.5) * ((wx * q0 + wz * q2) + (-wy) * q3);
+    d[8] = S(0.5) * ((wy * q0 + (-wz) * q1) + wx * q3);
+    d[9] = S(0.5) * ((wz * q0 + wy * q1) + (-wx) * q2);
+    // torque = r_T_B x T_B, r_T_B = (-l/2, 0, 0)   (rocket.py:147-148)
+    const S a0 = -l / S(2);
+    const S tq[3] = {S(0), S(0) - a0 * T[2], a0 * T[1]};
+    const S Jw[3] = {Jx * wx, Jy * wy, Jz * wz};
+    const S cr[3] = {wy * Jw[2] - wz * Jw[1], wz * Jw[0] - wx * Jw[2], wx * Jw[1] - wy * Jw[0]};
+    d[10] = (S(1) / Jx) * (tq[0] - cr[0]);
+    d[11] = (S(1) / Jy) * (tq[1] - cr[1]);
+    d[12] = (S(1) / Jz) * (tq[2] - cr[2]);
+#pragma unroll
+    for (int i = 0; i < 13; ++i) xn[i] = x[i] + d[i] * dt;
+  }
+
+  DILQR_DEVICE static bool trig_reusable(const S*) { return true; }
+
+  DILQR_DEVICE static void jacobian(const DynParams<S>& P, const S* tau, const S* /*xnext*/,
+                                    S (*F)[N]) {
+    EnvTables<S, DYN_ROCKET>::eval_D(P, tau, &tau[NS], F);
   }
 };
 

@@ -36,6 +36,7 @@
 #pragma once
 #include "common.cuh"
 #include "dynamics.cuh"
+#include "env_tables_gen.cuh"
 #include "smallmat.cuh"
 
 namespace dilqr {
@@ -415,14 +416,7 @@ struct IterKernel {
       if (t < T - 1) {
         S Fm[NS][N];
         if constexpr (kEnv) {
-          S sp, cp;
-          if (D::kTrigFromNext && D::trig_reusable(&tau[NS])) {
-            sp = xnext[DYN == DYN_PENDULUM ? 1 : 3];
-            cp = xnext[DYN == DYN_PENDULUM ? 0 : 2];
-          } else {
-            D::trig(p.dyn, tau, &tau[NS], &sp, &cp);
-          }
-          D::jac(p.dyn, tau, &tau[NS], sp, cp, Fm);
+          D::jacobian(p.dyn, tau, xnext, Fm);
         } else {
           const S* Fs = blk.F;
 #pragma unroll

@@ -184,9 +184,7 @@ __global__ void linearize_kernel(DynParams<S> P, int T, int B, const S* __restri
 #pragma unroll
   for (int a = 0; a < NC; ++a) tau[NS + a] = u[((size_t)t * B + b) * NC + a];
   D::step(P, tau, &tau[NS], xn);
-  S sp, cp;
-  D::trig(P, tau, &tau[NS], &sp, &cp);
-  D::jac(P, tau, &tau[NS], sp, cp, Fm);
+  D::jacobian(P, tau, xn, Fm);   // sin/cos of the new angle come from xn (same rollout)
   S* Fo = F + ((size_t)t * B + b) * (NS * N);
 #pragma unroll
   for (int i = 0; i < NS; ++i) {

@@ -567,7 +567,8 @@ def kkt_backward(dl_dx, dl_du, x_init, C, c, F, f, x, u, n_state, n_ctrl,
 def env_tables(dynamics, x, u):
     """get_matrices (cartpole.py:105-716 / pendulum.py:152-382), generated."""
     import env_tables_gen as G
-    fn = G.cartpole_tables if isinstance(dynamics, CartpoleDx) else G.pendulum_tables
+    fn = (G.cartpole_tables if isinstance(dynamics, CartpoleDx) else
+          G.rocket_tables if isinstance(dynamics, RocketDx) else G.pendulum_tables)
     return fn(x, u, dynamics.params.detach())
 
 
@@ -656,3 +657,66 @@ def dilqr_backward(dl_dx, dl_du, x_init, C, c, x, u, dynamics, n_state, n_ctrl,
     dtheta = torch.einsum("tbnm,tbnmk->bk", k.dF, grad_D) + \
         torch.einsum("tbn,tbnk->bk", k.df, grad_d)
     return DilqrOut(k.dC, k.dc, dtheta, w, passes, resid)
+
+
+class RocketDx:
+    """env_dx/rocket.py:14-164 (6-DoF rocket, quaternion attitude) and its analytic
+    Jacobian get_linear_dyn 324-426.  State r(3), v(3), q(4), w(3); control thrust
+    (3); params (Jx, Jy, Jz, mass, l), dt = 0.1.  Mirrors the reference's quirk of
+    returning the UN-normalised quaternion (rocket.py:158-164)."""
+    n_state, n_ctrl = 13, 3
+    dt = 0.1
+    max_thrust = 400.0
+    lower, upper = -20.0, 20.0          # SURVEY 8d config 3 (float bounds)
+    mpc_eps, linesearch_decay, max_linesearch_iter = 1e-3, 0.2, 5
+
+    def __init__(self, params=None, dtype=torch.float32):
+        self.params = (torch.tensor((0.5, 1.0, 1.0, 1.0, 1.0), dtype=dtype)
+                       if params is None else params)
+
+    def get_true_obj(self):                            # rocket.py:212-232
+        dt = self.params.dtype
+        gw = torch.ones(13, dtype=dt)
+        gw[0:3] = 10.0
+        gw[6:10] = 0.1
+        gs = torch.zeros(13, dtype=dt)
+        gs[6] = 1.0
+        cp = torch.tensor([1.0, 1.0, 0.4], dtype=dt)
+        tilt_Q = 50.0 * torch.tensor([0., 0., 4., 4.], dtype=dt)
+        q = torch.cat((gw, cp))
+        q[6:10] = tilt_Q * 50.0                        # tilt_penalty applied twice (:74-77,225)
+        px = -torch.sqrt(gw) * gs
+        px[6:10] = 0.0
+        p = torch.cat((px, torch.zeros(3, dtype=dt)))
+        return q, p
+
+    def __call__(self, x, u):                          # rocket.py:82-164
+        Jx, Jy, Jz, mass, l = torch.unbind(self.params.detach())
+        v, q, w = x[:, 3:6], x[:, 6:10], x[:, 10:13]
+        T_B = torch.clamp(u, -self.max_thrust, self.max_thrust)
+        q0, q1, q2, q3 = q.unbind(-1)
+        C_B_I = torch.stack([
+            torch.stack([1 - 2 * (q2 ** 2 + q3 ** 2), 2 * (q1 * q2 + q0 * q3), 2 * (q1 * q3 - q0 * q2)], -1),
+            torch.stack([2 * (q1 * q2 - q0 * q3), 1 - 2 * (q1 ** 2 + q3 ** 2), 2 * (q2 * q3 + q0 * q1)], -1),
+            torch.stack([2 * (q1 * q3 + q0 * q2), 2 * (q2 * q3 - q0 * q1), 1 - 2 * (q1 ** 2 + q2 ** 2)], -1),
+        ], 1)
+        tg = torch.bmm(C_B_I.transpose(1, 2), T_B.unsqueeze(-1)).squeeze(-1)
+        g = torch.tensor([-10., 0., 0.], dtype=x.dtype).expand(x.shape[0], 3)
+        dv = tg / mass + g
+        wx, wy, wz = w.unbind(-1)
+        z = torch.zeros_like(wx)
+        om = torch.stack([
+            torch.stack([z, -wx, -wy, -wz], -1), torch.stack([wx, z, wz, -wy], -1),
+            torch.stack([wy, -wz, z, wx], -1), torch.stack([wz, wy, -wx, z], -1)], 1)
+        dq = 0.5 * torch.bmm(om, q.unsqueeze(-1)).squeeze(-1)
+        rT = torch.stack([-l / 2, torch.zeros_like(l), torch.zeros_like(l)]).to(x.dtype).expand(x.shape[0], 3)
+        torque = torch.linalg.cross(rT, T_B, dim=1)
+        J = torch.stack([Jx, Jy, Jz]).to(x.dtype)
+        Jw = w * J
+        dw = (1.0 / J) * (torque - torch.linalg.cross(w, Jw, dim=1))
+        deriv = torch.cat([v, dv, dq, dw], 1)
+        return x + deriv * self.dt
+
+    def get_linear_dyn(self, x, u):                    # rocket.py:324-426
+        import env_tables_gen as G
+        return G.rocket_tables(x, u, self.params.detach())[0]

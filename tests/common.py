@@ -41,6 +41,13 @@ def env_problem(port, name, T, B, dtype, sigma=0.5, seed=0):
         pdx = port.CartpoleDx(dtype=dtype)
         r = (torch.rand(B, 4, generator=g, dtype=f64) * 2 - 1) * sigma
         x0 = torch.stack((r[:, 0], r[:, 1], torch.cos(r[:, 2]), torch.sin(r[:, 2]), r[:, 3]), 1)
+    elif name == "rocket":
+        pdx = port.RocketDx(dtype=dtype)
+        qv = torch.cat((torch.ones(B, 1, dtype=f64), 0.1 * torch.randn(B, 3, generator=g, dtype=f64)), 1)
+        x0 = torch.cat(((torch.rand(B, 3, generator=g, dtype=f64) * 2 - 1) * 15,
+                        torch.rand(B, 3, generator=g, dtype=f64) * 2 - 1,
+                        qv / qv.norm(dim=1, keepdim=True),
+                        (torch.rand(B, 3, generator=g, dtype=f64) * 2 - 1) * 0.1), 1)
     else:
         pdx = port.PendulumDx(dtype=dtype)
         th = (torch.rand(B, generator=g, dtype=f64) - 0.5) * 3.14159

@@ -99,11 +99,12 @@ def tables():
     torch.set_default_dtype(torch.float64)
     out = {}
     for env, cls, ns, nth in (("cartpole", R.cartpole.CartpoleDx, 5, 4),
-                              ("pendulum", R.pendulum.PendulumDx, 3, 3)):
+                              ("pendulum", R.pendulum.PendulumDx, 3, 3),
+                              ("rocket", R.rocket.RocketDx, 13, 5)):
         theta = torch.rand(nth) * 2 + 0.3
         dx = cls(theta.clone())
         x = torch.randn(6, ns)
-        u = torch.randn(6, 1)
+        u = torch.randn(6, dx.n_ctrl)
         names = ["D", "D_theta", "D_x", "D_u", "x_theta", "x_x", "x_u"]
         res = dx.get_matrices(x, u)
         out.update({env + "_theta": theta, env + "_x": x, env + "_u": u})

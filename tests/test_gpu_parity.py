@@ -107,12 +107,14 @@ def test_env_golden_forward(dilqr, env, dev, name, tol, med):
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 @pytest.mark.parametrize("name,T,B,L", [("cartpole", 50, 128, 10), ("pendulum", 20, 64, 10),
-                                        ("cartpole", 20, 33, 1), ("pendulum", 20, 1, 1)])
+                                        ("cartpole", 20, 33, 1), ("pendulum", 20, 1, 1),
+                                        ("rocket", 12, 8, 1), ("rocket", 30, 40, 6)])
 def test_env_vs_oracle(dilqr, port, env, dev, dtype, name, T, B, L):
     pdx, x0, C, c, kw = env_problem(port, name, T, B, dtype)
     o = port.mpc_forward(x0, port.QuadCost(C, c), pdx, pdx.n_state, pdx.n_ctrl, T, lqr_iter=L,
                          final_pass=False, **kw)
-    gdx = (env.CartpoleDx if name == "cartpole" else env.PendulumDx)(pdx.params.to(dev))
+    gdx = {"cartpole": env.CartpoleDx, "pendulum": env.PendulumDx,
+           "rocket": env.RocketDx}[name](pdx.params.to(dev))
     m = dilqr.MPC(pdx.n_state, pdx.n_ctrl, T, lqr_iter=L, verbose=-1, exit_unconverged=False, **kw)
     with torch.no_grad():
         x, u, costs = m(x0.to(dev), dilqr.QuadCost(C.to(dev), c.to(dev)), gdx)
@@ -177,12 +179,12 @@ def test_cartpole_fixture(dilqr, env, dev):
     assert float((u - us).abs().max()) < 5e-2
 
 
-@pytest.mark.parametrize("name", ["pendulum", "cartpole"])
+@pytest.mark.parametrize("name", ["pendulum", "cartpole", "rocket"])
 def test_tables_first_order_and_step(env, dev, name):
     """Device step / analytic Jacobian vs the reference's outputs (golden)."""
     g = golden("ref_tables.npz")
     x, u, th = g[name + "_x"].to(dev), g[name + "_u"].to(dev), g[name + "_theta"].to(dev)
-    dx = (env.CartpoleDx if name == "cartpole" else env.PendulumDx)(th)
+    dx = {"cartpole": env.CartpoleDx, "pendulum": env.PendulumDx, "rocket": env.RocketDx}[name](th)
     assert rel(dx(x, u), g[name + "_step"]) < 1e-13
     assert rel(dx.get_linear_dyn(x, u), g[name + "_lin"]) < 1e-12
 

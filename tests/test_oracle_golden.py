@@ -87,7 +87,7 @@ def test_dilqr_backward_matches_reference_dense_solve(port, env):
     assert rel(d.dc, g["dc"]) < 1e-10
 
 
-@pytest.mark.parametrize("env", ["pendulum", "cartpole"])
+@pytest.mark.parametrize("env", ["pendulum", "cartpole", "rocket"])
 def test_tables_and_first_order(port, env):
     """Generated get_matrices tables + step + analytic Jacobian vs the reference."""
     import env_tables_gen as G
@@ -96,7 +96,8 @@ def test_tables_and_first_order(port, env):
     out = getattr(G, env + "_tables")(x, u, th)
     for nm, a in zip(["D", "D_theta", "D_x", "D_u", "x_theta", "x_x", "x_u"], out):
         assert rel(a, g[env + "_" + nm]) < 1e-13, nm
-    pdx = (port.PendulumDx if env == "pendulum" else port.CartpoleDx)(params=th, dtype=torch.float64)
+    pdx = {"pendulum": port.PendulumDx, "cartpole": port.CartpoleDx,
+           "rocket": port.RocketDx}[env](params=th, dtype=torch.float64)
     assert rel(pdx(x, u), g[env + "_step"]) < 1e-15
     assert rel(pdx.get_linear_dyn(x, u), g[env + "_lin"]) < 1e-13
 

@@ -53,8 +53,8 @@ class SymT(np.ndarray):
         return np.ndarray.reshape(self, shape).view(SymT)
 
     @property
-    def ndim_(self):
-        return self.ndim
+    def device(self):
+        return "sym"
 
 
 def sym(a):
@@ -80,7 +80,7 @@ class TorchShim:
         return sym(np.full(np.shape(a), sp.Integer(0), dtype=object))
 
     @staticmethod
-    def zeros(*shape):
+    def zeros(*shape, **kw):
         if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
             shape = tuple(shape[0])
         return sym(np.full(shape, sp.Integer(0), dtype=object))
@@ -211,6 +211,25 @@ def emit(name, tables, state_syms, ctrl_syms, param_syms, ns, nc, nth, out):
     for (nm, idx), e in zip(index, red):
         w("    %s%s = %s;\n" % (cname[nm], "".join("[%d]" % i for i in idx), pr.doprint(e)))
     w("  }\n")
+    # first-order Jacobian only (the iLQR linearisation)
+    Dflat = [sp.sympify(tables["D"][idx]) for idx in np.ndindex(tables["D"].shape)]
+    replD, redD = sp.cse(Dflat, symbols=sp.numbered_symbols("d"), optimizations=None, order="none")
+    w("  DILQR_DEVICE static void eval_D(const DynParams<S>& P, const S* xs_, const S* us_, S (*D)[N]) {\n")
+    usedD = set().union(*[e.free_symbols for e in Dflat])
+    for i, s_ in enumerate(state_syms):
+        if s_ in usedD:
+            w("    const S %s = xs_[%d];\n" % (s_, i))
+    for i, s_ in enumerate(ctrl_syms):
+        if s_ in usedD:
+            w("    const S %s = us_[%d];\n" % (s_, i))
+    for i, s_ in enumerate(param_syms):
+        if s_ in usedD:
+            w("    const S %s = P.p[%d];\n" % (s_, i))
+    for sym_, e in replD:
+        w("    const S %s = %s;\n" % (sym_, pr.doprint(e)))
+    for idx, e in zip(np.ndindex(tables["D"].shape), redD):
+        w("    D%s = %s;\n" % ("".join("[%d]" % i for i in idx), pr.doprint(e)))
+    w("  }\n")
     # structural non-zero masks (compile-time pruning of the contractions)
     for nm in ["D", "D_theta", "D_x", "D_u", "x_theta", "x_x", "x_u"]:
         a = tables[nm]
@@ -285,6 +304,11 @@ def main():
         emit("cartpole", tabs, [xx_, xd_, c, s, w], [u], [g, mc, mp, l], 5, 1, 4, out)
         tabs = symbolic_tables("pendulum", "PendulumDx", [c, s, w], [u], [g, m, l])
         emit("pendulum", tabs, [c, s, w], [u], [g, m, l], 3, 1, 3, out)
+        rx = list(sp.symbols("r0 r1 r2 v0 v1 v2 q0 q1 q2 q3 wx wy wz", real=True))
+        ru = list(sp.symbols("ux uy uz", real=True))
+        rp = list(sp.symbols("Jx Jy Jz mass l", real=True, positive=True))
+        tabs = symbolic_tables("rocket", "RocketDx", rx, ru, rp)
+        emit("rocket", tabs, rx, ru, rp, 13, 3, 5, out)
         out.write("}  // namespace dilqr\n")
     print("wrote", out_path)
     py_path = os.path.join(ROOT, "oracle", "env_tables_gen.py")
@@ -297,6 +321,8 @@ def main():
         emit_py("cartpole", tabs, [xx_, xd_, c, s, w], [u], [g, mc, mp, l], out)
         tabs = symbolic_tables("pendulum", "PendulumDx", [c, s, w], [u], [g, m, l])
         emit_py("pendulum", tabs, [c, s, w], [u], [g, m, l], out)
+        tabs = symbolic_tables("rocket", "RocketDx", rx, ru, rp)
+        emit_py("rocket", tabs, rx, ru, rp, out)
     print("wrote", py_path)
 
 
