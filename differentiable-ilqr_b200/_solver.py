@@ -312,8 +312,8 @@ def dilqr_backward(dl_dx, dl_du, x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u
     C_ = _contig(C_.detach())
     c_ = _contig(c_.detach())
     scalar_bounds = u_lower is None or (isinstance(u_lower, float) and isinstance(u_upper, float))
-    if not scalar_bounds:
-        factored = False
+    if not scalar_bounds or kind == _lib.DYN_ROCKET:
+        factored = False      # factored adjoint kernels: pendulum / cartpole only (round 1)
     # (1) gains of the final no-op LQR pass at tau* (lqr_step_explicit.py:604-618)
     dyn = DynSpec(kind, params=list(theta))
     _, _, _, info = solve_mpc(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower=u_lower,

@@ -519,8 +519,9 @@ static int launch_costate(const double* dp, int T, int B, const void* C, const v
   using S = Scalar;
   DynParams<S> P;
   for (int i = 0; i < 8; ++i) P.p[i] = (S)dp[i];
-  const int wpb = 2;
+  const int wpb = CostateStage<S, DYN>::smem_per_warp() * 2 <= 200 * 1024 ? 2 : 1;
   const size_t smem = CostateStage<S, DYN>::smem_per_warp() * wpb;
+  if (smem > 227 * 1024) return DILQR_EUNSUPPORTED;
   auto kern = costate_tables_kernel<S, DYN>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int warps = (B + kWarp - 1) / kWarp;
@@ -537,6 +538,7 @@ int DILQR_SUFFIX(costate_tables)(int dynamics, const double* dp, int T, int B, c
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dynamics == DYN_PENDULUM) return launch_costate<DYN_PENDULUM>(dp, T, B, C, c, x, u, lam, Lam, st);
   if (dynamics == DYN_CARTPOLE) return launch_costate<DYN_CARTPOLE>(dp, T, B, C, c, x, u, lam, Lam, st);
+  if (dynamics == DYN_ROCKET) return launch_costate<DYN_ROCKET>(dp, T, B, C, c, x, u, lam, Lam, st);
   return DILQR_EUNSUPPORTED;
 }
 
@@ -562,6 +564,7 @@ int DILQR_SUFFIX(sens_theta)(int dynamics, const double* dp, int T, int B, const
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dynamics == DYN_PENDULUM) return launch_sens<DYN_PENDULUM>(dp, T, B, x, u, K, lam, dx, du, df, dtheta, st);
   if (dynamics == DYN_CARTPOLE) return launch_sens<DYN_CARTPOLE>(dp, T, B, x, u, K, lam, dx, du, df, dtheta, st);
+  if (dynamics == DYN_ROCKET) return launch_sens<DYN_ROCKET>(dp, T, B, x, u, K, lam, dx, du, df, dtheta, st);
   return DILQR_EUNSUPPORTED;
 }
 

@@ -71,6 +71,13 @@ def dilqr(env, T, B, lqr_iter, sigma):
         th = (torch.rand(B) - 0.5) * 3.14159
         w = torch.rand(B) * 2 - 1
         x0 = torch.stack((torch.cos(th), torch.sin(th), w), 1)
+    elif env == "rocket":
+        theta = torch.tensor((0.5, 1.0, 1.0, 1.0, 1.0), dtype=dt, requires_grad=True)
+        dx = R.rocket.RocketDx(theta)
+        dx.lower, dx.upper = -20.0, 20.0          # float bounds
+        qv = torch.cat((torch.ones(B, 1), 0.1 * torch.randn(B, 3)), 1)
+        x0 = torch.cat(((torch.rand(B, 3) * 2 - 1) * 3, torch.rand(B, 3) * 2 - 1,
+                        qv / qv.norm(dim=1, keepdim=True), (torch.rand(B, 3) * 2 - 1) * 0.1), 1)
     else:
         theta = torch.tensor((9.8, 1.0, 0.1, 0.5), dtype=dt, requires_grad=True)
         dx = R.cartpole.CartpoleDx(theta)
@@ -152,6 +159,7 @@ if __name__ == "__main__":
     lindx(True)
     dilqr("pendulum", 20, 4, 60, None)
     dilqr("cartpole", 12, 8, 80, 0.05)
+    dilqr("rocket", 10, 4, 60, None)
     tables()
     env_forward("cartpole", 25, 16, 6, torch.float64)
     env_forward("pendulum", 20, 16, 8, torch.float64)

@@ -189,19 +189,20 @@ def test_tables_first_order_and_step(env, dev, name):
     assert rel(dx.get_linear_dyn(x, u), g[name + "_lin"]) < 1e-12
 
 
-@pytest.mark.parametrize("name", ["pendulum", "cartpole"])
+@pytest.mark.parametrize("name", ["pendulum", "cartpole", "rocket"])
 def test_dilqr_gradient_golden(dilqr, env, dev, name):
     """DiLQR implicit gradient vs the reference's dense fix_point_equ (golden)."""
     g = golden("ref_dilqr_%s.npz" % name)
     T, B = int(g["T"]), g["x0"].shape[0]
     theta = g["theta"].to(dev).requires_grad_()
-    dx = (env.CartpoleDx if name == "cartpole" else env.PendulumDx)(theta)
+    dx = {"cartpole": env.CartpoleDx, "pendulum": env.PendulumDx, "rocket": env.RocketDx}[name](theta)
     C = torch.diag(g["q"]).to(dev)[None, None].repeat(T, B, 1, 1).requires_grad_()
     c = g["p"].to(dev)[None, None].repeat(T, B, 1).requires_grad_()
     m = dilqr.mpc_explicit.MPC(dx.n_state, dx.n_ctrl, T, u_lower=dx.lower, u_upper=dx.upper,
                                lqr_iter=int(g["lqr_iter"]), verbose=-1, exit_unconverged=False,
                                detach_unconverged=False, linesearch_decay=dx.linesearch_decay,
-                               max_linesearch_iter=dx.max_linesearch_iter, eps=1e-9)
+                               max_linesearch_iter=dx.max_linesearch_iter, eps=1e-9,
+                               richardson_passes=80)
     x, u, costs = m(g["x0"].to(dev), dilqr.QuadCost(C, c), dx)
     assert rel(x, g["x"]) < 1e-10 and rel(u, g["u"]) < 1e-10
     ((x * g["gx"].to(dev)).sum() + (u * g["gu"].to(dev)).sum()).backward()

@@ -68,20 +68,23 @@ def test_lindx_forward_and_kkt_backward(port, tag):
         assert rel(a, g[nm]) < 1e-13, nm
 
 
-@pytest.mark.parametrize("env", ["pendulum", "cartpole"])
+@pytest.mark.parametrize("env", ["pendulum", "cartpole", "rocket"])
 def test_dilqr_backward_matches_reference_dense_solve(port, env):
     """Matrix-free DiLQR gradient == the reference's fix_point_equ (dense solve)."""
     g = golden("ref_dilqr_%s.npz" % env)
     dt = torch.float64
-    pdx = (port.PendulumDx if env == "pendulum" else port.CartpoleDx)(params=g["theta"], dtype=dt)
+    pdx = {"pendulum": port.PendulumDx, "cartpole": port.CartpoleDx,
+           "rocket": port.RocketDx}[env](params=g["theta"], dtype=dt)
     T, B = int(g["T"]), g["x0"].shape[0]
     C = torch.diag(g["q"])[None, None].repeat(T, B, 1, 1)
     c = g["p"][None, None].repeat(T, B, 1)
     o = port.mpc_forward(g["x0"], port.QuadCost(C, c), pdx, pdx.n_state, pdx.n_ctrl, T,
                          final_pass=False, **_mpc_kw(pdx, int(g["lqr_iter"]), eps=1e-9))
-    assert float((o.x - g["x"]).abs().max()) == 0.0
+    # pendulum / cartpole: bit-exact; rocket's Jacobian is the generated (CSE-reordered)
+    # form of the reference's expressions, equal to round-off
+    assert float((o.x - g["x"]).abs().max()) <= (1e-14 if env == "rocket" else 0.0)
     d = port.dilqr_backward(g["gx"], g["gu"], g["x0"], C, c, o.x, o.u, pdx, pdx.n_state,
-                            pdx.n_ctrl, pdx.lower, pdx.upper, n_passes=40, tol=1e-15)
+                            pdx.n_ctrl, pdx.lower, pdx.upper, n_passes=80, tol=1e-15)
     assert rel(d.dtheta.sum(0), g["dtheta"]) < 1e-10
     assert rel(d.dC, g["dC"]) < 1e-10
     assert rel(d.dc, g["dc"]) < 1e-10
