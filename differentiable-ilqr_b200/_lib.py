@@ -19,7 +19,7 @@ PNQP_MAX_ITER = 20
 
 ERRORS = {0: "ok", -1: "invalid argument", -2: "unsupported (dtype, n_state, n_ctrl, dynamics)",
           -3: "pointer not 16-byte aligned", -4: "workspace too small",
-          -5: "CUDA launch failure"}
+          -5: "CUDA launch failure", -6: "lockstep launch: batch not co-resident"}
 
 
 class DilqrLibraryError(RuntimeError):
@@ -47,7 +47,7 @@ class DilqrSolve(C.Structure):
         ("dtype", C.c_int32), ("dynamics", C.c_int32), ("gain_solve", C.c_int32),
         ("bounds_kind", C.c_int32), ("solo", C.c_int32),
         ("max_linesearch_iter", C.c_int32), ("iteration", C.c_int32),
-        ("has_f", C.c_int32), ("gains_only", C.c_int32), ("reserved0", C.c_int32),
+        ("has_f", C.c_int32), ("gains_only", C.c_int32), ("lockstep", C.c_int32),
         ("linesearch_decay", C.c_double),
         ("u_lower", C.c_double), ("u_upper", C.c_double),
         ("best_cost_eps", C.c_double),
@@ -93,6 +93,7 @@ class DilqrAdjoint(C.Structure):
 SYMBOLS = {
     "dilqr_version": (C.c_char_p, []),
     "dilqr_supported": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "dilqr_lockstep_capacity": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "dilqr_workspace_bytes": (C.c_size_t, [C.POINTER(DilqrSolve)]),
     "dilqr_mpc_begin": (C.c_int, [C.POINTER(DilqrSolve), C.c_void_p]),
     "dilqr_mpc_iterate": (C.c_int, [C.POINTER(DilqrSolve), C.c_void_p]),

@@ -53,6 +53,8 @@ class Workspace:
 
 
 _ws_cache = {}
+_lockstep_cap = {}
+LOCKSTEP_AUTO = True
 
 
 def _require_cuda(t, name):
@@ -124,6 +126,15 @@ def _make_problem(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower, u_upper, u_z
         raise _lib.DilqrLibraryError(
             "no kernel compiled for dtype=%s n_state=%d n_ctrl=%d dynamics=%d "
             "(add it to DILQR_CONFIGS in csrc/api.cu)" % (dtype, n_state, n_ctrl, dyn.kind))
+    # multi-input box-constrained problems have long, unstable pnqp traces: resolve the
+    # batch-global decisions with grid barriers when the whole batch fits on the device
+    if s.bounds_kind != _lib.BOUNDS_NONE and not solo and n_ctrl > 1 and LOCKSTEP_AUTO:
+        cap = _lockstep_cap.get((s.dtype, n_state, n_ctrl, dyn.kind))
+        if cap is None:
+            cap = L.dilqr_lockstep_capacity(s.dtype, n_state, n_ctrl, dyn.kind)
+            _lockstep_cap[(s.dtype, n_state, n_ctrl, dyn.kind)] = cap
+        if B <= cap:
+            s.lockstep = 1
     need = L.dilqr_workspace_bytes(C.byref(s))
     key = (x_init.device.index, need)
     ws = _ws_cache.get(key)

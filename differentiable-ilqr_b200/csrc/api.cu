@@ -146,6 +146,7 @@ static IterParams<Scalar> make_params(const DilqrSolve* s, int role = 1) {
   p.dusq = reinterpret_cast<S*>(ws + w.dusq);
   p.take = reinterpret_cast<int*>(ws + w.take);
   p.gains_only = s->gains_only;
+  p.lockstep = s->lockstep;
   p.guess = reinterpret_cast<uint32_t*>(ws + w.guess);
   p.votes = reinterpret_cast<uint32_t*>(ws + w.votes);
   p.status = s->status;
@@ -229,6 +230,23 @@ static int launch_iterate(const DilqrSolve* s, cudaStream_t st) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (p.bounds_kind && !p.solo)
     cudaMemsetAsync(p.votes, 0, (size_t)p.T * kPnqpMaxIter * sizeof(uint32_t), st);
+  if (p.lockstep && p.bounds_kind && !p.solo) {
+    // cooperative launch, one warp per block so that every warp of the grid owns
+    // problems (all warps must reach every grid barrier); needs the whole batch
+    // resident -- dilqr_lockstep_capacity() tells the caller whether it fits.
+    const size_t smem1 = G::smem(1);
+    if (smem1 > 48 * 1024)
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+    void* args[] = {(void*)&p};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)kern, dim3(warps), dim3(kWarp), args,
+                                                smem1, st);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return DILQR_ELOCKSTEP;
+    }
+    return DILQR_OK;
+  }
+  p.lockstep = 0;
   kern<<<blocks, wpb * kWarp, smem, st>>>(p);
   return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
 }
@@ -238,7 +256,7 @@ static int launch_commit(const DilqrSolve* s, cudaStream_t st) {
   using S = Scalar;
   IterParams<S> p = make_params(s);
   trace_verify_kernel<<<1, 256, 0, st>>>(p.guess, p.votes, p.T, p.bounds_kind != 0, p.solo,
-                                         s->status);
+                                         s->status, p.lockstep);
   commit_kernel<S, NS + NC, NC><<<(p.B + 127) / 128, 128, 0, st>>>(p);
   return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
 }
@@ -260,6 +278,22 @@ static int launch_kkt(const DilqrKkt* k, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------ dispatch
+template <int NS, int NC, int DYN>
+static int lockstep_capacity() {
+  using S = Scalar;
+  using G = Geometry<S, NS, NC, DYN>;
+  auto kern = ilqr_iter_kernel<S, NS, NC, DYN, G::STAGED>;
+  const size_t smem1 = G::smem(1);
+  if (smem1 > 48 * 1024)
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+  int per_sm = 0, dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarp, smem1) != cudaSuccess)
+    return 0;
+  return per_sm * sms * kWarp;
+}
+
 enum Op { OP_BEGIN, OP_ITERATE, OP_COMMIT, OP_FINISH };
 
 static int dispatch(const DilqrSolve* s, Op op, cudaStream_t st) {
@@ -275,6 +309,14 @@ static int dispatch(const DilqrSolve* s, Op op, cudaStream_t st) {
   DILQR_CONFIGS(X)
 #undef X
   return DILQR_EUNSUPPORTED;
+}
+
+int DILQR_SUFFIX(lockstep_capacity)(int n_state, int n_ctrl, int dynamics) {
+#define X(NS_, NC_, DYN_) \
+  if (n_state == NS_ && n_ctrl == NC_ && dynamics == DYN_) return lockstep_capacity<NS_, NC_, DYN_>();
+  DILQR_CONFIGS(X)
+#undef X
+  return 0;
 }
 
 int DILQR_SUFFIX(supported)(int n_state, int n_ctrl, int dynamics) {

@@ -5,6 +5,7 @@
 namespace dilqr {
 #define DECL(sfx)                                                                         \
   int supported_##sfx(int, int, int);                                                     \
+  int lockstep_capacity_##sfx(int, int, int);                                                     \
   size_t workspace_bytes_##sfx(const DilqrSolve*);                                        \
   int mpc_begin_##sfx(const DilqrSolve*, void*);                                          \
   int mpc_iterate_##sfx(const DilqrSolve*, void*);                                        \
@@ -39,6 +40,12 @@ const char* dilqr_version(void) { return "dilqr-b200 0.1 (sm_100a)"; }
 int dilqr_supported(int dtype, int ns, int nc, int dyn) {
   if (dtype == DILQR_F32) return dilqr::supported_f32(ns, nc, dyn);
   if (dtype == DILQR_F64) return dilqr::supported_f64(ns, nc, dyn);
+  return 0;
+}
+
+int dilqr_lockstep_capacity(int dtype, int ns, int nc, int dyn) {
+  if (dtype == DILQR_F32) return dilqr::lockstep_capacity_f32(ns, nc, dyn);
+  if (dtype == DILQR_F64) return dilqr::lockstep_capacity_f64(ns, nc, dyn);
   return 0;
 }
 

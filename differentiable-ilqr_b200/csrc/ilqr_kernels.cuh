@@ -34,6 +34,7 @@
 // zero: the trace of the previous iLQR iteration is the next guess) the result
 // is exactly what the reference computes on the whole batch.
 #pragma once
+#include <cooperative_groups.h>
 #include "common.cuh"
 #include "dynamics.cuh"
 #include "env_tables_gen.cuh"
@@ -72,6 +73,7 @@ struct IterParams {
   int* take;          // [Bp] 1: the problem's best iterate is the CURRENT trajectory and
                       //         has not been copied to traj_best yet (lazy best tracking)
   int gains_only;     // skip the line-search rollout (only K,k are wanted)
+  int lockstep;       // cooperative launch: grid-wide barriers resolve the pnqp decisions
   S* cost_cur;    // [Bp]
   S* cost_new;
   S* cost_best;
@@ -136,7 +138,17 @@ template <class S, int N>
 DILQR_DEVICE void pnqp_thread(const S (&H)[N][N], const S (&q)[N], const S (&lo)[N],
                               const S (&hi)[N], bool have_init, S (&x)[N], bool (&If)[N],
                               LUpp<S, N>& lu, const uint32_t* __restrict__ guess, uint4 gpre,
-                              uint32_t* __restrict__ votes, bool solo, bool active, int lane) {
+                              uint32_t* __restrict__ votes, bool solo, bool active, int lane,
+                              bool lockstep = false) {
+  // lockstep: the kernel was launched cooperatively with the whole batch resident;
+  // every batch-global decision is an atomicOr into the vote word + a grid-wide
+  // barrier (no guessing, no re-runs) -- the better trade when the control-flow trace
+  // is long and unstable (multi-input problems with many active constraints).
+  auto grid_decide = [&](uint32_t* word, uint32_t mine) -> uint32_t {
+    if (mine && lane == 0) atomicOr(word, mine);
+    cooperative_groups::this_grid().sync();
+    return *reinterpret_cast<volatile uint32_t*>(word);
+  };
   // gpre = guess[0..3], loaded by the caller long before this point (the common
   // case never looks past the first two words; a global load here would sit on
   // the critical path of the sweep).
@@ -204,12 +216,15 @@ DILQR_DEVICE void pnqp_thread(const S (&H)[N][N], const S (&q)[N], const S (&lo)
     bool any_moving;
     if (solo) {
       any_moving = J;
+    } else if (lockstep) {
+      if (__ballot_sync(kFull, active && J)) vote |= 1u;
+      any_moving = (grid_decide(&votes[it], vote) & 1u) != 0;
     } else {
       if (__ballot_sync(kFull, active && J)) vote |= 1u;
       any_moving = (gword_at(it) & 1u) != 0;
     }
     if (!any_moving) {  // pnqp.py:57-59
-      if (!solo && vote && lane == 0) atomicOr(&votes[it], vote);
+      if (!solo && !lockstep && vote && lane == 0) atomicOr(&votes[it], vote);
       return;
     }
     // Armijo backtracking with a batch-global exit test (pnqp.py:61-76).
@@ -229,7 +244,7 @@ DILQR_DEVICE void pnqp_thread(const S (&H)[N][N], const S (&q)[N], const S (&lo)
     }
     S alpha = S(1);
     S mx[N];
-    const uint32_t gword = solo ? 0u : gword_at(it);
+    const uint32_t gword = (solo || lockstep) ? 0u : gword_at(it);
     for (int cnt = 0; cnt < kArmijoMax; ++cnt) {
 #pragma unroll
       for (int i = 0; i < N; ++i) mx[i] = eclamp<S>(x[i] + alpha * dx[i], lo[i], hi[i]);
@@ -254,6 +269,9 @@ DILQR_DEVICE void pnqp_thread(const S (&H)[N][N], const S (&q)[N], const S (&lo)
       bool exit_loop;
       if (solo) {
         exit_loop = !small;
+      } else if (lockstep) {
+        const uint32_t mine = __ballot_sync(kFull, active && !small) ? (2u << cnt) : 0u;
+        exit_loop = (grid_decide(&votes[it], mine) >> (1 + cnt)) & 1u;
       } else {
         // max_armijo > GAMMA  <=>  some problem has !(arm <= GAMMA)
         if (__ballot_sync(kFull, active && !small)) vote |= (2u << cnt);
@@ -263,7 +281,7 @@ DILQR_DEVICE void pnqp_thread(const S (&H)[N][N], const S (&q)[N], const S (&lo)
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) x[i] = mx[i];  // pnqp.py:78
-    if (!solo && vote && lane == 0) atomicOr(&votes[it], vote);
+    if (!solo && !lockstep && vote && lane == 0) atomicOr(&votes[it], vote);
   }
   // fell through n_iter iterations: the reference returns the factors / If of the
   // last iteration together with the stepped x (pnqp.py:81-82).
@@ -386,7 +404,7 @@ struct IterKernel {
       const int sg = (T - 1 - t) & 1;
       if (t > 0) issue_t(st, p, sg ^ 1, t - 1, b0, false, true, false);
       uint4 gpre = make_uint4(0, 0, 0, 0);
-      if (p.bounds_kind && !p.solo)
+      if (p.bounds_kind && !p.solo && !p.lockstep)
         gpre = __ldg(reinterpret_cast<const uint4*>(p.guess + (size_t)t * kPnqpMaxIter));
       if (STAGED) st.wait(sg);
       const Blk blk = blocks(p, st, sg, t, b, bw, lane);
@@ -536,7 +554,8 @@ struct IterKernel {
         LUpp<S, NC> lu;
         pnqp_thread<S, NC>(H, qu, lo, hi, have_prev, k, If, lu,
                            p.guess + (size_t)t * kPnqpMaxIter, gpre,
-                           p.votes + (size_t)t * kPnqpMaxIter, p.solo != 0, active, lane);
+                           p.votes + (size_t)t * kPnqpMaxIter, p.solo != 0, active, lane,
+                           p.lockstep != 0);
         have_prev = true;
 #pragma unroll
         for (int a = 0; a < NC; ++a) kprev[a] = k[a];

@@ -14,7 +14,8 @@ namespace dilqr {
 // resets the reduction fields of the status block.
 // ---------------------------------------------------------------------------
 static __global__ void trace_verify_kernel(uint32_t* __restrict__ guess, const uint32_t* __restrict__ votes,
-                                    int T, int boxed, int solo, DilqrStatus* status) {
+                                    int T, int boxed, int solo, DilqrStatus* status,
+                                    int lockstep = 0) {
   __shared__ int s_first;
   __shared__ unsigned s_nqp, s_unconv;
   const int n = T * kPnqpMaxIter;
@@ -33,7 +34,7 @@ static __global__ void trace_verify_kernel(uint32_t* __restrict__ guess, const u
       const int slot = t * kPnqpMaxIter + it;
       uint32_t v = votes[slot];
       if (!(v & 1u)) v = 0;
-      if (guess[slot] != v) atomicMin(&s_first, i);
+      if (!lockstep && guess[slot] != v) atomicMin(&s_first, i);   // lockstep: votes ARE the trace
     }
     __syncthreads();
     for (int t = threadIdx.x; t < T; t += blockDim.x) {

@@ -52,7 +52,8 @@ enum {
   DILQR_EUNSUPPORTED = -2, /* (dtype, n_state, n_ctrl, dynamics) not instantiated  */
   DILQR_EALIGN = -3,       /* a pointer is not 16-byte aligned                      */
   DILQR_EWORKSPACE = -4,   /* workspace too small                                   */
-  DILQR_ECUDA = -5         /* kernel launch failed (cudaGetLastError != success)    */
+  DILQR_ECUDA = -5,        /* kernel launch failed (cudaGetLastError != success)    */
+  DILQR_ELOCKSTEP = -6     /* lockstep requested but the batch is not co-resident   */
 };
 
 #define DILQR_PNQP_MAX_ITER 20   /* pnqp.py:5  n_iter=20 (lqr_step.py:137)           */
@@ -88,7 +89,9 @@ typedef struct DilqrSolve {
   int32_t has_f;            /* LinDx: f present (util.py:121)                        */
   int32_t gains_only;       /* iterate: only lqr_backward (K_out,k_out), no rollout --
                                the final no-op LQR pass of lqr_step_explicit.py:604-618 */
-  int32_t reserved0;
+  int32_t lockstep;         /* iterate: resolve the batch-global pnqp decisions with grid-wide
+                               barriers in a cooperative launch (whole batch resident, see
+                               dilqr_lockstep_capacity) instead of replaying a guessed trace */
   double  linesearch_decay; /* mpc.py:134                                           */
   double  u_lower, u_upper; /* scalar bounds (mpc.py:81-82)                         */
   double  best_cost_eps;    /* mpc.py:142                                           */
@@ -123,6 +126,10 @@ const char* dilqr_version(void);
 
 /* 1 if kernels for this combination are compiled in, else 0. */
 int dilqr_supported(int dtype, int n_state, int n_ctrl, int dynamics);
+
+/* Largest n_batch the lockstep (cooperative) variant of dilqr_mpc_iterate can hold
+ * resident on the current device for this shape; 0 if unsupported. */
+int dilqr_lockstep_capacity(int dtype, int n_state, int n_ctrl, int dynamics);
 
 /* Bytes of workspace the dilqr_mpc_* calls need. */
 size_t dilqr_workspace_bytes(const DilqrSolve* s);
