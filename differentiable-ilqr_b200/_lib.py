@@ -104,6 +104,8 @@ SYMBOLS = {
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dilqr_rollout": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dilqr_env_tables": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_void_p,
+                                   C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]),
     "dilqr_pnqp": (C.c_int, [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 10 + [C.c_int]
                    + [C.c_void_p] * 2),
     "dilqr_costate_tables": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int]
@@ -164,7 +166,7 @@ KERNELS_PER_CALL = {
     "dilqr_mpc_finish": 1, "dilqr_kkt_grads": 1, "dilqr_linearize": 1, "dilqr_rollout": 1,
     "dilqr_costate_tables": 1, "dilqr_richardson_update": 1, "dilqr_sens_theta": 1,
     "dilqr_adjoint_factor": 1, "dilqr_adjoint_pass": 1, "dilqr_adjoint_final": 1,
-    "dilqr_pnqp": 2,
+    "dilqr_pnqp": 2, "dilqr_env_tables": 1,
 }
 launch_count = 0     # running total of kernels launched through this binding
 profile = None       # set to a dict {name: [(start_event, end_event), ...]} to time calls

@@ -610,6 +610,31 @@ int DILQR_SUFFIX(sens_theta)(int dynamics, const double* dp, int T, int B, const
   return DILQR_EUNSUPPORTED;
 }
 
+template <int DYN>
+static int launch_tables(const double* dp, int n, const void* x, const void* u, void* const* out,
+                         cudaStream_t st) {
+  using S = Scalar;
+  DynParams<S> P;
+  for (int i = 0; i < 8; ++i) P.p[i] = (S)dp[i];
+  env_tables_kernel<S, DYN><<<(n + 63) / 64, 64, 0, st>>>(
+      P, n, static_cast<const S*>(x), static_cast<const S*>(u), static_cast<S*>(out[0]),
+      static_cast<S*>(out[1]), static_cast<S*>(out[2]), static_cast<S*>(out[3]),
+      static_cast<S*>(out[4]), static_cast<S*>(out[5]), static_cast<S*>(out[6]));
+  return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
+}
+
+int DILQR_SUFFIX(env_tables)(int dynamics, const double* dp, int n, const void* x, const void* u,
+                             void* const* out, void* stream) {
+  if (!dp || !x || !u || !out || n <= 0) return DILQR_EINVAL;
+  for (int i = 0; i < 7; ++i)
+    if (!out[i]) return DILQR_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dynamics == DYN_PENDULUM) return launch_tables<DYN_PENDULUM>(dp, n, x, u, out, st);
+  if (dynamics == DYN_CARTPOLE) return launch_tables<DYN_CARTPOLE>(dp, n, x, u, out, st);
+  if (dynamics == DYN_ROCKET) return launch_tables<DYN_ROCKET>(dp, n, x, u, out, st);
+  return DILQR_EUNSUPPORTED;
+}
+
 int DILQR_SUFFIX(richardson_update)(int ns, int nc, int T, int B, const void* g, const void* Lam,
                                     const void* dx, const void* du, void* w, void* negw,
                                     void* resid, void* stream) {

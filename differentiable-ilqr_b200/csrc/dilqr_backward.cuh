@@ -369,3 +369,57 @@ sens_theta_kernel(DynParams<S> P, int T, int B, const S* __restrict__ x,
 }
 
 }  // namespace dilqr
+
+namespace dilqr {
+
+// ---------------------------------------------------------------------------
+// get_matrices (cartpole.py:105-716, pendulum.py:152-382, rocket.py:258-261) as
+// materialised tensors, one thread per sample row of x[N_,ns], u[N_,nc]:
+//   D[N_,ns,n]  Dth[N_,ns,n,nth]  Dx[N_,ns,n,ns]  Du[N_,ns,n,nc]
+//   xth[N_,ns,nth]  xx[N_,ns,ns]  xu[N_,ns,nc]
+// (API compatibility; the backward pass itself never materialises them.)
+// ---------------------------------------------------------------------------
+template <class S, int DYN>
+__global__ void __launch_bounds__(64)
+env_tables_kernel(DynParams<S> P, int Nrows, const S* __restrict__ x, const S* __restrict__ u,
+                  S* __restrict__ oD, S* __restrict__ oDth, S* __restrict__ oDx,
+                  S* __restrict__ oDu, S* __restrict__ oxth, S* __restrict__ oxx,
+                  S* __restrict__ oxu) {
+  using D = Dyn<S, DYN>;
+  using TB = EnvTables<S, DYN>;
+  constexpr int NS = D::NS, NC = D::NC, N = D::N, NTH = TB::NTH;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= Nrows) return;
+  S tau[N];
+#pragma unroll
+  for (int i = 0; i < NS; ++i) tau[i] = x[(size_t)r * NS + i];
+#pragma unroll
+  for (int a = 0; a < NC; ++a) tau[NS + a] = u[(size_t)r * NC + a];
+  S Dm[NS][N], Dth[NS][N][NTH], Dx[NS][N][NS], Du[NS][N][NC], xth[NS][NTH], xx[NS][NS], xu[NS][NC];
+  TB::eval(P, tau, &tau[NS], Dm, Dth, Dx, Du, xth, xx, xu);
+#pragma unroll
+  for (int i = 0; i < NS; ++i) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      oD[((size_t)r * NS + i) * N + j] = TB::nz_D(i, j) ? Dm[i][j] : S(0);
+#pragma unroll
+      for (int q = 0; q < NTH; ++q)
+        oDth[(((size_t)r * NS + i) * N + j) * NTH + q] = TB::nz_Dth(i, j, q) ? Dth[i][j][q] : S(0);
+#pragma unroll
+      for (int k = 0; k < NS; ++k)
+        oDx[(((size_t)r * NS + i) * N + j) * NS + k] = TB::nz_Dx(i, j, k) ? Dx[i][j][k] : S(0);
+#pragma unroll
+      for (int a = 0; a < NC; ++a)
+        oDu[(((size_t)r * NS + i) * N + j) * NC + a] = TB::nz_Du(i, j, a) ? Du[i][j][a] : S(0);
+    }
+#pragma unroll
+    for (int q = 0; q < NTH; ++q)
+      oxth[((size_t)r * NS + i) * NTH + q] = TB::nz_xth(i, q) ? xth[i][q] : S(0);
+#pragma unroll
+    for (int k = 0; k < NS; ++k) oxx[((size_t)r * NS + i) * NS + k] = TB::nz_xx(i, k) ? xx[i][k] : S(0);
+#pragma unroll
+    for (int a = 0; a < NC; ++a) oxu[((size_t)r * NS + i) * NC + a] = TB::nz_xu(i, a) ? xu[i][a] : S(0);
+  }
+}
+
+}  // namespace dilqr

@@ -21,6 +21,7 @@ namespace dilqr {
                        const void*, const void*, const void*, const void*, void*, void*);   \
   int richardson_update_##sfx(int, int, int, int, const void*, const void*, const void*,      \
                               const void*, void*, void*, void*, void*);                     \
+  int env_tables_##sfx(int, const double*, int, const void*, const void*, void* const*, void*); \
   int pnqp_##sfx(int, int, const void*, const void*, const void*, const void*, const void*,    \
                  void*, void*, int32_t*, void*, uint32_t*, int, DilqrStatus*, void*);         \
   size_t adjoint_workspace_bytes_##sfx(const DilqrAdjoint*);                                 \
@@ -102,6 +103,12 @@ int dilqr_richardson_update(int dtype, int ns, int nc, int T, int B, const void*
                             void* resid, void* st) {
   return ROUTE(dtype, dilqr::richardson_update_f32(ns, nc, T, B, g, Lam, dx, du, w, negw, resid, st),
                dilqr::richardson_update_f64(ns, nc, T, B, g, Lam, dx, du, w, negw, resid, st));
+}
+
+int dilqr_env_tables(int dtype, int dyn, const double* dp, int n, const void* x, const void* u,
+                     void* const* out, void* st) {
+  return ROUTE(dtype, dilqr::env_tables_f32(dyn, dp, n, x, u, out, st),
+               dilqr::env_tables_f64(dyn, dp, n, x, u, out, st));
 }
 
 int dilqr_pnqp(int dtype, int n, int B, const void* H, const void* q, const void* lower,

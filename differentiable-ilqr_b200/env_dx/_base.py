@@ -61,6 +61,63 @@ class EnvDx(nn.Module):
                                               _stream())
         return F, f
 
+    _n_theta = None
+
+    def get_matrices(self, x, u):
+        """The reference's get_matrices (cartpole.py:105-716 / pendulum.py:152-382 /
+        rocket.py:258-261): D, D_grad_params, D_grad_x, D_grad_u, x_grad_theta,
+        x_grad_xtm1, x_grad_utm1 for rows x[N,ns], u[N,nc]."""
+        N = x.shape[0]
+        ns, nc = self.n_state, self.n_ctrl
+        n, nth = ns + nc, len(self.params)
+        dt, dev = x.dtype, x.device
+        shapes = [(N, ns, n), (N, ns, n, nth), (N, ns, n, ns), (N, ns, n, nc), (N, ns, nth),
+                  (N, ns, ns), (N, ns, nc)]
+        outs = [torch.empty(s, dtype=dt, device=dev) for s in shapes]
+        arr = (C.c_void_p * 7)(*[o.data_ptr() for o in outs])
+        _lib.call("dilqr_env_tables", _DT[dt], self._dilqr_kind, self._theta(), N,
+                  _ptr(x.detach().contiguous()), _ptr(u.detach().to(dt).contiguous()), arr,
+                  _stream())
+        return tuple(outs)
+
+    def grad_input(self, X, U, K=None):
+        """Closed-loop parameter-sensitivity rollout (cartpole.py:717-788, pendulum.py:
+        383-443, rocket.py:263-323) returning the reference's seven tensors.  The tables
+        come from the device kernel; the short recursion over T is batched device glue
+        (the backward pass proper never materialises these tensors, see
+        csrc/dilqr_backward.cuh)."""
+        T, B, ns = X.shape
+        nc = U.shape[2]
+        n = ns + nc
+        D, Dth, Dx, Du, xth, xx, xu = self.get_matrices(X.reshape(T * B, ns), U.reshape(T * B, nc))
+        nth = Dth.shape[-1]
+        D, Dth = D.reshape(T, B, ns, n), Dth.reshape(T, B, ns, n, nth)
+        Dx, Du = Dx.reshape(T, B, ns, n, ns), Du.reshape(T, B, ns, n, nc)
+        xth, xx, xu = xth.reshape(T, B, ns, nth), xx.reshape(T, B, ns, ns), xu.reshape(T, B, ns, nc)
+        XU = torch.cat((X, U), -1)
+        d_x = torch.einsum("tbnmk,tbm->tbnk", -Dx, XU)
+        d_u = torch.einsum("tbnmk,tbm->tbnk", -Du, XU)
+        G = torch.zeros(B, ns, nth, dtype=X.dtype, device=X.device)
+        zK = torch.zeros(B, nc, ns, dtype=X.dtype, device=X.device)
+        grad_D, grad_d = [], []
+        Gm1 = None
+        Ktm1 = zK
+        for t in range(T):
+            Kt = zK if K is None else K[t]
+            if t > 0:
+                Ktm1 = zK if K is None else K[t - 1]
+                Gm1 = G
+                G = xth[t] + torch.matmul(xx[t] + torch.matmul(xu[t], Ktm1), G)
+            if t < T - 1:
+                grad_D.append(Dth[t] + torch.matmul(Dx[t] + torch.matmul(Du[t], Kt.unsqueeze(1)),
+                                                    G.unsqueeze(1)))
+            if t > 0:
+                Z = torch.cat((Gm1, torch.matmul(Ktm1, Gm1)), 1)
+                grad_d.append(G - torch.einsum("bnmk,bm->bnk", grad_D[t - 1], XU[t - 1])
+                              - torch.matmul(D[t - 1], Z))
+        return (torch.stack(grad_D), torch.stack(grad_d), Dx[:T - 1], Du[:T - 1], D[:T - 1],
+                d_x[:T - 1], d_u[:T - 1])
+
     def get_true_obj(self):
         q = torch.cat((self.goal_weights, self.ctrl_penalty * torch.ones(self.n_ctrl)))
         px = -torch.sqrt(self.goal_weights) * self.goal_state

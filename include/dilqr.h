@@ -223,6 +223,13 @@ int dilqr_richardson_update(int dtype, int n_state, int n_ctrl, int T, int n_bat
                             const void* Lam, const void* dx, const void* du, void* w, void* negw,
                             void* resid, void* stream);
 
+/* get_matrices (cartpole.py:105-716, pendulum.py:152-382, rocket.py:258-261) as
+ * materialised tensors for n sample rows x[n,ns], u[n,nc]; out[0..6] =
+ * D[n,ns,N], D_grad_params[n,ns,N,nth], D_grad_x[n,ns,N,ns], D_grad_u[n,ns,N,nc],
+ * x_grad_theta[n,ns,nth], x_grad_xtm1[n,ns,ns], x_grad_utm1[n,ns,nc]. */
+int dilqr_env_tables(int dtype, int dynamics, const double* dyn_params, int n, const void* x,
+                     const void* u, void* const* out, void* stream);
+
 /* Adjoint (KKT) LQR solves of the DiLQR backward for env_dx dynamics, factored
  * once and replayed per Richardson pass (lqr_step_explicit.py:276-303 restated;
  * see csrc/adjoint_kernels.cuh).  F_t = D(x*_t,u*_t) is re-derived on the fly. */

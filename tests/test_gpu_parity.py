@@ -347,3 +347,26 @@ def test_util_helpers(dilqr, port, env, dev):
     x = dilqr.util.get_traj(20, u.to(dev), x0.to(dev), gdx)
     cost = dilqr.util.get_cost(20, u.to(dev), dilqr.QuadCost(C.to(dev), c.to(dev)), x=x)
     assert rel(x, xr) < 1e-13 and rel(cost, cr) < 1e-13
+
+
+@pytest.mark.parametrize("name", ["pendulum", "cartpole", "rocket"])
+def test_get_matrices_and_grad_input(port, env, dev, name):
+    """get_matrices vs the reference's outputs (golden, incl. the entries that are not
+    true derivatives) and grad_input vs the oracle restatement."""
+    g = golden("ref_tables.npz")
+    x, u, th = g[name + "_x"].to(dev), g[name + "_u"].to(dev), g[name + "_theta"].to(dev)
+    dx = {"cartpole": env.CartpoleDx, "pendulum": env.PendulumDx, "rocket": env.RocketDx}[name](th)
+    out = dx.get_matrices(x, u)
+    for nm, a in zip(["D", "D_theta", "D_x", "D_u", "x_theta", "x_x", "x_u"], out):
+        assert rel(a, g[name + "_" + nm]) < 1e-12, nm
+    pdx = {"pendulum": port.PendulumDx, "cartpole": port.CartpoleDx,
+           "rocket": port.RocketDx}[name](params=g[name + "_theta"], dtype=torch.float64)
+    T, B = 3, 2
+    X = g[name + "_x"].reshape(T, B, -1)
+    U = g[name + "_u"].reshape(T, B, -1)
+    gen = torch.Generator().manual_seed(2)
+    K = 0.3 * torch.randn(T, B, pdx.n_ctrl, pdx.n_state, generator=gen, dtype=torch.float64)
+    ref = port.grad_input(pdx, X, U, K)
+    got = dx.grad_input(X.to(dev), U.to(dev), K.to(dev))
+    for a, b in zip(got, ref):
+        assert rel(a, b) < 1e-11
