@@ -122,7 +122,7 @@ def run_b200(args):
     x0_h, uexp_h = x0_h.pin_memory(), uexp_h.pin_memory()
     theta_h = torch.tensor(THETA, dtype=dtype).pin_memory()
     step = il.ImitationStep(env.CartpoleDx, T=T_H, lqr_iter=LQR_ITER, dtype=dtype, device=dev,
-                            n_richardson=args.richardson)
+                            n_richardson=args.richardson, tile=not args.broadcast_cost)
     q_h, p_h = [t.to(dtype).pin_memory() for t in env.CartpoleDx().get_true_obj()]
 
     # resident inputs for the device-timed `value`
@@ -203,6 +203,7 @@ def run_b200(args):
                 "parallelism": "batch-sharded x%d, no data-path collective" % world,
                 "roofline_frac_of_solve": value / world * tot_b / (hbm * 1e9),
                 "bytes_per_solve": tot_b, "richardson_passes": args.richardson,
+                "cost_layout": "broadcast [n,n]" if args.broadcast_cost else "dense [T,B,n,n]",
                 "trace_retries": step.retries,
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
@@ -305,6 +306,9 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=2048)
     ap.add_argument("--richardson", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--broadcast-cost", action="store_true",
+                    help="hand MPC the [n,n]/[n] cost (mpc.py:205-219 broadcast) instead of the "
+                         "dense [T,B,n,n] tiling of il_env.py:159-162 (not the headline config)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

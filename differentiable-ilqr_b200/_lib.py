@@ -40,6 +40,13 @@ class DilqrStatus(C.Structure):
     ]
 
 
+class DilqrControl(C.Structure):
+    _fields_ = [
+        ("halt", C.c_uint32), ("iters_done", C.c_uint32), ("n_not_improved", C.c_uint32),
+        ("not_improved_lim", C.c_uint32), ("eps", C.c_double), ("reserved", C.c_uint32 * 10),
+    ]
+
+
 class DilqrSolve(C.Structure):
     _fields_ = [
         ("n_state", C.c_int32), ("n_ctrl", C.c_int32), ("T", C.c_int32),
@@ -47,7 +54,8 @@ class DilqrSolve(C.Structure):
         ("dtype", C.c_int32), ("dynamics", C.c_int32), ("gain_solve", C.c_int32),
         ("bounds_kind", C.c_int32), ("solo", C.c_int32),
         ("max_linesearch_iter", C.c_int32), ("iteration", C.c_int32),
-        ("has_f", C.c_int32), ("gains_only", C.c_int32), ("lockstep", C.c_int32),
+        ("has_f", C.c_int32), ("gains_only", C.c_int32), ("C_bcast", C.c_int32),
+        ("c_bcast", C.c_int32), ("lockstep", C.c_int32),
         ("linesearch_decay", C.c_double),
         ("u_lower", C.c_double), ("u_upper", C.c_double),
         ("best_cost_eps", C.c_double),
@@ -59,7 +67,7 @@ class DilqrSolve(C.Structure):
         ("x_out", C.c_void_p), ("u_out", C.c_void_p), ("cost_out", C.c_void_p),
         ("du_out", C.c_void_p), ("alpha_out", C.c_void_p), ("K_out", C.c_void_p),
         ("k_out", C.c_void_p),
-        ("status", C.c_void_p),
+        ("status", C.c_void_p), ("control", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]
 
@@ -80,7 +88,7 @@ class DilqrAdjoint(C.Structure):
     _fields_ = [
         ("n_state", C.c_int32), ("n_ctrl", C.c_int32), ("T", C.c_int32), ("n_batch", C.c_int32),
         ("dtype", C.c_int32), ("dynamics", C.c_int32), ("bounds_kind", C.c_int32),
-        ("gain_solve", C.c_int32),
+        ("gain_solve", C.c_int32), ("C_bcast", C.c_int32), ("c_bcast", C.c_int32),
         ("u_lower", C.c_double), ("u_upper", C.c_double), ("dyn_params", C.c_double * 8),
         ("C", C.c_void_p), ("x", C.c_void_p), ("u", C.c_void_p), ("g", C.c_void_p),
         ("Lam", C.c_void_p), ("w", C.c_void_p), ("dC", C.c_void_p), ("dc", C.c_void_p),
@@ -109,7 +117,7 @@ SYMBOLS = {
     "dilqr_pnqp": (C.c_int, [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 10 + [C.c_int]
                    + [C.c_void_p] * 2),
     "dilqr_costate_tables": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int]
-                             + [C.c_void_p] * 7),
+                             + [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_void_p]),
     "dilqr_richardson_update": (C.c_int, [C.c_int] * 5 + [C.c_void_p] * 8),
     "dilqr_sens_theta": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int]
                          + [C.c_void_p] * 9),
@@ -162,7 +170,7 @@ def check(code, what):
 
 # kernels enqueued per C-ABI call (memsets not counted)
 KERNELS_PER_CALL = {
-    "dilqr_mpc_begin": 1, "dilqr_mpc_iterate": 1, "dilqr_mpc_commit": 2,
+    "dilqr_mpc_begin": 1, "dilqr_mpc_iterate": 1, "dilqr_mpc_commit": 3,
     "dilqr_mpc_finish": 1, "dilqr_kkt_grads": 1, "dilqr_linearize": 1, "dilqr_rollout": 1,
     "dilqr_costate_tables": 1, "dilqr_richardson_update": 1, "dilqr_sens_theta": 1,
     "dilqr_adjoint_factor": 1, "dilqr_adjoint_pass": 1, "dilqr_adjoint_final": 1,

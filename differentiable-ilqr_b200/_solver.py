@@ -43,13 +43,19 @@ class SolveInfo:
         self.full_du_norm = None
 
 
+MAX_PIPELINED_ITERS = 1024
+
+
 class Workspace:
-    """Device scratch + status block for one (shape, dtype) family; reused."""
+    """Device scratch + status / control blocks for one (shape, dtype) family; reused."""
 
     def __init__(self, nbytes, device):
         self.buf = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=device)
         self.status_dev = torch.zeros(64, dtype=torch.uint8, device=device)
         self.status_host = torch.zeros(64, dtype=torch.uint8).pin_memory()
+        # pipelined outer loop: [control block | one status block per iteration]
+        self.pipe_dev = torch.zeros(64 * (1 + MAX_PIPELINED_ITERS), dtype=torch.uint8, device=device)
+        self.pipe_host = torch.zeros(64 * (1 + MAX_PIPELINED_ITERS), dtype=torch.uint8).pin_memory()
 
 
 _ws_cache = {}
@@ -65,6 +71,33 @@ def _require_cuda(t, name):
 
 def _contig(t):
     return t if t is None or t.is_contiguous() else t.contiguous()
+
+
+def cost_layout(t, T, B, tail_ndim):
+    """Classify a cost tensor handed to the solver (mpc.py:205-219 accepts C[n,n],
+    C[T,n,n], C[T,B,n,n] and expands with stride 0).  Returns (mode, base) with
+    mode 0: dense [T,B,..] contiguous; 1: batch-broadcast, base [T,..]; 2: base [..]."""
+    t = t.detach()
+    if t.ndimension() == tail_ndim:
+        return 2, t.contiguous()
+    if t.ndimension() == tail_ndim + 1:
+        return 1, t.contiguous()
+    st = t.stride()
+    if t.shape[1] > 1 and st[1] == 0:
+        if st[0] == 0:
+            return 2, t[0, 0].contiguous()
+        return 1, t[:, 0].contiguous()
+    return 0, t.contiguous()
+
+
+def dense_cost(t, T, B, tail_ndim):
+    """Materialise any accepted cost layout as [T,B,..] (generic / LinDx-KKT paths)."""
+    t = t.detach()
+    if t.ndimension() == tail_ndim:
+        t = t.unsqueeze(0).unsqueeze(0)
+    elif t.ndimension() == tail_ndim + 1:
+        t = t.unsqueeze(1)
+    return t.expand(T, B, *t.shape[2:]).contiguous()
 
 
 def _make_problem(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower, u_upper, u_zero_I,
@@ -98,7 +131,11 @@ def _make_problem(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower, u_upper, u_z
         return t
 
     xi = dev(x_init, "x_init")
-    Cd, cd = dev(C_, "C"), dev(c_, "c")
+    _require_cuda(C_, "C")
+    _require_cuda(c_, "c")
+    s.C_bcast, Cd = cost_layout(C_.to(dtype), T, B, 2)
+    s.c_bcast, cd = cost_layout(c_.to(dtype), T, B, 1)
+    keep.extend((Cd, cd))
     s.x_init, s.C, s.c = _ptr(xi), _ptr(Cd), _ptr(cd)
     if dyn.kind == _lib.DYN_LINDX:
         Fd = dev(dyn.F, "F")
@@ -174,11 +211,60 @@ def _iterate_committed(L, s, ws, info, sync=True):
     raise _lib.DilqrLibraryError("pnqp control-flow trace did not stabilise")
 
 
+def _solve_pipelined(L, s, ws, info, n_loops, eps_cmp, not_improved_lim, verbose):
+    """Outer iLQR loop with the stop rule and the trace check on the device
+    (DilqrControl): all iterations are enqueued back to back, ONE host sync at the
+    end; a wrong pnqp trace guess halts the queue and the loop resumes from there."""
+    st = _stream()
+    ctrl = _lib.DilqrControl()
+    ctrl.eps = eps_cmp
+    ctrl.not_improved_lim = not_improved_lim
+    ws.pipe_host[:64].copy_(torch.frombuffer(bytearray(bytes(ctrl)), dtype=torch.uint8))
+    ws.pipe_dev[:64].copy_(ws.pipe_host[:64], non_blocking=True)
+    base = ws.pipe_dev.data_ptr()
+    s.control = C.c_void_p(base)
+    start = 0
+    nbytes = 64 * (1 + n_loops)
+    for _ in range(MAX_TRACE_RETRIES * 4):
+        for j in range(start, n_loops):
+            s.iteration = j
+            s.status = C.c_void_p(base + 64 * (1 + j))
+            _lib.call("dilqr_mpc_iterate", C.byref(s), st)
+            _lib.call("dilqr_mpc_commit", C.byref(s), st)
+        ws.pipe_host[:nbytes].copy_(ws.pipe_dev[:nbytes], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        raw = ws.pipe_host[:nbytes].numpy().tobytes()
+        c = _lib.DilqrControl.from_buffer_copy(raw[:64])
+        if c.halt == 2:                      # trace mismatch: redo iteration c.iters_done
+            info.retries += 1
+            start = c.iters_done
+            ws.pipe_dev[:4].zero_()
+            continue
+        break
+    else:
+        raise _lib.DilqrLibraryError("pnqp control-flow trace did not stabilise")
+    n_done = c.iters_done
+    for j in range(n_done):
+        stt = _lib.DilqrStatus.from_buffer_copy(raw[64 * (1 + j):64 * (2 + j)])
+        info.qp_iters.append(stt.n_total_qp_iter)
+        info.pnqp_unconverged += stt.pnqp_unconverged
+        info.log.append((stt.n_total_qp_iter, stt.max_full_du, stt.mean_alpha, stt.mean_best_cost))
+        if stt.pnqp_unconverged and verbose >= 0:
+            for _ in range(stt.pnqp_unconverged):
+                print("[WARNING] pnqp warning: Did not converge")   # pnqp.py:81
+        info.max_full_du, info.mean_alpha = stt.max_full_du, stt.mean_alpha
+        info.mean_best_cost = stt.mean_best_cost
+    info.n_iters = n_done
+    s.iteration = n_done - 1
+    s.control = None
+    s.status = _ptr(ws.status_dev)
+
+
 def solve_mpc(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower=None, u_upper=None,
               u_zero_I=None, u_init=None, lqr_iter=10, eps=1e-7, linesearch_decay=0.2,
               max_linesearch_iter=10, not_improved_lim=5, best_cost_eps=1e-4,
               gain_solve=_lib.GAIN_PLAIN, solo=False, verbose=0, x_cur=None,
-              want_gains=False, sync=True, gains_only=False):
+              want_gains=False, sync=True, gains_only=False, pipelined=True):
     """MPC.forward (mpc.py:184-306): returns (x, u, costs, info).  With ``x_cur``
     given this is a single LQRStep around (x_cur, u_init) (lqr_step.py:277-309)
     and returns the *new* iterate."""
@@ -209,6 +295,9 @@ def solve_mpc(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower=None, u_upper=Non
     n_not_improved = 0
     n_loops = 1 if x_cur is not None else lqr_iter
     nosync = (not sync) and n_loops == 1 and (s.bounds_kind == _lib.BOUNDS_NONE or solo)
+    if pipelined and n_loops > 1 and n_loops <= MAX_PIPELINED_ITERS and verbose <= 0:
+        _solve_pipelined(L, s, ws, info, n_loops, eps_cmp, not_improved_lim, verbose)
+        n_loops = 0
     for i in range(n_loops):
         s.iteration = i
         status = _iterate_committed(L, s, ws, info, sync=not nosync)
@@ -320,14 +409,20 @@ def dilqr_backward(dl_dx, dl_du, x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u
     theta = dxmod._theta()
     x = x.detach().contiguous()
     u = u.detach().contiguous()
-    C_ = _contig(C_.detach())
-    c_ = _contig(c_.detach())
     scalar_bounds = u_lower is None or (isinstance(u_lower, float) and isinstance(u_upper, float))
     if not scalar_bounds or kind == _lib.DYN_ROCKET:
         factored = False      # factored adjoint kernels: pendulum / cartpole only (round 1)
+    # cost layout: dense [T,B,..] or broadcast (C[n,n] / C[T,n,n]); the generic path
+    # (LinDx kernels + kkt_grads) wants dense tensors
+    C_in, c_in = C_, c_
+    Cb, C_ = cost_layout(C_in.to(dtype), T, B, 2)
+    cb, c_ = cost_layout(c_in.to(dtype), T, B, 1)
+    if not factored and (Cb or cb):
+        C_, c_ = dense_cost(C_in.to(dtype), T, B, 2), dense_cost(c_in.to(dtype), T, B, 1)
+        Cb = cb = 0
     # (1) gains of the final no-op LQR pass at tau* (lqr_step_explicit.py:604-618)
     dyn = DynSpec(kind, params=list(theta))
-    _, _, _, info = solve_mpc(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower=u_lower,
+    _, _, _, info = solve_mpc(x_init, C_in, c_in, dyn, n_state, n_ctrl, T, u_lower=u_lower,
                               u_upper=u_upper, u_init=u, x_cur=x, lqr_iter=1, max_linesearch_iter=1,
                               solo=solo, verbose=-1, gains_only=True)
     K = info.K
@@ -335,15 +430,18 @@ def dilqr_backward(dl_dx, dl_du, x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u
     lam = torch.empty(T, B, n_state, dtype=dtype, device=dev)
     Lam = torch.empty(T - 1, B, n, n, dtype=dtype, device=dev)
     _lib.call("dilqr_costate_tables", _DT[dtype], kind, theta, T, B, _ptr(C_), _ptr(c_), _ptr(x),
-              _ptr(u), _ptr(lam), _ptr(Lam), _stream())
+              _ptr(u), _ptr(lam), _ptr(Lam), Cb, cb, _stream())
     g = torch.cat((dl_dx, dl_du), 2).contiguous()
     w = g.clone()
     resid = torch.zeros(3, dtype=torch.float64, device=dev)
     passes = 0
     rel = None
     nth = len(dxmod.params)
-    dC = torch.empty(T, B, n, n, dtype=dtype, device=dev)
-    dc = torch.empty(T, B, n, dtype=dtype, device=dev)
+    # gradients of a broadcast cost come back as per-warp partial sums (summed below)
+    nwarp = (B + 31) // 32
+    dC = torch.empty({0: (T, B, n, n), 1: (T, nwarp, n, n), 2: (nwarp, n, n)}[Cb], dtype=dtype,
+                     device=dev)
+    dc = torch.empty({0: (T, B, n), 1: (T, nwarp, n), 2: (nwarp, n)}[cb], dtype=dtype, device=dev)
     df = torch.empty(T - 1, B, n_state, dtype=dtype, device=dev)
 
     def converged():
@@ -355,6 +453,7 @@ def dilqr_backward(dl_dx, dl_du, x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u
         a.n_state, a.n_ctrl, a.T, a.n_batch, a.dtype, a.dynamics = n_state, n_ctrl, T, B, _DT[dtype], kind
         a.bounds_kind = _lib.BOUNDS_NONE if u_lower is None else _lib.BOUNDS_SCALAR
         a.gain_solve = _lib.GAIN_CHOL_REG
+        a.C_bcast, a.c_bcast = Cb, cb
         if u_lower is not None:
             a.u_lower, a.u_upper = u_lower, u_upper
         for i in range(8):
@@ -422,4 +521,8 @@ def dilqr_backward(dl_dx, dl_du, x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u
         stats["passes"] = passes
         stats["resid"] = rel
         stats["factored"] = factored
+    if Cb:
+        dC = dC.sum(1 if Cb == 1 else 0)
+    if cb:
+        dc = dc.sum(1 if cb == 1 else 0)
     return dC, dc, dtheta

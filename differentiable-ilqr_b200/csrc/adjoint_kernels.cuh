@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include "dynamics.cuh"
 #include "smallmat.cuh"
+#include "ilqr_kernels.cuh"
 #include "../../include/dilqr.h"
 
 namespace dilqr {
@@ -43,6 +44,9 @@ struct AdjParams {
   int bounds_kind;   // 0: no active set; 1: scalar bounds -> I = |u - bound| <= 1e-8
   int gain_solve;
   int final_pass;
+  int C_bcast, c_bcast;  // cost layout (0 dense, 1 [T,..], 2 [..]); for a broadcast C (c) the
+                         // final pass writes per-warp partial sums of dC (dc) -- layout
+                         // [T][n_warps][..] (mode 1) or [n_warps][..] (mode 2) -- instead of slabs
   S lo, hi;
   const S* C;
   const S* x;
@@ -111,10 +115,10 @@ __global__ void __launch_bounds__(128) adjoint_factor_kernel(const __grid_consta
   char* wbase = smem + warp * per_warp;
   WarpStager<S> st;
   st.init(wbase + kStages * sizeof(uint64_t), reinterpret_cast<uint64_t*>(wbase), lane, nvalid, 1,
-          elems);
+          elems, 0, p.C_bcast ? 1u : 0u);
   const int T = p.T;
   auto issue = [&](int stage, int t) {
-    const S* src[1] = {p.C + ((size_t)t * p.B + b0) * (N * N)};
+    const S* src[1] = {cost_src<S>(p.C, p.C_bcast, t, p.B, b0, N * N)};
     st.issue(stage, src, 1);
   };
   S V[NS][NS], xnext[NS];
@@ -513,12 +517,28 @@ __global__ void __launch_bounds__(64) adjoint_pass_kernel(const __grid_constant_
   asm volatile("fence.proxy.async;" ::: "memory");
   __syncwarp();
   auto issue_b = [&](int stage, int t) {
-    const S* src[AS::kNSeg] = {slab(p.C, t, N * N), slab(p.w, t, N), slab(p.x, t, NS),
-                               slab(p.u, t, NC), nullptr, p.dtau + bidx(t, 0, N, b0, nW)};
+    const S* src[AS::kNSeg] = {cost_src<S>(p.C, p.C_bcast, t, p.B, b0, N * N), slab(p.w, t, N),
+                               slab(p.x, t, NS), slab(p.u, t, NC), nullptr,
+                               p.dtau + bidx(t, 0, N, b0, nW)};
     st.issue(stage, src, AS::kNSeg);
   };
   const bool bulk_out = (nvalid == kWarp) && ((((size_t)N * N * sizeof(S) * kWarp) & 15) == 0) &&
-                        ((((size_t)N * sizeof(S) * kWarp) & 15) == 0);
+                        ((((size_t)N * sizeof(S) * kWarp) & 15) == 0) &&
+                        (p.C_bcast == 0 || p.c_bcast == 0);
+  const int gwarp = b0 / kWarp;
+  auto warp_sum = [&](S v) -> S {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = v + __shfl_xor_sync(kFull, v, o);
+    return v;
+  };
+  S accC[N][N], accc[N];   // mode-2 accumulators (sum over t of this lane's contributions)
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    accc[i] = S(0);
+#pragma unroll
+    for (int j = 0; j < N; ++j) accC[i][j] = S(0);
+  }
+  st.seg_shared = p.C_bcast ? 1u : 0u;   // segment 0 now carries C
   S dlam[NS];
   issue_b(0, T - 1);
   for (int t = T - 1; t >= 0; --t) {
@@ -542,31 +562,63 @@ __global__ void __launch_bounds__(64) adjoint_pass_kernel(const __grid_constant_
 #pragma unroll
       for (int i = 0; i < NS; ++i) p.df[tb * NS + i] = -dlam[i];
     }
-    // outputs through shared memory, one bulk store per warp slab
+    // dense outputs go through shared memory, one bulk store per warp slab
     if (bulk_out) {
       bulk_wait_read0();
       __syncwarp();
     }
-    S* oC = bulk_out ? outC + lane * (N * N) : p.dC + tb * (N * N);
-    S* oc = bulk_out ? outc + lane * N : p.dc + tb * N;
-    if (act || bulk_out) {
-      if (p.dC) {
+    if (p.dC) {
+      if (p.C_bcast == 0) {
+        S* oC = bulk_out ? outC + lane * (N * N) : p.dC + tb * (N * N);
+        if (act || bulk_out) {
+#pragma unroll
+          for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int j = 0; j < N; ++j) oC[i * N + j] = S(-0.5) * (dtv[i] * tt[j] + tt[i] * dtv[j]);
+        }
+      } else {   // gradient of a broadcast C: sum over the batch (and time)
 #pragma unroll
         for (int i = 0; i < N; ++i)
 #pragma unroll
-          for (int j = 0; j < N; ++j) oC[i * N + j] = S(-0.5) * (dtv[i] * tt[j] + tt[i] * dtv[j]);
+          for (int j = 0; j < N; ++j) {
+            const S v = act ? S(-0.5) * (dtv[i] * tt[j] + tt[i] * dtv[j]) : S(0);
+            if (p.C_bcast == 2) {
+              accC[i][j] = accC[i][j] + v;
+            } else {
+              const S r = warp_sum(v);
+              if (lane == 0) p.dC[((size_t)t * gridDim.x * wpb + gwarp) * (N * N) + i * N + j] = r;
+            }
+          }
       }
-      if (p.dc) {
+    }
+    if (p.dc) {
+      if (p.c_bcast == 0) {
+        S* oc = bulk_out ? outc + lane * N : p.dc + tb * N;
+        if (act || bulk_out) {
 #pragma unroll
-        for (int i = 0; i < N; ++i) oc[i] = -dtv[i];
+          for (int i = 0; i < N; ++i) oc[i] = -dtv[i];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          const S v = act ? -dtv[i] : S(0);
+          if (p.c_bcast == 2) {
+            accc[i] = accc[i] + v;
+          } else {
+            const S r = warp_sum(v);
+            if (lane == 0) p.dc[((size_t)t * gridDim.x * wpb + gwarp) * N + i] = r;
+          }
+        }
       }
     }
     if (bulk_out) {
       fence_async_smem();
       __syncwarp();
       if (lane == 0) {
-        if (p.dC) bulk_s2g(p.dC + ((size_t)t * p.B + b0) * (N * N), outC, kWarp * N * N * sizeof(S));
-        if (p.dc) bulk_s2g(p.dc + ((size_t)t * p.B + b0) * N, outc, kWarp * N * sizeof(S));
+        if (p.dC && p.C_bcast == 0)
+          bulk_s2g(p.dC + ((size_t)t * p.B + b0) * (N * N), outC, kWarp * N * N * sizeof(S));
+        if (p.dc && p.c_bcast == 0)
+          bulk_s2g(p.dc + ((size_t)t * p.B + b0) * N, outc, kWarp * N * sizeof(S));
         bulk_commit();
       }
     }
@@ -598,6 +650,22 @@ __global__ void __launch_bounds__(64) adjoint_pass_kernel(const __grid_constant_
     }
   }
   if (bulk_out) bulk_wait0();
+  if (p.dC && p.C_bcast == 2) {
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const S r = warp_sum(accC[i][j]);
+        if (lane == 0) p.dC[(size_t)gwarp * (N * N) + i * N + j] = r;
+      }
+  }
+  if (p.dc && p.c_bcast == 2) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const S r = warp_sum(accc[i]);
+      if (lane == 0) p.dc[(size_t)gwarp * N + i] = r;
+    }
+  }
 }
 
 }  // namespace dilqr

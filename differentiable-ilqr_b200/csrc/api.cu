@@ -146,10 +146,14 @@ static IterParams<Scalar> make_params(const DilqrSolve* s, int role = 1) {
   p.dusq = reinterpret_cast<S*>(ws + w.dusq);
   p.take = reinterpret_cast<int*>(ws + w.take);
   p.gains_only = s->gains_only;
+  p.C_bcast = s->C_bcast;
+  p.c_bcast = s->c_bcast;
   p.lockstep = s->lockstep;
   p.guess = reinterpret_cast<uint32_t*>(ws + w.guess);
   p.votes = reinterpret_cast<uint32_t*>(ws + w.votes);
   p.status = s->status;
+  p.control = s->control;
+  p.halt = s->control ? &s->control->halt : nullptr;
   p.x_out = static_cast<S*>(s->x_out);
   p.u_out = static_cast<S*>(s->u_out);
   p.cost_out = static_cast<S*>(s->cost_out);
@@ -167,6 +171,7 @@ static int check(const DilqrSolve* s, bool need_ws) {
   if (s->dynamics == DILQR_DYN_LINDX && s->T > 1 && !s->F) return DILQR_EINVAL;
   if (s->bounds_kind == DILQR_BOUNDS_TENSOR && (!s->u_lower_t || !s->u_upper_t)) return DILQR_EINVAL;
   if (s->bounds_kind < 0 || s->bounds_kind > 2) return DILQR_EINVAL;
+  if (s->C_bcast < 0 || s->C_bcast > 2 || s->c_bcast < 0 || s->c_bcast > 2) return DILQR_EINVAL;
   auto mis = [](const void* p) { return p && (reinterpret_cast<uintptr_t>(p) & 15u); };
   if (mis(s->C) || mis(s->c) || mis(s->F) || mis(s->f) || mis(s->workspace)) return DILQR_EALIGN;
   if (need_ws) {
@@ -256,8 +261,9 @@ static int launch_commit(const DilqrSolve* s, cudaStream_t st) {
   using S = Scalar;
   IterParams<S> p = make_params(s);
   trace_verify_kernel<<<1, 256, 0, st>>>(p.guess, p.votes, p.T, p.bounds_kind != 0, p.solo,
-                                         s->status, p.lockstep);
+                                         s->status, p.lockstep, s->control);
   commit_kernel<S, NS + NC, NC><<<(p.B + 127) / 128, 128, 0, st>>>(p);
+  if (s->control) control_kernel<<<1, 1, 0, st>>>(s->control, s->status, s->iteration);
   return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
 }
 
@@ -482,6 +488,8 @@ static int adj_run(const DilqrAdjoint* a, int what, cudaStream_t st) {
   p.bounds_kind = a->bounds_kind;
   p.gain_solve = a->gain_solve;
   p.final_pass = what == 2;
+  p.C_bcast = a->C_bcast;
+  p.c_bcast = a->c_bcast;
   p.lo = (S)a->u_lower;
   p.hi = (S)a->u_upper;
   p.C = static_cast<const S*>(a->C);
@@ -557,7 +565,8 @@ int DILQR_SUFFIX(adjoint_run)(const DilqrAdjoint* a, int what, void* stream) {
 // ------------------------------------------------- DiLQR implicit backward
 template <int DYN>
 static int launch_costate(const double* dp, int T, int B, const void* C, const void* c,
-                          const void* x, const void* u, void* lam, void* Lam, cudaStream_t st) {
+                          const void* x, const void* u, void* lam, void* Lam, int Cb, int cb,
+                          cudaStream_t st) {
   using S = Scalar;
   DynParams<S> P;
   for (int i = 0; i < 8; ++i) P.p[i] = (S)dp[i];
@@ -569,18 +578,19 @@ static int launch_costate(const double* dp, int T, int B, const void* C, const v
   const int warps = (B + kWarp - 1) / kWarp;
   kern<<<(warps + wpb - 1) / wpb, wpb * kWarp, smem, st>>>(
       P, T, B, static_cast<const S*>(C), static_cast<const S*>(c), static_cast<const S*>(x),
-      static_cast<const S*>(u), static_cast<S*>(lam), static_cast<S*>(Lam));
+      static_cast<const S*>(u), static_cast<S*>(lam), static_cast<S*>(Lam), Cb, cb);
   return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
 }
 
 int DILQR_SUFFIX(costate_tables)(int dynamics, const double* dp, int T, int B, const void* C,
                                  const void* c, const void* x, const void* u, void* lam,
-                                 void* Lam, void* stream) {
+                                 void* Lam, int Cb, int cb, void* stream) {
   if (!dp || !C || !c || !x || !u || !lam || !Lam || T <= 0 || B <= 0) return DILQR_EINVAL;
+  if (Cb < 0 || Cb > 2 || cb < 0 || cb > 2) return DILQR_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dynamics == DYN_PENDULUM) return launch_costate<DYN_PENDULUM>(dp, T, B, C, c, x, u, lam, Lam, st);
-  if (dynamics == DYN_CARTPOLE) return launch_costate<DYN_CARTPOLE>(dp, T, B, C, c, x, u, lam, Lam, st);
-  if (dynamics == DYN_ROCKET) return launch_costate<DYN_ROCKET>(dp, T, B, C, c, x, u, lam, Lam, st);
+  if (dynamics == DYN_PENDULUM) return launch_costate<DYN_PENDULUM>(dp, T, B, C, c, x, u, lam, Lam, Cb, cb, st);
+  if (dynamics == DYN_CARTPOLE) return launch_costate<DYN_CARTPOLE>(dp, T, B, C, c, x, u, lam, Lam, Cb, cb, st);
+  if (dynamics == DYN_ROCKET) return launch_costate<DYN_ROCKET>(dp, T, B, C, c, x, u, lam, Lam, Cb, cb, st);
   return DILQR_EUNSUPPORTED;
 }
 

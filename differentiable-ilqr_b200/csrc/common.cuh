@@ -107,36 +107,37 @@ struct WarpStager {
   uint32_t seg_off[kMaxSeg];    // byte offset of each segment in a stage
   uint32_t seg_elems[kMaxSeg];  // scalars per problem in each segment
   uint32_t seg_full;            // bit i: segment i always holds 32 problems (workspace chunks)
+  uint32_t seg_shared;          // bit i: segment i is ONE block shared by all lanes
+                                //        (broadcast cost: C[n,n] / C[T,n,n], mpc.py:205-219)
   uint32_t parity;   // bit s = parity to wait for on stage s
-  uint32_t via_tma;  // bit s = stage s was filled by a bulk copy (else lane copies)
+  uint32_t via_tma;  // bit s = stage s has bulk copies in flight
   int nvalid;        // problems this warp really has (<= 32)
-  bool tma;          // slabs are 16B-aligned/sized -> bulk copies
   int lane;
 
   DILQR_DEVICE uint32_t seg_bytes(int i) const {
-    return seg_elems[i] * (((seg_full >> i) & 1u) ? kWarp : nvalid) * (uint32_t)sizeof(S);
+    const uint32_t cnt = ((seg_shared >> i) & 1u) ? 1u : (((seg_full >> i) & 1u) ? kWarp : nvalid);
+    return seg_elems[i] * cnt * (uint32_t)sizeof(S);
   }
 
   // `full_mask` bit i = segment i is a warp-blocked workspace chunk [elems][32]
-  // (always complete, lane-interleaved) rather than an API slab [nvalid][elems].
+  // (always complete, lane-interleaved) rather than an API slab [nvalid][elems];
+  // `shared_mask` bit i = a single [elems] block read by every lane.
   DILQR_DEVICE void init(char* smem_base, uint64_t* bars, int lane_, int nvalid_, int nseg,
-                         const uint32_t* elems, uint32_t full_mask = 0) {
+                         const uint32_t* elems, uint32_t full_mask = 0, uint32_t shared_mask = 0) {
     base = smem_base;
     seg_full = full_mask;
+    seg_shared = shared_mask;
     bar = bars;
     lane = lane_;
     nvalid = nvalid_;
     parity = 0;
     via_tma = 0;
     uint32_t off = 0;
-    tma = true;
 #pragma unroll
     for (int i = 0; i < kMaxSeg; ++i) {
       seg_off[i] = off;
       seg_elems[i] = i < nseg ? elems[i] : 0;
       uint32_t full = seg_elems[i] * kWarp * sizeof(S);
-      uint32_t now = seg_bytes(i);
-      if (now % 16u) tma = false;
       off += (full + 15u) & ~15u;
     }
     stage_bytes = off;
@@ -154,36 +155,37 @@ struct WarpStager {
     return off * kStages;
   }
 
-  // Start copying the slabs for one timestep into `stage`.  src[i] points at the
-  // first scalar of this warp's slab of segment i (or nullptr to skip).
+  // Start copying the operands of one timestep into `stage`.  src[i] points at the
+  // first scalar of this warp's slab of segment i (or nullptr to skip).  Each segment
+  // goes by one bulk (TMA) copy if its size and source are 16-byte aligned, else by a
+  // lane-strided copy.
   DILQR_DEVICE void issue(int stage, const S* const* src, int nseg) {
     char* dst = base + stage * stage_bytes;
     __syncwarp();  // all lanes are done reading this stage (WAR)
-    bool bulk = tma;   // sizes are fine; sources must be 16-byte aligned too
+    uint32_t bulk_mask = 0, total = 0;
 #pragma unroll
-    for (int i = 0; i < kMaxSeg; ++i)
-      if (i < nseg && src[i] && (reinterpret_cast<uintptr_t>(src[i]) & 15u)) bulk = false;
-    via_tma = bulk ? (via_tma | (1u << stage)) : (via_tma & ~(1u << stage));
-    if (bulk) {
-      if (lane == 0) {
-        uint32_t total = 0;
-#pragma unroll
-        for (int i = 0; i < kMaxSeg; ++i)
-          if (i < nseg && src[i]) total += seg_bytes(i);
-        mbar_expect_tx(&bar[stage], total);
-#pragma unroll
-        for (int i = 0; i < kMaxSeg; ++i)
-          if (i < nseg && src[i])
-            bulk_g2s(dst + seg_off[i], src[i], seg_bytes(i), &bar[stage]);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < kMaxSeg; ++i) {
-        if (i < nseg && src[i]) {
-          S* d = reinterpret_cast<S*>(dst + seg_off[i]);
-          const int cnt = seg_bytes(i) / sizeof(S);
-          for (int e = lane; e < cnt; e += kWarp) d[e] = __ldg(src[i] + e);
+    for (int i = 0; i < kMaxSeg; ++i) {
+      if (i < nseg && src[i]) {
+        const uint32_t nb = seg_bytes(i);
+        if (nb && !(nb & 15u) && !(reinterpret_cast<uintptr_t>(src[i]) & 15u)) {
+          bulk_mask |= 1u << i;
+          total += nb;
         }
+      }
+    }
+    via_tma = bulk_mask ? (via_tma | (1u << stage)) : (via_tma & ~(1u << stage));
+    if (bulk_mask && lane == 0) {
+      mbar_expect_tx(&bar[stage], total);
+#pragma unroll
+      for (int i = 0; i < kMaxSeg; ++i)
+        if ((bulk_mask >> i) & 1u) bulk_g2s(dst + seg_off[i], src[i], seg_bytes(i), &bar[stage]);
+    }
+#pragma unroll
+    for (int i = 0; i < kMaxSeg; ++i) {
+      if (i < nseg && src[i] && !((bulk_mask >> i) & 1u)) {
+        S* d = reinterpret_cast<S*>(dst + seg_off[i]);
+        const int cnt = seg_bytes(i) / sizeof(S);
+        for (int e = lane; e < cnt; e += kWarp) d[e] = __ldg(src[i] + e);
       }
     }
   }
@@ -192,9 +194,8 @@ struct WarpStager {
     if ((via_tma >> stage) & 1u) {
       mbar_wait(&bar[stage], (parity >> stage) & 1u);
       parity ^= (1u << stage);
-    } else {
-      __syncwarp();
     }
+    __syncwarp();   // lane-copied segments
   }
 
   // Base of segment i in `stage` (blocked chunks: element e of this lane is [e*32+lane]).
@@ -205,7 +206,7 @@ struct WarpStager {
   // Pointer to this lane's block of segment i in `stage`.
   DILQR_DEVICE const S* lane_ptr(int stage, int seg) const {
     return reinterpret_cast<const S*>(base + stage * stage_bytes + seg_off[seg]) +
-           lane * seg_elems[seg];
+           (((seg_shared >> seg) & 1u) ? 0 : lane * seg_elems[seg]);
   }
 };
 

@@ -55,7 +55,7 @@ template <class S, int DYN>
 __global__ void __launch_bounds__(64)
 costate_tables_kernel(DynParams<S> P, int T, int B, const S* __restrict__ C,
                       const S* __restrict__ c, const S* __restrict__ x, const S* __restrict__ u,
-                      S* __restrict__ lam_out, S* __restrict__ Lam_out) {
+                      S* __restrict__ lam_out, S* __restrict__ Lam_out, int C_bcast, int c_bcast) {
   using D = Dyn<S, DYN>;
   using TB = EnvTables<S, DYN>;
   using CS = CostateStage<S, DYN>;
@@ -73,12 +73,13 @@ costate_tables_kernel(DynParams<S> P, int T, int B, const S* __restrict__ C,
     uint32_t e[CS::kNSeg];
     CS::seg_elems(e);
     st.init(wbase + kStages * sizeof(uint64_t), reinterpret_cast<uint64_t*>(wbase), lane, nvalid,
-            CS::kNSeg, e);
+            CS::kNSeg, e, 0, (C_bcast ? 1u : 0u) | (c_bcast ? 2u : 0u));
   }
   S* outL = reinterpret_cast<S*>(wbase + CS::smem_per_warp() - CS::out_bytes());
   auto issue = [&](int stage, int t) {
     const size_t o = (size_t)t * B + b0;
-    const S* src[CS::kNSeg] = {C + o * (N * N), c + o * N, x + o * NS, u + o * NC};
+    const S* src[CS::kNSeg] = {cost_src<S>(C, C_bcast, t, B, b0, N * N),
+                               cost_src<S>(c, c_bcast, t, B, b0, N), x + o * NS, u + o * NC};
     st.issue(stage, src, CS::kNSeg);
   };
   const bool bulk_out = (nvalid == kWarp) && ((((size_t)N * N * sizeof(S) * kWarp) & 15) == 0);

@@ -16,7 +16,7 @@ namespace dilqr {
                       void*);                                                             \
   int rollout_##sfx(int, const double*, int, int, const void*, const void*, void*, void*);     \
   int costate_tables_##sfx(int, const double*, int, int, const void*, const void*, const void*, \
-                           const void*, void*, void*, void*);                               \
+                           const void*, void*, void*, int, int, void*);                               \
   int sens_theta_##sfx(int, const double*, int, int, const void*, const void*, const void*,   \
                        const void*, const void*, const void*, const void*, void*, void*);   \
   int richardson_update_##sfx(int, int, int, int, const void*, const void*, const void*,      \
@@ -88,9 +88,10 @@ int dilqr_rollout(int dtype, int dyn, const double* dp, int T, int B, const void
 
 int dilqr_costate_tables(int dtype, int dyn, const double* dp, int T, int B, const void* C,
                          const void* c, const void* x, const void* u, void* lam, void* Lam,
-                         void* st) {
-  return ROUTE(dtype, dilqr::costate_tables_f32(dyn, dp, T, B, C, c, x, u, lam, Lam, st),
-               dilqr::costate_tables_f64(dyn, dp, T, B, C, c, x, u, lam, Lam, st));
+                         int C_bcast, int c_bcast, void* st) {
+  return ROUTE(dtype,
+               dilqr::costate_tables_f32(dyn, dp, T, B, C, c, x, u, lam, Lam, C_bcast, c_bcast, st),
+               dilqr::costate_tables_f64(dyn, dp, T, B, C, c, x, u, lam, Lam, C_bcast, c_bcast, st));
 }
 int dilqr_sens_theta(int dtype, int dyn, const double* dp, int T, int B, const void* x,
                      const void* u, const void* K, const void* lam, const void* dx,

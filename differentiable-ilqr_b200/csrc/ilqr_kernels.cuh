@@ -74,6 +74,7 @@ struct IterParams {
                       //         has not been copied to traj_best yet (lazy best tracking)
   int gains_only;     // skip the line-search rollout (only K,k are wanted)
   int lockstep;       // cooperative launch: grid-wide barriers resolve the pnqp decisions
+  int C_bcast, c_bcast;  // cost layout: 0 dense [T,B,..], 1 batch-broadcast [T,..], 2 [..] only
   S* cost_cur;    // [Bp]
   S* cost_new;
   S* cost_best;
@@ -83,6 +84,8 @@ struct IterParams {
   uint32_t* guess;  // [T][kPnqpMaxIter]
   uint32_t* votes;  // [T][kPnqpMaxIter]
   void* status;     // DilqrStatus*
+  const uint32_t* halt;  // DilqrControl::halt (or nullptr): non-zero -> this launch is a no-op
+  void* control;    // DilqrControl*
   S* x_out;
   S* u_out;
   S* cost_out;
@@ -97,6 +100,14 @@ struct IterParams {
 // stage cost  0.5 tau' C tau + c' tau   (util.py:145-147: bquad then bdot)
 // C, c are this lane's blocks in shared memory (row-major).
 // ---------------------------------------------------------------------------
+// Source of the cost block(s) of timestep t for the warp starting at problem b0
+// (dense: the warp's slab; broadcast: the single shared block, mpc.py:205-219).
+template <class S>
+DILQR_DEVICE const S* cost_src(const S* base, int bcast, int t, int B, int b0, int elems) {
+  return bcast == 0 ? base + ((size_t)t * B + b0) * elems
+                    : (bcast == 1 ? base + (size_t)t * elems : base);
+}
+
 template <class S, int N>
 DILQR_DEVICE S stage_cost(const S* __restrict__ Cs, const S* __restrict__ cs, const S* tau) {
   S quad = S(0);
@@ -339,8 +350,8 @@ struct IterKernel {
       k.tau = st.seg_ptr(sg, 4) + lane;
       k.Kk = st.seg_ptr(sg, 5) + lane;
     } else {
-      k.C = p.C + ((size_t)t * p.B + b) * (N * N);
-      k.c = p.c + ((size_t)t * p.B + b) * N;
+      k.C = cost_src<S>(p.C, p.C_bcast, t, p.B, b, N * N);
+      k.c = cost_src<S>(p.c, p.c_bcast, t, p.B, b, N);
       k.F = (kEnv || t >= p.T - 1) ? nullptr : p.F + ((size_t)t * p.B + b) * (NS * N);
       k.f = (kEnv || !p.has_f || t >= p.T - 1) ? nullptr : p.f + ((size_t)t * p.B + b) * NS;
       k.tau = p.traj_cur + bidx(t, 0, N, bw, p.nW);
@@ -371,8 +382,8 @@ struct IterKernel {
                                    int b0, bool want_f, bool want_traj, bool want_K) {
     if (!STAGED) return;
     const S* src[kNSeg];
-    src[0] = p.C + ((size_t)t * p.B + b0) * (N * N);
-    src[1] = p.c + ((size_t)t * p.B + b0) * N;
+    src[0] = cost_src<S>(p.C, p.C_bcast, t, p.B, b0, N * N);
+    src[1] = cost_src<S>(p.c, p.c_bcast, t, p.B, b0, N);
     src[2] = nullptr;
     src[3] = nullptr;
     if (!kEnv) {
@@ -722,6 +733,7 @@ ilqr_iter_kernel(const __grid_constant__ IterParams<S> p) {
   const int wpb = blockDim.x >> 5;
   const int b0 = (blockIdx.x * wpb + warp) * kWarp;
   if (b0 >= p.B) return;
+  if (p.halt && *reinterpret_cast<const volatile uint32_t*>(p.halt)) return;  // pipelined loop stopped
   const int nvalid = min(kWarp, p.B - b0);
   const bool active = lane < nvalid;
   const int b = b0 + lane;   // padded lanes index their own (padded) workspace column
@@ -733,7 +745,8 @@ ilqr_iter_kernel(const __grid_constant__ IterParams<S> p) {
   if (STAGED) {
     uint32_t e[IK::kNSeg];
     IK::seg_elems(e);
-    st.init(wbase + kStages * sizeof(uint64_t), bars, lane, nvalid, IK::kNSeg, e, IK::kFullMask);
+    st.init(wbase + kStages * sizeof(uint64_t), bars, lane, nvalid, IK::kNSeg, e, IK::kFullMask,
+            (p.C_bcast ? 1u : 0u) | (p.c_bcast ? 2u : 0u));
   }
   // padded lanes (tail warp) read the API tensors of the warp's first problem
   const int bsafe = active ? b : b0;
@@ -770,17 +783,20 @@ ilqr_begin_kernel(const __grid_constant__ IterParams<S> p) {
     uint32_t e[IK::kNSeg];
     IK::seg_elems(e);
     st.init(wbase + kStages * sizeof(uint64_t), reinterpret_cast<uint64_t*>(wbase), lane, nvalid,
-            IK::kNSeg, e, IK::kFullMask);
+            IK::kNSeg, e, IK::kFullMask, (p.C_bcast ? 1u : 0u) | (p.c_bcast ? 2u : 0u));
   }
   const int T = p.T;
   S xh[NS];
 #pragma unroll
   for (int i = 0; i < NS; ++i) xh[i] = __ldg(p.x_init + (size_t)b * NS + i);
   S cost = S(0);
-  IK::issue_t(st, p, 0, 0, b0, true, false, false);
+  // gains_only (final no-op LQR pass): the trajectory is only re-laid-out, no cost, so
+  // C and c are not streamed at all
+  const bool want_cost = !(p.gains_only && p.x_cur);
+  if (want_cost) IK::issue_t(st, p, 0, 0, b0, true, false, false);
   for (int t = 0; t < T; ++t) {
     const int sg = t & 1;
-    if (t + 1 < T) IK::issue_t(st, p, sg ^ 1, t + 1, b0, true, false, false);
+    if (want_cost && t + 1 < T) IK::issue_t(st, p, sg ^ 1, t + 1, b0, true, false, false);
     S th[N];
     if (p.x_cur) {
 #pragma unroll
@@ -797,6 +813,7 @@ ilqr_begin_kernel(const __grid_constant__ IterParams<S> p) {
 #pragma unroll
       for (int i = 0; i < N; ++i) to[i * kWarp] = th[i];
     }
+    if (!want_cost) continue;
     if (STAGED) st.wait(sg);
     const typename IK::Blk blk = IK::blocks(p, st, sg, t, b, b0 + lane, lane);
     cost = cost + stage_cost<S, N>(blk.C, blk.c, th);

@@ -15,7 +15,8 @@ namespace dilqr {
 // ---------------------------------------------------------------------------
 static __global__ void trace_verify_kernel(uint32_t* __restrict__ guess, const uint32_t* __restrict__ votes,
                                     int T, int boxed, int solo, DilqrStatus* status,
-                                    int lockstep = 0) {
+                                    int lockstep = 0, DilqrControl* ctrl = nullptr) {
+  if (ctrl && ctrl->halt) return;   // uniform: whole block leaves
   __shared__ int s_first;
   __shared__ unsigned s_nqp, s_unconv;
   const int n = T * kPnqpMaxIter;
@@ -68,7 +69,18 @@ static __global__ void trace_verify_kernel(uint32_t* __restrict__ guess, const u
     status->max_full_du = 0.0;
     status->mean_alpha = 0.0;
     status->mean_best_cost = 0.0;
+    if (ctrl && s_first < n) ctrl->halt = 2u;
   }
+}
+
+// Device-side stop rule of the outer loop (mpc.py:266,281,299-301), one thread.
+static __global__ void control_kernel(DilqrControl* ctrl, const DilqrStatus* status, int iteration) {
+  if (ctrl->halt) return;
+  uint32_t n = ctrl->n_not_improved + 1u;
+  if (iteration > 0 && status->any_improved) n = 0u;
+  ctrl->n_not_improved = n;
+  ctrl->iters_done = (uint32_t)iteration + 1u;
+  if (status->max_full_du < ctrl->eps || n > ctrl->not_improved_lim) ctrl->halt = 1u;
 }
 
 // ---------------------------------------------------------------------------
@@ -78,6 +90,7 @@ static __global__ void trace_verify_kernel(uint32_t* __restrict__ guess, const u
 template <class S, int N, int NCc>
 __global__ void commit_kernel(const __grid_constant__ IterParams<S> p) {
   DilqrStatus* status = reinterpret_cast<DilqrStatus*>(p.status);
+  if (p.halt && *p.halt) return;
   if (status->trace_match == 0) return;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   double du = 0.0, al = 0.0, bc = 0.0;

@@ -12,7 +12,10 @@ from .definitions import QuadCost
 
 class ImitationStep:
     def __init__(self, dx_cls, T, lqr_iter, dtype, device, n_richardson=4, richardson_tol=None,
-                 group=None):
+                 group=None, tile=True):
+        # tile=True: materialise Q,p as [T,B,n,n] / [T,B,n] exactly like il_env.py:159-162;
+        # tile=False: hand MPC the [n,n] / [n] tensors (mpc.py:205-219 broadcasts them)
+        self.tile = tile
         self.dx_cls = dx_cls
         self.T = T
         self.dtype, self.device = dtype, device
@@ -32,6 +35,8 @@ class ImitationStep:
     # -- pieces -----------------------------------------------------------
     def tile_cost(self, q, p, B):
         """il_env.py:159-162: Q = diag(q) tiled to [T,B,n,n], p tiled to [T,B,n]."""
+        if not self.tile:
+            return torch.diag(q), p
         C = torch.diag(q).unsqueeze(0).unsqueeze(0).repeat(self.T, B, 1, 1)
         c = p.unsqueeze(0).repeat(self.T, B, 1)
         return C, c
@@ -44,6 +49,7 @@ class ImitationStep:
         for t in (q, p, theta):
             t.grad = None
         B = x0.shape[0]
+        self.mpc.n_batch = B
         C, c = self.tile_cost(q, p, B)
         dx = self.dx_cls(theta)
         x, u, _ = self.mpc(x0, QuadCost(C, c), dx)

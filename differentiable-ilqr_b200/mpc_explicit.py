@@ -52,8 +52,10 @@ class _MPCExplicitFn(Function):
             mod.n_ctrl, mod.u_lower, mod.u_upper, n_passes=mod.richardson_passes,
             tol=mod.richardson_tol, back_eps=mod.back_eps, solo=mod.solo, stats=stats)
         mod.last_backward = stats
-        # the reference returns dtheta[B, n_theta]; autograd sums it to theta's shape
-        return None, None, None, dC, dc, dtheta.sum(0)
+        # dC / dc come back in the layout of the cost tensors handed in (dense, or already
+        # summed over the broadcast axes for C[n,n] / C[T,n,n]); the reference returns
+        # dtheta[B, n_theta] and autograd sums it to theta's shape
+        return None, None, None, dC.reshape(C.shape), dc.reshape(c.shape), dtheta.sum(0)
 
 
 class MPC(_BaseMPC):
@@ -79,6 +81,8 @@ class MPC(_BaseMPC):
             print('MPC Error: Could not infer batch size, pass in as n_batch')
             import sys
             sys.exit(-1)
-        C, c = self._expand_cost(cost, n_batch)
+        self._expand_cost(cost, n_batch)      # shape validation (mpc_explicit.py:203-224)
         assert x_init.ndimension() == 2 and x_init.size(0) == n_batch
-        return _MPCExplicitFn.apply(self, dx, x_init, C, c, dx.params)
+        # broadcast costs (C[n,n], C[T,n,n]) are NOT tiled: the kernels read the shared
+        # block and the backward returns the gradient already reduced to that shape
+        return _MPCExplicitFn.apply(self, dx, x_init, cost.C, cost.c, dx.params)

@@ -73,6 +73,21 @@ typedef struct DilqrStatus {
   uint32_t reserved[5];
 } DilqrStatus;
 
+/* Optional device-resident outer-loop state: with `control` set in DilqrSolve the
+ * caller may enqueue ALL iterations (iterate+commit pairs, status = one DilqrStatus per
+ * iteration) without synchronising; the stop rule of mpc.py:299-301 and the trace
+ * check run on the device and later launches turn into no-ops once `halt` is set.
+ * The host reads the block once at the end: halt == 2 means iteration `iters_done`
+ * must be re-enqueued (its pnqp trace guess was wrong and has been corrected). */
+typedef struct DilqrControl {
+  uint32_t halt;            /* 0 running, 1 stop rule fired, 2 pnqp trace mismatch     */
+  uint32_t iters_done;      /* committed iLQR iterations                               */
+  uint32_t n_not_improved;  /* mpc.py:245,266,281                                      */
+  uint32_t not_improved_lim;/* mpc.py:141                                              */
+  double   eps;             /* mpc.py:131, already rounded to the data dtype           */
+  uint32_t reserved[10];
+} DilqrControl;
+
 /* One batched MPC / LQR problem instance.  Unused pointers may be NULL. */
 typedef struct DilqrSolve {
   int32_t n_state, n_ctrl, T, n_batch;
@@ -89,6 +104,9 @@ typedef struct DilqrSolve {
   int32_t has_f;            /* LinDx: f present (util.py:121)                        */
   int32_t gains_only;       /* iterate: only lqr_backward (K_out,k_out), no rollout --
                                the final no-op LQR pass of lqr_step_explicit.py:604-618 */
+  int32_t C_bcast, c_bcast; /* cost layout (mpc.py:205-219): 0 dense C[T,B,n,n] / c[T,B,n];
+                               1 batch-broadcast C[T,n,n] / c[T,n]; 2 C[n,n] / c[n] -- the
+                               kernels read the single shared block, nothing is tiled   */
   int32_t lockstep;         /* iterate: resolve the batch-global pnqp decisions with grid-wide
                                barriers in a cooperative launch (whole batch resident, see
                                dilqr_lockstep_capacity) instead of replaying a guessed trace */
@@ -99,8 +117,8 @@ typedef struct DilqrSolve {
                                g,m_c,m_p,l; rocket Jx,Jy,Jz,mass,l), host copy      */
   /* inputs */
   const void* x_init;       /* [B,ns]                                               */
-  const void* C;            /* [T,B,n,n]                                            */
-  const void* c;            /* [T,B,n]                                              */
+  const void* C;            /* [T,B,n,n]  (or [T,n,n] / [n,n], see C_bcast)          */
+  const void* c;            /* [T,B,n]    (or [T,n] / [n], see c_bcast)              */
   const void* F;            /* [T-1,B,ns,n]  (LinDx)                                */
   const void* f;            /* [T-1,B,ns]    (LinDx, optional)                      */
   const void* u_init;       /* [T,B,nc] or NULL (zeros, mpc.py:230-231)             */
@@ -116,7 +134,8 @@ typedef struct DilqrSolve {
   void* alpha_out;          /* [B]  accepted line-search step (lqr_step only)       */
   void* K_out;              /* [T,B,nc,ns] gains, FORWARD time order (optional)     */
   void* k_out;              /* [T,B,nc]    (optional)                               */
-  DilqrStatus* status;      /* device                                               */
+  DilqrStatus* status;      /* device; the block this iteration's commit writes      */
+  DilqrControl* control;    /* device, optional (see DilqrControl)                   */
   /* scratch */
   void*  workspace;
   size_t workspace_bytes;
@@ -213,7 +232,7 @@ int dilqr_kkt_grads(const DilqrKkt* k, void* stream);
  * pendulum.py:152-382). */
 int dilqr_costate_tables(int dtype, int dynamics, const double* dyn_params, int T, int n_batch,
                          const void* C, const void* c, const void* x, const void* u, void* lam,
-                         void* Lam, void* stream);
+                         void* Lam, int C_bcast, int c_bcast, void* stream);
 
 /* One Richardson update of A' w = g:  w_t = g_t - Lam_t dtau_t (t < T-1),
  * w_{T-1} = g_{T-1}; writes w and -w, and resid[0] = max|w_new - w_old|,
@@ -237,6 +256,10 @@ typedef struct DilqrAdjoint {
   int32_t n_state, n_ctrl, T, n_batch, dtype, dynamics;
   int32_t bounds_kind;   /* NONE: no active set; SCALAR: I = |u*-bound| <= 1e-8 (:690-691) */
   int32_t gain_solve;    /* DILQR_GAIN_CHOL_REG for the explicit variant (mpc_backup)      */
+  int32_t C_bcast, c_bcast; /* cost layout as in DilqrSolve; for a broadcast C (c) the final
+                               pass writes per-warp PARTIAL sums of the gradient:
+                               dC[T][ceil(B/32)][n*n] (mode 1) or [ceil(B/32)][n*n] (mode 2),
+                               to be summed over the warp axis by the caller            */
   double u_lower, u_upper;
   double dyn_params[8];
   const void *C;         /* [T,B,n,n]                                                  */

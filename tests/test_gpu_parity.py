@@ -370,3 +370,36 @@ def test_get_matrices_and_grad_input(port, env, dev, name):
     got = dx.grad_input(X.to(dev), U.to(dev), K.to(dev))
     for a, b in zip(got, ref):
         assert rel(a, b) < 1e-11
+
+
+@pytest.mark.parametrize("mode", ["nn", "Tnn"])
+def test_broadcast_cost_equals_dense(dilqr, port, env, dev, mode):
+    """C[n,n] / C[T,n,n] (mpc.py:205-219) are read as shared blocks, never tiled: same
+    solution as the dense tiling, and gradients equal the dense ones summed over the
+    broadcast axes (what autograd's expand-backward does in the reference)."""
+    dtype = torch.float64
+    T, B = 20, 70
+    pdx, x0, C, c, kw = env_problem(port, "cartpole", T, B, dtype, sigma=0.05)
+    kw["eps"] = 1e-9
+    q, p = pdx.get_true_obj()
+    outs = {}
+    for name in ("dense", mode):
+        theta = pdx.params.to(dev).requires_grad_()
+        if name == "dense":
+            Cg, cg = C.to(dev).requires_grad_(), c.to(dev).requires_grad_()
+        elif name == "nn":
+            Cg, cg = torch.diag(q).to(dev).requires_grad_(), p.to(dev).requires_grad_()
+        else:
+            Cg = torch.diag(q).to(dev).repeat(T, 1, 1).requires_grad_()
+            cg = p.to(dev).repeat(T, 1).requires_grad_()
+        m = dilqr.mpc_explicit.MPC(5, 1, T, lqr_iter=40, verbose=-1, exit_unconverged=False,
+                                   detach_unconverged=False, n_batch=B, **kw)
+        x, u, costs = m(x0.to(dev), dilqr.QuadCost(Cg, cg), env.CartpoleDx(theta))
+        (x.pow(2).sum() + u.sum()).backward()
+        outs[name] = (x, u, costs, Cg.grad, cg.grad, theta.grad)
+    d_, b_ = outs["dense"], outs[mode]
+    assert torch.equal(d_[0], b_[0]) and torch.equal(d_[1], b_[1]) and torch.equal(d_[2], b_[2])
+    red = (0, 1) if mode == "nn" else (1,)
+    assert rel(b_[3], d_[3].sum(red)) < 1e-12
+    assert rel(b_[4], d_[4].sum(red)) < 1e-12
+    assert rel(b_[5], d_[5]) < 1e-12
