@@ -43,6 +43,16 @@ def bytes_per_solve(s, L=LQR_ITER, T=T_H, n=N, ns=NS, nc=NC, ntheta=4):
     return it, bwd, L * it + bwd
 
 
+def ncu_traffic(dtype):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture."""
+    p = os.path.join(ROOT, "profiles", "r1_iter_traffic.json")
+    if dtype == "f64" and os.path.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d["dram_bytes_read"] + d["dram_bytes_write"]
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -207,7 +217,9 @@ def run_b200(args):
                 "trace_retries": step.retries,
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                         "frac": achieved / hbm, "traffic": None, "peak_source": which,
+                         "frac": achieved / hbm,
+                         "traffic": None if args.broadcast_cost else ncu_traffic(args.dtype),
+                         "peak_source": which,
                          "kernel": "ilqr_iter_kernel<double,5,1,CARTPOLE>",
                          "algorithmic_bytes_per_launch": it_b * B,
                          "avg_launch_ms": it_avg},

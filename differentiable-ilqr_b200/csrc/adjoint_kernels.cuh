@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(64) adjoint_pass_kernel(const __grid_constant_
 #pragma unroll
     for (int j = 0; j < N; ++j) accC[i][j] = S(0);
   }
-  st.seg_shared = p.C_bcast ? 1u : 0u;   // segment 0 now carries C
+  st.set_shared(p.C_bcast ? 1u : 0u);   // segment 0 now carries C
   S dlam[NS];
   issue_b(0, T - 1);
   for (int t = T - 1; t >= 0; --t) {

@@ -3,6 +3,7 @@
 // dispatch.cu routes on DilqrSolve::dtype.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/dilqr.h"
@@ -230,28 +231,44 @@ static int launch_iterate(const DilqrSolve* s, cudaStream_t st) {
   const int warps = (p.B + kWarp - 1) / kWarp;
   const int blocks = (warps + wpb - 1) / wpb;
   const size_t smem = G::smem(wpb);
-  auto kern = ilqr_iter_kernel<S, NS, NC, DYN, G::STAGED>;
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (p.bounds_kind && !p.solo)
     cudaMemsetAsync(p.votes, 0, (size_t)p.T * kPnqpMaxIter * sizeof(uint32_t), st);
-  if (p.lockstep && p.bounds_kind && !p.solo) {
-    // cooperative launch, one warp per block so that every warp of the grid owns
-    // problems (all warps must reach every grid barrier); needs the whole batch
-    // resident -- dilqr_lockstep_capacity() tells the caller whether it fits.
-    const size_t smem1 = G::smem(1);
-    if (smem1 > 48 * 1024)
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
-    void* args[] = {(void*)&p};
-    cudaError_t e = cudaLaunchCooperativeKernel((const void*)kern, dim3(warps), dim3(kWarp), args,
-                                                smem1, st);
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      return DILQR_ELOCKSTEP;
+  if constexpr (NC > 1) {
+    if (p.lockstep && p.bounds_kind && !p.solo) {
+      // cooperative launch, one warp per block so that every warp of the grid owns
+      // problems (all warps must reach every grid barrier); needs the whole batch
+      // resident -- dilqr_lockstep_capacity() tells the caller whether it fits.
+      auto kern = ilqr_iter_kernel<S, NS, NC, DYN, G::STAGED, true>;
+      const size_t smem1 = G::smem(1);
+      if (smem1 > 48 * 1024)
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+      void* args[] = {(void*)&p};
+      cudaError_t e = cudaLaunchCooperativeKernel((const void*)kern, dim3(warps), dim3(kWarp), args,
+                                                  smem1, st);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        return DILQR_ELOCKSTEP;
+      }
+      return DILQR_OK;
     }
-    return DILQR_OK;
   }
+  if (s->lockstep && NC == 1 && p.bounds_kind && !p.solo) return DILQR_ELOCKSTEP;
   p.lockstep = 0;
+  static const bool split = getenv("DILQR_SPLIT_PHASES") != nullptr;   // experiment switch
+  if (split && !p.gains_only) {
+    auto ka = ilqr_iter_kernel<S, NS, NC, DYN, G::STAGED, false, 1>;
+    auto kb = ilqr_iter_kernel<S, NS, NC, DYN, G::STAGED, false, 2>;
+    if (smem > 48 * 1024) {
+      cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
+    ka<<<blocks, wpb * kWarp, smem, st>>>(p);
+    kb<<<blocks, wpb * kWarp, smem, st>>>(p);
+    return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
+  }
+  auto kern = ilqr_iter_kernel<S, NS, NC, DYN, G::STAGED, false>;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   kern<<<blocks, wpb * kWarp, smem, st>>>(p);
   return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
 }
@@ -288,7 +305,8 @@ template <int NS, int NC, int DYN>
 static int lockstep_capacity() {
   using S = Scalar;
   using G = Geometry<S, NS, NC, DYN>;
-  auto kern = ilqr_iter_kernel<S, NS, NC, DYN, G::STAGED>;
+  if (NC == 1) return 0;   // single-input problems replay the (always right) closed-form trace
+  auto kern = ilqr_iter_kernel<S, NS, NC, DYN, G::STAGED, true>;
   const size_t smem1 = G::smem(1);
   if (smem1 > 48 * 1024)
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);

@@ -99,6 +99,13 @@ DILQR_DEVICE void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t*
 constexpr int kStages = 2;
 constexpr int kMaxSeg = 6;
 
+// rarely taken path (tail warps / unaligned slabs): kept out of line so the hot
+// sweeps stay small
+template <class S>
+__device__ __noinline__ void lane_copy(S* dst, const S* src, int cnt, int lane) {
+  for (int e = lane; e < cnt; e += kWarp) dst[e] = __ldg(src + e);
+}
+
 template <class S>
 struct WarpStager {
   char* base;        // this warp's staging area (kStages * stage_bytes)
@@ -106,6 +113,8 @@ struct WarpStager {
   uint32_t stage_bytes;
   uint32_t seg_off[kMaxSeg];    // byte offset of each segment in a stage
   uint32_t seg_elems[kMaxSeg];  // scalars per problem in each segment
+  uint32_t seg_nbytes[kMaxSeg]; // bytes copied per issue for each segment
+  uint32_t seg_sized;           // bit i: seg_nbytes[i] is a non-zero multiple of 16
   uint32_t seg_full;            // bit i: segment i always holds 32 problems (workspace chunks)
   uint32_t seg_shared;          // bit i: segment i is ONE block shared by all lanes
                                 //        (broadcast cost: C[n,n] / C[T,n,n], mpc.py:205-219)
@@ -133,10 +142,13 @@ struct WarpStager {
     parity = 0;
     via_tma = 0;
     uint32_t off = 0;
+    seg_sized = 0;
 #pragma unroll
     for (int i = 0; i < kMaxSeg; ++i) {
       seg_off[i] = off;
       seg_elems[i] = i < nseg ? elems[i] : 0;
+      seg_nbytes[i] = seg_bytes(i);
+      if (seg_nbytes[i] && !(seg_nbytes[i] & 15u)) seg_sized |= 1u << i;
       uint32_t full = seg_elems[i] * kWarp * sizeof(S);
       off += (full + 15u) & ~15u;
     }
@@ -147,6 +159,17 @@ struct WarpStager {
       mbar_fence_init();
     }
     __syncwarp();
+  }
+
+  // change which segments are shared blocks (a stage reused for different tensors)
+  DILQR_DEVICE void set_shared(uint32_t shared_mask) {
+    seg_shared = shared_mask;
+    seg_sized = 0;
+#pragma unroll
+    for (int i = 0; i < kMaxSeg; ++i) {
+      seg_nbytes[i] = seg_bytes(i);
+      if (seg_nbytes[i] && !(seg_nbytes[i] & 15u)) seg_sized |= 1u << i;
+    }
   }
 
   static __host__ __device__ uint32_t bytes_per_warp(int nseg, const uint32_t* elems) {
@@ -165,12 +188,10 @@ struct WarpStager {
     uint32_t bulk_mask = 0, total = 0;
 #pragma unroll
     for (int i = 0; i < kMaxSeg; ++i) {
-      if (i < nseg && src[i]) {
-        const uint32_t nb = seg_bytes(i);
-        if (nb && !(nb & 15u) && !(reinterpret_cast<uintptr_t>(src[i]) & 15u)) {
-          bulk_mask |= 1u << i;
-          total += nb;
-        }
+      if (i < nseg && src[i] && ((seg_sized >> i) & 1u) &&
+          !(reinterpret_cast<uintptr_t>(src[i]) & 15u)) {
+        bulk_mask |= 1u << i;
+        total += seg_nbytes[i];
       }
     }
     via_tma = bulk_mask ? (via_tma | (1u << stage)) : (via_tma & ~(1u << stage));
@@ -178,15 +199,12 @@ struct WarpStager {
       mbar_expect_tx(&bar[stage], total);
 #pragma unroll
       for (int i = 0; i < kMaxSeg; ++i)
-        if ((bulk_mask >> i) & 1u) bulk_g2s(dst + seg_off[i], src[i], seg_bytes(i), &bar[stage]);
+        if ((bulk_mask >> i) & 1u) bulk_g2s(dst + seg_off[i], src[i], seg_nbytes[i], &bar[stage]);
     }
 #pragma unroll
     for (int i = 0; i < kMaxSeg; ++i) {
-      if (i < nseg && src[i] && !((bulk_mask >> i) & 1u)) {
-        S* d = reinterpret_cast<S*>(dst + seg_off[i]);
-        const int cnt = seg_bytes(i) / sizeof(S);
-        for (int e = lane; e < cnt; e += kWarp) d[e] = __ldg(src[i] + e);
-      }
+      if (i < nseg && src[i] && !((bulk_mask >> i) & 1u))
+        lane_copy<S>(reinterpret_cast<S*>(dst + seg_off[i]), src[i], seg_nbytes[i] / sizeof(S), lane);
     }
   }
 

@@ -145,20 +145,24 @@ DILQR_DEVICE void lin_step(const S* __restrict__ Fs, const S* __restrict__ fs, b
 // last evaluated iteration -- exactly what lqr_backward consumes
 // (lqr_step.py:135-148).
 // ---------------------------------------------------------------------------
-template <class S, int N>
+template <class S, int N, bool LOCKSTEP = false>
 DILQR_DEVICE void pnqp_thread(const S (&H)[N][N], const S (&q)[N], const S (&lo)[N],
                               const S (&hi)[N], bool have_init, S (&x)[N], bool (&If)[N],
                               LUpp<S, N>& lu, const uint32_t* __restrict__ guess, uint4 gpre,
-                              uint32_t* __restrict__ votes, bool solo, bool active, int lane,
-                              bool lockstep = false) {
+                              uint32_t* __restrict__ votes, bool solo, bool active, int lane) {
+  constexpr bool lockstep = LOCKSTEP;
   // lockstep: the kernel was launched cooperatively with the whole batch resident;
   // every batch-global decision is an atomicOr into the vote word + a grid-wide
   // barrier (no guessing, no re-runs) -- the better trade when the control-flow trace
   // is long and unstable (multi-input problems with many active constraints).
   auto grid_decide = [&](uint32_t* word, uint32_t mine) -> uint32_t {
-    if (mine && lane == 0) atomicOr(word, mine);
-    cooperative_groups::this_grid().sync();
-    return *reinterpret_cast<volatile uint32_t*>(word);
+    if constexpr (LOCKSTEP) {
+      if (mine && lane == 0) atomicOr(word, mine);
+      cooperative_groups::this_grid().sync();
+      return *reinterpret_cast<volatile uint32_t*>(word);
+    } else {
+      return 0u;
+    }
   };
   // gpre = guess[0..3], loaded by the caller long before this point (the common
   // case never looks past the first two words; a global load here would sit on
@@ -301,7 +305,7 @@ DILQR_DEVICE void pnqp_thread(const S (&H)[N][N], const S (&q)[N], const S (&lo)
 // ---------------------------------------------------------------------------
 // The fused iLQR iteration.
 // ---------------------------------------------------------------------------
-template <class S, int NS, int NC, int DYN, bool STAGED>
+template <class S, int NS, int NC, int DYN, bool STAGED, bool LOCKSTEP = false>
 struct IterKernel {
   static constexpr int N = NS + NC;
   static constexpr int NK = NC * NS + NC;
@@ -415,7 +419,7 @@ struct IterKernel {
       const int sg = (T - 1 - t) & 1;
       if (t > 0) issue_t(st, p, sg ^ 1, t - 1, b0, false, true, false);
       uint4 gpre = make_uint4(0, 0, 0, 0);
-      if (p.bounds_kind && !p.solo && !p.lockstep)
+      if (p.bounds_kind && !p.solo && !LOCKSTEP)
         gpre = __ldg(reinterpret_cast<const uint4*>(p.guess + (size_t)t * kPnqpMaxIter));
       if (STAGED) st.wait(sg);
       const Blk blk = blocks(p, st, sg, t, b, bw, lane);
@@ -563,10 +567,9 @@ struct IterKernel {
         }
         bool If[NC];
         LUpp<S, NC> lu;
-        pnqp_thread<S, NC>(H, qu, lo, hi, have_prev, k, If, lu,
-                           p.guess + (size_t)t * kPnqpMaxIter, gpre,
-                           p.votes + (size_t)t * kPnqpMaxIter, p.solo != 0, active, lane,
-                           p.lockstep != 0);
+        pnqp_thread<S, NC, LOCKSTEP>(H, qu, lo, hi, have_prev, k, If, lu,
+                                     p.guess + (size_t)t * kPnqpMaxIter, gpre,
+                                     p.votes + (size_t)t * kPnqpMaxIter, p.solo != 0, active, lane);
         have_prev = true;
 #pragma unroll
         for (int a = 0; a < NC; ++a) kprev[a] = k[a];
@@ -723,10 +726,10 @@ struct IterKernel {
   }
 };
 
-template <class S, int NS, int NC, int DYN, bool STAGED>
+template <class S, int NS, int NC, int DYN, bool STAGED, bool LOCKSTEP = false, int PHASE = 0>
 __global__ void __launch_bounds__(128)
 ilqr_iter_kernel(const __grid_constant__ IterParams<S> p) {
-  using IK = IterKernel<S, NS, NC, DYN, STAGED>;
+  using IK = IterKernel<S, NS, NC, DYN, STAGED, LOCKSTEP>;
   extern __shared__ __align__(128) char smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -750,8 +753,8 @@ ilqr_iter_kernel(const __grid_constant__ IterParams<S> p) {
   }
   // padded lanes (tail warp) read the API tensors of the warp's first problem
   const int bsafe = active ? b : b0;
-  IK::backward_sweep(p, st, b0, bsafe, b, active, lane);
-  if (!p.gains_only) IK::forward_linesearch(p, st, b0, bsafe, b, active, lane);
+  if (PHASE != 2) IK::backward_sweep(p, st, b0, bsafe, b, active, lane);
+  if (PHASE != 1 && !p.gains_only) IK::forward_linesearch(p, st, b0, bsafe, b, active, lane);
 }
 
 // ---------------------------------------------------------------------------

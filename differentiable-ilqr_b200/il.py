@@ -81,3 +81,60 @@ class ImitationStep:
         out = flat.cpu()                                   # loss + gradients back to the host
         self.d2h_bytes = out.numel() * out.element_size()
         return out
+
+
+class ImitationLearner:
+    """The `il_exp --mode empc --learn_dx` loop (il_exp.py:183-429) on the device:
+    learn the dynamics parameters theta by differentiating the imitation loss
+    mean((u_mpc - u_expert)^2) through the MPC (DiLQR implicit gradient), RMSprop
+    lr 1e-2 alpha 0.5 (il_exp.py:228-238), warm-start cache of the previous
+    controls (il_exp.py:269-275,338-344).  Under torch.distributed each rank owns a
+    contiguous shard of the problems (parallel.shard_range) and one small
+    all-reduce per step sums the parameter gradients; every rank then takes the
+    identical optimiser step."""
+
+    def __init__(self, dx_cls, theta_init, T, lqr_iter=100, dtype=torch.float64,
+                 device=None, lr=1e-2, alpha=0.5, richardson_passes=30, richardson_tol=1e-10,
+                 group=None):
+        self.dx_cls, self.T = dx_cls, T
+        self.dtype, self.device, self.group = dtype, device, group
+        proto = dx_cls()
+        self.ns, self.nc = proto.n_state, proto.n_ctrl
+        self.q, self.p = [t.to(dtype).to(device) for t in proto.get_true_obj()]
+        self.theta = torch.tensor(theta_init, dtype=dtype, device=device, requires_grad=True)
+        self.opt = torch.optim.RMSprop([{"params": [self.theta], "lr": lr, "alpha": alpha}])
+        self.mpc = mpc_explicit.MPC(
+            self.ns, self.nc, T, u_lower=proto.lower, u_upper=proto.upper, lqr_iter=lqr_iter,
+            verbose=-1, exit_unconverged=False, detach_unconverged=True,
+            linesearch_decay=proto.linesearch_decay,
+            max_linesearch_iter=proto.max_linesearch_iter, eps=proto.mpc_eps,
+            richardson_passes=richardson_passes, richardson_tol=richardson_tol)
+        self.warm = None
+
+    def expert(self, theta_true, x_init):
+        """populate_data (il_env.py:81-94): one batched open-loop solve with the true model."""
+        dx = self.dx_cls(torch.tensor(theta_true, dtype=self.dtype, device=self.device))
+        self.mpc.n_batch = x_init.shape[0]
+        self.mpc.u_init = None
+        with torch.no_grad():
+            _, u, _ = self.mpc(x_init, QuadCost(torch.diag(self.q), self.p), dx)
+        return u
+
+    def step(self, x_init, u_expert, n_global=None):
+        """One il_exp training step on this rank's shard; returns the global loss."""
+        B = x_init.shape[0]
+        n_global = n_global or B
+        self.opt.zero_grad()
+        self.mpc.n_batch = B
+        self.mpc.u_init = self.warm
+        dx = self.dx_cls(self.theta)
+        _, u, _ = self.mpc(x_init, QuadCost(torch.diag(self.q), self.p), dx)
+        self.warm = u.detach()
+        # mean over the GLOBAL batch: local sum / (T * n_global * nc)
+        loss = (u - u_expert).pow(2).sum() / (self.T * n_global * self.nc)
+        loss.backward()
+        flat = torch.cat((self.theta.grad, loss.detach().reshape(1)))
+        parallel.allreduce_sum_(flat, self.group)
+        self.theta.grad.copy_(flat[:-1])
+        self.opt.step()
+        return float(flat[-1])

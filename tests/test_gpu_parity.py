@@ -403,3 +403,17 @@ def test_broadcast_cost_equals_dense(dilqr, port, env, dev, mode):
     assert rel(b_[3], d_[3].sum(red)) < 1e-12
     assert rel(b_[4], d_[4].sum(red)) < 1e-12
     assert rel(b_[5], d_[5]) < 1e-12
+
+
+def test_imitation_learning_loop(dilqr, env, dev):
+    """BASELINE config 4 shape (il_exp.py --mode empc --learn_dx): differentiating the
+    imitation loss through the MPC moves theta so that the loss falls."""
+    g = torch.Generator().manual_seed(0)
+    B, T = 256, 20
+    r = (torch.rand(B, 4, generator=g, dtype=torch.float64) * 2 - 1) * 0.2
+    x0 = torch.stack((r[:, 0], r[:, 1], torch.cos(r[:, 2]), torch.sin(r[:, 2]), r[:, 3]), 1).to(dev)
+    L = dilqr.il.ImitationLearner(env.CartpoleDx, (9.8, 3.0, 0.1, 1.0), T, lqr_iter=60, device=dev)
+    u_exp = L.expert((9.8, 1.0, 0.1, 0.5), x0)
+    losses = [L.step(x0, u_exp) for _ in range(8)]
+    assert all(b < a for a, b in zip(losses, losses[1:])), losses
+    assert losses[-1] < 0.9 * losses[0]
