@@ -132,7 +132,7 @@ _lib = None
 
 def build(verbose=False, extra=""):
     """Compile libdilqr.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    cmd = ["make", "-C", CSRC, "-j", str(min(8, os.cpu_count() or 1))]
+    cmd = ["make", "-C", CSRC, "-j", str(min(9, os.cpu_count() or 1))]
     if extra:
         cmd.append("EXTRA=" + extra)
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

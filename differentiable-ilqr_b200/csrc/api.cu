@@ -14,16 +14,25 @@
 
 namespace dilqr {
 
+// Compiled once per (scalar type, shape group): -DDILQR_SCALAR_F64=0/1 -DDILQR_GROUP=0..3.
+// The shape-specialised kernels are split over four groups purely to parallelise the
+// build; group 0 also carries every entry point that does not depend on (ns, nc).
+#ifndef DILQR_GROUP
+#define DILQR_GROUP 0
+#endif
+#define DILQR_PASTE2(a, b, c) a##_##b##_g##c
+#define DILQR_PASTE(a, b, c) DILQR_PASTE2(a, b, c)
 #if DILQR_SCALAR_F64
 using Scalar = double;
-#define DILQR_SUFFIX(name) name##_f64
+#define DILQR_SUFFIX(name) DILQR_PASTE(name, f64, DILQR_GROUP)
 #else
 using Scalar = float;
-#define DILQR_SUFFIX(name) name##_f32
+#define DILQR_SUFFIX(name) DILQR_PASTE(name, f32, DILQR_GROUP)
 #endif
 
-// (n_state, n_ctrl, dynamics) combinations compiled in.
-#ifdef DILQR_FAST_BUILD   // developer builds: a handful of shapes, seconds to compile
+// (n_state, n_ctrl, dynamics) combinations compiled into this group.
+#ifdef DILQR_FAST_BUILD   // developer builds: a handful of shapes, all in group 0
+#if DILQR_GROUP == 0
 #define DILQR_CONFIGS(X)       \
   X(3, 1, DYN_LINDX)           \
   X(4, 2, DYN_LINDX)           \
@@ -33,23 +42,32 @@ using Scalar = float;
   X(5, 1, DYN_CARTPOLE)        \
   X(13, 3, DYN_ROCKET)
 #else
+#define DILQR_CONFIGS(X)
+#endif
+#elif DILQR_GROUP == 0
+#define DILQR_CONFIGS(X)       \
+  X(3, 1, DYN_LINDX)           \
+  X(5, 1, DYN_LINDX)           \
+  X(3, 1, DYN_PENDULUM)        \
+  X(5, 1, DYN_CARTPOLE)        \
+  X(13, 3, DYN_ROCKET)
+#elif DILQR_GROUP == 1
 #define DILQR_CONFIGS(X)       \
   X(2, 1, DYN_LINDX)           \
-  X(3, 1, DYN_LINDX)           \
   X(4, 1, DYN_LINDX)           \
   X(4, 2, DYN_LINDX)           \
   X(4, 4, DYN_LINDX)           \
-  X(5, 1, DYN_LINDX)           \
   X(8, 1, DYN_LINDX)           \
-  X(8, 2, DYN_LINDX)           \
+  X(8, 2, DYN_LINDX)
+#elif DILQR_GROUP == 2
+#define DILQR_CONFIGS(X)       \
   X(8, 4, DYN_LINDX)           \
   X(13, 3, DYN_LINDX)          \
-  X(16, 1, DYN_LINDX)          \
+  X(16, 1, DYN_LINDX)
+#else
+#define DILQR_CONFIGS(X)       \
   X(16, 2, DYN_LINDX)          \
-  X(16, 4, DYN_LINDX)          \
-  X(3, 1, DYN_PENDULUM)        \
-  X(5, 1, DYN_CARTPOLE)        \
-  X(13, 3, DYN_ROCKET)
+  X(16, 4, DYN_LINDX)
 #endif
 
 constexpr size_t kStageBudget = 56 * 1024;  // per-warp staging budget (>= 4 warps / SM)
@@ -254,18 +272,6 @@ static int launch_iterate(const DilqrSolve* s, cudaStream_t st) {
   }
   if (s->lockstep && NC == 1 && p.bounds_kind && !p.solo) return DILQR_ELOCKSTEP;
   p.lockstep = 0;
-  static const bool split = getenv("DILQR_SPLIT_PHASES") != nullptr;   // experiment switch
-  if (split && !p.gains_only) {
-    auto ka = ilqr_iter_kernel<S, NS, NC, DYN, G::STAGED, false, 1>;
-    auto kb = ilqr_iter_kernel<S, NS, NC, DYN, G::STAGED, false, 2>;
-    if (smem > 48 * 1024) {
-      cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    }
-    ka<<<blocks, wpb * kWarp, smem, st>>>(p);
-    kb<<<blocks, wpb * kWarp, smem, st>>>(p);
-    return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
-  }
   auto kern = ilqr_iter_kernel<S, NS, NC, DYN, G::STAGED, false>;
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -351,9 +357,12 @@ int DILQR_SUFFIX(supported)(int n_state, int n_ctrl, int dynamics) {
   return 0;
 }
 
+#if DILQR_GROUP == 0
 size_t DILQR_SUFFIX(workspace_bytes)(const DilqrSolve* s) {
   return ws_layout(s, sizeof(Scalar)).total;
 }
+
+#endif
 
 int DILQR_SUFFIX(mpc_begin)(const DilqrSolve* s, void* stream) {
   int e = check(s, true);
@@ -387,6 +396,7 @@ int DILQR_SUFFIX(kkt_grads)(const DilqrKkt* k, void* stream) {
   return DILQR_EUNSUPPORTED;
 }
 
+#if DILQR_GROUP == 0
 template <int DYN>
 static int launch_linearize(const double* dp, int T, int B, const void* x, const void* u, void* F,
                             void* f, cudaStream_t st) {
@@ -662,6 +672,8 @@ int DILQR_SUFFIX(env_tables)(int dynamics, const double* dp, int n, const void* 
   if (dynamics == DYN_ROCKET) return launch_tables<DYN_ROCKET>(dp, n, x, u, out, st);
   return DILQR_EUNSUPPORTED;
 }
+
+#endif  // DILQR_GROUP == 0
 
 int DILQR_SUFFIX(richardson_update)(int ns, int nc, int T, int B, const void* g, const void* Lam,
                                     const void* dx, const void* du, void* w, void* negw,

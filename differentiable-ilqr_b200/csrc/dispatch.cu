@@ -3,139 +3,167 @@
 #include "../../include/dilqr.h"
 
 namespace dilqr {
-#define DECL(sfx)                                                                         \
+// shape-specialised entry points: one copy per (dtype, shape group)
+#define DECL_G(sfx)                                                                       \
   int supported_##sfx(int, int, int);                                                     \
-  int lockstep_capacity_##sfx(int, int, int);                                                     \
-  size_t workspace_bytes_##sfx(const DilqrSolve*);                                        \
+  int lockstep_capacity_##sfx(int, int, int);                                             \
   int mpc_begin_##sfx(const DilqrSolve*, void*);                                          \
   int mpc_iterate_##sfx(const DilqrSolve*, void*);                                        \
   int mpc_commit_##sfx(const DilqrSolve*, void*);                                         \
   int mpc_finish_##sfx(const DilqrSolve*, void*);                                         \
   int kkt_grads_##sfx(const DilqrKkt*, void*);                                            \
+  int richardson_update_##sfx(int, int, int, int, const void*, const void*, const void*,   \
+                              const void*, void*, void*, void*, void*);
+// shape-independent entry points: group 0 only
+#define DECL_0(sfx)                                                                       \
+  size_t workspace_bytes_##sfx(const DilqrSolve*);                                        \
   int linearize_##sfx(int, const double*, int, int, const void*, const void*, void*, void*, \
                       void*);                                                             \
-  int rollout_##sfx(int, const double*, int, int, const void*, const void*, void*, void*);     \
+  int rollout_##sfx(int, const double*, int, int, const void*, const void*, void*, void*); \
   int costate_tables_##sfx(int, const double*, int, int, const void*, const void*, const void*, \
-                           const void*, void*, void*, int, int, void*);                               \
-  int sens_theta_##sfx(int, const double*, int, int, const void*, const void*, const void*,   \
-                       const void*, const void*, const void*, const void*, void*, void*);   \
-  int richardson_update_##sfx(int, int, int, int, const void*, const void*, const void*,      \
-                              const void*, void*, void*, void*, void*);                     \
+                           const void*, void*, void*, int, int, void*);                   \
+  int sens_theta_##sfx(int, const double*, int, int, const void*, const void*, const void*, \
+                       const void*, const void*, const void*, const void*, void*, void*); \
   int env_tables_##sfx(int, const double*, int, const void*, const void*, void* const*, void*); \
-  int pnqp_##sfx(int, int, const void*, const void*, const void*, const void*, const void*,    \
-                 void*, void*, int32_t*, void*, uint32_t*, int, DilqrStatus*, void*);         \
-  size_t adjoint_workspace_bytes_##sfx(const DilqrAdjoint*);                                 \
+  int pnqp_##sfx(int, int, const void*, const void*, const void*, const void*, const void*, \
+                 void*, void*, int32_t*, void*, uint32_t*, int, DilqrStatus*, void*);     \
+  size_t adjoint_workspace_bytes_##sfx(const DilqrAdjoint*);                              \
   int adjoint_run_##sfx(const DilqrAdjoint*, int, void*);
-DECL(f32)
-DECL(f64)
-#undef DECL
+DECL_G(f32_g0) DECL_G(f32_g1) DECL_G(f32_g2) DECL_G(f32_g3)
+DECL_G(f64_g0) DECL_G(f64_g1) DECL_G(f64_g2) DECL_G(f64_g3)
+DECL_0(f32_g0) DECL_0(f64_g0)
+#undef DECL_G
+#undef DECL_0
 }  // namespace dilqr
 
 #define ROUTE(dtype, call32, call64)                   \
   ((dtype) == DILQR_F32 ? (call32) : ((dtype) == DILQR_F64 ? (call64) : DILQR_EINVAL))
+
+// try the shape groups in turn until one has the (n_state, n_ctrl, dynamics) kernels
+#define TRY_GROUPS(T, fn, ...)                                   \
+  do {                                                           \
+    int rc_ = dilqr::fn##_##T##_g0(__VA_ARGS__);                 \
+    if (rc_ == DILQR_EUNSUPPORTED) rc_ = dilqr::fn##_##T##_g1(__VA_ARGS__); \
+    if (rc_ == DILQR_EUNSUPPORTED) rc_ = dilqr::fn##_##T##_g2(__VA_ARGS__); \
+    if (rc_ == DILQR_EUNSUPPORTED) rc_ = dilqr::fn##_##T##_g3(__VA_ARGS__); \
+    return rc_;                                                  \
+  } while (0)
+#define BY_DTYPE_GROUPS(dtype, fn, ...)                          \
+  do {                                                           \
+    if ((dtype) == DILQR_F32) TRY_GROUPS(f32, fn, __VA_ARGS__);  \
+    if ((dtype) == DILQR_F64) TRY_GROUPS(f64, fn, __VA_ARGS__);  \
+    return DILQR_EINVAL;                                         \
+  } while (0)
 
 extern "C" {
 
 const char* dilqr_version(void) { return "dilqr-b200 0.1 (sm_100a)"; }
 
 int dilqr_supported(int dtype, int ns, int nc, int dyn) {
-  if (dtype == DILQR_F32) return dilqr::supported_f32(ns, nc, dyn);
-  if (dtype == DILQR_F64) return dilqr::supported_f64(ns, nc, dyn);
+  if (dtype == DILQR_F32)
+    return dilqr::supported_f32_g0(ns, nc, dyn) | dilqr::supported_f32_g1(ns, nc, dyn) |
+           dilqr::supported_f32_g2(ns, nc, dyn) | dilqr::supported_f32_g3(ns, nc, dyn);
+  if (dtype == DILQR_F64)
+    return dilqr::supported_f64_g0(ns, nc, dyn) | dilqr::supported_f64_g1(ns, nc, dyn) |
+           dilqr::supported_f64_g2(ns, nc, dyn) | dilqr::supported_f64_g3(ns, nc, dyn);
   return 0;
 }
 
 int dilqr_lockstep_capacity(int dtype, int ns, int nc, int dyn) {
-  if (dtype == DILQR_F32) return dilqr::lockstep_capacity_f32(ns, nc, dyn);
-  if (dtype == DILQR_F64) return dilqr::lockstep_capacity_f64(ns, nc, dyn);
+  if (dtype == DILQR_F32)
+    return dilqr::lockstep_capacity_f32_g0(ns, nc, dyn) + dilqr::lockstep_capacity_f32_g1(ns, nc, dyn) +
+           dilqr::lockstep_capacity_f32_g2(ns, nc, dyn) + dilqr::lockstep_capacity_f32_g3(ns, nc, dyn);
+  if (dtype == DILQR_F64)
+    return dilqr::lockstep_capacity_f64_g0(ns, nc, dyn) + dilqr::lockstep_capacity_f64_g1(ns, nc, dyn) +
+           dilqr::lockstep_capacity_f64_g2(ns, nc, dyn) + dilqr::lockstep_capacity_f64_g3(ns, nc, dyn);
   return 0;
 }
 
 size_t dilqr_workspace_bytes(const DilqrSolve* s) {
   if (!s) return 0;
-  return s->dtype == DILQR_F32 ? dilqr::workspace_bytes_f32(s) : dilqr::workspace_bytes_f64(s);
+  return s->dtype == DILQR_F32 ? dilqr::workspace_bytes_f32_g0(s) : dilqr::workspace_bytes_f64_g0(s);
 }
 
 int dilqr_mpc_begin(const DilqrSolve* s, void* st) {
   if (!s) return DILQR_EINVAL;
-  return ROUTE(s->dtype, dilqr::mpc_begin_f32(s, st), dilqr::mpc_begin_f64(s, st));
+  BY_DTYPE_GROUPS(s->dtype, mpc_begin, s, st);
 }
 int dilqr_mpc_iterate(const DilqrSolve* s, void* st) {
   if (!s) return DILQR_EINVAL;
-  return ROUTE(s->dtype, dilqr::mpc_iterate_f32(s, st), dilqr::mpc_iterate_f64(s, st));
+  BY_DTYPE_GROUPS(s->dtype, mpc_iterate, s, st);
 }
 int dilqr_mpc_commit(const DilqrSolve* s, void* st) {
   if (!s) return DILQR_EINVAL;
-  return ROUTE(s->dtype, dilqr::mpc_commit_f32(s, st), dilqr::mpc_commit_f64(s, st));
+  BY_DTYPE_GROUPS(s->dtype, mpc_commit, s, st);
 }
 int dilqr_mpc_finish(const DilqrSolve* s, void* st) {
   if (!s) return DILQR_EINVAL;
-  return ROUTE(s->dtype, dilqr::mpc_finish_f32(s, st), dilqr::mpc_finish_f64(s, st));
+  BY_DTYPE_GROUPS(s->dtype, mpc_finish, s, st);
 }
 int dilqr_kkt_grads(const DilqrKkt* k, void* st) {
   if (!k) return DILQR_EINVAL;
-  return ROUTE(k->dtype, dilqr::kkt_grads_f32(k, st), dilqr::kkt_grads_f64(k, st));
+  BY_DTYPE_GROUPS(k->dtype, kkt_grads, k, st);
 }
 int dilqr_linearize(int dtype, int dyn, const double* dp, int T, int B, const void* x,
                     const void* u, void* F, void* f, void* st) {
-  return ROUTE(dtype, dilqr::linearize_f32(dyn, dp, T, B, x, u, F, f, st),
-               dilqr::linearize_f64(dyn, dp, T, B, x, u, F, f, st));
+  return ROUTE(dtype, dilqr::linearize_f32_g0(dyn, dp, T, B, x, u, F, f, st),
+               dilqr::linearize_f64_g0(dyn, dp, T, B, x, u, F, f, st));
 }
 int dilqr_rollout(int dtype, int dyn, const double* dp, int T, int B, const void* x0,
                   const void* u, void* x, void* st) {
-  return ROUTE(dtype, dilqr::rollout_f32(dyn, dp, T, B, x0, u, x, st),
-               dilqr::rollout_f64(dyn, dp, T, B, x0, u, x, st));
+  return ROUTE(dtype, dilqr::rollout_f32_g0(dyn, dp, T, B, x0, u, x, st),
+               dilqr::rollout_f64_g0(dyn, dp, T, B, x0, u, x, st));
 }
 
 int dilqr_costate_tables(int dtype, int dyn, const double* dp, int T, int B, const void* C,
                          const void* c, const void* x, const void* u, void* lam, void* Lam,
                          int C_bcast, int c_bcast, void* st) {
   return ROUTE(dtype,
-               dilqr::costate_tables_f32(dyn, dp, T, B, C, c, x, u, lam, Lam, C_bcast, c_bcast, st),
-               dilqr::costate_tables_f64(dyn, dp, T, B, C, c, x, u, lam, Lam, C_bcast, c_bcast, st));
+               dilqr::costate_tables_f32_g0(dyn, dp, T, B, C, c, x, u, lam, Lam, C_bcast, c_bcast, st),
+               dilqr::costate_tables_f64_g0(dyn, dp, T, B, C, c, x, u, lam, Lam, C_bcast, c_bcast, st));
 }
 int dilqr_sens_theta(int dtype, int dyn, const double* dp, int T, int B, const void* x,
                      const void* u, const void* K, const void* lam, const void* dx,
                      const void* du, const void* df, void* dtheta, void* st) {
-  return ROUTE(dtype, dilqr::sens_theta_f32(dyn, dp, T, B, x, u, K, lam, dx, du, df, dtheta, st),
-               dilqr::sens_theta_f64(dyn, dp, T, B, x, u, K, lam, dx, du, df, dtheta, st));
+  return ROUTE(dtype, dilqr::sens_theta_f32_g0(dyn, dp, T, B, x, u, K, lam, dx, du, df, dtheta, st),
+               dilqr::sens_theta_f64_g0(dyn, dp, T, B, x, u, K, lam, dx, du, df, dtheta, st));
 }
 int dilqr_richardson_update(int dtype, int ns, int nc, int T, int B, const void* g,
                             const void* Lam, const void* dx, const void* du, void* w, void* negw,
                             void* resid, void* st) {
-  return ROUTE(dtype, dilqr::richardson_update_f32(ns, nc, T, B, g, Lam, dx, du, w, negw, resid, st),
-               dilqr::richardson_update_f64(ns, nc, T, B, g, Lam, dx, du, w, negw, resid, st));
+  BY_DTYPE_GROUPS(dtype, richardson_update, ns, nc, T, B, g, Lam, dx, du, w, negw, resid, st);
 }
 
 int dilqr_env_tables(int dtype, int dyn, const double* dp, int n, const void* x, const void* u,
                      void* const* out, void* st) {
-  return ROUTE(dtype, dilqr::env_tables_f32(dyn, dp, n, x, u, out, st),
-               dilqr::env_tables_f64(dyn, dp, n, x, u, out, st));
+  return ROUTE(dtype, dilqr::env_tables_f32_g0(dyn, dp, n, x, u, out, st),
+               dilqr::env_tables_f64_g0(dyn, dp, n, x, u, out, st));
 }
 
 int dilqr_pnqp(int dtype, int n, int B, const void* H, const void* q, const void* lower,
                const void* upper, const void* x_init, void* x, void* lu, int32_t* pivots, void* If,
                uint32_t* trace, int solo, DilqrStatus* status, void* st) {
   return ROUTE(dtype,
-               dilqr::pnqp_f32(n, B, H, q, lower, upper, x_init, x, lu, pivots, If, trace, solo, status, st),
-               dilqr::pnqp_f64(n, B, H, q, lower, upper, x_init, x, lu, pivots, If, trace, solo, status, st));
+               dilqr::pnqp_f32_g0(n, B, H, q, lower, upper, x_init, x, lu, pivots, If, trace, solo, status, st),
+               dilqr::pnqp_f64_g0(n, B, H, q, lower, upper, x_init, x, lu, pivots, If, trace, solo, status, st));
 }
 
 size_t dilqr_adjoint_workspace_bytes(const DilqrAdjoint* a) {
   if (!a) return 0;
-  return a->dtype == DILQR_F32 ? dilqr::adjoint_workspace_bytes_f32(a)
-                               : dilqr::adjoint_workspace_bytes_f64(a);
+  return a->dtype == DILQR_F32 ? dilqr::adjoint_workspace_bytes_f32_g0(a)
+                               : dilqr::adjoint_workspace_bytes_f64_g0(a);
 }
 int dilqr_adjoint_factor(const DilqrAdjoint* a, void* st) {
   if (!a) return DILQR_EINVAL;
-  return ROUTE(a->dtype, dilqr::adjoint_run_f32(a, 0, st), dilqr::adjoint_run_f64(a, 0, st));
+  return ROUTE(a->dtype, dilqr::adjoint_run_f32_g0(a, 0, st), dilqr::adjoint_run_f64_g0(a, 0, st));
 }
 int dilqr_adjoint_pass(const DilqrAdjoint* a, void* st) {
   if (!a) return DILQR_EINVAL;
-  return ROUTE(a->dtype, dilqr::adjoint_run_f32(a, 1, st), dilqr::adjoint_run_f64(a, 1, st));
+  return ROUTE(a->dtype, dilqr::adjoint_run_f32_g0(a, 1, st), dilqr::adjoint_run_f64_g0(a, 1, st));
 }
 int dilqr_adjoint_final(const DilqrAdjoint* a, void* st) {
   if (!a) return DILQR_EINVAL;
-  return ROUTE(a->dtype, dilqr::adjoint_run_f32(a, 2, st), dilqr::adjoint_run_f64(a, 2, st));
+  return ROUTE(a->dtype, dilqr::adjoint_run_f32_g0(a, 2, st), dilqr::adjoint_run_f64_g0(a, 2, st));
 }
 
 }  // extern "C"
