@@ -120,6 +120,7 @@ struct WarpStager {
                                 //        (broadcast cost: C[n,n] / C[T,n,n], mpc.py:205-219)
   uint32_t parity;   // bit s = parity to wait for on stage s
   uint32_t via_tma;  // bit s = stage s has bulk copies in flight
+  uint32_t via_lane; // bit s = stage s has lane-copied segments
   int nvalid;        // problems this warp really has (<= 32)
   int lane;
 
@@ -141,6 +142,7 @@ struct WarpStager {
     nvalid = nvalid_;
     parity = 0;
     via_tma = 0;
+    via_lane = 0;
     uint32_t off = 0;
     seg_sized = 0;
 #pragma unroll
@@ -179,12 +181,37 @@ struct WarpStager {
   }
 
   // Start copying the operands of one timestep into `stage`.  src[i] points at the
-  // first scalar of this warp's slab of segment i (or nullptr to skip).  Each segment
-  // goes by one bulk (TMA) copy if its size and source are 16-byte aligned, else by a
-  // lane-strided copy.
+  // first scalar of this warp's slab of segment i (or nullptr to skip).  Fast path
+  // (every requested segment 16-byte sized and aligned -- full warps, even shapes):
+  // one elected lane posts the byte count and one bulk TMA copy per segment.  Slow
+  // path (tail warps, odd sizes): per segment, bulk if possible else a lane copy.
   DILQR_DEVICE void issue(int stage, const S* const* src, int nseg) {
     char* dst = base + stage * stage_bytes;
     __syncwarp();  // all lanes are done reading this stage (WAR)
+    uintptr_t orp = 0;
+    uint32_t need = 0;
+#pragma unroll
+    for (int i = 0; i < kMaxSeg; ++i) {
+      if (i < nseg && src[i]) {
+        orp |= reinterpret_cast<uintptr_t>(src[i]);
+        need |= 1u << i;
+      }
+    }
+    if (((need & ~seg_sized) == 0u) && !(orp & 15u)) {
+      via_tma |= 1u << stage;
+      via_lane &= ~(1u << stage);
+      if (lane == 0) {
+        uint32_t total = 0;
+#pragma unroll
+        for (int i = 0; i < kMaxSeg; ++i)
+          if (i < nseg && src[i]) total += seg_nbytes[i];
+        mbar_expect_tx(&bar[stage], total);
+#pragma unroll
+        for (int i = 0; i < kMaxSeg; ++i)
+          if (i < nseg && src[i]) bulk_g2s(dst + seg_off[i], src[i], seg_nbytes[i], &bar[stage]);
+      }
+      return;
+    }
     uint32_t bulk_mask = 0, total = 0;
 #pragma unroll
     for (int i = 0; i < kMaxSeg; ++i) {
@@ -195,6 +222,7 @@ struct WarpStager {
       }
     }
     via_tma = bulk_mask ? (via_tma | (1u << stage)) : (via_tma & ~(1u << stage));
+    via_lane |= 1u << stage;
     if (bulk_mask && lane == 0) {
       mbar_expect_tx(&bar[stage], total);
 #pragma unroll
@@ -213,7 +241,7 @@ struct WarpStager {
       mbar_wait(&bar[stage], (parity >> stage) & 1u);
       parity ^= (1u << stage);
     }
-    __syncwarp();   // lane-copied segments
+    if ((via_lane >> stage) & 1u) __syncwarp();   // lane-copied segments
   }
 
   // Base of segment i in `stage` (blocked chunks: element e of this lane is [e*32+lane]).
