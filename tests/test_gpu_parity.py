@@ -417,3 +417,34 @@ def test_imitation_learning_loop(dilqr, env, dev):
     losses = [L.step(x0, u_exp) for _ in range(8)]
     assert all(b < a for a, b in zip(losses, losses[1:])), losses
     assert losses[-1] < 0.9 * losses[0]
+
+
+def test_tensor_bounds_and_broadcast_cost_lindx(dilqr, port, dev):
+    """u_lower / u_upper as [T,B,nc] tensors (lqr_step.py:264-272) and a broadcast
+    C[n,n] through mpc.MPC (forward + KKT backward) on a LinDx problem."""
+    ns, nc, T, B = 4, 2, 10, 24
+    C, c, F, f, x0 = lindx_problem(ns, nc, T, B, torch.float64, seed=5)
+    g = torch.Generator().manual_seed(9)
+    lo = -0.5 - torch.rand(T, B, nc, generator=g, dtype=torch.float64)
+    hi = 0.5 + torch.rand(T, B, nc, generator=g, dtype=torch.float64)
+    o = port.mpc_forward(x0, port.QuadCost(C, c), port.LinDx(F, f), ns, nc, T, u_lower=lo,
+                         u_upper=hi, lqr_iter=15)
+    m = dilqr.MPC(ns, nc, T, u_lower=lo.to(dev), u_upper=hi.to(dev), lqr_iter=15, verbose=-1,
+                  exit_unconverged=False)
+    with torch.no_grad():
+        x, u, costs = m(x0.to(dev), dilqr.QuadCost(C.to(dev), c.to(dev)), dilqr.LinDx(F.to(dev), f.to(dev)))
+    assert m.last_info.n_iters == o.n_iters and m.last_info.qp_iters == o.qp_iters
+    assert rel(x, o.x) < 1e-9 and rel(u, o.u) < 1e-9
+    # broadcast cost C[n,n], c[n]: same as the tiled problem, gradient = tiled gradient summed
+    C1, c1 = C[0, 0].clone(), c[0, 0].clone()
+    outs = []
+    for Cin, cin in ((C1.expand(T, B, -1, -1).contiguous(), c1.expand(T, B, -1).contiguous()),
+                     (C1, c1)):
+        Cg, cg = Cin.to(dev).requires_grad_(), cin.to(dev).requires_grad_()
+        m = dilqr.MPC(ns, nc, T, lqr_iter=15, verbose=-1, exit_unconverged=False, n_batch=B)
+        x, u, _ = m(x0.to(dev), dilqr.QuadCost(Cg, cg), dilqr.LinDx(F.to(dev), f.to(dev)))
+        (x.sum() + u.pow(2).sum()).backward()
+        outs.append((x, u, Cg.grad, cg.grad))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert rel(outs[1][2], outs[0][2].sum((0, 1))) < 1e-12
+    assert rel(outs[1][3], outs[0][3].sum((0, 1))) < 1e-12
