@@ -117,7 +117,8 @@ SYMBOLS = {
     "dilqr_pnqp": (C.c_int, [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 10 + [C.c_int]
                    + [C.c_void_p] * 2),
     "dilqr_costate_tables": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int]
-                             + [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_void_p]),
+                             + [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "dilqr_lam_pack_size": (C.c_int, [C.c_int]),
     "dilqr_richardson_update": (C.c_int, [C.c_int] * 5 + [C.c_void_p] * 8),
     "dilqr_sens_theta": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int]
                          + [C.c_void_p] * 9),

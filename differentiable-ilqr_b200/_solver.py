@@ -428,9 +428,13 @@ def dilqr_backward(dl_dx, dl_du, x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u
     K = info.K
     # (2) primal costates + contracted second-order tables
     lam = torch.empty(T, B, n_state, dtype=dtype, device=dev)
-    Lam = torch.empty(T - 1, B, n, n, dtype=dtype, device=dev)
+    if factored:   # packed, warp-blocked Lam (only the structurally non-zero entries)
+        nlam = _lib.lib().dilqr_lam_pack_size(kind)
+        Lam = torch.empty(T - 1, (B + 31) // 32, nlam, 32, dtype=dtype, device=dev)
+    else:
+        Lam = torch.empty(T - 1, B, n, n, dtype=dtype, device=dev)
     _lib.call("dilqr_costate_tables", _DT[dtype], kind, theta, T, B, _ptr(C_), _ptr(c_), _ptr(x),
-              _ptr(u), _ptr(lam), _ptr(Lam), Cb, cb, _stream())
+              _ptr(u), _ptr(lam), _ptr(Lam), Cb, cb, 1 if factored else 0, _stream())
     g = torch.cat((dl_dx, dl_du), 2).contiguous()
     w = g.clone()
     resid = torch.zeros(3, dtype=torch.float64, device=dev)

@@ -24,6 +24,7 @@
 #include "dynamics.cuh"
 #include "smallmat.cuh"
 #include "ilqr_kernels.cuh"
+#include "env_tables_gen.cuh"
 #include "../../include/dilqr.h"
 
 namespace dilqr {
@@ -37,6 +38,27 @@ DILQR_DEVICE void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" :::
 DILQR_DEVICE void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 DILQR_DEVICE void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 DILQR_DEVICE void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Lam_t[k][j] = sum_i lam_{t+1}[i] dD_t[i][j]/dtau_k is structurally sparse (cartpole:
+// D does not depend on x, dx and has constant columns) -- the factored path stores only
+// the entries that can be non-zero, warp-blocked [T-1][B/32][NLAM][32].
+template <class S, int DYN>
+struct LamPack {
+  using TB = EnvTables<S, DYN>;
+  static constexpr int NS = Dyn<S, DYN>::NS, NC = Dyn<S, DYN>::NC, N = NS + NC;
+  __host__ __device__ static constexpr bool nz(int k, int j) {
+    for (int i = 0; i < NS; ++i)
+      if (k < NS ? TB::nz_Dx(i, j, k < NS ? k : 0) : TB::nz_Du(i, j, k < NS ? 0 : k - NS)) return true;
+    return false;
+  }
+  __host__ __device__ static constexpr int idx(int k, int j) {   // position of (k,j) in the pack
+    int c = 0;
+    for (int e = 0; e < k * N + j; ++e)
+      if (nz(e / N, e % N)) ++c;
+    return c;
+  }
+  static constexpr int NLAM = idx(N - 1, N - 1) + (nz(N - 1, N - 1) ? 1 : 0);
+};
 
 template <class S>
 struct AdjParams {
@@ -276,28 +298,32 @@ template <class S, int DYN>
 struct AdjStage {
   using A = Adj<S, DYN>;
   static constexpr int NS = A::NS, NC = A::NC, N = A::N, NFAC = A::NFAC;
-  // segments: 0 big[N*N] (Lam_t or C_t)  1 vec[N] (w_t or g_t)  2 x[NS]  3 u[NC]
+  // segments: 0 big: packed Lam_t[NLAM] (blocked; passes) or C_t[N*N] (slab; final pass)
+  //           1 vec[N] (w_t or g_t)  2 x[NS]  3 u[NC]
   //           4 fac[NFAC] (blocked)      5 kv[N] (blocked: kvec_t[NC] or dtau_t[N])
   static constexpr int kNSeg = 6;
-  static constexpr uint32_t kFullMask = (1u << 4) | (1u << 5);
-  static __host__ __device__ void seg_elems(uint32_t* e) {
-    e[0] = N * N;
+  static constexpr int NLAM = LamPack<S, DYN>::NLAM;
+  static __host__ __device__ uint32_t full_mask(bool fin) {
+    return (1u << 4) | (1u << 5) | (fin ? 0u : 1u);
+  }
+  static __host__ __device__ void seg_elems(uint32_t* e, bool fin) {
+    e[0] = fin ? N * N : NLAM;
     e[1] = N;
     e[2] = NS;
     e[3] = NC;
     e[4] = NFAC;
     e[5] = N;
   }
-  static __host__ __device__ size_t stage_bytes() {
+  static __host__ __device__ size_t stage_bytes(bool fin) {
     uint32_t e[kNSeg];
-    seg_elems(e);
+    seg_elems(e, fin);
     return WarpStager<S>::bytes_per_warp(kNSeg, e);
   }
   static __host__ __device__ size_t out_bytes(bool fin) {
     return fin ? (((size_t)kWarp * (N * N + N) * sizeof(S) + 15) & ~(size_t)15) : 0;
   }
   static __host__ __device__ size_t smem_per_warp(bool fin) {
-    return stage_bytes() + kStages * sizeof(uint64_t) + out_bytes(fin);
+    return stage_bytes(fin) + kStages * sizeof(uint64_t) + out_bytes(fin);
   }
 };
 
@@ -321,11 +347,11 @@ __global__ void __launch_bounds__(64) adjoint_pass_kernel(const __grid_constant_
   WarpStager<S> st;
   {
     uint32_t e[AS::kNSeg];
-    AS::seg_elems(e);
+    AS::seg_elems(e, FINAL);
     st.init(wbase + kStages * sizeof(uint64_t), reinterpret_cast<uint64_t*>(wbase), lane, nvalid,
-            AS::kNSeg, e, AS::kFullMask);
+            AS::kNSeg, e, AS::full_mask(FINAL));
   }
-  S* outC = reinterpret_cast<S*>(wbase + kStages * sizeof(uint64_t) + AS::stage_bytes());
+  S* outC = reinterpret_cast<S*>(wbase + kStages * sizeof(uint64_t) + AS::stage_bytes(FINAL));
   S* outc = outC + kWarp * N * N;
 
   auto slab = [&](const S* base, int t, int elems) { return base + ((size_t)t * p.B + b0) * elems; };
@@ -409,7 +435,7 @@ __global__ void __launch_bounds__(64) adjoint_pass_kernel(const __grid_constant_
 
   // ---------------- linear rollout (+ Richardson update)
   auto issue_f = [&](int stage, int t) {
-    const S* src[AS::kNSeg] = {(!FINAL && t < T - 1) ? slab(p.Lam, t, N * N) : nullptr,
+    const S* src[AS::kNSeg] = {(!FINAL && t < T - 1) ? p.Lam + bidx(t, 0, AS::NLAM, b0, nW) : nullptr,
                                FINAL ? nullptr : slab(p.g, t, N), slab(p.x, t, NS),
                                slab(p.u, t, NC), p.fac + bidx(t, 0, NFAC, b0, nW),
                                p.kvec + bidx(t, 0, NC, b0, nW)};
@@ -478,15 +504,21 @@ __global__ void __launch_bounds__(64) adjoint_pass_kernel(const __grid_constant_
         }
       }
     } else {
-      const S* Ls = st.lane_ptr(sg, 0);
+      const S* Ls = st.seg_ptr(sg, 0) + lane;     // packed Lam_t, lane-interleaved
       const S* gs = st.lane_ptr(sg, 1);
       const size_t tb = (size_t)t * p.B + b;
-#pragma unroll
-      for (int k2 = 0; k2 < N; ++k2) {
+      using LP = LamPack<S, DYN>;
+      static_for<0, N>([&](auto K2) {
+        constexpr int k2 = decltype(K2)::value;
         S acc = S(0);
         if (t < T - 1) {
-#pragma unroll
-          for (int j = 0; j < N; ++j) acc = fmaS<S>(Ls[k2 * N + j], dt[j], acc);
+          static_for<0, N>([&](auto J) {
+            constexpr int j = decltype(J)::value;
+            if constexpr (LP::nz(k2, j)) {
+              constexpr int e = LP::idx(k2, j);
+              acc = fmaS<S>(Ls[e * kWarp], dt[j], acc);
+            }
+          });
         }
         const S wn = gs[k2] - acc;
         if (act) {
@@ -495,7 +527,7 @@ __global__ void __launch_bounds__(64) adjoint_pass_kernel(const __grid_constant_
           wmax = fmax(wmax, fabs((double)wn));
           p.w[tb * N + k2] = wn;
         }
-      }
+      });
     }
   }
   if (!FINAL) {

@@ -581,6 +581,13 @@ size_t DILQR_SUFFIX(adjoint_workspace_bytes)(const DilqrAdjoint* a) {
   return 0;
 }
 
+int DILQR_SUFFIX(lam_pack_size)(int dynamics) {
+  if (dynamics == DYN_PENDULUM) return LamPack<Scalar, DYN_PENDULUM>::NLAM;
+  if (dynamics == DYN_CARTPOLE) return LamPack<Scalar, DYN_CARTPOLE>::NLAM;
+  if (dynamics == DYN_ROCKET) return LamPack<Scalar, DYN_ROCKET>::NLAM;
+  return 0;
+}
+
 int DILQR_SUFFIX(adjoint_run)(const DilqrAdjoint* a, int what, void* stream) {
   int e = adj_check(a, what);
   if (e) return e;
@@ -594,14 +601,14 @@ int DILQR_SUFFIX(adjoint_run)(const DilqrAdjoint* a, int what, void* stream) {
 template <int DYN>
 static int launch_costate(const double* dp, int T, int B, const void* C, const void* c,
                           const void* x, const void* u, void* lam, void* Lam, int Cb, int cb,
-                          cudaStream_t st) {
+                          int packed, cudaStream_t st) {
   using S = Scalar;
   DynParams<S> P;
   for (int i = 0; i < 8; ++i) P.p[i] = (S)dp[i];
   const int wpb = CostateStage<S, DYN>::smem_per_warp() * 2 <= 200 * 1024 ? 2 : 1;
   const size_t smem = CostateStage<S, DYN>::smem_per_warp() * wpb;
   if (smem > 227 * 1024) return DILQR_EUNSUPPORTED;
-  auto kern = costate_tables_kernel<S, DYN>;
+  auto kern = packed ? costate_tables_kernel<S, DYN, true> : costate_tables_kernel<S, DYN, false>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int warps = (B + kWarp - 1) / kWarp;
   kern<<<(warps + wpb - 1) / wpb, wpb * kWarp, smem, st>>>(
@@ -612,13 +619,13 @@ static int launch_costate(const double* dp, int T, int B, const void* C, const v
 
 int DILQR_SUFFIX(costate_tables)(int dynamics, const double* dp, int T, int B, const void* C,
                                  const void* c, const void* x, const void* u, void* lam,
-                                 void* Lam, int Cb, int cb, void* stream) {
+                                 void* Lam, int Cb, int cb, int packed, void* stream) {
   if (!dp || !C || !c || !x || !u || !lam || !Lam || T <= 0 || B <= 0) return DILQR_EINVAL;
   if (Cb < 0 || Cb > 2 || cb < 0 || cb > 2) return DILQR_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dynamics == DYN_PENDULUM) return launch_costate<DYN_PENDULUM>(dp, T, B, C, c, x, u, lam, Lam, Cb, cb, st);
-  if (dynamics == DYN_CARTPOLE) return launch_costate<DYN_CARTPOLE>(dp, T, B, C, c, x, u, lam, Lam, Cb, cb, st);
-  if (dynamics == DYN_ROCKET) return launch_costate<DYN_ROCKET>(dp, T, B, C, c, x, u, lam, Lam, Cb, cb, st);
+  if (dynamics == DYN_PENDULUM) return launch_costate<DYN_PENDULUM>(dp, T, B, C, c, x, u, lam, Lam, Cb, cb, packed, st);
+  if (dynamics == DYN_CARTPOLE) return launch_costate<DYN_CARTPOLE>(dp, T, B, C, c, x, u, lam, Lam, Cb, cb, packed, st);
+  if (dynamics == DYN_ROCKET) return launch_costate<DYN_ROCKET>(dp, T, B, C, c, x, u, lam, Lam, Cb, cb, packed, st);
   return DILQR_EUNSUPPORTED;
 }
 

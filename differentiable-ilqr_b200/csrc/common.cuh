@@ -10,6 +10,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 namespace dilqr {
 
@@ -39,6 +40,16 @@ template <> DILQR_DEVICE double atan2S<double>(double y, double x) { return atan
 template <class S> DILQR_DEVICE void sincosS(S a, S* s, S* c);
 template <> DILQR_DEVICE void sincosS<float>(float a, float* s, float* c) { sincosf(a, s, c); }
 template <> DILQR_DEVICE void sincosS<double>(double a, double* s, double* c) { sincos(a, s, c); }
+
+// compile-time loop: f(std::integral_constant<int, I>{}) for I in [0, N) -- used where an
+// index must be a constant expression (packed-table offsets computed by constexpr code)
+template <int I, int N, class F>
+DILQR_DEVICE void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(f);
+  }
+}
 
 // eclamp (util.py:58-72): two masked assignments, NaN passes through.
 template <class S> DILQR_DEVICE S eclamp(S x, S lo, S hi) {

@@ -51,7 +51,9 @@ struct CostateStage {
   }
 };
 
-template <class S, int DYN>
+// PACKED: Lam_out is the packed, warp-blocked layout [T-1][B/32][NLAM][32] consumed by
+// the factored adjoint passes; otherwise dense [T-1,B,n,n] (richardson_update_kernel).
+template <class S, int DYN, bool PACKED>
 __global__ void __launch_bounds__(64)
 costate_tables_kernel(DynParams<S> P, int T, int B, const S* __restrict__ C,
                       const S* __restrict__ c, const S* __restrict__ x, const S* __restrict__ u,
@@ -82,7 +84,10 @@ costate_tables_kernel(DynParams<S> P, int T, int B, const S* __restrict__ C,
                                cost_src<S>(c, c_bcast, t, B, b0, N), x + o * NS, u + o * NC};
     st.issue(stage, src, CS::kNSeg);
   };
-  const bool bulk_out = (nvalid == kWarp) && ((((size_t)N * N * sizeof(S) * kWarp) & 15) == 0);
+  const bool bulk_out = !PACKED && (nvalid == kWarp) &&
+                        ((((size_t)N * N * sizeof(S) * kWarp) & 15) == 0);
+  using LP = LamPack<S, DYN>;
+  const int nWp = (B + kWarp - 1) / kWarp;
   S lam[NS];
   issue(0, T - 1);
   for (int t = T - 1; t >= 0; --t) {
@@ -109,24 +114,33 @@ costate_tables_kernel(DynParams<S> P, int T, int B, const S* __restrict__ C,
         __syncwarp();
       }
       S* Lo = bulk_out ? outL + lane * (N * N) : Lam_out + tb * (N * N);
-      if (act || bulk_out) {
+      if (PACKED) Lo = Lam_out + bidx(t, 0, LP::NLAM, b0 + lane, nWp);   // own (padded) column
+      if (act || bulk_out || PACKED) {
+static_for<0, N>([&](auto KK) {
+          constexpr int k = decltype(KK)::value;
+          static_for<0, N>([&](auto JJ) {
+            constexpr int j = decltype(JJ)::value;
+            if constexpr (!PACKED || LP::nz(k, j)) {
+              S acc = S(0);
 #pragma unroll
-        for (int k = 0; k < N; ++k)
-#pragma unroll
-          for (int j = 0; j < N; ++j) {
-            S acc = S(0);
-#pragma unroll
-            for (int i = 0; i < NS; ++i) {
-              if (k < NS) {
-                if (TB::nz_Dx(i, j, k < NS ? k : 0))
-                  acc = fmaS<S>(lam[i], Dx[i][j][k < NS ? k : 0], acc);
+              for (int i = 0; i < NS; ++i) {
+                if (k < NS) {
+                  if (TB::nz_Dx(i, j, k < NS ? k : 0))
+                    acc = fmaS<S>(lam[i], Dx[i][j][k < NS ? k : 0], acc);
+                } else {
+                  if (TB::nz_Du(i, j, k < NS ? 0 : k - NS))
+                    acc = fmaS<S>(lam[i], Du[i][j][k < NS ? 0 : k - NS], acc);
+                }
+              }
+              if constexpr (PACKED) {
+                constexpr int e = LP::idx(k, j);
+                Lo[e * kWarp] = acc;
               } else {
-                if (TB::nz_Du(i, j, k < NS ? 0 : k - NS))
-                  acc = fmaS<S>(lam[i], Du[i][j][k < NS ? 0 : k - NS], acc);
+                Lo[k * N + j] = acc;
               }
             }
-            Lo[k * N + j] = acc;
-          }
+          });
+        });
       }
       if (bulk_out) {
         fence_async_smem();

@@ -21,7 +21,8 @@ namespace dilqr {
                       void*);                                                             \
   int rollout_##sfx(int, const double*, int, int, const void*, const void*, void*, void*); \
   int costate_tables_##sfx(int, const double*, int, int, const void*, const void*, const void*, \
-                           const void*, void*, void*, int, int, void*);                   \
+                           const void*, void*, void*, int, int, int, void*);              \
+  int lam_pack_size_##sfx(int);                                                           \
   int sens_theta_##sfx(int, const double*, int, int, const void*, const void*, const void*, \
                        const void*, const void*, const void*, const void*, void*, void*); \
   int env_tables_##sfx(int, const double*, int, const void*, const void*, void* const*, void*); \
@@ -117,10 +118,14 @@ int dilqr_rollout(int dtype, int dyn, const double* dp, int T, int B, const void
 
 int dilqr_costate_tables(int dtype, int dyn, const double* dp, int T, int B, const void* C,
                          const void* c, const void* x, const void* u, void* lam, void* Lam,
-                         int C_bcast, int c_bcast, void* st) {
+                         int C_bcast, int c_bcast, int packed, void* st) {
   return ROUTE(dtype,
-               dilqr::costate_tables_f32_g0(dyn, dp, T, B, C, c, x, u, lam, Lam, C_bcast, c_bcast, st),
-               dilqr::costate_tables_f64_g0(dyn, dp, T, B, C, c, x, u, lam, Lam, C_bcast, c_bcast, st));
+               dilqr::costate_tables_f32_g0(dyn, dp, T, B, C, c, x, u, lam, Lam, C_bcast, c_bcast,
+                                            packed, st),
+               dilqr::costate_tables_f64_g0(dyn, dp, T, B, C, c, x, u, lam, Lam, C_bcast, c_bcast,
+                                            packed, st));
+}
+int dilqr_lam_pack_size(int dynamics) { return dilqr::lam_pack_size_f64_g0(dynamics);
 }
 int dilqr_sens_theta(int dtype, int dyn, const double* dp, int T, int B, const void* x,
                      const void* u, const void* K, const void* lam, const void* dx,

@@ -227,12 +227,15 @@ int dilqr_kkt_grads(const DilqrKkt* k, void* stream);
  * fix_point_equ (lqr_step_explicit.py:652-712, 458-598), matrix-free -------- */
 
 /* Primal costates lam[T,B,ns] (lqr_step_explicit.py:305-319) and contracted
- * second-order tables Lam[T-1,B,n,n], Lam_t[k][j] = sum_i lam_{t+1}[i]
- * dD_t[i][j]/dtau_k with dD/dtau from get_matrices (cartpole.py:425-613,
- * pendulum.py:152-382). */
+ * second-order tables Lam_t[k][j] = sum_i lam_{t+1}[i] dD_t[i][j]/dtau_k with dD/dtau
+ * from get_matrices (cartpole.py:425-613, pendulum.py:152-382).  packed == 0: dense
+ * Lam[T-1,B,n,n] (for dilqr_richardson_update); packed == 1: only the structurally
+ * non-zero entries, warp-blocked [T-1][ceil(B/32)][dilqr_lam_pack_size()][32] (for
+ * dilqr_adjoint_pass). */
+int dilqr_lam_pack_size(int dynamics);
 int dilqr_costate_tables(int dtype, int dynamics, const double* dyn_params, int T, int n_batch,
                          const void* C, const void* c, const void* x, const void* u, void* lam,
-                         void* Lam, int C_bcast, int c_bcast, void* stream);
+                         void* Lam, int C_bcast, int c_bcast, int packed, void* stream);
 
 /* One Richardson update of A' w = g:  w_t = g_t - Lam_t dtau_t (t < T-1),
  * w_{T-1} = g_{T-1}; writes w and -w, and resid[0] = max|w_new - w_old|,
@@ -265,7 +268,7 @@ typedef struct DilqrAdjoint {
   const void *C;         /* [T,B,n,n]                                                  */
   const void *x, *u;     /* solution tau* [T,B,ns], [T,B,nc]                           */
   const void *g;         /* [T,B,n]  cat(dl_dx, dl_du)                                 */
-  const void *Lam;       /* [T-1,B,n,n] from dilqr_costate_tables                      */
+  const void *Lam;       /* packed Lam from dilqr_costate_tables(packed = 1)            */
   void *w;               /* [T,B,n]  Richardson iterate, in/out (initialise to g)      */
   void *dC, *dc, *df;    /* final pass outputs: [T,B,n,n], [T,B,n], [T-1,B,ns]         */
   void *dx_out, *du_out; /* final pass: adjoint solution (optional)                    */
