@@ -36,7 +36,8 @@ class DilqrStatus(C.Structure):
         ("mean_alpha", C.c_double),
         ("mean_best_cost", C.c_double),
         ("first_mismatch", C.c_uint32),
-        ("reserved", C.c_uint32 * 5),
+        ("n_active", C.c_uint32),
+        ("reserved", C.c_uint32 * 4),
     ]
 
 

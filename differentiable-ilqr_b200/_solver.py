@@ -114,7 +114,7 @@ def _make_problem(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower, u_upper, u_z
     s.dtype = _DT[dtype]
     s.dynamics = dyn.kind
     s.gain_solve = gain_solve
-    s.solo = 1 if solo else 0
+    s.solo = int(solo)   # 0 batch-global, 1 per-problem QP flags, 2 per-problem outer loop too
     s.max_linesearch_iter = max_linesearch_iter
     s.linesearch_decay = float(linesearch_decay)
     s.best_cost_eps = float(best_cost_eps)
@@ -295,7 +295,10 @@ def solve_mpc(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower=None, u_upper=Non
     n_not_improved = 0
     n_loops = 1 if x_cur is not None else lqr_iter
     nosync = (not sync) and n_loops == 1 and (s.bounds_kind == _lib.BOUNDS_NONE or solo)
-    if pipelined and n_loops > 1 and n_loops <= MAX_PIPELINED_ITERS and verbose <= 0:
+    if int(solo) == 2 and n_loops > 1 and not n_loops <= MAX_PIPELINED_ITERS:
+        raise ValueError("solo=2 needs lqr_iter <= %d" % MAX_PIPELINED_ITERS)
+    if n_loops > 1 and n_loops <= MAX_PIPELINED_ITERS and (
+            (pipelined and verbose <= 0) or int(solo) == 2):
         _solve_pipelined(L, s, ws, info, n_loops, eps_cmp, not_improved_lim, verbose)
         n_loops = 0
     for i in range(n_loops):

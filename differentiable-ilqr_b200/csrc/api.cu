@@ -286,7 +286,7 @@ static int launch_commit(const DilqrSolve* s, cudaStream_t st) {
   trace_verify_kernel<<<1, 256, 0, st>>>(p.guess, p.votes, p.T, p.bounds_kind != 0, p.solo,
                                          s->status, p.lockstep, s->control);
   commit_kernel<S, NS + NC, NC><<<(p.B + 127) / 128, 128, 0, st>>>(p);
-  if (s->control) control_kernel<<<1, 1, 0, st>>>(s->control, s->status, s->iteration);
+  if (s->control) control_kernel<<<1, 1, 0, st>>>(s->control, s->status, s->iteration, s->solo);
   return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
 }
 

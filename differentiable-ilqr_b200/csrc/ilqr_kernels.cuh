@@ -413,7 +413,7 @@ struct IterKernel {
     const int T = p.T;
     // lazy best-iterate tracking (mpc.py:272-285): if the previous iteration made the
     // current trajectory this problem's best, park it in traj_best while it streams by.
-    const bool flush = p.take[bw] != 0;
+    const bool flush = (p.take[bw] & 1) != 0;
     issue_t(st, p, 0, T - 1, b0, false, true, false);
     for (int t = T - 1; t >= 0; --t) {
       const int sg = (T - 1 - t) & 1;

@@ -64,6 +64,7 @@ static __global__ void trace_verify_kernel(uint32_t* __restrict__ guess, const u
     status->trace_match = (s_first >= n) ? 1u : 0u;
     status->first_mismatch = (uint32_t)s_first;
     status->any_improved = 0;
+    status->n_active = 0;
     status->n_total_qp_iter = s_nqp;
     status->pnqp_unconverged = s_unconv;
     status->max_full_du = 0.0;
@@ -74,8 +75,14 @@ static __global__ void trace_verify_kernel(uint32_t* __restrict__ guess, const u
 }
 
 // Device-side stop rule of the outer loop (mpc.py:266,281,299-301), one thread.
-static __global__ void control_kernel(DilqrControl* ctrl, const DilqrStatus* status, int iteration) {
+static __global__ void control_kernel(DilqrControl* ctrl, const DilqrStatus* status, int iteration,
+                                      int solo) {
   if (ctrl->halt) return;
+  if (solo == 2) {   // per-problem stop rule lives in commit_kernel; halt once nobody is left
+    ctrl->iters_done = (uint32_t)iteration + 1u;
+    if (status->n_active == 0u) ctrl->halt = 1u;
+    return;
+  }
   uint32_t n = ctrl->n_not_improved + 1u;
   if (iteration > 0 && status->any_improved) n = 0u;
   ctrl->n_not_improved = n;
@@ -95,7 +102,46 @@ __global__ void commit_kernel(const __grid_constant__ IterParams<S> p) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   double du = 0.0, al = 0.0, bc = 0.0;
   bool improved = false;
-  if (b < p.B) {
+  bool active = false;
+  if (b < p.B && p.solo == 2) {
+    // Every problem is its own batch of one (the closed-loop driver il_env.py:96-151 calls
+    // MPC with n_batch = 1): plain per-problem ||du||, and the stop rule mpc.py:266,281,
+    // 299-301 per problem.  take[b]: bit 0 = take, bits 8..29 = n_not_improved, bit 30 =
+    // stopped (a stopped problem keeps iterating with the others but is never taken again).
+    const int state = p.take[b];
+    const bool frozen = (state >> 30) & 1;
+    int nni = (state >> 8) & 0x3fffff;
+    S acc = S(0);
+    for (int k = 0; k < p.T * NCc; ++k) acc = acc + p.dusq[(size_t)k * p.B + b];
+    const S dn = sqrtS<S>(acc);
+    const S cn = p.cost_new[b];
+    bool take = false, stop = frozen;
+    if (!frozen) {
+      p.du_new[b] = dn;
+      nni += 1;
+      if (p.first_iteration) {
+        take = true;
+      } else if (cn <= p.cost_best[b] + p.best_cost_eps) {
+        take = true;
+        improved = true;
+        nni = 0;
+      }
+      if (take) {
+        p.cost_best[b] = cn;
+        p.du_best[b] = dn;
+      }
+      if (p.control) {
+        const DilqrControl* ctl = reinterpret_cast<const DilqrControl*>(p.control);
+        stop = (double)dn < ctl->eps || (uint32_t)nni > ctl->not_improved_lim;
+      }
+      active = !stop;
+      du = (double)dn;
+      al = (double)p.alpha_new[b];
+    }
+    p.take[b] = (take ? 1 : 0) | (nni << 8) | (stop ? (1 << 30) : 0);
+    p.cost_cur[b] = cn;
+    bc = (double)p.cost_best[b];
+  } else if (b < p.B) {
     // full_du_norm[b]: norm of row b of the [T,nc,B] squares re-read as [B, T*nc]
     // (lqr_step.py:243-245, see the note in forward_linesearch)
     {
@@ -132,7 +178,9 @@ __global__ void commit_kernel(const __grid_constant__ IterParams<S> p) {
   }
   const unsigned imp = __ballot_sync(kFull, improved);
   const unsigned nn = __ballot_sync(kFull, nan_du);
+  const unsigned act = __ballot_sync(kFull, active);
   if ((threadIdx.x & 31) == 0) {
+    if (act) atomicAdd(&status->n_active, (uint32_t)__popc(act));
     if (nn) du = __longlong_as_double(0x7ff8000000000000LL);  // propagate NaN like python max()
     atomicMax(reinterpret_cast<unsigned long long*>(&status->max_full_du), dbits(du));
     atomicAdd(&status->mean_alpha, al / p.B);
@@ -154,7 +202,7 @@ __global__ void finish_kernel(const __grid_constant__ IterParams<S> p) {
   const int t = blockIdx.y;
   if (b >= p.B) return;
   // best iterate: parked in traj_best, or still the latest trajectory (take flag)
-  const S* src = (p.take[b] ? p.traj_new : p.traj_best) + bidx(t, 0, N, b, p.nW);
+  const S* src = ((p.take[b] & 1) ? p.traj_new : p.traj_best) + bidx(t, 0, N, b, p.nW);
   if (p.x_out) {
 #pragma unroll
     for (int i = 0; i < NS; ++i) p.x_out[((size_t)t * p.B + b) * NS + i] = src[i * kWarp];

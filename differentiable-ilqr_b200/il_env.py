@@ -1,0 +1,159 @@
+"""IL_Env -- the caller either side of the hot path (il_env.py:32-188 of the reference):
+expert-data generation by open-loop MPC (`populate_data`), by closed-loop
+receding-horizon MPC (`populate_data2`) and the `mpc` helper the training loop calls.
+
+Same names and arguments as the reference.  What is B200-first here:
+
+* the diagonal cost is handed to the solver as the `[n,n]` / `[n]` tensors it is
+  (broadcast-aware kernels) instead of being `.repeat`-ed to `[T,B,n,n]`
+  (il_env.py:159-162); `tile=True` restores the dense layout, results are identical;
+* `populate_data2` runs its `n_total` closed loops as ONE batch: the reference calls
+  MPC once per (sample, time step) with n_batch=1 (il_env.py:112-143), i.e. every problem
+  has its own pnqp / line-search / stop-rule flags.  `solo=2` gives exactly those
+  per-problem semantics inside a batched launch, so T solves of B=n_total replace
+  n_total*T solves of B=1; the plant step and the warm-start shift stay on the device.
+"""
+import numpy as np
+import torch
+
+from . import mpc_explicit
+from .definitions import QuadCost
+from .env_dx import cartpole, pendulum
+from .mpc_explicit import GradMethods
+
+
+class IL_Env:
+    def __init__(self, env, lqr_iter=100, mpc_T=35, slew_rate_penalty=None, dtype=None,
+                 device=None, tile=False):
+        self.env = env
+        if env == 'pendulum':
+            self.true_dx = pendulum.PendulumDx()
+        elif env == 'cartpole':
+            self.true_dx = cartpole.CartpoleDx()
+        elif env == 'pendulum-complex':
+            raise NotImplementedError("pendulum-complex (5-parameter damped model, "
+                                      "il_env.py:40-42) has no device tables")
+        else:
+            assert False
+        self.lqr_iter = lqr_iter
+        self.mpc_T = mpc_T
+        self.slew_rate_penalty = slew_rate_penalty     # unused by the reference too (il_env.py:185)
+        self.grad_method = GradMethods.ANALYTIC
+        self.dtype = dtype or torch.get_default_dtype()
+        self.device = torch.device(device if device is not None else "cuda")
+        self.tile = tile
+        self.train_data = None
+        self.val_data = None
+        self.test_data = None
+
+    # ------------------------------------------------------------------ sampling
+    def sample_xinit(self, n_batch=1):
+        """il_env.py:57-79, same draw order from the CPU generator so that a seed
+        reproduces the reference's initial states (returned on the host)."""
+        def uniform(shape, low, high):
+            r = high - low
+            return torch.rand(shape) * r + low
+
+        if self.env in ['pendulum', 'pendulum-complex']:
+            th = uniform(n_batch, -(1 / 2) * np.pi, (1 / 2) * np.pi)
+            thdot = uniform(n_batch, -1., 1.)
+            xinit = torch.stack((torch.cos(th), torch.sin(th), thdot), dim=1)
+        elif self.env == 'cartpole':
+            x = uniform(n_batch, -0.5, 0.5) * 0
+            dx = uniform(n_batch, -0.5, 0.5) * 0
+            th = uniform(n_batch, -np.pi, np.pi) * 0 + torch.ones(n_batch) * 3.1415926 / 1.05
+            dth = uniform(n_batch, -1., 1.) * 0
+            xinit = torch.stack((x, dx, torch.cos(th), torch.sin(th), dth), dim=1)
+        else:
+            assert False
+        return xinit
+
+    def _dev(self, t):
+        return t.detach().to(device=self.device, dtype=self.dtype)
+
+    def _cost(self, q, p, T, n_batch):
+        q, p = self._dev(q), self._dev(p)
+        if self.tile:                                    # il_env.py:159-162
+            Q = torch.diag(q).unsqueeze(0).unsqueeze(0).repeat(T, n_batch, 1, 1)
+            return QuadCost(Q, p.unsqueeze(0).repeat(T, n_batch, 1))
+        return QuadCost(torch.diag(q), p)
+
+    # ------------------------------------------------------------------ open loop
+    def populate_data(self, n_train, n_val, n_test, seed=0):
+        """il_env.py:81-94."""
+        torch.manual_seed(seed)
+        n_data = n_train + n_val + n_test
+        xinit = self.sample_xinit(n_batch=n_data)
+        true_q, true_p = self.true_dx.get_true_obj()
+        true_x_mpc, true_u_mpc = self.mpc(self.true_dx, xinit, true_q, true_p)
+        tau = torch.cat((true_x_mpc, true_u_mpc), dim=2).transpose(0, 1)
+        self.train_data = tau[:n_train]
+        self.val_data = tau[n_train:n_train + n_val]
+        self.test_data = tau[-n_test:]
+
+    # ------------------------------------------------------------------ closed loop
+    def closed_loop(self, x_init, n_steps=None):
+        """Receding-horizon rollout of il_env.py:112-143 for a batch of initial states
+        [B,ns]: returns tau [B, n_steps, ns+nc] (states before each applied control)."""
+        T = self.mpc_T
+        n_steps = T if n_steps is None else n_steps
+        dx = self.true_dx
+        q, p = dx.get_true_obj()
+        x = self._dev(x_init)
+        B = x.shape[0]
+        cost = self._cost(q, p, T, B)
+        ctrl = mpc_explicit.MPC(
+            dx.n_state, dx.n_ctrl, T, u_lower=dx.lower, u_upper=dx.upper,
+            lqr_iter=self.lqr_iter, verbose=-1, exit_unconverged=False,
+            detach_unconverged=False, linesearch_decay=dx.linesearch_decay,
+            max_linesearch_iter=dx.max_linesearch_iter, grad_method=self.grad_method,
+            eps=dx.mpc_eps, n_batch=B, solo=2)
+        xs = torch.empty(n_steps, B, dx.n_state, dtype=self.dtype, device=self.device)
+        us = torch.empty(n_steps, B, dx.n_ctrl, dtype=self.dtype, device=self.device)
+        u_init = None
+        with torch.no_grad():
+            for t in range(n_steps):
+                ctrl.u_init = u_init
+                _, nominal_actions, _ = ctrl(x, cost, dx)
+                xs[t] = x
+                us[t] = nominal_actions[0]
+                x = dx(x, nominal_actions[0])                      # plant step (il_env.py:138)
+                # warm start: shift by one, pad (il_env.py:141-142)
+                u_init = torch.cat((nominal_actions[1:], torch.zeros_like(nominal_actions[:1])), 0)
+                u_init[-2] = u_init[-3]
+        return torch.cat((xs, us), 2).transpose(0, 1).contiguous()
+
+    def populate_data2(self, n_train, n_val, n_test, seed=0):
+        """il_env.py:96-151."""
+        torch.manual_seed(seed)
+        n_total = n_train + n_val + n_test
+        x_init_all = self.sample_xinit(n_batch=n_total)
+        all_tau = self.closed_loop(x_init_all)
+        self.train_data = all_tau[:n_train]
+        self.val_data = all_tau[n_train:n_train + n_val]
+        self.test_data = all_tau[n_train + n_val:]
+
+    # ------------------------------------------------------------------ training-loop helper
+    def mpc(self, dx, xinit, q, p, u_init=None, eps_override=None, lqr_iter_override=None):
+        """il_env.py:153-188 (differentiable in dx.params, q, p)."""
+        xinit = xinit.to(device=self.device, dtype=self.dtype)
+        n_batch = xinit.shape[0]
+        if self.tile:
+            q_, p_ = q.to(self.device, self.dtype), p.to(self.device, self.dtype)
+            Q = torch.diag(q_).unsqueeze(0).unsqueeze(0).repeat(self.mpc_T, n_batch, 1, 1)
+            cost = QuadCost(Q, p_.unsqueeze(0).repeat(self.mpc_T, n_batch, 1))
+        else:
+            cost = QuadCost(torch.diag(q.to(self.device, self.dtype)), p.to(self.device, self.dtype))
+        eps = eps_override if eps_override else self.true_dx.mpc_eps
+        lqr_iter = lqr_iter_override if lqr_iter_override else self.lqr_iter
+        if u_init is not None:
+            u_init = u_init.to(device=self.device, dtype=self.dtype)
+        x_mpc, u_mpc, objs_mpc = mpc_explicit.MPC(
+            self.true_dx.n_state, self.true_dx.n_ctrl, self.mpc_T,
+            u_lower=self.true_dx.lower, u_upper=self.true_dx.upper, u_init=u_init,
+            lqr_iter=lqr_iter, verbose=0, exit_unconverged=False, detach_unconverged=True,
+            linesearch_decay=self.true_dx.linesearch_decay,
+            max_linesearch_iter=self.true_dx.max_linesearch_iter,
+            grad_method=self.grad_method, eps=eps,
+        )(xinit, cost, dx)
+        return x_mpc, u_mpc

@@ -70,7 +70,8 @@ typedef struct DilqrStatus {
   double   mean_alpha;      /* mean_b alpha_b                     (lqr_step.py:259)  */
   double   mean_best_cost;  /* mean_b best cost (verbose table,   mpc.py:288)        */
   uint32_t first_mismatch;  /* slot index of first trace mismatch (debug)            */
-  uint32_t reserved[5];
+  uint32_t n_active;        /* solo == 2: problems whose own stop rule has not fired */
+  uint32_t reserved[4];
 } DilqrStatus;
 
 /* Optional device-resident outer-loop state: with `control` set in DilqrSolve the
@@ -96,7 +97,12 @@ typedef struct DilqrSolve {
   int32_t gain_solve;       /* DILQR_GAIN_*                                         */
   int32_t bounds_kind;      /* DILQR_BOUNDS_*                                       */
   int32_t solo;             /* 0: batch-global pnqp control flow (== reference on
-                               the same batch); 1: per-problem (== reference B=1)   */
+                               the same batch); 1: per-problem pnqp / Armijo flags
+                               (== reference B=1 for one LQR step); 2: additionally the
+                               outer loop per problem -- own ||du||, own n_not_improved,
+                               own stop rule (mpc.py:266,281,299-301): every problem ==
+                               the reference called with n_batch=1 (il_env.py:96-151).
+                               2 needs `control` for the stop thresholds             */
   int32_t max_linesearch_iter; /* mpc.py:135                                        */
   int32_t iteration;        /* 0-based iLQR iteration index of this iterate/commit call
                                (0: first -> best := new, mpc.py:271; parity selects

@@ -720,3 +720,54 @@ class RocketDx:
     def get_linear_dyn(self, x, u):                    # rocket.py:324-426
         import env_tables_gen as G
         return G.rocket_tables(x, u, self.params.detach())[0]
+
+
+# ---------------------------------------------------------------------------
+# Closed-loop expert data (il_env.py:57-79, 96-151)
+# ---------------------------------------------------------------------------
+def sample_xinit(env, n_batch):                        # il_env.py:57-79
+    import math
+
+    def uniform(shape, low, high):
+        return torch.rand(shape) * (high - low) + low
+
+    if env == "pendulum":
+        th = uniform(n_batch, -(1 / 2) * math.pi, (1 / 2) * math.pi)
+        thdot = uniform(n_batch, -1., 1.)
+        return torch.stack((torch.cos(th), torch.sin(th), thdot), dim=1)
+    assert env == "cartpole"
+    x = uniform(n_batch, -0.5, 0.5) * 0
+    dx = uniform(n_batch, -0.5, 0.5) * 0
+    th = uniform(n_batch, -math.pi, math.pi) * 0 + torch.ones(n_batch) * 3.1415926 / 1.05
+    dth = uniform(n_batch, -1., 1.) * 0
+    return torch.stack((x, dx, torch.cos(th), torch.sin(th), dth), dim=1)
+
+
+def closed_loop(dynamics, x_init_all, T, lqr_iter):
+    """populate_data2 (il_env.py:96-151): for every sample, T receding-horizon MPC
+    calls with n_batch = 1; apply the first control, shift the warm start."""
+    q, p = dynamics.get_true_obj()
+    n = q.shape[0]
+    dtype = x_init_all.dtype
+    Q = torch.diag(q.to(dtype)).reshape(1, 1, n, n).repeat(T, 1, 1, 1)
+    pp = p.to(dtype).reshape(1, 1, n).repeat(T, 1, 1)
+    taus = []
+    for i in range(x_init_all.shape[0]):
+        x = x_init_all[i].unsqueeze(0)
+        u_init = None
+        xs, us = [x.squeeze(0)], []
+        for _ in range(T):
+            o = mpc_forward(x, QuadCost(Q.clone(), pp.clone()), dynamics, dynamics.n_state,
+                            dynamics.n_ctrl, T, u_lower=dynamics.lower, u_upper=dynamics.upper,
+                            u_init=u_init, lqr_iter=lqr_iter, eps=dynamics.mpc_eps,
+                            linesearch_decay=dynamics.linesearch_decay,
+                            max_linesearch_iter=dynamics.max_linesearch_iter,
+                            final_pass=False)
+            a = o.u[0]
+            us.append(a.squeeze(0))
+            x = dynamics(x, a)
+            xs.append(x.squeeze(0))
+            u_init = torch.cat((o.u[1:], torch.zeros(1, 1, dynamics.n_ctrl, dtype=dtype)), 0)
+            u_init[-2] = u_init[-3]
+        taus.append(torch.cat((torch.stack(xs[:-1]), torch.stack(us)), 1))
+    return torch.stack(taus)

@@ -153,6 +153,19 @@ def env_forward(env, T, B, lqr_iter, dtype):
     torch.set_default_dtype(torch.float32)
 
 
+def closed_loop(env, mpc_T, lqr_iter, n_train, n_val, n_test):
+    """IL_Env.populate_data2 (il_env.py:96-151): closed-loop receding-horizon expert data,
+    one B=1 MPC call per (sample, step)."""
+    torch.set_default_dtype(torch.float64)
+    e = R.il_env.IL_Env(env, lqr_iter=lqr_iter, mpc_T=mpc_T)
+    torch.manual_seed(0)
+    x0 = e.sample_xinit(n_batch=n_train + n_val + n_test)
+    e.populate_data2(n_train, n_val, n_test, seed=0)
+    npz("ref_closed_loop_%s.npz" % env, x0=x0, train=e.train_data, val=e.val_data,
+        test=e.test_data, mpc_T=mpc_T, lqr_iter=lqr_iter)
+    torch.set_default_dtype(torch.float32)
+
+
 if __name__ == "__main__":
     fixtures()
     lindx(False)
@@ -164,3 +177,5 @@ if __name__ == "__main__":
     env_forward("cartpole", 25, 16, 6, torch.float64)
     env_forward("pendulum", 20, 16, 8, torch.float64)
     env_forward("cartpole", 25, 16, 6, torch.float32)
+    closed_loop("pendulum", 20, 50, 4, 1, 1)
+    closed_loop("cartpole", 12, 30, 1, 1, 1)

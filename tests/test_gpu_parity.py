@@ -249,6 +249,56 @@ def test_solo_mode_equals_batch_of_one(dilqr, port, env, dev):
             assert rel(u[:, j:j + 1], o.u) < 1e-6
 
 
+def test_per_problem_outer_loop(dilqr, port, env, dev):
+    """solo=2: pnqp flags, line search, ||du||, n_not_improved and the stop rule per
+    problem == the reference called once per problem with n_batch=1 (il_env.py:112-131),
+    including problems that stop at different iterations."""
+    dtype = torch.float64
+    pdx, x0, C, c, kw = env_problem(port, "pendulum", 20, 12, dtype)
+    gdx = env.PendulumDx(pdx.params.to(dev))
+    m = dilqr.MPC(3, 1, 20, lqr_iter=40, verbose=-1, exit_unconverged=False, solo=2, **kw)
+    with torch.no_grad():
+        x, u, costs = m(x0.to(dev), dilqr.QuadCost(C.to(dev), c.to(dev)), gdx)
+    n_it = set()
+    for j in range(12):
+        o = port.mpc_forward(x0[j:j + 1], port.QuadCost(C[:, j:j + 1], c[:, j:j + 1]), pdx, 3, 1,
+                             20, lqr_iter=40, final_pass=False, **kw)
+        n_it.add(o.n_iters)
+        assert rel(u[:, j:j + 1], o.u) < 1e-8, (j, o.n_iters)
+        assert rel(x[:, j:j + 1], o.x) < 1e-8
+        assert rel(costs[j:j + 1], o.costs) < 1e-9
+    assert len(n_it) > 1          # the case really has problems stopping at different times
+    assert m.last_info.n_iters == max(n_it)
+
+
+@pytest.mark.parametrize("name", ["pendulum", "cartpole"])
+def test_closed_loop_golden(dilqr, dev, name):
+    """il_env.IL_Env.populate_data2 against the reference's own output
+    (tests/golden/make_golden.py closed_loop): n_total closed loops as one batch."""
+    il_env = importlib.import_module("differentiable-ilqr_b200.il_env")
+    g = golden("ref_closed_loop_%s.npz" % name)
+    e = il_env.IL_Env(name, lqr_iter=int(g["lqr_iter"]), mpc_T=int(g["mpc_T"]),
+                      dtype=torch.float64, device=dev)
+    torch.manual_seed(0)
+    torch.set_default_dtype(torch.float64)
+    try:
+        x0 = e.sample_xinit(g["x0"].shape[0])
+    finally:
+        torch.set_default_dtype(torch.float32)
+    assert float((x0 - g["x0"]).abs().max()) == 0.0
+    tau = e.closed_loop(g["x0"])
+    ref = torch.cat((g["train"], g["val"], g["test"]))
+    assert tau.shape == ref.shape
+    assert rel(tau, ref) < 1e-6
+    nt = g["train"].shape[0]
+    torch.set_default_dtype(torch.float64)
+    try:
+        e.populate_data2(nt, 1, 1, seed=0)
+    finally:
+        torch.set_default_dtype(torch.float32)
+    assert rel(e.train_data, g["train"]) < 1e-6 and rel(e.test_data, g["test"]) < 1e-6
+
+
 def test_full_size_properties(dilqr, env, dev):
     """BASELINE size (cartpole T=50, B=65536, fp64): size-independent properties --
     rollouts are dynamics-consistent, controls respect the box, the iLQR never

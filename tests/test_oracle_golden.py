@@ -119,3 +119,22 @@ def test_env_forward(port, name):
                          final_pass=False, **_mpc_kw(pdx, int(g["lqr_iter"])))
     assert float((o.x - g["x"]).abs().max()) == 0.0
     assert float((o.u - g["u"]).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("name,n_samples", [("pendulum", 2), ("cartpole", 1)])
+def test_closed_loop_bit_exact(port, name, n_samples):
+    """IL_Env.populate_data2 (il_env.py:96-151) run through the unmodified reference:
+    sample_xinit and the receding-horizon closed loop are reproduced with max diff 0.0."""
+    g = golden("ref_closed_loop_%s.npz" % name)
+    cls = port.PendulumDx if name == "pendulum" else port.CartpoleDx
+    torch.manual_seed(0)
+    torch.set_default_dtype(torch.float64)
+    try:
+        x0 = port.sample_xinit(name, g["x0"].shape[0])
+    finally:
+        torch.set_default_dtype(torch.float32)
+    assert float((x0 - g["x0"]).abs().max()) == 0.0
+    ref = torch.cat((g["train"], g["val"], g["test"]))[:n_samples]
+    tau = port.closed_loop(cls(dtype=torch.float64), g["x0"][:n_samples], int(g["mpc_T"]),
+                           int(g["lqr_iter"]))
+    assert float((tau - ref).abs().max()) == 0.0
