@@ -127,6 +127,9 @@ SYMBOLS = {
     "dilqr_adjoint_factor": (C.c_int, [C.POINTER(DilqrAdjoint), C.c_void_p]),
     "dilqr_adjoint_pass": (C.c_int, [C.POINTER(DilqrAdjoint), C.c_void_p]),
     "dilqr_adjoint_final": (C.c_int, [C.POINTER(DilqrAdjoint), C.c_void_p]),
+    "dilqr_tile_cost": (C.c_int, [C.c_int] * 4 + [C.c_void_p] * 5),
+    "dilqr_tile_cost_grad_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "dilqr_tile_cost_grad": (C.c_int, [C.c_int] * 4 + [C.c_void_p] * 5 + [C.c_size_t, C.c_void_p]),
 }
 
 _lib = None
@@ -176,7 +179,7 @@ KERNELS_PER_CALL = {
     "dilqr_mpc_finish": 1, "dilqr_kkt_grads": 1, "dilqr_linearize": 1, "dilqr_rollout": 1,
     "dilqr_costate_tables": 1, "dilqr_richardson_update": 1, "dilqr_sens_theta": 1,
     "dilqr_adjoint_factor": 1, "dilqr_adjoint_pass": 1, "dilqr_adjoint_final": 1,
-    "dilqr_pnqp": 2, "dilqr_env_tables": 1,
+    "dilqr_pnqp": 2, "dilqr_env_tables": 1, "dilqr_tile_cost": 2, "dilqr_tile_cost_grad": 2,
 }
 launch_count = 0     # running total of kernels launched through this binding
 profile = None       # set to a dict {name: [(start_event, end_event), ...]} to time calls

@@ -37,6 +37,7 @@ using Scalar = float;
   X(3, 1, DYN_LINDX)           \
   X(4, 2, DYN_LINDX)           \
   X(5, 1, DYN_LINDX)           \
+  X(6, 2, DYN_LINDX)           \
   X(13, 3, DYN_LINDX)          \
   X(3, 1, DYN_PENDULUM)        \
   X(5, 1, DYN_CARTPOLE)        \
@@ -54,6 +55,8 @@ using Scalar = float;
 #elif DILQR_GROUP == 1
 #define DILQR_CONFIGS(X)       \
   X(2, 1, DYN_LINDX)           \
+  X(2, 2, DYN_LINDX)           \
+  X(6, 2, DYN_LINDX)           \
   X(4, 1, DYN_LINDX)           \
   X(4, 2, DYN_LINDX)           \
   X(4, 4, DYN_LINDX)           \

@@ -6,8 +6,47 @@ the only collective is one all-reduce of the (n_theta + 2 n) gradient scalars.
 """
 import torch
 
-from . import mpc_explicit, parallel
+import ctypes as C
+
+from torch.autograd import Function
+
+from . import _lib, mpc_explicit, parallel
+from ._solver import _DT, _ptr, _stream
 from .definitions import QuadCost
+
+
+class TileCost(Function):
+    """(q[n], p[n]) -> dense C[T,B,n,n] = diag(q), c[T,B,n] = p, the tensors
+    il_env.py:159-162 builds with ``.repeat``; the backward is the adjoint of that
+    tiling (what autograd does for the reference at il_exp.py:373) as one streaming
+    reduction kernel instead of a strided torch sum."""
+
+    @staticmethod
+    def forward(ctx, q, p, T, B):
+        n = q.shape[0]
+        q_, p_ = q.detach().contiguous(), p.detach().contiguous()
+        Cm = torch.empty(T, B, n, n, dtype=q.dtype, device=q.device)
+        cv = torch.empty(T, B, n, dtype=q.dtype, device=q.device)
+        _lib.call("dilqr_tile_cost", _DT[q.dtype], n, T, B, _ptr(q_), _ptr(p_), _ptr(Cm), _ptr(cv),
+                  _stream())
+        ctx.dims = (n, T, B)
+        return Cm, cv
+
+    @staticmethod
+    def backward(ctx, dC, dc):
+        n, T, B = ctx.dims
+        if dC is None:
+            dC = torch.zeros(T, B, n, n, dtype=dc.dtype, device=dc.device)
+        if dc is None:
+            dc = torch.zeros(T, B, n, dtype=dC.dtype, device=dC.device)
+        dC, dc = dC.contiguous(), dc.contiguous()
+        dq = torch.empty(n, dtype=dC.dtype, device=dC.device)
+        dp = torch.empty(n, dtype=dC.dtype, device=dC.device)
+        nbytes = _lib.lib().dilqr_tile_cost_grad_workspace_bytes(n)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dC.device)
+        _lib.call("dilqr_tile_cost_grad", _DT[dC.dtype], n, T, B, _ptr(dC), _ptr(dc), _ptr(dq),
+                  _ptr(dp), _ptr(ws), C.c_size_t(nbytes), _stream())
+        return dq, dp, None, None
 
 
 class ImitationStep:
@@ -37,9 +76,7 @@ class ImitationStep:
         """il_env.py:159-162: Q = diag(q) tiled to [T,B,n,n], p tiled to [T,B,n]."""
         if not self.tile:
             return torch.diag(q), p
-        C = torch.diag(q).unsqueeze(0).unsqueeze(0).repeat(self.T, B, 1, 1)
-        c = p.unsqueeze(0).repeat(self.T, B, 1)
-        return C, c
+        return TileCost.apply(q, p, self.T, B)
 
     def prepare(self, x0, q, p, theta):
         return {"x0": x0, "q": q.clone().requires_grad_(), "p": p.clone().requires_grad_(),

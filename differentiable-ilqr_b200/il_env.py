@@ -19,6 +19,7 @@ import torch
 from . import mpc_explicit
 from .definitions import QuadCost
 from .env_dx import cartpole, pendulum
+from .il import TileCost
 from .mpc_explicit import GradMethods
 
 
@@ -74,8 +75,7 @@ class IL_Env:
     def _cost(self, q, p, T, n_batch):
         q, p = self._dev(q), self._dev(p)
         if self.tile:                                    # il_env.py:159-162
-            Q = torch.diag(q).unsqueeze(0).unsqueeze(0).repeat(T, n_batch, 1, 1)
-            return QuadCost(Q, p.unsqueeze(0).repeat(T, n_batch, 1))
+            return QuadCost(*TileCost.apply(q, p, T, n_batch))
         return QuadCost(torch.diag(q), p)
 
     # ------------------------------------------------------------------ open loop
@@ -140,8 +140,7 @@ class IL_Env:
         n_batch = xinit.shape[0]
         if self.tile:
             q_, p_ = q.to(self.device, self.dtype), p.to(self.device, self.dtype)
-            Q = torch.diag(q_).unsqueeze(0).unsqueeze(0).repeat(self.mpc_T, n_batch, 1, 1)
-            cost = QuadCost(Q, p_.unsqueeze(0).repeat(self.mpc_T, n_batch, 1))
+            cost = QuadCost(*TileCost.apply(q_, p_, self.mpc_T, n_batch))
         else:
             cost = QuadCost(torch.diag(q.to(self.device, self.dtype)), p.to(self.device, self.dtype))
         eps = eps_override if eps_override else self.true_dx.mpc_eps

@@ -15,6 +15,7 @@ from torch.autograd import Function
 
 from . import _lib, _solver
 from .definitions import QuadCost, LinDx
+from .dynamics import AffineDynamics
 
 
 class GradMethods(Enum):          # mpc.py:29-33
@@ -103,8 +104,8 @@ class MPC(nn.Module):
         super().__init__()
         assert (u_lower is None) == (u_upper is None)      # mpc.py:146
         assert max_linesearch_iter > 0                     # mpc.py:147
-        if delta_u is not None or slew_rate_penalty is not None:
-            raise NotImplementedError("delta_u / slew_rate_penalty are out of scope (SURVEY 8a-13)")
+        if delta_u is not None:
+            raise NotImplementedError("delta_u trust region is out of scope (SURVEY 8a-13)")
         self.n_state, self.n_ctrl, self.T = n_state, n_ctrl, T
         det = lambda v: v if (v is None or isinstance(v, float)) else v.detach()
         self.u_lower, self.u_upper = det(u_lower), det(u_upper)
@@ -157,9 +158,63 @@ class MPC(nn.Module):
             sys.exit(-1)
         C, c = self._expand_cost(cost, n_batch)
         assert x_init.ndimension() == 2 and x_init.size(0) == n_batch
+        if isinstance(dx, AffineDynamics):      # time-invariant LinDx (dynamics.py:159-202)
+            dx = LinDx(*dx.as_lindx(self.T, n_batch, x_init.dtype, x_init.device))
+        if self.slew_rate_penalty is not None:
+            return self._forward_slew(x_init, C, c, dx, n_batch)
         if isinstance(dx, LinDx):
             F, f = dx.F, dx.f
         else:
             F = f = None
         x, u, costs = self._Fn.apply(self, dx, x_init, C, c, F, f)
         return x, u, costs
+
+    def _forward_slew(self, x_init, C, c, dx, n_batch):
+        """Slew-rate penalty gamma * ||u_t - u_{t-1}||^2 by state augmentation
+        x~ = (u_{t-1}, x) -- mpc.py:362-445.  The augmented problem is itself an LQR
+        problem with linear dynamics, so it runs through the same kernels with
+        n_state + n_ctrl states; autograd carries the KKT gradients of the augmented
+        tensors back to C, c, F, f, x_init.  (The reference supports this only for
+        Module dynamics -- its LinDx branch calls ``None`` at lqr_step.py:224 -- so the
+        reference-equivalent entry is ``AffineDynamics``; LinDx is accepted as well.)"""
+        if not isinstance(dx, LinDx):
+            raise NotImplementedError("slew_rate_penalty: LinDx / AffineDynamics only")
+        ns, nc, T = self.n_state, self.n_ctrl, self.T
+        n, nt = ns + nc, ns + 2 * nc
+        dt, dev = x_init.dtype, x_init.device
+        F, f = dx.F, dx.f
+        gamI = self.slew_rate_penalty * torch.eye(nc, dtype=dt, device=dev)
+        _C = torch.zeros(T, n_batch, nt, nt, dtype=dt, device=dev)
+        _C[:, :, :nc, :nc] = gamI
+        _C[:, :, -nc:, :nc] = -gamI
+        _C[:, :, :nc, -nc:] = -gamI
+        _C[:, :, -nc:, -nc:] = gamI
+        _C = _C + torch.nn.functional.pad(C, (nc, 0, nc, 0))
+        _c = torch.cat((torch.zeros(T, n_batch, nc, dtype=dt, device=dev), c), 2)
+        _F0 = torch.cat((torch.zeros(nc, n, dtype=dt, device=dev),
+                         torch.eye(nc, dtype=dt, device=dev)), 1).expand(T - 1, n_batch, nc, nt)
+        _F1 = torch.cat((torch.zeros(T - 1, n_batch, ns, nc, dtype=dt, device=dev), F), 3)
+        _F = torch.cat((_F0, _F1), 2)
+        _f = None
+        if f is not None and f.nelement() > 0:
+            _f = torch.cat((torch.zeros(T - 1, n_batch, nc, dtype=dt, device=dev), f), 2)
+        if self.prev_ctrl is not None:
+            prev_u = self.prev_ctrl.detach().to(device=dev, dtype=dt)
+            while prev_u.ndimension() < 3:
+                prev_u = prev_u.unsqueeze(0)
+        else:
+            prev_u = torch.zeros(1, n_batch, nc, dtype=dt, device=dev)
+        _x_init = torch.cat((prev_u[0].expand(n_batch, nc), x_init), 1)
+        inner = MPC(ns + nc, nc, T, u_lower=self.u_lower, u_upper=self.u_upper,
+                    u_zero_I=self.u_zero_I, u_init=self.u_init, lqr_iter=self.lqr_iter,
+                    grad_method=self.grad_method, verbose=self.verbose, eps=self.eps,
+                    back_eps=self.back_eps, n_batch=n_batch,
+                    linesearch_decay=self.linesearch_decay,
+                    max_linesearch_iter=self.max_linesearch_iter,
+                    exit_unconverged=self.exit_unconverged,
+                    detach_unconverged=self.detach_unconverged, backprop=self.backprop,
+                    not_improved_lim=self.not_improved_lim, best_cost_eps=self.best_cost_eps,
+                    solo=self.solo)
+        x, u, costs = inner(_x_init, QuadCost(_C, _c), LinDx(_F, _f))
+        self.last_info = inner.last_info
+        return x[:, :, nc:], u, costs

@@ -75,6 +75,10 @@ class MPC(_BaseMPC):
             raise AttributeError("'LinDx' object has no attribute 'params'")
         if not isinstance(cost, QuadCost):
             raise NotImplementedError("only QuadCost is supported (SURVEY 8a-2)")
+        if self.slew_rate_penalty is not None:
+            raise NotImplementedError("slew_rate_penalty: supported by mpc.MPC (LinDx / "
+                                      "AffineDynamics); the env_dx models have no "
+                                      "control-passthrough kernels")
         n_batch = self.n_batch if self.n_batch is not None else (
             cost.C.size(1) if cost.C.ndimension() == 4 else None)
         if n_batch is None:

@@ -299,6 +299,19 @@ int dilqr_sens_theta(int dtype, int dynamics, const double* dyn_params, int T, i
                      const void* x, const void* u, const void* K, const void* lam, const void* dx,
                      const void* du, const void* df, void* dtheta, void* stream);
 
+/* The cost plumbing either side of the solve in the imitation-learning loop.
+ * dilqr_tile_cost: C[T,B,n,n] = diag(q), c[T,B,n] = p for every (t, b) -- what
+ * il_env.py:159-162 builds with .repeat (C or c may be NULL to skip one).
+ * dilqr_tile_cost_grad: the adjoint of that tiling, dq[i] = sum_{t,b} dC[t,b,i,i],
+ * dp[i] = sum_{t,b} dc[t,b,i] (what autograd computes for il_exp.py:373), one pass over
+ * dC, dc with a fixed summation order; workspace: dilqr_tile_cost_grad_workspace_bytes(n). */
+int dilqr_tile_cost(int dtype, int n, int T, int n_batch, const void* q, const void* p, void* C,
+                    void* c, void* stream);
+size_t dilqr_tile_cost_grad_workspace_bytes(int n);
+int dilqr_tile_cost_grad(int dtype, int n, int T, int n_batch, const void* dC, const void* dc,
+                         void* dq, void* dp, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,52 @@ def lindx(boxed):
         costs=costs, gx=gx, gu=gu, dx0=x0g.grad, dC=Cg.grad, dc=cg.grad, dF=Fg.grad, df=fg.grad)
 
 
+def slew_affine():
+    """mpc.MPC with slew_rate_penalty + prev_ctrl on a LinDx problem (mpc.py:362-445) and
+    with dynamics.AffineDynamics (dynamics.py:159-202), forward and KKT gradients."""
+    torch.manual_seed(11)
+    torch.set_default_dtype(torch.float64)
+    ns, nc, T, B = 4, 2, 10, 6
+    n = ns + nc
+    A = torch.randn(T, B, n, n)
+    C = A.transpose(2, 3) @ A + torch.eye(n)
+    c = torch.randn(T, B, n)
+    F = torch.cat((torch.eye(ns).expand(T - 1, B, ns, ns) + 0.2 * torch.randn(T - 1, B, ns, ns) / ns ** 0.5,
+                   torch.randn(T - 1, B, ns, nc) / ns ** 0.5), 3)
+    f = 0.1 * torch.randn(T - 1, B, ns)
+    x0 = torch.randn(B, ns)
+    prev = 0.3 * torch.randn(B, nc)
+    g = torch.Generator().manual_seed(7)
+    gx = torch.randn(T, B, ns, generator=g)
+    gu = torch.randn(T, B, nc, generator=g)
+    out = dict(C=C, c=c, F=F, f=f, x0=x0, prev=prev, gx=gx, gu=gu)
+    # affine dynamics, time-invariant
+    import dynamics as refdyn
+    Am = (torch.eye(ns) + 0.2 * torch.randn(ns, ns) / ns ** 0.5).requires_grad_()
+    Bm = (torch.randn(ns, nc) / ns ** 0.5).requires_grad_()
+    cm = (0.1 * torch.randn(ns)).requires_grad_()
+    Cg, cg, x0g = [t.clone().requires_grad_() for t in (C, c, x0)]
+    m = R.mpc.MPC(ns, nc, T, lqr_iter=20, verbose=-1, exit_unconverged=False, u_lower=-1.0,
+                  u_upper=1.0, grad_method=R.mpc.GradMethods.ANALYTIC)
+    x, u, costs = m(x0g, R.mpc.QuadCost(Cg, cg), refdyn.AffineDynamics(Am, Bm, cm))
+    ((x * gx).sum() + (u * gu).sum()).backward()
+    out.update(A=Am, B=Bm, cvec=cm, a_x=x, a_u=u, a_costs=costs, a_dx0=x0g.grad, a_dC=Cg.grad,
+               a_dc=cg.grad, a_dA=Am.grad, a_dB=Bm.grad, a_dcvec=cm.grad)
+    # slew-rate penalty: the reference's LinDx branch is broken (true_dynamics=None is called,
+    # lqr_step.py:224), the Module-dynamics branch (CtrlPassthroughDynamics) works
+    Am2, Bm2, cm2 = [t.detach().clone().requires_grad_() for t in (Am, Bm, cm)]
+    Cg, cg, x0g = [t.clone().requires_grad_() for t in (C, c, x0)]
+    m = R.mpc.MPC(ns, nc, T, lqr_iter=20, verbose=-1, exit_unconverged=False, u_lower=-1.0,
+                  u_upper=1.0, slew_rate_penalty=0.4, prev_ctrl=prev,
+                  grad_method=R.mpc.GradMethods.ANALYTIC)
+    x, u, costs = m(x0g, R.mpc.QuadCost(Cg, cg), refdyn.AffineDynamics(Am2, Bm2, cm2))
+    ((x * gx).sum() + (u * gu).sum()).backward()
+    out.update(s_x=x, s_u=u, s_costs=costs, s_dx0=x0g.grad, s_dC=Cg.grad, s_dc=cg.grad,
+               s_dA=Am2.grad, s_dB=Bm2.grad, s_dcvec=cm2.grad)
+    npz("ref_slew_affine.npz", **out)
+    torch.set_default_dtype(torch.float32)
+
+
 def dilqr(env, T, B, lqr_iter, sigma):
     torch.manual_seed(0)
     torch.set_default_dtype(torch.float64)
@@ -179,3 +225,4 @@ if __name__ == "__main__":
     env_forward("cartpole", 25, 16, 6, torch.float32)
     closed_loop("pendulum", 20, 50, 4, 1, 1)
     closed_loop("cartpole", 12, 30, 1, 1, 1)
+    slew_affine()

@@ -498,3 +498,45 @@ def test_tensor_bounds_and_broadcast_cost_lindx(dilqr, port, dev):
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
     assert rel(outs[1][2], outs[0][2].sum((0, 1))) < 1e-12
     assert rel(outs[1][3], outs[0][3].sum((0, 1))) < 1e-12
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("n,T,B", [(6, 7, 33), (4, 5, 1), (16, 3, 65), (3, 4, 2)])
+def test_tile_cost_and_its_adjoint(dev, dtype, n, T, B):
+    """dilqr_tile_cost == the .repeat of il_env.py:159-162 bit for bit; its backward ==
+    autograd's sum over the tiled axes (to summation-order roundoff)."""
+    il = importlib.import_module("differentiable-ilqr_b200.il")
+    g = torch.Generator().manual_seed(5)
+    q = torch.rand(n, generator=g, dtype=torch.float64).to(dtype).to(dev).requires_grad_()
+    p = torch.randn(n, generator=g, dtype=torch.float64).to(dtype).to(dev).requires_grad_()
+    C, c = il.TileCost.apply(q, p, T, B)
+    Cr = torch.diag(q).unsqueeze(0).unsqueeze(0).repeat(T, B, 1, 1)
+    cr = p.unsqueeze(0).repeat(T, B, 1)
+    assert torch.equal(C, Cr.detach()) and torch.equal(c, cr.detach())
+    gC = torch.randn(T, B, n, n, generator=g, dtype=torch.float64).to(dtype).to(dev)
+    gc = torch.randn(T, B, n, generator=g, dtype=torch.float64).to(dtype).to(dev)
+    (C * gC).sum().add((c * gc).sum()).backward()
+    dq, dp = q.grad.clone(), p.grad.clone()
+    q.grad = p.grad = None
+    (Cr * gC).sum().add((cr * gc).sum()).backward()
+    tol = 1e-12 if dtype == torch.float64 else 1e-5
+    assert rel(dq, q.grad) < tol and rel(dp, p.grad) < tol
+
+
+def test_affine_dynamics_and_slew_rate_golden(dilqr, dev):
+    """mpc.MPC with dynamics.AffineDynamics, and with slew_rate_penalty + prev_ctrl
+    (mpc.py:362-445), forward and KKT gradients against the reference's output."""
+    g = {k: v.to(dev) for k, v in golden("ref_slew_affine.npz").items()}
+    ns, nc, T = 4, 2, 10
+    for tag, extra in (("a", {}), ("s", dict(slew_rate_penalty=0.4, prev_ctrl=g["prev"]))):
+        A, Bm, cv = [g[k].clone().requires_grad_() for k in ("A", "B", "cvec")]
+        Cg, cg, x0 = [g[k].clone().requires_grad_() for k in ("C", "c", "x0")]
+        m = dilqr.MPC(ns, nc, T, lqr_iter=20, verbose=-1, exit_unconverged=False, u_lower=-1.0,
+                      u_upper=1.0, **extra)
+        x, u, costs = m(x0, dilqr.QuadCost(Cg, cg), dilqr.AffineDynamics(A, Bm, cv))
+        assert rel(x, g[tag + "_x"]) < 1e-8 and rel(u, g[tag + "_u"]) < 1e-8
+        assert rel(costs, g[tag + "_costs"]) < 1e-9
+        ((x * g["gx"]).sum() + (u * g["gu"]).sum()).backward()
+        for mine, name in ((x0.grad, "dx0"), (Cg.grad, "dC"), (cg.grad, "dc"), (A.grad, "dA"),
+                           (Bm.grad, "dB"), (cv.grad, "dcvec")):
+            assert rel(mine, g[tag + "_" + name]) < 1e-7, (tag, name)

@@ -64,8 +64,9 @@ def test_env_models_expose_reference_attributes():
 
 
 def test_unsupported_features_fail_loudly(dilqr):
-    with pytest.raises(NotImplementedError):
-        dilqr.MPC(3, 1, 5, slew_rate_penalty=1.0)
+    m = dilqr.mpc_explicit.MPC(3, 1, 5, slew_rate_penalty=1.0)
+    with pytest.raises(NotImplementedError):       # slew rate: KKT path (mpc.MPC) only
+        m(torch.zeros(2, 3), dilqr.QuadCost(torch.eye(4), torch.zeros(4)), dilqr.env_dx.PendulumDx())
     with pytest.raises(NotImplementedError):
         dilqr.MPC(3, 1, 5, u_lower=-1.0, u_upper=1.0, delta_u=0.1)
 
@@ -76,3 +77,20 @@ def test_bytes_per_solve_model():
     it, bwd, tot = bench.bytes_per_solve(8)
     assert it == 2457 * 8 and bwd == 4809 * 8 and tot == 235032
     assert bench.bytes_per_solve(4)[2] == 117516
+
+
+def test_affine_dynamics_container(dilqr):
+    """dynamics.py:159-202: forward / grad_input / the LinDx view handed to the solver."""
+    A, B, c = torch.randn(3, 3), torch.randn(3, 2), torch.randn(3)
+    d = dilqr.AffineDynamics(A, B, c)
+    x, u = torch.randn(5, 3), torch.randn(5, 2)
+    assert torch.allclose(d(x, u), x @ A.t() + u @ B.t() + c)
+    assert d(x[0], u[0]).shape == (3,)
+    R, S = d.grad_input(x, u)
+    assert R.shape == (5, 3, 3) and S.shape == (5, 3, 2) and torch.equal(R[2], A)
+    F, f = d.as_lindx(4, 5, torch.float32, "cpu")
+    assert F.shape == (3, 5, 3, 5) and f.shape == (3, 5, 3)
+    assert torch.equal(F[1, 2], torch.cat((A, B), 1)) and torch.equal(f[0, 0], c)
+    p = dilqr.CtrlPassthroughDynamics(d)
+    xt = torch.cat((torch.randn(5, 2), x), 1)
+    assert torch.allclose(p(xt, u), torch.cat((u, d(x, u)), 1))

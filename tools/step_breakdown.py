@@ -11,7 +11,7 @@ env = importlib.import_module("differentiable-ilqr_b200.env_dx")
 il = importlib.import_module("differentiable-ilqr_b200.il")
 dev = torch.device("cuda:0")
 dtype = torch.float64
-B = 65536
+B = int(os.environ.get("BD_B", "65536"))
 x0, uexp = [t.to(dev) for t in bench.make_inputs(torch, B, dtype, 0)]
 step = il.ImitationStep(env.CartpoleDx, T=50, lqr_iter=10, dtype=dtype, device=dev, n_richardson=4)
 q, p = [t.to(dtype).to(dev).requires_grad_() for t in env.CartpoleDx().get_true_obj()]
