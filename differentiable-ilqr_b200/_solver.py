@@ -391,6 +391,7 @@ def kkt_backward(dl_dx, dl_du, x_init, C_, c_, F, f, x, u, n_state, n_ctrl, u_lo
 
 def dilqr_backward(dl_dx, dl_du, x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u_lower=None,
                    u_upper=None, n_passes=8, tol=None, back_eps=1e-7, solo=False, stats=None,
+                   theta_host=None,
                    factored=True):
     """DiLQR implicit gradient (lqr_step_explicit.py:652-712 + fix_point_equ
     458-598) in matrix-free form (derivation in
@@ -409,7 +410,9 @@ def dilqr_backward(dl_dx, dl_du, x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u
     dtype, dev = x.dtype, x.device
     n = n_state + n_ctrl
     kind = dxmod._dilqr_kind
-    theta = dxmod._theta()
+    # theta_host: the host copy the forward pass already fetched (saves a device sync)
+    theta = dxmod._theta() if theta_host is None else (C.c_double * 8)(
+        *(list(theta_host) + [0.0] * (8 - len(theta_host))))
     x = x.detach().contiguous()
     u = u.detach().contiguous()
     scalar_bounds = u_lower is None or (isinstance(u_lower, float) and isinstance(u_upper, float))
@@ -523,7 +526,7 @@ def dilqr_backward(dl_dx, dl_du, x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u
         if n_rej:
             return dilqr_backward(dl_dx, dl_du, x_init, C_, c_, x, u, dxmod, n_state, n_ctrl,
                                   u_lower, u_upper, n_passes, tol, back_eps, solo, stats,
-                                  factored=False)
+                                  theta_host=theta_host, factored=False)
     if stats is not None:
         stats["passes"] = passes
         stats["resid"] = rel

@@ -1,3 +1,4 @@
+#include <cstdlib>
 // api.cu -- extern "C" entry points of libdilqr (see include/dilqr.h).
 // Compiled once per scalar type (-DDILQR_SCALAR_F64=0/1) into separate objects;
 // dispatch.cu routes on DilqrSolve::dtype.
@@ -214,6 +215,8 @@ struct Geometry {
     int w = (int)((112 * 1024) / per);  // <= ~112 KB / block so two blocks fit one SM
     if (w > 4) w = 4;
     if (w < 1) w = 1;
+    static const int forced = getenv("DILQR_WPB") ? atoi(getenv("DILQR_WPB")) : 0;  // tuning knob
+    if (forced >= 1 && forced <= w) w = forced;
     return w;
   }
   static size_t smem(int wpb) { return STAGED ? IK::smem_per_warp() * wpb : 0; }

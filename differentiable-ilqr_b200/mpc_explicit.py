@@ -25,6 +25,7 @@ class _MPCExplicitFn(Function):
             gain_solve=_lib.GAIN_PLAIN, solo=mod.solo, verbose=mod.verbose)
         mod.last_info = info
         ctx.mod, ctx.dx = mod, dx
+        ctx.theta_host = dyn.params
         ctx.mask = None
         eps_cmp = float(torch.tensor(mod.eps, dtype=x.dtype))
         if mod.detach_unconverged:                       # mpc_explicit.py:343-356
@@ -50,7 +51,8 @@ class _MPCExplicitFn(Function):
         dC, dc, dtheta = _solver.dilqr_backward(
             dl_dx.contiguous(), dl_du.contiguous(), x_init, C, c, x, u, dx, mod.n_state,
             mod.n_ctrl, mod.u_lower, mod.u_upper, n_passes=mod.richardson_passes,
-            tol=mod.richardson_tol, back_eps=mod.back_eps, solo=mod.solo, stats=stats)
+            tol=mod.richardson_tol, back_eps=mod.back_eps, solo=mod.solo, stats=stats,
+            theta_host=ctx.theta_host)
         mod.last_backward = stats
         # dC / dc come back in the layout of the cost tensors handed in (dense, or already
         # summed over the broadcast axes for C[n,n] / C[T,n,n]); the reference returns

@@ -540,3 +540,38 @@ def test_affine_dynamics_and_slew_rate_golden(dilqr, dev):
         for mine, name in ((x0.grad, "dx0"), (Cg.grad, "dC"), (cg.grad, "dc"), (A.grad, "dA"),
                            (Bm.grad, "dB"), (cv.grad, "dcvec")):
             assert rel(mine, g[tag + "_" + name]) < 1e-7, (tag, name)
+
+
+@pytest.mark.parametrize("ns,nc,T,B,boxed", [(3, 1, 2, 1, True), (4, 2, 2, 3, True), (5, 1, 3, 32, False),
+                                             (2, 1, 2, 65, True), (4, 2, 1, 4, True)])
+def test_edge_horizons_and_batches(dilqr, port, dev, ns, nc, T, B, boxed):
+    """Smallest horizons (T = 1, 2, 3), single-problem and one-past-a-warp batches,
+    forward and KKT gradients against the oracle."""
+    dtype = torch.float64
+    if T == 1:
+        g = torch.Generator().manual_seed(3)
+        n = ns + nc
+        A = torch.randn(T, B, n, n, generator=g, dtype=dtype)
+        C = A.transpose(2, 3) @ A + torch.eye(n, dtype=dtype)
+        c = torch.randn(T, B, n, generator=g, dtype=dtype)
+        F = torch.zeros(0, B, ns, n, dtype=dtype)
+        f = torch.zeros(0, B, ns, dtype=dtype)
+        x0 = torch.randn(B, ns, generator=g, dtype=dtype)
+    else:
+        C, c, F, f, x0 = lindx_problem(ns, nc, T, B, dtype, seed=4)
+    kw = dict(u_lower=-0.5, u_upper=0.5) if boxed else {}
+    o = port.mpc_forward(x0, port.QuadCost(C, c), port.LinDx(F, f), ns, nc, T, lqr_iter=5, **kw)
+    Cg, cg, Fg, fg, xg = [t.to(dev).requires_grad_() for t in (C, c, F, f, x0)]
+    m = dilqr.MPC(ns, nc, T, lqr_iter=5, verbose=-1, exit_unconverged=False, **kw)
+    x, u, costs = m(xg, dilqr.QuadCost(Cg, cg), dilqr.LinDx(Fg, fg))
+    assert m.last_info.n_iters == o.n_iters
+    assert rel(x, o.x) < 1e-9 and rel(u, o.u) < 1e-9 and rel(costs, o.costs) < 1e-9
+    g2 = torch.Generator().manual_seed(9)
+    gx = torch.randn(T, B, ns, generator=g2, dtype=dtype)
+    gu = torch.randn(T, B, nc, generator=g2, dtype=dtype)
+    ((x * gx.to(dev)).sum() + (u * gu.to(dev)).sum()).backward()
+    ref = port.kkt_backward(gx, gu, x0, C, c, F, f, o.x, o.u, ns, nc, **kw)
+    assert rel(Cg.grad, ref.dC) < 1e-8 and rel(cg.grad, ref.dc) < 1e-8
+    assert rel(xg.grad, ref.dx_init) < 1e-8
+    if T > 1:
+        assert rel(Fg.grad, ref.dF) < 1e-8 and rel(fg.grad, ref.df) < 1e-8

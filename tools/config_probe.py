@@ -34,7 +34,13 @@ def rocket(B=16384, T=100, dtype=torch.float64, bound=20.0):
         with torch.no_grad():
             return m(x0, d.QuadCost(C, c), dx)
     ms = timed(run)
+    lib = importlib.import_module("differentiable-ilqr_b200._lib")
+    lib.profile = {}
     x, u, _ = run()
+    torch.cuda.synchronize()
+    prof = {k: (len(v), round(sum(a.elapsed_time(b) for a, b in v), 3)) for k, v in lib.profile.items()}
+    lib.profile = None
+    print("  per-call (n, total ms):", prof)
     info = m.last_info
     sat = float((u.abs() >= bound - 1e-9).double().mean())
     print(json.dumps({"config": "rocket T=%d B=%d %s bound=%g" % (T, B, str(dtype)[6:], bound), "ms": ms,
