@@ -88,7 +88,7 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
   size_t traj[2], best, Kk, cost_cur, cost_new, cost_best, du_new, du_best, alpha_new, dusq, take,
-      guess, votes, total;
+      guess, votes, cpk_state, Cpk, total;
   int Bp;
 };
 
@@ -117,6 +117,15 @@ static WsLayout ws_layout(const DilqrSolve* s, size_t esz) {
   w.take = take((size_t)w.Bp * sizeof(int));
   w.guess = take((size_t)s->T * kPnqpMaxIter * sizeof(uint32_t));
   w.votes = take((size_t)s->T * kPnqpMaxIter * sizeof(uint32_t));
+  w.cpk_state = take(sizeof(uint32_t));
+  // packed symmetric copy of C: only shapes whose sweeps are staged use it (staged_v)
+  {
+    const bool env = s->dynamics != DILQR_DYN_LINDX;
+    const size_t per = (size_t)kWarp * esz *
+                       ((size_t)N * N + N + (env ? 0 : (size_t)s->n_state * N + s->n_state));
+    const bool staged = per * kStages <= kStageBudget;
+    w.Cpk = take(staged && !s->C_bcast ? (size_t)s->T * w.Bp * (N * (N + 1) / 2) * esz : 0);
+  }
   w.total = off;
   return w;
 }
@@ -168,6 +177,8 @@ static IterParams<Scalar> make_params(const DilqrSolve* s, int role = 1) {
   p.alpha_new = reinterpret_cast<S*>(ws + w.alpha_new);
   p.dusq = reinterpret_cast<S*>(ws + w.dusq);
   p.take = reinterpret_cast<int*>(ws + w.take);
+  p.cpk_state = reinterpret_cast<uint32_t*>(ws + w.cpk_state);
+  p.Cpk = reinterpret_cast<S*>(ws + w.Cpk);
   p.gains_only = s->gains_only;
   p.C_bcast = s->C_bcast;
   p.c_bcast = s->c_bcast;
@@ -242,6 +253,12 @@ static int launch_begin(const DilqrSolve* s, cudaStream_t st) {
   if (p.T > 1)
     cudaMemset2DAsync(p.guess, kPnqpMaxIter * sizeof(uint32_t), 3, 1, p.T - 1, st);
   (void)w;
+  {  // 1: begin packs the upper triangle of C for the sweeps (ilqr_kernels.cuh), 0: dense
+    static const bool off = getenv("DILQR_NO_PACK") != nullptr;   // tuning / A-B knob
+    const bool pack = G::STAGED && !p.C_bcast && !(p.gains_only && p.x_cur) && !off;
+    cudaMemsetAsync(p.cpk_state, 0, sizeof(uint32_t), st);
+    if (pack) cudaMemsetAsync(p.cpk_state, 1, 1, st);   // little-endian: word value 1
+  }
   kern<<<blocks, wpb * kWarp, smem, st>>>(p);
   return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
 }

@@ -64,6 +64,9 @@ struct IterParams {
   const S* f;
   const S* u_init;
   const S* x_cur;
+  S* Cpk;             // [T][Bp/32][N(N+1)/2][32] upper triangle of C, written by begin when
+                      // every C[t,b] is bitwise symmetric (see cpk_state)
+  uint32_t* cpk_state;  // 1: Cpk is valid and the sweeps stream it instead of the dense C
   const S* traj_cur;  // [T][Bp/32][N][32]  current iterate (read)
   S* traj_new;        // [T][Bp/32][N][32]  new iterate (written)
   S* traj_best;       // [T][Bp/32][N][32]  best iterate so far
@@ -116,6 +119,30 @@ DILQR_DEVICE S stage_cost(const S* __restrict__ Cs, const S* __restrict__ cs, co
     S row = S(0);
 #pragma unroll
     for (int i = 0; i < N; ++i) row = fmaS<S>(tau[i], Cs[i * N + j], row);
+    quad = fmaS<S>(row, tau[j], quad);
+  }
+  S dot = S(0);
+#pragma unroll
+  for (int i = 0; i < N; ++i) dot = fmaS<S>(tau[i], cs[i], dot);
+  return S(0.5) * quad + dot;
+}
+
+// Slot of C[i][j] in the packed upper triangle (row-major over i <= j).
+template <int N>
+DILQR_DEVICE constexpr int pk_idx(int i, int j) {
+  return i <= j ? i * N - (i * (i - 1)) / 2 + (j - i) : j * N - (j * (j - 1)) / 2 + (i - j);
+}
+
+// stage_cost on the packed, lane-interleaved copy: the same operations in the same order
+// (C[j][i] is read from the slot of C[i][j]; the two are bitwise equal when Cpk is valid).
+template <class S, int N>
+DILQR_DEVICE S stage_cost_packed(const S* __restrict__ Cp, const S* __restrict__ cs, const S* tau) {
+  S quad = S(0);
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    S row = S(0);
+#pragma unroll
+    for (int i = 0; i < N; ++i) row = fmaS<S>(tau[i], Cp[pk_idx<N>(i, j) * kWarp], row);
     quad = fmaS<S>(row, tau[j], quad);
   }
   S dot = S(0);
@@ -315,6 +342,12 @@ struct IterKernel {
   //                 4 traj_cur[t] chunk [N][32]   5 Kk[t] chunk [NK][32]   (workspace)
   static constexpr int kNSeg = 6;
   static constexpr uint32_t kFullMask = (1u << 4) | (1u << 5);
+  static constexpr int NP = N * (N + 1) / 2;   // packed symmetric C
+
+  // Does this launch stream the packed copy of C?  (uniform over the grid)
+  DILQR_DEVICE static bool use_packed(const IterParams<S>& p) {
+    return STAGED && p.cpk_state && !p.C_bcast && *reinterpret_cast<const volatile uint32_t*>(p.cpk_state) == 1u;
+  }
 
   static __host__ __device__ void seg_elems(uint32_t* e) {
     e[0] = N * N;
@@ -335,7 +368,8 @@ struct IterKernel {
   // (shapes too large to stage) straight global memory.  C,c,F,f are this lane's
   // row-major blocks; tau / Kk are lane-interleaved (element e at [e * tstride]).
   struct Blk {
-    const S* C;
+    const S* C;       // dense: this lane's row-major block; packed: slot e at C[e * 32]
+    bool packed;
     const S* c;
     const S* F;
     const S* f;
@@ -346,8 +380,9 @@ struct IterKernel {
   DILQR_DEVICE static Blk blocks(const IterParams<S>& p, const WarpStager<S>& st, int sg, int t,
                                  int b, int bw, int lane) {
     Blk k;
+    k.packed = STAGED && ((st.seg_full >> 0) & 1u);
     if (STAGED) {
-      k.C = st.lane_ptr(sg, 0);
+      k.C = k.packed ? st.seg_ptr(sg, 0) + lane : st.lane_ptr(sg, 0);
       k.c = st.lane_ptr(sg, 1);
       k.F = kEnv ? nullptr : st.lane_ptr(sg, 2);
       k.f = kEnv ? nullptr : st.lane_ptr(sg, 3);
@@ -386,7 +421,8 @@ struct IterKernel {
                                    int b0, bool want_f, bool want_traj, bool want_K) {
     if (!STAGED) return;
     const S* src[kNSeg];
-    src[0] = cost_src<S>(p.C, p.C_bcast, t, p.B, b0, N * N);
+    src[0] = ((st.seg_full >> 0) & 1u) ? p.Cpk + bidx(t, 0, NP, b0, p.nW)
+                                        : cost_src<S>(p.C, p.C_bcast, t, p.B, b0, N * N);
     src[1] = cost_src<S>(p.c, p.c_bcast, t, p.B, b0, N);
     src[2] = nullptr;
     src[3] = nullptr;
@@ -435,15 +471,22 @@ struct IterKernel {
       }
 
       S Q[N][N], qv[N];
+      if (blk.packed) {
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+          for (int j = 0; j < N; ++j) Q[i][j] = Cs[pk_idx<N>(i, j) * kWarp];
+      } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+          for (int j = 0; j < N; ++j) Q[i][j] = Cs[i * N + j];
+      }
 #pragma unroll
       for (int i = 0; i < N; ++i) {  // c_back = C tau + c   (lqr_step.py:294)
         S acc = S(0);
 #pragma unroll
-        for (int j = 0; j < N; ++j) {
-          const S cij = Cs[i * N + j];
-          Q[i][j] = cij;
-          acc = fmaS<S>(cij, tau[j], acc);
-        }
+        for (int j = 0; j < N; ++j) acc = fmaS<S>(Q[i][j], tau[j], acc);
         qv[i] = acc + cs[i];
       }
       if (t < T - 1) {
@@ -703,7 +746,8 @@ struct IterKernel {
 #pragma unroll
           for (int i = 0; i < N; ++i) to[i * kWarp] = th[i];
         }
-        cost = cost + stage_cost<S, N>(blk.C, blk.c, th);
+        cost = cost + (blk.packed ? stage_cost_packed<S, N>(blk.C, blk.c, th)
+                                  : stage_cost<S, N>(blk.C, blk.c, th));
         if (t < T - 1) {
           if constexpr (kEnv) {
             D::step(p.dyn, th, &th[NS], xh);
@@ -748,8 +792,10 @@ ilqr_iter_kernel(const __grid_constant__ IterParams<S> p) {
   if (STAGED) {
     uint32_t e[IK::kNSeg];
     IK::seg_elems(e);
-    st.init(wbase + kStages * sizeof(uint64_t), bars, lane, nvalid, IK::kNSeg, e, IK::kFullMask,
-            (p.C_bcast ? 1u : 0u) | (p.c_bcast ? 2u : 0u));
+    const bool packed = IK::use_packed(p);
+    if (packed) e[0] = IK::NP;     // segment 0 = warp-blocked packed chunk instead of the slab
+    st.init(wbase + kStages * sizeof(uint64_t), bars, lane, nvalid, IK::kNSeg, e,
+            IK::kFullMask | (packed ? 1u : 0u), (p.C_bcast ? 1u : 0u) | (p.c_bcast ? 2u : 0u));
   }
   // padded lanes (tail warp) read the API tensors of the warp's first problem
   const int bsafe = active ? b : b0;
@@ -796,6 +842,11 @@ ilqr_begin_kernel(const __grid_constant__ IterParams<S> p) {
   // gains_only (final no-op LQR pass): the trajectory is only re-laid-out, no cost, so
   // C and c are not streamed at all
   const bool want_cost = !(p.gains_only && p.x_cur);
+  // the sweeps read C twice per iteration: when every block is bitwise symmetric they
+  // stream this packed copy (N(N+1)/2 instead of N*N scalars) instead
+  const bool do_pack = STAGED && want_cost && !p.C_bcast && p.cpk_state &&
+                       *reinterpret_cast<const volatile uint32_t*>(p.cpk_state) == 1u;
+  bool asym = false;
   if (want_cost) IK::issue_t(st, p, 0, 0, b0, true, false, false);
   for (int t = 0; t < T; ++t) {
     const int sg = t & 1;
@@ -820,6 +871,17 @@ ilqr_begin_kernel(const __grid_constant__ IterParams<S> p) {
     if (STAGED) st.wait(sg);
     const typename IK::Blk blk = IK::blocks(p, st, sg, t, b, b0 + lane, lane);
     cost = cost + stage_cost<S, N>(blk.C, blk.c, th);
+    if (do_pack) {   // upper triangle into the warp-blocked workspace copy; symmetry check
+      S* po = p.Cpk + bidx(t, 0, IK::NP, b0 + lane, p.nW);
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = i; j < N; ++j) {
+          const S cij = blk.C[i * N + j];
+          if (j > i && !(cij == blk.C[j * N + i])) asym = true;
+          po[pk_idx<N>(i, j) * kWarp] = cij;
+        }
+    }
     if (t < T - 1 && !p.x_cur) {
       if constexpr (kEnv) {
         D::step(p.dyn, th, &th[NS], xh);
@@ -830,6 +892,7 @@ ilqr_begin_kernel(const __grid_constant__ IterParams<S> p) {
   }
   if (active) p.cost_cur[b] = cost;
   p.take[b0 + lane] = 0;
+  if (do_pack && __any_sync(kFull, asym && active) && lane == 0) atomicExch(p.cpk_state, 2u);
 }
 
 }  // namespace dilqr
