@@ -134,6 +134,12 @@ struct WarpStager {
   uint32_t via_lane; // bit s = stage s has lane-copied segments
   int nvalid;        // problems this warp really has (<= 32)
   int lane;
+  // bound sources (bind / issue_bound): segment i of timestep t lives at
+  // bnd_base[i] + t * bnd_stride[i] (bytes); bnd_fast bit i = every such address and
+  // the copy size are 16-byte multiples, so the segment can always go by bulk copy
+  const char* bnd_base[kMaxSeg];
+  long long bnd_stride[kMaxSeg];
+  uint32_t bnd_fast;
 
   DILQR_DEVICE uint32_t seg_bytes(int i) const {
     const uint32_t cnt = ((seg_shared >> i) & 1u) ? 1u : (((seg_full >> i) & 1u) ? kWarp : nvalid);
@@ -154,6 +160,12 @@ struct WarpStager {
     parity = 0;
     via_tma = 0;
     via_lane = 0;
+    bnd_fast = 0;
+#pragma unroll
+    for (int i = 0; i < kMaxSeg; ++i) {
+      bnd_base[i] = nullptr;
+      bnd_stride[i] = 0;
+    }
     uint32_t off = 0;
     seg_sized = 0;
 #pragma unroll
@@ -245,6 +257,46 @@ struct WarpStager {
       if (i < nseg && src[i] && !((bulk_mask >> i) & 1u))
         lane_copy<S>(reinterpret_cast<S*>(dst + seg_off[i]), src[i], seg_nbytes[i] / sizeof(S), lane);
     }
+  }
+
+  // Describe where segment i comes from for the rest of a sweep (nullptr: never issued).
+  DILQR_DEVICE void bind(int i, const void* base, long long stride_bytes) {
+    bnd_base[i] = static_cast<const char*>(base);
+    bnd_stride[i] = stride_bytes;
+    const bool ok = base && ((seg_sized >> i) & 1u) &&
+                    !(reinterpret_cast<uintptr_t>(base) & 15u) && !(stride_bytes & 15);
+    bnd_fast = ok ? (bnd_fast | (1u << i)) : (bnd_fast & ~(1u << i));
+  }
+
+  // issue() for bound sources: `mask` = segments wanted for timestep t.  When all of
+  // them are bulk-eligible only the elected lane computes addresses.
+  DILQR_DEVICE void issue_bound(int stage, int t, uint32_t mask) {
+    if ((mask & ~bnd_fast) == 0u) {
+      __syncwarp();  // all lanes are done reading this stage (WAR)
+      via_tma |= 1u << stage;
+      via_lane &= ~(1u << stage);
+      if (lane == 0) {
+        char* dst = base + stage * stage_bytes;
+        uint32_t total = 0;
+#pragma unroll
+        for (int i = 0; i < kMaxSeg; ++i)
+          if ((mask >> i) & 1u) total += seg_nbytes[i];
+        mbar_expect_tx(&bar[stage], total);
+#pragma unroll
+        for (int i = 0; i < kMaxSeg; ++i)
+          if ((mask >> i) & 1u)
+            bulk_g2s(dst + seg_off[i], bnd_base[i] + (long long)t * bnd_stride[i], seg_nbytes[i],
+                     &bar[stage]);
+      }
+      return;
+    }
+    const S* src[kMaxSeg];
+#pragma unroll
+    for (int i = 0; i < kMaxSeg; ++i)
+      src[i] = (((mask >> i) & 1u) && bnd_base[i])
+                   ? reinterpret_cast<const S*>(bnd_base[i] + (long long)t * bnd_stride[i])
+                   : nullptr;
+    issue(stage, src, kMaxSeg);
   }
 
   DILQR_DEVICE void wait(int stage) {

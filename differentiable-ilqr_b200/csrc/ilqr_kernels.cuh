@@ -176,8 +176,14 @@ template <class S, int N, bool LOCKSTEP = false>
 DILQR_DEVICE void pnqp_thread(const S (&H)[N][N], const S (&q)[N], const S (&lo)[N],
                               const S (&hi)[N], bool have_init, S (&x)[N], bool (&If)[N],
                               LUpp<S, N>& lu, const uint32_t* __restrict__ guess, uint4 gpre,
-                              uint32_t* __restrict__ votes, bool solo, bool active, int lane) {
+                              uint32_t* __restrict__ votes, bool solo, bool active, int lane,
+                              S* rinv_out = nullptr) {
   constexpr bool lockstep = LOCKSTEP;
+  // N == 1: 1 / (masked Hessian) of the last evaluated iteration, handed to the caller
+  // (which needs the same quotient for K, lqr_step.py:144-146) and reused across
+  // iterations while the operand is unchanged -- same value, one division instead of three.
+  S h_last = S(0), r_last = S(0);
+  bool have_r = false;
   // lockstep: the kernel was launched cooperatively with the whole batch resident;
   // every batch-global decision is an atomicOr into the vote word + a grid-wide
   // barrier (no guessing, no re-runs) -- the better trade when the control-flow trace
@@ -243,7 +249,13 @@ DILQR_DEVICE void pnqp_thread(const S (&H)[N][N], const S (&q)[N], const S (&lo)
       dx[i] = If[i] ? g[i] : S(0);
     }
     if (N == 1) {  // pnqp.py:50-51
-      dx[0] = -(S(1) / lu.a[0][0]) * dx[0];
+      if (!(have_r && lu.a[0][0] == h_last)) {
+        h_last = lu.a[0][0];
+        r_last = S(1) / h_last;
+        have_r = true;
+      }
+      if (rinv_out) *rinv_out = r_last;
+      dx[0] = -r_last * dx[0];
     } else {
       lu.factor();
       lu.solve(dx);
@@ -253,7 +265,9 @@ DILQR_DEVICE void pnqp_thread(const S (&H)[N][N], const S (&q)[N], const S (&lo)
     S nrm2 = S(0);
 #pragma unroll
     for (int i = 0; i < N; ++i) nrm2 = fmaS<S>(dx[i], dx[i], nrm2);
-    const bool J = sqrtS<S>(nrm2) >= S(1e-4);  // pnqp.py:56
+    // pnqp.py:56.  N == 1: sqrt(dx*dx) == |dx| exactly (correctly rounded square root of a
+    // correctly rounded square; in the under/overflow ranges both sides of the test agree)
+    const bool J = (N == 1) ? (absS<S>(dx[0]) >= S(1e-4)) : (sqrtS<S>(nrm2) >= S(1e-4));
     uint32_t vote = 0;
     bool any_moving;
     if (solo) {
@@ -416,23 +430,38 @@ struct IterKernel {
     }
   }
 
+  // Tell the stager where this warp's slabs / chunks of each segment live (once per
+  // kernel): address of timestep 0 and the byte stride between timesteps.
+  DILQR_DEVICE static void bind_sources(WarpStager<S>& st, const IterParams<S>& p, int b0) {
+    if (!STAGED) return;
+    const long long sz = (long long)sizeof(S);
+    if ((st.seg_full >> 0) & 1u)
+      st.bind(0, p.Cpk + bidx(0, 0, NP, b0, p.nW), (long long)p.nW * NP * kWarp * sz);
+    else
+      st.bind(0, cost_src<S>(p.C, p.C_bcast, 0, p.B, b0, N * N),
+              p.C_bcast == 0 ? (long long)p.B * N * N * sz : (p.C_bcast == 1 ? (long long)N * N * sz : 0));
+    st.bind(1, cost_src<S>(p.c, p.c_bcast, 0, p.B, b0, N),
+            p.c_bcast == 0 ? (long long)p.B * N * sz : (p.c_bcast == 1 ? (long long)N * sz : 0));
+    if (!kEnv) {
+      st.bind(2, p.F ? p.F + (size_t)b0 * (NS * N) : nullptr, (long long)p.B * NS * N * sz);
+      st.bind(3, (p.has_f && p.f) ? p.f + (size_t)b0 * NS : nullptr, (long long)p.B * NS * sz);
+    }
+    st.bind(4, p.traj_cur + bidx(0, 0, N, b0, p.nW), (long long)p.nW * N * kWarp * sz);
+    st.bind(5, p.Kk + bidx(0, 0, NK, b0, p.nW), (long long)p.nW * NK * kWarp * sz);
+  }
+
   // issue the operands of timestep t for this warp into `stage`
   DILQR_DEVICE static void issue_t(WarpStager<S>& st, const IterParams<S>& p, int stage, int t,
                                    int b0, bool want_f, bool want_traj, bool want_K) {
     if (!STAGED) return;
-    const S* src[kNSeg];
-    src[0] = ((st.seg_full >> 0) & 1u) ? p.Cpk + bidx(t, 0, NP, b0, p.nW)
-                                        : cost_src<S>(p.C, p.C_bcast, t, p.B, b0, N * N);
-    src[1] = cost_src<S>(p.c, p.c_bcast, t, p.B, b0, N);
-    src[2] = nullptr;
-    src[3] = nullptr;
-    if (!kEnv) {
-      if (t < p.T - 1) src[2] = p.F + ((size_t)t * p.B + b0) * (NS * N);
-      if (want_f && p.has_f && t < p.T - 1) src[3] = p.f + ((size_t)t * p.B + b0) * NS;
+    uint32_t mask = 3u;   // C, c
+    if (!kEnv && t < p.T - 1) {
+      if (p.F) mask |= 1u << 2;
+      if (want_f && p.has_f && p.f) mask |= 1u << 3;
     }
-    src[4] = want_traj ? p.traj_cur + bidx(t, 0, N, b0, p.nW) : nullptr;
-    src[5] = want_K ? p.Kk + bidx(t, 0, NK, b0, p.nW) : nullptr;
-    st.issue(stage, src, kNSeg);
+    if (want_traj) mask |= 1u << 4;
+    if (want_K) mask |= 1u << 5;
+    st.issue_bound(stage, t, mask);
   }
 
   // ======================================================================
@@ -610,14 +639,16 @@ struct IterKernel {
         }
         bool If[NC];
         LUpp<S, NC> lu;
+        S rinv = S(0);
         pnqp_thread<S, NC, LOCKSTEP>(H, qu, lo, hi, have_prev, k, If, lu,
                                      p.guess + (size_t)t * kPnqpMaxIter, gpre,
-                                     p.votes + (size_t)t * kPnqpMaxIter, p.solo != 0, active, lane);
+                                     p.votes + (size_t)t * kPnqpMaxIter, p.solo != 0, active, lane,
+                                     &rinv);
         have_prev = true;
 #pragma unroll
         for (int a = 0; a < NC; ++a) kprev[a] = k[a];
         if (NC == 1) {  // lqr_step.py:144-146
-          const S r = S(1) / lu.a[0][0];
+          const S r = rinv;   // == 1 / lu.a[0][0], computed inside pnqp_thread
 #pragma unroll
           for (int j = 0; j < NS; ++j) K[0][j] = -(r * (If[0] ? Q[NS][j] : S(0)));
         } else {        // lqr_step.py:148
@@ -796,6 +827,7 @@ ilqr_iter_kernel(const __grid_constant__ IterParams<S> p) {
     if (packed) e[0] = IK::NP;     // segment 0 = warp-blocked packed chunk instead of the slab
     st.init(wbase + kStages * sizeof(uint64_t), bars, lane, nvalid, IK::kNSeg, e,
             IK::kFullMask | (packed ? 1u : 0u), (p.C_bcast ? 1u : 0u) | (p.c_bcast ? 2u : 0u));
+    IK::bind_sources(st, p, b0);
   }
   // padded lanes (tail warp) read the API tensors of the warp's first problem
   const int bsafe = active ? b : b0;
@@ -833,6 +865,7 @@ ilqr_begin_kernel(const __grid_constant__ IterParams<S> p) {
     IK::seg_elems(e);
     st.init(wbase + kStages * sizeof(uint64_t), reinterpret_cast<uint64_t*>(wbase), lane, nvalid,
             IK::kNSeg, e, IK::kFullMask, (p.C_bcast ? 1u : 0u) | (p.c_bcast ? 2u : 0u));
+    IK::bind_sources(st, p, b0);
   }
   const int T = p.T;
   S xh[NS];
