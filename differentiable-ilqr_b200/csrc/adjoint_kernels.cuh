@@ -357,11 +357,13 @@ __global__ void __launch_bounds__(64) adjoint_pass_kernel(const __grid_constant_
   auto slab = [&](const S* base, int t, int elems) { return base + ((size_t)t * p.B + b0) * elems; };
 
   // ---------------- affine backward sweep
-  auto issue_a = [&](int stage, int t) {
-    const S* src[AS::kNSeg] = {nullptr, slab(p.w, t, N), slab(p.x, t, NS), slab(p.u, t, NC),
-                               p.fac + bidx(t, 0, NFAC, b0, nW), nullptr};
-    st.issue(stage, src, AS::kNSeg);
-  };
+  const long long sz = (long long)sizeof(S);
+  const long long chunk = (long long)nW * kWarp * sz;   // bytes per timestep per component
+  st.bind(1, slab(p.w, 0, N), (long long)p.B * N * sz);
+  st.bind(2, slab(p.x, 0, NS), (long long)p.B * NS * sz);
+  st.bind(3, slab(p.u, 0, NC), (long long)p.B * NC * sz);
+  st.bind(4, p.fac + bidx(0, 0, NFAC, b0, nW), chunk * NFAC);
+  auto issue_a = [&](int stage, int t) { st.issue_bound(stage, t, 0x1eu); };
   S v[NS], xnext[NS];
   S pred = S(0);
   issue_a(0, T - 1);
@@ -434,12 +436,13 @@ __global__ void __launch_bounds__(64) adjoint_pass_kernel(const __grid_constant_
   __syncwarp();
 
   // ---------------- linear rollout (+ Richardson update)
+  if (!FINAL) {
+    st.bind(0, p.Lam + bidx(0, 0, AS::NLAM, b0, nW), chunk * AS::NLAM);
+    st.bind(1, slab(p.g, 0, N), (long long)p.B * N * sz);
+  }
+  st.bind(5, p.kvec + bidx(0, 0, NC, b0, nW), chunk * NC);
   auto issue_f = [&](int stage, int t) {
-    const S* src[AS::kNSeg] = {(!FINAL && t < T - 1) ? p.Lam + bidx(t, 0, AS::NLAM, b0, nW) : nullptr,
-                               FINAL ? nullptr : slab(p.g, t, N), slab(p.x, t, NS),
-                               slab(p.u, t, NC), p.fac + bidx(t, 0, NFAC, b0, nW),
-                               p.kvec + bidx(t, 0, NC, b0, nW)};
-    st.issue(stage, src, AS::kNSeg);
+    st.issue_bound(stage, t, FINAL ? 0x3cu : ((t < T - 1) ? 0x3fu : 0x3eu));
   };
   S dt[N], tprev[N];
   double dmax = 0.0, wmax = 0.0;
@@ -452,6 +455,13 @@ __global__ void __launch_bounds__(64) adjoint_pass_kernel(const __grid_constant_
     const S* us_ = st.lane_ptr(sg, 3);
     const S* f = st.seg_ptr(sg, 4) + lane;
     const S* kv = st.seg_ptr(sg, 5) + lane;
+    // previous iterate w_t (for the residual of the Richardson update): fetched now, used
+    // at the end of the step, so the global-load latency hides behind the step's arithmetic
+    S wold[N];
+    if (!FINAL) {
+#pragma unroll
+      for (int k2 = 0; k2 < N; ++k2) wold[k2] = act ? p.w[((size_t)t * p.B + b) * N + k2] : S(0);
+    }
     S tau[N];
 #pragma unroll
     for (int i = 0; i < NS; ++i) tau[i] = xs_[i];
@@ -522,7 +532,7 @@ __global__ void __launch_bounds__(64) adjoint_pass_kernel(const __grid_constant_
         }
         const S wn = gs[k2] - acc;
         if (act) {
-          const S wo = p.w[tb * N + k2];
+          const S wo = wold[k2];
           dmax = fmax(dmax, fabs((double)wn - (double)wo));
           wmax = fmax(wmax, fabs((double)wn));
           p.w[tb * N + k2] = wn;
@@ -548,12 +558,9 @@ __global__ void __launch_bounds__(64) adjoint_pass_kernel(const __grid_constant_
   __threadfence();
   asm volatile("fence.proxy.async;" ::: "memory");
   __syncwarp();
-  auto issue_b = [&](int stage, int t) {
-    const S* src[AS::kNSeg] = {cost_src<S>(p.C, p.C_bcast, t, p.B, b0, N * N), slab(p.w, t, N),
-                               slab(p.x, t, NS), slab(p.u, t, NC), nullptr,
-                               p.dtau + bidx(t, 0, N, b0, nW)};
-    st.issue(stage, src, AS::kNSeg);
-  };
+  st.bind(1, slab(p.w, 0, N), (long long)p.B * N * sz);
+  st.bind(5, p.dtau + bidx(0, 0, N, b0, nW), chunk * N);
+  auto issue_b = [&](int stage, int t) { st.issue_bound(stage, t, 0x2fu); };
   const bool bulk_out = (nvalid == kWarp) && ((((size_t)N * N * sizeof(S) * kWarp) & 15) == 0) &&
                         ((((size_t)N * sizeof(S) * kWarp) & 15) == 0) &&
                         (p.C_bcast == 0 || p.c_bcast == 0);
@@ -571,6 +578,8 @@ __global__ void __launch_bounds__(64) adjoint_pass_kernel(const __grid_constant_
     for (int j = 0; j < N; ++j) accC[i][j] = S(0);
   }
   st.set_shared(p.C_bcast ? 1u : 0u);   // segment 0 now carries C
+  st.bind(0, cost_src<S>(p.C, p.C_bcast, 0, p.B, b0, N * N),
+          p.C_bcast == 0 ? (long long)p.B * N * N * sz : (p.C_bcast == 1 ? (long long)N * N * sz : 0));
   S dlam[NS];
   issue_b(0, T - 1);
   for (int t = T - 1; t >= 0; --t) {

@@ -95,6 +95,11 @@ DILQR_DEVICE void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t*
       : "memory");
 }
 
+// Software prefetch of the cache line holding *p (kernels that read AoS operands directly).
+DILQR_DEVICE void prefetch_l1(const void* p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
 // ---------------------------------------------------------------------------
 // Per-warp double-buffered slab stager.
 //

@@ -258,6 +258,16 @@ sens_theta_kernel(DynParams<S> P, int T, int B, const S* __restrict__ x,
     for (int q = 0; q < NTH; ++q) G[i][q] = S(0);
   for (int t = 0; t < T; ++t) {
     const size_t tb = (size_t)t * B + b;
+    if (t + 1 < T) {   // next step's operands on their way while this step's tables are evaluated
+      const size_t nb = tb + B;
+      prefetch_l1(x + nb * NS);
+      prefetch_l1(dx + nb * NS);
+      prefetch_l1(u + nb * NC);
+      prefetch_l1(du + nb * NC);
+      prefetch_l1(lam + nb * NS);
+      prefetch_l1(df + tb * NS);
+      if (t + 2 < T) prefetch_l1(K + ((size_t)(T - 2 - t) * B + b) * (NC * NS));
+    }
     S tau[N], dtau[N];
 #pragma unroll
     for (int i = 0; i < NS; ++i) {
