@@ -389,23 +389,15 @@ def kkt_backward(dl_dx, dl_du, x_init, C_, c_, F, f, x, u, n_state, n_ctrl, u_lo
     return kkt_grads(C_, c_, F, x, u, dx, du, r, n_state, n_ctrl, want_df)
 
 
-def dilqr_backward(dl_dx, dl_du, x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u_lower=None,
-                   u_upper=None, n_passes=8, tol=None, back_eps=1e-7, solo=False, stats=None,
-                   theta_host=None,
-                   factored=True):
-    """DiLQR implicit gradient (lqr_step_explicit.py:652-712 + fix_point_equ
-    458-598) in matrix-free form (SURVEY Appendix C; derivation in
-    csrc/dilqr_backward.cuh).  Returns (dC, dc, dtheta[B, n_theta]).
-
-    n_passes Richardson passes solve A' w = g (each = one adjoint LQR solve); with
-    ``tol`` the loop stops early once max|dw| <= tol * max|w| (one host sync per
-    pass).  The adjoint solves follow mpc_backup / lqr_step_backup (Cholesky +
-    1e-6 I for unconstrained multi-input problems, lqr_step_backup.py:202-205).
-
-    ``factored=True`` runs the adjoint solves with the factor-once / affine-pass
-    kernels (csrc/adjoint_kernels.cuh); if any problem's adjoint step would have been
-    rejected by the reference's line search (non-convex model), the whole backward is
-    recomputed with the generic line-searching kernels (``factored=False``)."""
+def dilqr_prepare(x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u_lower=None, u_upper=None,
+                  solo=False, theta_host=None, factored=True):
+    """Everything of the DiLQR backward that depends only on the forward solution
+    (x*, u*), the cost and theta -- NOT on the upstream gradient: the gains of the final
+    no-op LQR pass (lqr_step_explicit.py:604-618), the primal costates with the
+    contracted second-order tables, and the factorisation of the adjoint LQR solves.
+    ``MPC.forward`` enqueues this right behind the solve when a gradient will be asked
+    for, so the device works through it while the host is busy with the loss and the
+    autograd dispatch."""
     T, B = x.shape[0], x.shape[1]
     dtype, dev = x.dtype, x.device
     n = n_state + n_ctrl
@@ -441,24 +433,10 @@ def dilqr_backward(dl_dx, dl_du, x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u
         Lam = torch.empty(T - 1, B, n, n, dtype=dtype, device=dev)
     _lib.call("dilqr_costate_tables", _DT[dtype], kind, theta, T, B, _ptr(C_), _ptr(c_), _ptr(x),
               _ptr(u), _ptr(lam), _ptr(Lam), Cb, cb, 1 if factored else 0, _stream())
-    g = torch.cat((dl_dx, dl_du), 2).contiguous()
-    w = g.clone()
-    resid = torch.zeros(3, dtype=torch.float64, device=dev)
-    passes = 0
-    rel = None
-    nth = len(dxmod.params)
-    # gradients of a broadcast cost come back as per-warp partial sums (summed below)
-    nwarp = (B + 31) // 32
-    dC = torch.empty({0: (T, B, n, n), 1: (T, nwarp, n, n), 2: (nwarp, n, n)}[Cb], dtype=dtype,
-                     device=dev)
-    dc = torch.empty({0: (T, B, n), 1: (T, nwarp, n), 2: (nwarp, n)}[cb], dtype=dtype, device=dev)
-    df = torch.empty(T - 1, B, n_state, dtype=dtype, device=dev)
-
-    def converged():
-        r = resid.cpu()
-        return float(r[0]) / (float(r[1]) + 1e-300)
-
+    prep = dict(theta=theta, kind=kind, factored=factored, Cb=Cb, cb=cb, C_=C_, c_=c_, x=x, u=u,
+                K=K, lam=lam, Lam=Lam, x_init=x_init, C_in=C_in, c_in=c_in)
     if factored:
+        # (3a) factor the adjoint LQR solves once (csrc/adjoint_kernels.cuh)
         a = _lib.DilqrAdjoint()
         a.n_state, a.n_ctrl, a.T, a.n_batch, a.dtype, a.dynamics = n_state, n_ctrl, T, B, _DT[dtype], kind
         a.bounds_kind = _lib.BOUNDS_NONE if u_lower is None else _lib.BOUNDS_SCALAR
@@ -468,16 +446,69 @@ def dilqr_backward(dl_dx, dl_du, x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u
             a.u_lower, a.u_upper = u_lower, u_upper
         for i in range(8):
             a.dyn_params[i] = theta[i]
-        dxa = torch.empty(T, B, n_state, dtype=dtype, device=dev)
-        dua = torch.empty(T, B, n_ctrl, dtype=dtype, device=dev)
-        a.C, a.x, a.u, a.g, a.Lam, a.w = _ptr(C_), _ptr(x), _ptr(u), _ptr(g), _ptr(Lam), _ptr(w)
-        a.dC, a.dc, a.df, a.dx_out, a.du_out = _ptr(dC), _ptr(dc), _ptr(df), _ptr(dxa), _ptr(dua)
+        resid = torch.zeros(3, dtype=torch.float64, device=dev)
+        a.C, a.x, a.u, a.Lam = _ptr(C_), _ptr(x), _ptr(u), _ptr(Lam)
         a.resid = _ptr(resid)
         need = _lib.lib().dilqr_adjoint_workspace_bytes(C.byref(a))
         ws = torch.empty(need, dtype=torch.uint8, device=dev)
         a.workspace, a.workspace_bytes = _ptr(ws), need
+        _lib.call("dilqr_adjoint_factor", C.byref(a), _stream())
+        prep.update(a=a, ws=ws, resid=resid)
+    return prep
+
+
+def dilqr_backward(dl_dx, dl_du, x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u_lower=None,
+                   u_upper=None, n_passes=8, tol=None, back_eps=1e-7, solo=False, stats=None,
+                   theta_host=None, factored=True, prep=None):
+    """DiLQR implicit gradient (lqr_step_explicit.py:652-712 + fix_point_equ
+    458-598) in matrix-free form (SURVEY Appendix C; derivation in
+    csrc/dilqr_backward.cuh).  Returns (dC, dc, dtheta[B, n_theta]).
+
+    n_passes Richardson passes solve A' w = g (each = one adjoint LQR solve); with
+    ``tol`` the loop stops early once max|dw| <= tol * max|w| (one host sync per
+    pass).  The adjoint solves follow mpc_backup / lqr_step_backup (Cholesky +
+    1e-6 I for unconstrained multi-input problems, lqr_step_backup.py:202-205).
+
+    ``factored=True`` runs the adjoint solves with the factor-once / affine-pass
+    kernels (csrc/adjoint_kernels.cuh); if any problem's adjoint step would have been
+    rejected by the reference's line search (non-convex model), the whole backward is
+    recomputed with the generic line-searching kernels (``factored=False``).
+
+    ``prep``: the gradient-independent part (``dilqr_prepare``) if the forward pass
+    already enqueued it."""
+    if prep is None:
+        prep = dilqr_prepare(x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u_lower, u_upper,
+                             solo, theta_host, factored)
+    T, B = x.shape[0], x.shape[1]
+    dtype, dev = x.dtype, x.device
+    n = n_state + n_ctrl
+    kind, theta, factored = prep["kind"], prep["theta"], prep["factored"]
+    Cb, cb, C_d, c_d = prep["Cb"], prep["cb"], prep["C_"], prep["c_"]
+    x, u, K, lam, Lam = prep["x"], prep["u"], prep["K"], prep["lam"], prep["Lam"]
+    g = torch.cat((dl_dx, dl_du), 2).contiguous()
+    w = g.clone()
+    passes = 0
+    rel = None
+    nth = len(dxmod.params)
+    # gradients of a broadcast cost come back as per-warp partial sums (summed below)
+    nwarp = (B + 31) // 32
+    dC = torch.empty({0: (T, B, n, n), 1: (T, nwarp, n, n), 2: (nwarp, n, n)}[Cb], dtype=dtype,
+                     device=dev)
+    dc = torch.empty({0: (T, B, n), 1: (T, nwarp, n), 2: (nwarp, n)}[cb], dtype=dtype, device=dev)
+    df = torch.empty(T - 1, B, n_state, dtype=dtype, device=dev)
+    resid = prep["resid"] if factored else torch.zeros(3, dtype=torch.float64, device=dev)
+
+    def converged():
+        r = resid.cpu()
+        return float(r[0]) / (float(r[1]) + 1e-300)
+
+    if factored:
+        a = prep["a"]
+        dxa = torch.empty(T, B, n_state, dtype=dtype, device=dev)
+        dua = torch.empty(T, B, n_ctrl, dtype=dtype, device=dev)
+        a.g, a.w = _ptr(g), _ptr(w)
+        a.dC, a.dc, a.df, a.dx_out, a.du_out = _ptr(dC), _ptr(dc), _ptr(df), _ptr(dxa), _ptr(dua)
         st = _stream()
-        _lib.call("dilqr_adjoint_factor", C.byref(a), st)
         for _ in range(n_passes):
             _lib.call("dilqr_adjoint_pass", C.byref(a), st)
             passes += 1
@@ -500,7 +531,7 @@ def dilqr_backward(dl_dx, dl_du, x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u
         lin = DynSpec(_lib.DYN_LINDX, F=F, f=None)
 
         def adjoint():
-            return solve_mpc(zero, C_, negw, lin, n_state, n_ctrl, T, u_zero_I=I, lqr_iter=1,
+            return solve_mpc(zero, C_d, negw, lin, n_state, n_ctrl, T, u_zero_I=I, lqr_iter=1,
                              eps=back_eps, gain_solve=_lib.GAIN_CHOL_REG, verbose=-1,
                              sync=False)[:2]
 
@@ -514,7 +545,7 @@ def dilqr_backward(dl_dx, dl_du, x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u
                 if rel <= tol:
                     break
         dxa, dua = adjoint()
-        _, dC, dc, _, df = kkt_grads(C_, c_, F, x, u, dxa, dua, w, n_state, n_ctrl, want_df=True,
+        _, dC, dc, _, df = kkt_grads(C_d, c_d, F, x, u, dxa, dua, w, n_state, n_ctrl, want_df=True,
                                      want_dF=False)
     # (3) dtheta through the closed-loop sensitivity rollout
     dtheta = torch.empty(B, nth, dtype=dtype, device=dev)
@@ -524,9 +555,9 @@ def dilqr_backward(dl_dx, dl_du, x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u
         # one sync at the end: did the reference's line search reject any adjoint step?
         n_rej = int(resid[2:3].view(torch.int64).item())
         if n_rej:
-            return dilqr_backward(dl_dx, dl_du, x_init, C_, c_, x, u, dxmod, n_state, n_ctrl,
-                                  u_lower, u_upper, n_passes, tol, back_eps, solo, stats,
-                                  theta_host=theta_host, factored=False)
+            return dilqr_backward(dl_dx, dl_du, x_init, prep["C_in"], prep["c_in"], x, u, dxmod,
+                                  n_state, n_ctrl, u_lower, u_upper, n_passes, tol, back_eps, solo,
+                                  stats, theta_host=theta_host, factored=False)
     if stats is not None:
         stats["passes"] = passes
         stats["resid"] = rel

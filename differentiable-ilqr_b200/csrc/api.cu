@@ -586,8 +586,9 @@ static int adj_run(const DilqrAdjoint* a, int what, cudaStream_t st) {
 }
 
 static int adj_check(const DilqrAdjoint* a, int what) {
-  if (!a || a->T < 2 || a->n_batch <= 0 || !a->C || !a->x || !a->u || !a->w || !a->resid)
+  if (!a || a->T < 2 || a->n_batch <= 0 || !a->C || !a->x || !a->u || !a->resid)
     return DILQR_EINVAL;
+  if (what != 0 && !a->w) return DILQR_EINVAL;     // the factorisation needs no right-hand side
   if (what == 1 && (!a->g || !a->Lam)) return DILQR_EINVAL;
   if (a->bounds_kind != DILQR_BOUNDS_NONE && a->bounds_kind != DILQR_BOUNDS_SCALAR)
     return DILQR_EINVAL;

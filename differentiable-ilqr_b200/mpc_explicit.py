@@ -38,6 +38,14 @@ class _MPCExplicitFn(Function):
                 ctx.mask = (info.full_du_norm < eps_cmp).to(x.dtype)
         ctx.save_for_backward(x_init, C, c, x, u)
         ctx.mark_non_differentiable(costs)
+        # a gradient wrt the cost or theta will be asked for: enqueue the part of the
+        # backward that only needs the solution right behind the solve (the final no-op
+        # LQR pass is part of the reference's forward too, mpc_explicit.py:325-340)
+        ctx.prep = None
+        if mod.backprop and mod.prepare_in_forward and any(ctx.needs_input_grad[3:6]):
+            ctx.prep = _solver.dilqr_prepare(
+                x_init, C, c, x, u, dx, mod.n_state, mod.n_ctrl, mod.u_lower, mod.u_upper,
+                solo=mod.solo, theta_host=dyn.params)
         return x, u, costs
 
     @staticmethod
@@ -52,7 +60,8 @@ class _MPCExplicitFn(Function):
             dl_dx.contiguous(), dl_du.contiguous(), x_init, C, c, x, u, dx, mod.n_state,
             mod.n_ctrl, mod.u_lower, mod.u_upper, n_passes=mod.richardson_passes,
             tol=mod.richardson_tol, back_eps=mod.back_eps, solo=mod.solo, stats=stats,
-            theta_host=ctx.theta_host)
+            theta_host=ctx.theta_host, prep=ctx.prep)
+        ctx.prep = None
         mod.last_backward = stats
         # dC / dc come back in the layout of the cost tensors handed in (dense, or already
         # summed over the broadcast axes for C[n,n] / C[T,n,n]); the reference returns
@@ -65,8 +74,10 @@ class MPC(_BaseMPC):
     matrix-free fixed-point solve: ``richardson_passes`` (max adjoint-LQR passes)
     and ``richardson_tol`` (relative stop tolerance; None = fixed pass count)."""
 
-    def __init__(self, *args, richardson_passes=30, richardson_tol=1e-14, **kw):
+    def __init__(self, *args, richardson_passes=30, richardson_tol=1e-14,
+                 prepare_in_forward=True, **kw):
         super().__init__(*args, **kw)
+        self.prepare_in_forward = prepare_in_forward
         self.richardson_passes = richardson_passes
         self.richardson_tol = richardson_tol
         self.last_backward = None

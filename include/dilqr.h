@@ -284,7 +284,9 @@ typedef struct DilqrAdjoint {
   size_t workspace_bytes;
 } DilqrAdjoint;
 size_t dilqr_adjoint_workspace_bytes(const DilqrAdjoint* a);
-/* Masked Riccati sweep at tau*: gains and the r-independent blocks. */
+/* Masked Riccati sweep at tau*: gains and the r-independent blocks.  Needs only C, x, u,
+ * bounds, dyn_params, resid and the workspace (not w, g, Lam or the outputs), so it can be
+ * enqueued right behind the forward solve, before any upstream gradient exists. */
 int dilqr_adjoint_factor(const DilqrAdjoint* a, void* stream);
 /* One Richardson pass: adjoint solve with r = w fused with w <- g - Lam dtau. */
 int dilqr_adjoint_pass(const DilqrAdjoint* a, void* stream);
