@@ -14,9 +14,19 @@ class EnvDx(nn.Module):
     n_state = 0
     n_ctrl = 0
 
+    def _theta_list(self):
+        """Host copy of the parameters (the kernels take them by value).  Cached per
+        tensor version so one device->host sync serves every call of a step."""
+        p = self.params
+        key = (p.data_ptr(), p._version)
+        if getattr(self, "_theta_key", None) != key:
+            self._theta_cache = p.detach().double().cpu().tolist()
+            self._theta_key = key
+        return self._theta_cache
+
     def _theta(self):
         th = (C.c_double * 8)()
-        for i, v in enumerate(self.params.detach().double().cpu().tolist()):
+        for i, v in enumerate(self._theta_list()):
             th[i] = v
         return th
 

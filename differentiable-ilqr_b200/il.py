@@ -87,8 +87,9 @@ class ImitationStep:
             t.grad = None
         B = x0.shape[0]
         self.mpc.n_batch = B
-        C, c = self.tile_cost(q, p, B)
         dx = self.dx_cls(theta)
+        dx._theta_list()          # the one device->host read of a step, before anything is queued
+        C, c = self.tile_cost(q, p, B)
         x, u, _ = self.mpc(x0, QuadCost(C, c), dx)
         loss = (u - uexp).pow(2).mean() * world_frac      # il_exp.py:346
         loss.backward()                                    # il_exp.py:373

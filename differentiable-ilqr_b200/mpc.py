@@ -33,7 +33,8 @@ def _dyn_spec(dx):
         raise NotImplementedError(
             "dynamics of type %s: only LinDx and the env_dx models of this package "
             "(analytic linearisation) are supported" % type(dx).__name__)
-    return _solver.DynSpec(kind, params=dx.params.detach().double().cpu().tolist())
+    params = dx._theta_list() if hasattr(dx, "_theta_list") else dx.params.detach().double().cpu().tolist()
+    return _solver.DynSpec(kind, params=params)
 
 
 class _MPCFn(Function):
