@@ -122,25 +122,31 @@ class ImitationStep:
 
 
 class ImitationLearner:
-    """The `il_exp --mode empc --learn_dx` loop (il_exp.py:183-429) on the device:
-    learn the dynamics parameters theta by differentiating the imitation loss
-    mean((u_mpc - u_expert)^2) through the MPC (DiLQR implicit gradient), RMSprop
-    lr 1e-2 alpha 0.5 (il_exp.py:228-238), warm-start cache of the previous
-    controls (il_exp.py:269-275,338-344).  Under torch.distributed each rank owns a
-    contiguous shard of the problems (parallel.shard_range) and one small
-    all-reduce per step sums the parameter gradients; every rank then takes the
-    identical optimiser step."""
+    """The `il_exp --mode empc` loop (il_exp.py:183-429) on the device: learn the dynamics
+    parameters theta (`learn_dx`) and / or the cost (`learn_cost`: q = sigmoid(q_logit),
+    p = sqrt(q) * learn_p, il_exp.py:127-133,331-333) by differentiating the imitation loss
+    mean((u_mpc - u_expert)^2) through the MPC (DiLQR implicit gradient), RMSprop lr 1e-2
+    alpha 0.5 (il_exp.py:228-238), warm-start cache of the previous controls
+    (il_exp.py:269-275,338-344).  Under torch.distributed each rank owns a contiguous
+    shard of the problems (parallel.shard_range) and one small all-reduce per step sums
+    the parameter gradients; every rank then takes the identical optimiser step."""
 
     def __init__(self, dx_cls, theta_init, T, lqr_iter=100, dtype=torch.float64,
                  device=None, lr=1e-2, alpha=0.5, richardson_passes=30, richardson_tol=1e-10,
-                 group=None):
+                 group=None, learn_dx=True, learn_cost=False):
         self.dx_cls, self.T = dx_cls, T
         self.dtype, self.device, self.group = dtype, device, group
+        self.learn_dx, self.learn_cost = learn_dx, learn_cost
         proto = dx_cls()
         self.ns, self.nc = proto.n_state, proto.n_ctrl
         self.q, self.p = [t.to(dtype).to(device) for t in proto.get_true_obj()]
-        self.theta = torch.tensor(theta_init, dtype=dtype, device=device, requires_grad=True)
-        self.opt = torch.optim.RMSprop([{"params": [self.theta], "lr": lr, "alpha": alpha}])
+        self.theta = torch.tensor(theta_init, dtype=dtype, device=device, requires_grad=learn_dx)
+        # il_exp.py:127-133: the learnt cost starts from q = 1/2, p = 0
+        self.learn_q_logit = torch.zeros_like(self.q, requires_grad=learn_cost)
+        self.learn_p = torch.zeros_like(self.p, requires_grad=learn_cost)
+        self.params = ([self.learn_q_logit, self.learn_p] if learn_cost else []) + (
+            [self.theta] if learn_dx else [])
+        self.opt = torch.optim.RMSprop([{"params": self.params, "lr": lr, "alpha": alpha}])
         self.mpc = mpc_explicit.MPC(
             self.ns, self.nc, T, u_lower=proto.lower, u_upper=proto.upper, lqr_iter=lqr_iter,
             verbose=-1, exit_unconverged=False, detach_unconverged=True,
@@ -148,6 +154,13 @@ class ImitationLearner:
             max_linesearch_iter=proto.max_linesearch_iter, eps=proto.mpc_eps,
             richardson_passes=richardson_passes, richardson_tol=richardson_tol)
         self.warm = None
+
+    def cost(self):
+        """(q, p) the controller runs with (il_exp.py:331-335)."""
+        if self.learn_cost:
+            q = torch.sigmoid(self.learn_q_logit)
+            return q, q.sqrt() * self.learn_p
+        return self.q, self.p
 
     def expert(self, theta_true, x_init):
         """populate_data (il_env.py:81-94): one batched open-loop solve with the true model."""
@@ -166,13 +179,17 @@ class ImitationLearner:
         self.mpc.n_batch = B
         self.mpc.u_init = self.warm
         dx = self.dx_cls(self.theta)
-        _, u, _ = self.mpc(x_init, QuadCost(torch.diag(self.q), self.p), dx)
+        q, p = self.cost()
+        _, u, _ = self.mpc(x_init, QuadCost(torch.diag(q), p), dx)
         self.warm = u.detach()
         # mean over the GLOBAL batch: local sum / (T * n_global * nc)
         loss = (u - u_expert).pow(2).sum() / (self.T * n_global * self.nc)
         loss.backward()
-        flat = torch.cat((self.theta.grad, loss.detach().reshape(1)))
+        flat = torch.cat([t.grad.reshape(-1) for t in self.params] + [loss.detach().reshape(1)])
         parallel.allreduce_sum_(flat, self.group)
-        self.theta.grad.copy_(flat[:-1])
+        off = 0
+        for t in self.params:
+            t.grad.copy_(flat[off:off + t.numel()].view_as(t))
+            off += t.numel()
         self.opt.step()
         return float(flat[-1])

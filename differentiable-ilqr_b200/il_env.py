@@ -85,7 +85,8 @@ class IL_Env:
         n_data = n_train + n_val + n_test
         xinit = self.sample_xinit(n_batch=n_data)
         true_q, true_p = self.true_dx.get_true_obj()
-        true_x_mpc, true_u_mpc = self.mpc(self.true_dx, xinit, true_q, true_p)
+        with torch.no_grad():     # expert data: no gradient is ever asked for
+            true_x_mpc, true_u_mpc = self.mpc(self.true_dx, xinit, true_q, true_p)
         tau = torch.cat((true_x_mpc, true_u_mpc), dim=2).transpose(0, 1)
         self.train_data = tau[:n_train]
         self.val_data = tau[n_train:n_train + n_val]
@@ -153,6 +154,6 @@ class IL_Env:
             lqr_iter=lqr_iter, verbose=0, exit_unconverged=False, detach_unconverged=True,
             linesearch_decay=self.true_dx.linesearch_decay,
             max_linesearch_iter=self.true_dx.max_linesearch_iter,
-            grad_method=self.grad_method, eps=eps,
+            grad_method=self.grad_method, eps=eps, n_batch=n_batch,
         )(xinit, cost, dx)
         return x_mpc, u_mpc

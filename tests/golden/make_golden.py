@@ -199,6 +199,18 @@ def env_forward(env, T, B, lqr_iter, dtype):
     torch.set_default_dtype(torch.float32)
 
 
+def open_loop(env, mpc_T, lqr_iter, n_train, n_val, n_test):
+    """IL_Env.populate_data (il_env.py:81-94): one batched open-loop expert solve."""
+    torch.set_default_dtype(torch.float64)
+    e = R.il_env.IL_Env(env, lqr_iter=lqr_iter, mpc_T=mpc_T)
+    torch.manual_seed(0)
+    x0 = e.sample_xinit(n_batch=n_train + n_val + n_test)
+    e.populate_data(n_train, n_val, n_test, seed=0)
+    npz("ref_open_loop_%s.npz" % env, x0=x0, train=e.train_data, val=e.val_data,
+        test=e.test_data, mpc_T=mpc_T, lqr_iter=lqr_iter)
+    torch.set_default_dtype(torch.float32)
+
+
 def closed_loop(env, mpc_T, lqr_iter, n_train, n_val, n_test):
     """IL_Env.populate_data2 (il_env.py:96-151): closed-loop receding-horizon expert data,
     one B=1 MPC call per (sample, step)."""
@@ -226,3 +238,4 @@ if __name__ == "__main__":
     closed_loop("pendulum", 20, 50, 4, 1, 1)
     closed_loop("cartpole", 12, 30, 1, 1, 1)
     slew_affine()
+    open_loop("pendulum", 20, 60, 5, 2, 1)

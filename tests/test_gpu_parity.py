@@ -469,6 +469,23 @@ def test_imitation_learning_loop(dilqr, env, dev):
     assert losses[-1] < 0.9 * losses[0]
 
 
+def test_imitation_learning_cost(dilqr, env, dev):
+    """il_exp.py --mode empc --learn_cost (il_exp.py:127-133,331-333): the learnt cost
+    (q = sigmoid(logit), p = sqrt(q) learn_p) moves so that the imitation loss falls."""
+    g = torch.Generator().manual_seed(1)
+    B, T = 128, 20
+    th = (torch.rand(B, generator=g, dtype=torch.float64) - 0.5) * 3.0
+    w = torch.rand(B, generator=g, dtype=torch.float64) * 2 - 1
+    x0 = torch.stack((torch.cos(th), torch.sin(th), w), 1).to(dev)
+    L = dilqr.il.ImitationLearner(env.PendulumDx, (10., 1., 1.), T, lqr_iter=60, device=dev,
+                                  learn_dx=False, learn_cost=True)
+    u_exp = L.expert((10., 1., 1.), x0)
+    losses = [L.step(x0, u_exp) for _ in range(10)]
+    assert all(b < a for a, b in zip(losses, losses[1:])), losses
+    assert losses[-1] < 0.9 * losses[0], losses
+    assert L.theta.grad is None and L.learn_q_logit.grad is not None
+
+
 def test_tensor_bounds_and_broadcast_cost_lindx(dilqr, port, dev):
     """u_lower / u_upper as [T,B,nc] tensors (lqr_step.py:264-272) and a broadcast
     C[n,n] through mpc.MPC (forward + KKT backward) on a LinDx problem."""
@@ -575,3 +592,23 @@ def test_edge_horizons_and_batches(dilqr, port, dev, ns, nc, T, B, boxed):
     assert rel(xg.grad, ref.dx_init) < 1e-8
     if T > 1:
         assert rel(Fg.grad, ref.dF) < 1e-8 and rel(fg.grad, ref.df) < 1e-8
+
+
+def test_open_loop_expert_data_golden(dilqr, dev):
+    """il_env.IL_Env.populate_data (il_env.py:81-94) against the reference's own output:
+    one batched solve, batch-global semantics, train/val/test split."""
+    il_env = importlib.import_module("differentiable-ilqr_b200.il_env")
+    g = golden("ref_open_loop_pendulum.npz")
+    nt, nv, ns_ = g["train"].shape[0], g["val"].shape[0], g["test"].shape[0]
+    for tile in (False, True):
+        e = il_env.IL_Env("pendulum", lqr_iter=int(g["lqr_iter"]), mpc_T=int(g["mpc_T"]),
+                          dtype=torch.float64, device=dev, tile=tile)
+        torch.set_default_dtype(torch.float64)
+        try:
+            e.populate_data(nt, nv, ns_, seed=0)
+        finally:
+            torch.set_default_dtype(torch.float32)
+        assert e.train_data.shape == g["train"].shape
+        for mine, ref in ((e.train_data, g["train"]), (e.val_data, g["val"]),
+                          (e.test_data, g["test"])):
+            assert rel(mine, ref) < 1e-6
