@@ -801,8 +801,17 @@ struct IterKernel {
   }
 };
 
+// FP32, small env shapes: cap the registers at 128 (no extra spills) so that 16 warps fit
+// one SM: a 65536-problem batch (2048 warps, 13.8 per SM) then runs as ONE wave instead of
+// two, which saves a whole per-warp latency (cartpole: 0.445 -> 0.30 ms per launch).  The
+// FP64 build needs 252 registers and 27.6 KB of stage per warp and stays at 8 warps/SM.
+template <class S, int NS, int NC, int DYN, bool STAGED>
+constexpr int iter_min_blocks() {
+  return (sizeof(S) == 4 && STAGED && DYN != DYN_LINDX && NS + NC <= 6) ? 4 : 1;
+}
+
 template <class S, int NS, int NC, int DYN, bool STAGED, bool LOCKSTEP = false, int PHASE = 0>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, iter_min_blocks<S, NS, NC, DYN, STAGED>())
 ilqr_iter_kernel(const __grid_constant__ IterParams<S> p) {
   using IK = IterKernel<S, NS, NC, DYN, STAGED, LOCKSTEP>;
   extern __shared__ __align__(128) char smem[];
