@@ -612,3 +612,29 @@ def test_open_loop_expert_data_golden(dilqr, dev):
         for mine, ref in ((e.train_data, g["train"]), (e.val_data, g["val"]),
                           (e.test_data, g["test"])):
             assert rel(mine, ref) < 1e-6
+
+
+@pytest.mark.parametrize("name,T,B", [("cartpole", 20, 33), ("pendulum", 15, 64)])
+def test_asymmetric_cost_uses_dense_path(dilqr, port, env, dev, name, T, B):
+    """The sweeps stream a packed upper triangle of C only when every block is bitwise
+    symmetric; a non-symmetric C (which the reference uses exactly as given, e.g.
+    lqr_step.py:294, util.py:148) must go through the dense path and still match."""
+    dtype = torch.float64
+    pdx, x0, C, c, kw = env_problem(port, name, T, B, dtype)
+    g = torch.Generator().manual_seed(21)
+    n = C.shape[-1]
+    skew = torch.randn(T, B, n, n, generator=g, dtype=dtype) * 1e-3
+    skew[:, :, -1, :] = 0.0          # keep Quu and the control row clean: Quu stays SPD
+    skew[:, :, :, -1] = 0.0
+    Ca = C + torch.triu(skew, 1)     # upper triangle only -> C != C'
+    o = port.mpc_forward(x0, port.QuadCost(Ca, c), pdx, pdx.n_state, pdx.n_ctrl, T, lqr_iter=1,
+                         final_pass=False, **kw)
+    gdx = {"cartpole": env.CartpoleDx, "pendulum": env.PendulumDx}[name](pdx.params.to(dev))
+    m = dilqr.MPC(pdx.n_state, pdx.n_ctrl, T, lqr_iter=1, verbose=-1, exit_unconverged=False, **kw)
+    with torch.no_grad():
+        x, u, costs = m(x0.to(dev), dilqr.QuadCost(Ca.to(dev), c.to(dev)), gdx)
+    assert rel(x, o.x) < 1e-10 and rel(u, o.u) < 1e-10 and rel(costs, o.costs) < 1e-10
+    # and the symmetric part alone gives a different answer (the test is not vacuous)
+    with torch.no_grad():
+        _, us, _ = m(x0.to(dev), dilqr.QuadCost(C.to(dev), c.to(dev)), gdx)
+    assert rel(us, o.u) > 1e-8
