@@ -173,10 +173,13 @@ def _make_problem(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower, u_upper, u_z
         if B <= cap:
             s.lockstep = 1
     need = L.dilqr_workspace_bytes(C.byref(s))
-    key = (x_init.device.index, need)
+    # one workspace per (device, stream): solves on different streams never share scratch;
+    # it only ever grows (the layout comes from the problem struct, not the buffer size)
+    key = (x_init.device.index, torch.cuda.current_stream(x_init.device).cuda_stream)
     ws = _ws_cache.get(key)
-    if ws is None:
-        _ws_cache.clear()  # one live workspace per device is enough
+    if ws is None or ws.buf.numel() < need:
+        ws = None
+        _ws_cache.pop(key, None)      # release the smaller buffer before allocating
         ws = Workspace(need, x_init.device)
         _ws_cache[key] = ws
     s.workspace = _ptr(ws.buf)
