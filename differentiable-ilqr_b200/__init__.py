@@ -9,13 +9,13 @@ from . import _lib
 from .definitions import QuadCost, LinDx
 from .mpc import MPC, GradMethods
 from . import mpc, mpc_explicit, env_dx, il, il_env, parallel, lqr_step, util, dynamics  # noqa: F401
-from .dynamics import AffineDynamics, CtrlPassthroughDynamics
+from .dynamics import AffineDynamics, CtrlPassthroughDynamics, NNDynamics
 from . import pnqp as _pnqp_mod  # noqa: F401
 from .pnqp import pnqp
 from .lqr_step import LQRStep
 
 __all__ = ["MPC", "GradMethods", "QuadCost", "LinDx", "LQRStep", "pnqp", "build",
-           "AffineDynamics", "CtrlPassthroughDynamics"]
+           "AffineDynamics", "CtrlPassthroughDynamics", "NNDynamics"]
 
 
 def build(verbose=False):

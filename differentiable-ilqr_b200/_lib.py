@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libdilqr.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 F32, F64 = 0, 1
-DYN_LINDX, DYN_PENDULUM, DYN_CARTPOLE, DYN_ROCKET = 0, 1, 2, 3
+DYN_LINDX, DYN_PENDULUM, DYN_CARTPOLE, DYN_ROCKET, DYN_NN = 0, 1, 2, 3, 4
 GAIN_PLAIN, GAIN_CHOL_REG = 0, 1
 BOUNDS_NONE, BOUNDS_SCALAR, BOUNDS_TENSOR = 0, 1, 2
 PNQP_MAX_ITER = 20
@@ -70,6 +70,7 @@ class DilqrSolve(C.Structure):
         ("k_out", C.c_void_p),
         ("status", C.c_void_p), ("control", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("dyn_aux", C.c_void_p), ("dyn_ai", C.c_int32 * 4),
     ]
 
 

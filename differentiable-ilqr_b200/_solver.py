@@ -25,11 +25,13 @@ def _stream():
 class DynSpec:
     """What the rollouts integrate: LinDx tensors or an env_dx model id + theta."""
 
-    def __init__(self, kind, params=None, F=None, f=None):
+    def __init__(self, kind, params=None, F=None, f=None, aux=None, ai=None):
         self.kind = kind
         self.params = list(params) if params is not None else []
         self.F = F
         self.f = f
+        self.aux = aux      # DYN_NN: packed weight buffer (device tensor)
+        self.ai = list(ai) if ai is not None else []
 
 
 class SolveInfo:
@@ -137,6 +139,11 @@ def _make_problem(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower, u_upper, u_z
     s.c_bcast, cd = cost_layout(c_.to(dtype), T, B, 1)
     keep.extend((Cd, cd))
     s.x_init, s.C, s.c = _ptr(xi), _ptr(Cd), _ptr(cd)
+    if dyn.kind == _lib.DYN_NN:
+        aux = dev(dyn.aux, "network weights")
+        s.dyn_aux = _ptr(aux)
+        for i, v in enumerate(dyn.ai):
+            s.dyn_ai[i] = int(v)
     if dyn.kind == _lib.DYN_LINDX:
         Fd = dev(dyn.F, "F")
         fd = dev(dyn.f, "f") if (dyn.f is not None and dyn.f.nelement() > 0) else None

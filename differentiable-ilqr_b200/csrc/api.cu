@@ -42,7 +42,8 @@ using Scalar = float;
   X(13, 3, DYN_LINDX)          \
   X(3, 1, DYN_PENDULUM)        \
   X(5, 1, DYN_CARTPOLE)        \
-  X(13, 3, DYN_ROCKET)
+  X(13, 3, DYN_ROCKET)         \
+  X(3, 1, DYN_NN)
 #else
 #define DILQR_CONFIGS(X)
 #endif
@@ -71,7 +72,10 @@ using Scalar = float;
 #else
 #define DILQR_CONFIGS(X)       \
   X(16, 2, DYN_LINDX)          \
-  X(16, 4, DYN_LINDX)
+  X(16, 4, DYN_LINDX)          \
+  X(3, 1, DYN_NN)              \
+  X(4, 2, DYN_NN)              \
+  X(5, 1, DYN_NN)
 #endif
 
 constexpr size_t kStageBudget = 56 * 1024;  // per-warp staging budget (>= 4 warps / SM)
@@ -196,6 +200,8 @@ static IterParams<Scalar> make_params(const DilqrSolve* s, int role = 1) {
   p.K_out = static_cast<S*>(s->K_out);
   p.k_out = static_cast<S*>(s->k_out);
   for (int i = 0; i < 8; ++i) p.dyn.p[i] = (S)s->dyn_params[i];
+  p.dyn.aux = static_cast<const S*>(s->dyn_aux);
+  for (int i = 0; i < 4; ++i) p.dyn.ai[i] = s->dyn_ai[i];
   return p;
 }
 
@@ -203,6 +209,9 @@ static int check(const DilqrSolve* s, bool need_ws) {
   if (!s || s->n_state <= 0 || s->n_ctrl <= 0 || s->T <= 0 || s->n_batch <= 0) return DILQR_EINVAL;
   if (!s->x_init || !s->C || !s->c) return DILQR_EINVAL;
   if (s->dynamics == DILQR_DYN_LINDX && s->T > 1 && !s->F) return DILQR_EINVAL;
+  if (s->dynamics == DILQR_DYN_NN &&
+      (!s->dyn_aux || s->dyn_ai[0] < 1 || s->dyn_ai[0] > 65536 || s->dyn_ai[1] < 0 || s->dyn_ai[1] > 1))
+    return DILQR_EINVAL;
   if (s->bounds_kind == DILQR_BOUNDS_TENSOR && (!s->u_lower_t || !s->u_upper_t)) return DILQR_EINVAL;
   if (s->bounds_kind < 0 || s->bounds_kind > 2) return DILQR_EINVAL;
   if (s->C_bcast < 0 || s->C_bcast > 2 || s->c_bcast < 0 || s->c_bcast > 2) return DILQR_EINVAL;

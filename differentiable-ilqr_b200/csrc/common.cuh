@@ -33,6 +33,9 @@ template <class S> DILQR_DEVICE S absS(S a);
 template <> DILQR_DEVICE float absS<float>(float a) { return fabsf(a); }
 template <> DILQR_DEVICE double absS<double>(double a) { return fabs(a); }
 
+template <class S> DILQR_DEVICE S expS(S a);
+template <> DILQR_DEVICE float expS<float>(float a) { return expf(a); }
+template <> DILQR_DEVICE double expS<double>(double a) { return exp(a); }
 template <class S> DILQR_DEVICE S atan2S(S y, S x);
 template <> DILQR_DEVICE float atan2S<float>(float y, float x) { return atan2f(y, x); }
 template <> DILQR_DEVICE double atan2S<double>(double y, double x) { return atan2(y, x); }

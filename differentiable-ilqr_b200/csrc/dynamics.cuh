@@ -15,11 +15,13 @@
 
 namespace dilqr {
 
-enum { DYN_LINDX = 0, DYN_PENDULUM = 1, DYN_CARTPOLE = 2, DYN_ROCKET = 3 };
+enum { DYN_LINDX = 0, DYN_PENDULUM = 1, DYN_CARTPOLE = 2, DYN_ROCKET = 3, DYN_NN = 4 };
 
 template <class S>
 struct DynParams {
   S p[8];
+  const S* aux;   // DYN_NN: packed weights  W1[H][n] b1[H] W2[ns][H] b2[ns]  (device)
+  int ai[4];      // DYN_NN: {H, activation (0 sigmoid, 1 relu), passthrough, 0}
 };
 
 template <class S, int DYN>
@@ -35,6 +37,100 @@ struct Dyn<S, DYN_LINDX> {
   // structural non-zero pattern of F (dense for user-supplied LinDx)
   __host__ __device__ static constexpr bool nz(int, int) { return true; }
 };
+
+// ------------------------------------------------------- one-hidden-layer network
+// dynamics.NNDynamics (dynamics.py:15-130) with hidden_sizes=[H]:
+//   z = act(W1 [x;u] + b1),  x' = W2 z + b2 (+ x if passthrough)          (forward, :57-79)
+//   d x'/d[x;u] = W2 diag(act'(.)) W1 (+ [I 0])                          (grad_input, :81-130)
+// sigmoid: act' = z (1 - z); relu: rows with z <= 0 dropped (:104-110).  The weights are
+// shared by all problems (uniform, read-only loads); the hidden units are streamed, so
+// neither the activations nor the H x n products are ever stored.
+template <class S>
+struct Dyn<S, DYN_NN> {
+  static constexpr bool kEnv = true;
+  static constexpr bool kTrigFromNext = false;
+  __host__ __device__ static constexpr bool nz(int, int) { return true; }
+
+  DILQR_DEVICE static S act(S a, int kind) {
+    if (kind == 1) return a > S(0) ? a : S(0);
+    return S(1) / (S(1) + expS<S>(-a));
+  }
+
+  template <int NS, int NC>
+  DILQR_DEVICE static void step(const DynParams<S>& P, const S* x, const S* u, S* xn) {
+    constexpr int N = NS + NC;
+    const int H = P.ai[0];
+    const S* W1 = P.aux;
+    const S* b1 = W1 + (size_t)H * N;
+    const S* W2 = b1 + H;
+    const S* b2 = W2 + (size_t)NS * H;
+    S acc[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) acc[i] = S(0);
+    for (int h = 0; h < H; ++h) {
+      S a = S(0);
+#pragma unroll
+      for (int j = 0; j < NS; ++j) a = fmaS<S>(__ldg(W1 + h * N + j), x[j], a);
+#pragma unroll
+      for (int j = 0; j < NC; ++j) a = fmaS<S>(__ldg(W1 + h * N + NS + j), u[j], a);
+      const S z = act(a + __ldg(b1 + h), P.ai[1]);
+#pragma unroll
+      for (int i = 0; i < NS; ++i) acc[i] = fmaS<S>(__ldg(W2 + i * H + h), z, acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      S v = acc[i] + __ldg(b2 + i);
+      if (P.ai[2]) v = v + x[i];
+      xn[i] = v;
+    }
+  }
+
+  template <int NS, int N>
+  DILQR_DEVICE static void jacobian(const DynParams<S>& P, const S* tau, const S* /*xnext*/,
+                                    S (&F)[NS][N]) {
+    const int H = P.ai[0];
+    const S* W1 = P.aux;
+    const S* b1 = W1 + (size_t)H * N;
+    const S* W2 = b1 + H;
+#pragma unroll
+    for (int i = 0; i < NS; ++i)
+#pragma unroll
+      for (int j = 0; j < N; ++j) F[i][j] = S(0);
+    for (int h = 0; h < H; ++h) {
+      S w[N];
+      S a = S(0);
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        w[j] = __ldg(W1 + h * N + j);
+        a = fmaS<S>(w[j], tau[j], a);
+      }
+      const S z = act(a + __ldg(b1 + h), P.ai[1]);
+      S d;
+      if (P.ai[1] == 1) d = z <= S(0) ? S(0) : S(1);
+      else d = z * (S(1) - z);
+#pragma unroll
+      for (int j = 0; j < N; ++j) w[j] = w[j] * d;
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+        const S w2 = __ldg(W2 + i * H + h);
+#pragma unroll
+        for (int j = 0; j < N; ++j) F[i][j] = fmaS<S>(w2, w[j], F[i][j]);
+      }
+    }
+    if (P.ai[2]) {
+#pragma unroll
+      for (int i = 0; i < NS; ++i) F[i][i] = F[i][i] + S(1);
+    }
+  }
+};
+
+// One step of the dynamics `DYN` for a problem with NS states / NC controls (the env
+// models have fixed sizes; the network's sizes come from the kernel's template).
+template <class S, int NS, int NC, int DYN>
+DILQR_DEVICE void dyn_step(const DynParams<S>& P, const S* x, const S* u, S* xn) {
+  if constexpr (DYN == DYN_NN) Dyn<S, DYN_NN>::template step<NS, NC>(P, x, u, xn);
+  else Dyn<S, DYN>::step(P, x, u, xn);
+}
 
 // ------------------------------------------------------------------- pendulum
 template <class S>

@@ -781,7 +781,7 @@ struct IterKernel {
                                   : stage_cost<S, N>(blk.C, blk.c, th));
         if (t < T - 1) {
           if constexpr (kEnv) {
-            D::step(p.dyn, th, &th[NS], xh);
+            dyn_step<S, NS, NC, DYN>(p.dyn, th, &th[NS], xh);
           } else {
             lin_step<S, NS, N>(blk.F, blk.f, p.has_f != 0, th, xh);
           }
@@ -926,7 +926,7 @@ ilqr_begin_kernel(const __grid_constant__ IterParams<S> p) {
     }
     if (t < T - 1 && !p.x_cur) {
       if constexpr (kEnv) {
-        D::step(p.dyn, th, &th[NS], xh);
+        dyn_step<S, NS, NC, DYN>(p.dyn, th, &th[NS], xh);
       } else {
         lin_step<S, NS, N>(blk.F, blk.f, p.has_f != 0, th, xh);
       }

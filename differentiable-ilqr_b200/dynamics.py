@@ -1,5 +1,11 @@
 """Dynamics containers of the upstream mpc.pytorch API kept by the reference
-(dynamics.py:133-202): ``AffineDynamics`` and ``CtrlPassthroughDynamics``.
+(dynamics.py): ``NNDynamics``, ``AffineDynamics`` and ``CtrlPassthroughDynamics``.
+
+``NNDynamics`` (one hidden layer) runs inside the fused iteration kernels as the
+device dynamics ``DILQR_DYN_NN`` (csrc/dynamics.cuh): ``MPC.forward`` packs the weights
+once per call; the KKT gradients ``dF, df`` of the solve reach the weights through
+``grad_input`` evaluated (with autograd) at the solution, which is what the reference
+does in ``linearize_dynamics(diff=True)`` (mpc.py:490-523).
 
 ``AffineDynamics`` is a time-invariant LinDx: ``MPC.forward`` hands the solver
 ``F = [A B]`` and ``f = c`` broadcast over (T-1, B) and autograd sums the KKT
@@ -10,6 +16,85 @@ for callers that simulate the plant; the solve itself never calls them.
 """
 import torch
 from torch import nn
+
+
+ACTS = {'sigmoid': torch.sigmoid, 'relu': torch.relu, 'elu': torch.nn.functional.elu}
+
+
+class NNDynamics(nn.Module):
+    """dynamics.py:15-130: fully connected network x' = net([x, u]) (+ x)."""
+
+    def __init__(self, n_state, n_ctrl, hidden_sizes=[100], activation='sigmoid',
+                 passthrough=True):
+        super().__init__()
+        assert activation in ACTS
+        self.passthrough = passthrough
+        self.activation = activation
+        sizes = [n_state + n_ctrl] + list(hidden_sizes) + [n_state]
+        self.fcs = nn.ModuleList(nn.Linear(a, b) for a, b in zip(sizes[:-1], sizes[1:]))
+        self.zs = []      # hidden activations of the last forward (used by grad_input)
+
+    @property
+    def Ws(self):
+        return [fc.weight for fc in self.fcs]
+
+    def forward(self, x, u):                               # dynamics.py:57-79
+        x_dim = x.ndimension()
+        if x_dim == 1:
+            x = x.unsqueeze(0)
+        if u.ndimension() == 1:
+            u = u.unsqueeze(0)
+        z = torch.cat((x, u), 1)
+        zs = []
+        for i, fc in enumerate(self.fcs):
+            z = fc(z)
+            if i < len(self.fcs) - 1:
+                z = ACTS[self.activation](z)
+                zs.append(z)
+        self.zs = zs
+        if self.passthrough:
+            z = z + x
+        return z.squeeze(0) if x_dim == 1 else z
+
+    def grad_input(self, x, u):                            # dynamics.py:81-130
+        """R = dx'/dx, S = dx'/du at the inputs of the LAST forward call."""
+        x_dim = x.ndimension()
+        n_batch, n_state = x.shape[-2] if x_dim > 1 else 1, x.shape[-1]
+        diff = x.requires_grad or u.requires_grad or torch.is_grad_enabled()
+        Ws = self.Ws if diff else [W.detach() for W in self.Ws]
+        zs = self.zs if diff else [z.detach() for z in self.zs]
+        assert len(zs) == len(Ws) - 1
+        grad = Ws[-1].unsqueeze(0).expand(n_batch, -1, -1)
+        for i in range(len(zs) - 1, -1, -1):
+            if self.activation == 'relu':
+                d = (zs[i] > 0.).to(zs[i].dtype)
+            elif self.activation == 'sigmoid':
+                d = zs[i] * (1. - zs[i])
+            else:
+                assert False
+            grad = grad.bmm(Ws[i].unsqueeze(0) * d.unsqueeze(2))
+        R, S = grad[:, :, :n_state], grad[:, :, n_state:]
+        if self.passthrough:
+            R = R + torch.eye(n_state, dtype=R.dtype, device=R.device).unsqueeze(0)
+        if x_dim == 1:
+            R, S = R.squeeze(0), S.squeeze(0)
+        return R, S
+
+    # -- device side ---------------------------------------------------------
+    def _dilqr_pack(self, dtype, device):
+        """(weight buffer, ints) for DILQR_DYN_NN: W1[H][n] b1[H] W2[ns][H] b2[ns]."""
+        if len(self.fcs) != 2:
+            raise NotImplementedError("device NNDynamics: exactly one hidden layer "
+                                      "(hidden_sizes=[H]); got %d" % (len(self.fcs) - 1))
+        if self.activation not in ('sigmoid', 'relu'):
+            raise NotImplementedError("device NNDynamics: sigmoid / relu (grad_input of the "
+                                      "reference supports no other, dynamics.py:104-113)")
+        fc0, fc1 = self.fcs
+        buf = torch.cat([t.detach().reshape(-1) for t in
+                         (fc0.weight, fc0.bias, fc1.weight, fc1.bias)]).to(device=device, dtype=dtype)
+        ints = [fc0.weight.shape[0], 0 if self.activation == 'sigmoid' else 1,
+                1 if self.passthrough else 0, 0]
+        return buf.contiguous(), ints
 
 
 class AffineDynamics(nn.Module):

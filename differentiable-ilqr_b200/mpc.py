@@ -15,7 +15,7 @@ from torch.autograd import Function
 
 from . import _lib, _solver
 from .definitions import QuadCost, LinDx
-from .dynamics import AffineDynamics
+from .dynamics import AffineDynamics, NNDynamics
 
 
 class GradMethods(Enum):          # mpc.py:29-33
@@ -88,6 +88,32 @@ class _MPCFn(Function):
         if f.nelement() == 0:
             df = None
         return None, None, dx0, dC, dc, dF, df
+
+
+class _KKTAtSolutionFn(Function):
+    """The final no-op LQR step of the reference (mpc.py:314-315, lqr_step.py:278-282):
+    forward hands back the solution, backward is the KKT adjoint of the LQR subproblem
+    linearised there -- gradients wrt x_init, C, c AND the linearisation F, f, through
+    which autograd reaches the parameters of a Module dynamics."""
+
+    @staticmethod
+    def forward(ctx, mod, mask, x_init, C, c, F, f, x, u):
+        ctx.mod, ctx.mask = mod, mask
+        ctx.save_for_backward(x_init, C, c, F, f, x, u)
+        return x.clone(), u.clone()
+
+    @staticmethod
+    def backward(ctx, dl_dx, dl_du):
+        mod = ctx.mod
+        x_init, C, c, F, f, x, u = ctx.saved_tensors
+        if ctx.mask is not None:
+            dl_dx = dl_dx * ctx.mask.view(1, -1, 1)
+            dl_du = dl_du * ctx.mask.view(1, -1, 1)
+        dx0, dC, dc, dF, df = _solver.kkt_backward(
+            dl_dx.contiguous(), dl_du.contiguous(), x_init, C, c, F, f, x, u,
+            mod.n_state, mod.n_ctrl, mod.u_lower, mod.u_upper,
+            gain_solve=mod._gain_solve, back_eps=mod.back_eps)
+        return None, None, dx0, dC, dc, dF, df, None, None
 
 
 class MPC(nn.Module):
@@ -163,6 +189,8 @@ class MPC(nn.Module):
             dx = LinDx(*dx.as_lindx(self.T, n_batch, x_init.dtype, x_init.device))
         if self.slew_rate_penalty is not None:
             return self._forward_slew(x_init, C, c, dx, n_batch)
+        if isinstance(dx, NNDynamics):
+            return self._forward_network(x_init, C, c, dx, n_batch)
         if isinstance(dx, LinDx):
             F, f = dx.F, dx.f
         else:
@@ -219,3 +247,48 @@ class MPC(nn.Module):
         x, u, costs = inner(_x_init, QuadCost(_C, _c), LinDx(_F, _f))
         self.last_info = inner.last_info
         return x[:, :, nc:], u, costs
+
+    def _forward_network(self, x_init, C, c, dx, n_batch):
+        """Module dynamics ``dynamics.NNDynamics`` (mpc.py:248-337 with
+        grad_method=ANALYTIC): the iLQR solve runs in the fused kernels with the network
+        as device dynamics; the gradient is the KKT adjoint at the solution with F, f from
+        ``linearize_dynamics(diff=True)`` (mpc.py:490-523)."""
+        if self.grad_method != GradMethods.ANALYTIC:
+            raise NotImplementedError("Module dynamics: grad_method=ANALYTIC only")
+        dt, dev = x_init.dtype, x_init.device
+        aux, ints = dx._dilqr_pack(dt, dev)
+        dyn = _solver.DynSpec(_lib.DYN_NN, aux=aux, ai=ints)
+        x, u, costs, info = _solver.solve_mpc(
+            x_init, C, c, dyn, self.n_state, self.n_ctrl, self.T,
+            u_lower=self.u_lower, u_upper=self.u_upper, u_zero_I=self.u_zero_I,
+            u_init=self.u_init, lqr_iter=self.lqr_iter, eps=self.eps,
+            linesearch_decay=self.linesearch_decay,
+            max_linesearch_iter=self.max_linesearch_iter,
+            not_improved_lim=self.not_improved_lim, best_cost_eps=self.best_cost_eps,
+            gain_solve=self._gain_solve, solo=self.solo, verbose=self.verbose)
+        self.last_info = info
+        mask = None
+        eps_cmp = float(torch.tensor(self.eps, dtype=dt))
+        if self.detach_unconverged:                      # mpc.py:321-334
+            if float(info.full_du_norm.max()) > eps_cmp:
+                if self.exit_unconverged:
+                    assert False
+                if self.verbose >= 0:
+                    print("LQR Warning: All examples did not converge to a fixed point.")
+                    print("Detaching and *not* backpropping through the bad examples.")
+                mask = (info.full_du_norm < eps_cmp).to(dt)
+        if not (self.backprop and torch.is_grad_enabled()):
+            return x, u, costs
+        # linearise at the solution WITH the autograd graph (mpc.py:496-523)
+        T, ns, nc = self.T, self.n_state, self.n_ctrl
+        _x = x[:-1].reshape(-1, ns)
+        _u = u[:-1].reshape(-1, nc)
+        new_x = dx(_x, _u)
+        R, S = dx.grad_input(_x, _u)
+        f = new_x - torch.bmm(R, _x.unsqueeze(2)).squeeze(2) - torch.bmm(S, _u.unsqueeze(2)).squeeze(2)
+        F = torch.cat((R, S), 2).reshape(T - 1, n_batch, ns, ns + nc)
+        f = f.reshape(T - 1, n_batch, ns)
+        Cd = C if C.is_contiguous() else C.contiguous()
+        cd = c if c.is_contiguous() else c.contiguous()
+        xo, uo = _KKTAtSolutionFn.apply(self, mask, x_init, Cd, cd, F, f, x, u)
+        return xo, uo, costs

@@ -35,7 +35,8 @@ enum {
   DILQR_DYN_LINDX    = 0, /* definitions.py:4  LinDx(F,f): x' = F_t [x;u] (+ f_t)      */
   DILQR_DYN_PENDULUM = 1, /* env_dx/pendulum.py:60-95, Jacobian 444-475             */
   DILQR_DYN_CARTPOLE = 2, /* env_dx/cartpole.py:64-97, Jacobian 790-839             */
-  DILQR_DYN_ROCKET   = 3  /* env_dx/rocket.py:82-164,  Jacobian 324-426             */
+  DILQR_DYN_ROCKET   = 3, /* env_dx/rocket.py:82-164,  Jacobian 324-426             */
+  DILQR_DYN_NN       = 4  /* dynamics.py:15-130 NNDynamics, one hidden layer (dyn_aux)  */
 };
 
 /* How unconstrained multi-input gains are solved (the reference copies differ). */
@@ -145,6 +146,10 @@ typedef struct DilqrSolve {
   /* scratch */
   void*  workspace;
   size_t workspace_bytes;
+  /* DILQR_DYN_NN only: the network of dynamics.NNDynamics(hidden_sizes=[H]) */
+  const void* dyn_aux;      /* device, packed in the call's dtype: W1[H][n] (fc0.weight),
+                               b1[H], W2[ns][H] (fc1.weight), b2[ns]                  */
+  int32_t dyn_ai[4];        /* {H, activation (0 sigmoid / 1 relu), passthrough, 0}   */
 } DilqrSolve;
 
 const char* dilqr_version(void);

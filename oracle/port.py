@@ -771,3 +771,32 @@ def closed_loop(dynamics, x_init_all, T, lqr_iter):
             u_init[-2] = u_init[-3]
         taus.append(torch.cat((torch.stack(xs[:-1]), torch.stack(us)), 1))
     return torch.stack(taus)
+
+
+# ---------------------------------------------------------------------------
+# dynamics.NNDynamics (dynamics.py:15-130), one hidden layer, as an oracle dynamics
+# object for mpc_forward (same protocol as the env classes: __call__ / get_linear_dyn)
+# ---------------------------------------------------------------------------
+class NNDynamics:
+    def __init__(self, W1, b1, W2, b2, activation="sigmoid", passthrough=True):
+        self.W1, self.b1, self.W2, self.b2 = W1, b1, W2, b2
+        self.activation, self.passthrough = activation, passthrough
+        self.n_state = W2.shape[0]
+        self.n_ctrl = W1.shape[1] - self.n_state
+
+    def _hidden(self, x, u):
+        a = torch.cat((x, u), 1) @ self.W1.t() + self.b1          # dynamics.py:66-68
+        return torch.sigmoid(a) if self.activation == "sigmoid" else torch.relu(a)
+
+    def __call__(self, x, u):                                    # dynamics.py:57-79
+        z = self._hidden(x, u) @ self.W2.t() + self.b2
+        return z + x if self.passthrough else z
+
+    def get_linear_dyn(self, x, u):                              # grad_input, :81-130
+        z = self._hidden(x, u)
+        d = z * (1. - z) if self.activation == "sigmoid" else (z > 0.).to(z.dtype)
+        J = self.W2.unsqueeze(0).expand(x.shape[0], -1, -1).bmm(self.W1.unsqueeze(0) * d.unsqueeze(2))
+        if self.passthrough:
+            J = J.clone()
+            J[:, :, :self.n_state] += torch.eye(self.n_state, dtype=J.dtype)
+        return J

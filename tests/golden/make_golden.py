@@ -199,6 +199,40 @@ def env_forward(env, T, B, lqr_iter, dtype):
     torch.set_default_dtype(torch.float32)
 
 
+def nn_dynamics():
+    """mpc.MPC with dynamics.NNDynamics (one hidden layer, ANALYTIC linearisation): forward
+    and the KKT gradients wrt the network weights, the cost and x_init."""
+    import dynamics as refdyn
+    torch.set_default_dtype(torch.float64)
+    out = {}
+    for act in ("sigmoid", "relu"):
+        torch.manual_seed(5)
+        ns, nc, T, B = 3, 1, 10, 7
+        n = ns + nc
+        dx = refdyn.NNDynamics(ns, nc, hidden_sizes=[12], activation=act, passthrough=True)
+        for p_ in dx.parameters():
+            p_.data.mul_(0.5)
+        A = torch.randn(T, B, n, n)
+        C = A.transpose(2, 3) @ A + torch.eye(n)
+        c = torch.randn(T, B, n)
+        x0 = torch.randn(B, ns)
+        g = torch.Generator().manual_seed(7)
+        gx = torch.randn(T, B, ns, generator=g)
+        gu = torch.randn(T, B, nc, generator=g)
+        Cg, cg, x0g = [t.clone().requires_grad_() for t in (C, c, x0)]
+        m = R.mpc.MPC(ns, nc, T, lqr_iter=30, verbose=-1, exit_unconverged=False, u_lower=-1.0,
+                      u_upper=1.0, grad_method=R.mpc.GradMethods.ANALYTIC, detach_unconverged=False)
+        x, u, costs = m(x0g, R.mpc.QuadCost(Cg, cg), dx)
+        ((x * gx).sum() + (u * gu).sum()).backward()
+        W1, b1, W2, b2 = dx.fcs[0].weight, dx.fcs[0].bias, dx.fcs[1].weight, dx.fcs[1].bias
+        out.update({act + "_" + k: v for k, v in dict(
+            C=C, c=c, x0=x0, gx=gx, gu=gu, W1=W1, b1=b1, W2=W2, b2=b2, x=x, u=u, costs=costs,
+            dC=Cg.grad, dc=cg.grad, dx0=x0g.grad, dW1=W1.grad, db1=b1.grad, dW2=W2.grad,
+            db2=b2.grad).items()})
+    npz("ref_nn_dynamics.npz", **out)
+    torch.set_default_dtype(torch.float32)
+
+
 def open_loop(env, mpc_T, lqr_iter, n_train, n_val, n_test):
     """IL_Env.populate_data (il_env.py:81-94): one batched open-loop expert solve."""
     torch.set_default_dtype(torch.float64)
@@ -239,3 +273,4 @@ if __name__ == "__main__":
     closed_loop("cartpole", 12, 30, 1, 1, 1)
     slew_affine()
     open_loop("pendulum", 20, 60, 5, 2, 1)
+    nn_dynamics()

@@ -638,3 +638,56 @@ def test_asymmetric_cost_uses_dense_path(dilqr, port, env, dev, name, T, B):
     with torch.no_grad():
         _, us, _ = m(x0.to(dev), dilqr.QuadCost(C.to(dev), c.to(dev)), gdx)
     assert rel(us, o.u) > 1e-8
+
+
+def _nn_module(dilqr, g, act, dev, dtype=torch.float64):
+    t = lambda k: g[act + "_" + k].to(dev).to(dtype)
+    m = dilqr.NNDynamics(3, 1, hidden_sizes=[12], activation=act, passthrough=True).to(dev).to(dtype)
+    with torch.no_grad():
+        m.fcs[0].weight.copy_(t("W1"))
+        m.fcs[0].bias.copy_(t("b1"))
+        m.fcs[1].weight.copy_(t("W2"))
+        m.fcs[1].bias.copy_(t("b2"))
+    return m
+
+
+@pytest.mark.parametrize("act", ["sigmoid", "relu"])
+def test_nn_dynamics_step_vs_oracle(dilqr, port, dev, act):
+    """One LQR step with the network as device dynamics (DILQR_DYN_NN) against the oracle:
+    rollout, Jacobians inside the Riccati sweep, line search."""
+    g = golden("ref_nn_dynamics.npz")
+    t = lambda k: g[act + "_" + k]
+    dyn = port.NNDynamics(t("W1"), t("b1"), t("W2"), t("b2"), activation=act)
+    for L in (1, 3):
+        o = port.mpc_forward(t("x0"), port.QuadCost(t("C"), t("c")), dyn, 3, 1, 10, u_lower=-1.0,
+                             u_upper=1.0, lqr_iter=L, final_pass=False)
+        m = dilqr.MPC(3, 1, 10, lqr_iter=L, verbose=-1, exit_unconverged=False, u_lower=-1.0,
+                      u_upper=1.0, detach_unconverged=False)
+        with torch.no_grad():
+            x, u, costs = m(t("x0").to(dev), dilqr.QuadCost(t("C").to(dev), t("c").to(dev)),
+                            _nn_module(dilqr, g, act, dev))
+        tol = 1e-10 if L == 1 else 1e-7
+        assert rel(x, o.x) < tol and rel(u, o.u) < tol and rel(costs, o.costs) < tol
+        if L == 1:      # later iterations sit next to the 1e-4 step threshold of pnqp
+            assert m.last_info.qp_iters == o.qp_iters
+
+
+def test_nn_dynamics_golden_forward_backward(dilqr, dev):
+    """mpc.MPC + NNDynamics against the reference's own output: converged solve and the
+    KKT gradients wrt the network weights, the cost and x_init (through F, f)."""
+    g = golden("ref_nn_dynamics.npz")
+    act = "sigmoid"
+    t = lambda k: g[act + "_" + k].to(dev)
+    net = _nn_module(dilqr, g, act, dev)
+    Cg, cg, x0 = [t(k).clone().requires_grad_() for k in ("C", "c", "x0")]
+    m = dilqr.MPC(3, 1, 10, lqr_iter=30, verbose=-1, exit_unconverged=False, u_lower=-1.0,
+                  u_upper=1.0, detach_unconverged=False)
+    x, u, costs = m(x0, dilqr.QuadCost(Cg, cg), net)
+    # the solve stops once max|du| < eps = 1e-7: both sides are within that of the fixed point
+    assert rel(x, t("x")) < 1e-6 and rel(u, t("u")) < 1e-6 and rel(costs, t("costs")) < 1e-8
+    ((x * t("gx")).sum() + (u * t("gu")).sum()).backward()
+    errs = {name: rel(mine, t(name)) for mine, name in (
+        (x0.grad, "dx0"), (Cg.grad, "dC"), (cg.grad, "dc"), (net.fcs[0].weight.grad, "dW1"),
+        (net.fcs[0].bias.grad, "db1"), (net.fcs[1].weight.grad, "dW2"),
+        (net.fcs[1].bias.grad, "db2"))}
+    assert max(errs.values()) < 1e-6, errs

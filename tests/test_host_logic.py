@@ -94,3 +94,25 @@ def test_affine_dynamics_container(dilqr):
     p = dilqr.CtrlPassthroughDynamics(d)
     xt = torch.cat((torch.randn(5, 2), x), 1)
     assert torch.allclose(p(xt, u), torch.cat((u, d(x, u)), 1))
+
+
+@pytest.mark.parametrize("act", ["sigmoid", "relu"])
+def test_nn_dynamics_container(dilqr, act):
+    """dynamics.py:15-130: grad_input is the Jacobian of forward (checked with autograd);
+    the device packing is W1 b1 W2 b2."""
+    torch.manual_seed(0)
+    d = dilqr.NNDynamics(3, 2, hidden_sizes=[7], activation=act).double()
+    x, u = torch.randn(4, 3, dtype=torch.float64), torch.randn(4, 2, dtype=torch.float64)
+    y = d(x, u)
+    assert y.shape == (4, 3) and d(x[0], u[0]).shape == (3,)
+    d(x, u)
+    R, S = d.grad_input(x, u)
+    J = torch.autograd.functional.jacobian(lambda a, b: d(a, b), (x, u))
+    for b in range(4):
+        assert torch.allclose(R[b], J[0][b, :, b, :], atol=1e-12)
+        assert torch.allclose(S[b], J[1][b, :, b, :], atol=1e-12)
+    buf, ints = d._dilqr_pack(torch.float64, "cpu")
+    assert buf.numel() == 7 * 5 + 7 + 3 * 7 + 3 and ints[0] == 7 and ints[2] == 1
+    assert torch.equal(buf[:35].view(7, 5), d.fcs[0].weight.detach())
+    with pytest.raises(NotImplementedError):
+        dilqr.NNDynamics(3, 2, hidden_sizes=[4, 4])._dilqr_pack(torch.float64, "cpu")

@@ -138,3 +138,17 @@ def test_closed_loop_bit_exact(port, name, n_samples):
     tau = port.closed_loop(cls(dtype=torch.float64), g["x0"][:n_samples], int(g["mpc_T"]),
                            int(g["lqr_iter"]))
     assert float((tau - ref).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("act", ["sigmoid", "relu"])
+def test_nn_dynamics_bit_exact(port, act):
+    """mpc.MPC with dynamics.NNDynamics run through the unmodified reference
+    (tests/golden/make_golden.py nn_dynamics): the oracle's network dynamics reproduce
+    the trajectories with max diff 0.0."""
+    g = golden("ref_nn_dynamics.npz")
+    t = lambda k: g[act + "_" + k]
+    dyn = port.NNDynamics(t("W1"), t("b1"), t("W2"), t("b2"), activation=act)
+    o = port.mpc_forward(t("x0"), port.QuadCost(t("C"), t("c")), dyn, 3, 1, 10, u_lower=-1.0,
+                         u_upper=1.0, lqr_iter=30, final_pass=False)
+    assert float((o.x - t("x")).abs().max()) == 0.0
+    assert float((o.u - t("u")).abs().max()) == 0.0
