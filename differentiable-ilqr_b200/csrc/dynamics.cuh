@@ -21,7 +21,8 @@ template <class S>
 struct DynParams {
   S p[8];
   const S* aux;   // DYN_NN: packed weights  W1[H][n] b1[H] W2[ns][H] b2[ns]  (device)
-  int ai[4];      // DYN_NN: {H, activation (0 sigmoid, 1 relu), passthrough, 0}
+  int ai[4];      // DYN_NN: {H, activation (0 sigmoid, 1 relu), passthrough,
+                  //          linearisation (0 analytic grad_input, 1 central differences)}
 };
 
 template <class S, int DYN>
@@ -85,9 +86,34 @@ struct Dyn<S, DYN_NN> {
     }
   }
 
+  // GradMethods.FINITE_DIFF (mpc.py:567-583, util.py:10-20): central differences of the
+  // step with eps = 1e-4, one input coordinate at a time.
+  template <int NS, int N>
+  DILQR_DEVICE static void jacobian_fd(const DynParams<S>& P, const S* tau, S (&F)[NS][N]) {
+    constexpr int NC = N - NS;
+    const S eps = S(1e-4), two_eps = S(2. * 1e-4);
+    S tp[N], fp[NS], fm[NS];
+#pragma unroll
+    for (int j = 0; j < N; ++j) tp[j] = tau[j];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      tp[j] = tau[j] + eps;
+      step<NS, NC>(P, tp, tp + NS, fp);
+      tp[j] = tau[j] - eps;
+      step<NS, NC>(P, tp, tp + NS, fm);
+      tp[j] = tau[j];
+#pragma unroll
+      for (int i = 0; i < NS; ++i) F[i][j] = (fp[i] - fm[i]) / two_eps;
+    }
+  }
+
   template <int NS, int N>
   DILQR_DEVICE static void jacobian(const DynParams<S>& P, const S* tau, const S* /*xnext*/,
                                     S (&F)[NS][N]) {
+    if (P.ai[3] == 1) {
+      jacobian_fd<NS, N>(P, tau, F);
+      return;
+    }
     const int H = P.ai[0];
     const S* W1 = P.aux;
     const S* b1 = W1 + (size_t)H * N;

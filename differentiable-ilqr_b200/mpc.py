@@ -253,10 +253,16 @@ class MPC(nn.Module):
         grad_method=ANALYTIC): the iLQR solve runs in the fused kernels with the network
         as device dynamics; the gradient is the KKT adjoint at the solution with F, f from
         ``linearize_dynamics(diff=True)`` (mpc.py:490-523)."""
-        if self.grad_method != GradMethods.ANALYTIC:
-            raise NotImplementedError("Module dynamics: grad_method=ANALYTIC only")
+        if self.grad_method not in (GradMethods.ANALYTIC, GradMethods.AUTO_DIFF,
+                                    GradMethods.FINITE_DIFF):
+            raise NotImplementedError("Module dynamics: grad_method %s" % self.grad_method)
+        # AUTO_DIFF (mpc.py:541-551) differentiates the same network: it is served by the
+        # analytic grad_input Jacobian.  FINITE_DIFF (mpc.py:567-583): central differences
+        # of the step, eps = 1e-4, in the kernel and (with autograd) at the solution.
+        fd = self.grad_method == GradMethods.FINITE_DIFF
         dt, dev = x_init.dtype, x_init.device
         aux, ints = dx._dilqr_pack(dt, dev)
+        ints[3] = 1 if fd else 0
         dyn = _solver.DynSpec(_lib.DYN_NN, aux=aux, ai=ints)
         x, u, costs, info = _solver.solve_mpc(
             x_init, C, c, dyn, self.n_state, self.n_ctrl, self.T,
@@ -283,8 +289,26 @@ class MPC(nn.Module):
         T, ns, nc = self.T, self.n_state, self.n_ctrl
         _x = x[:-1].reshape(-1, ns)
         _u = u[:-1].reshape(-1, nc)
-        new_x = dx(_x, _u)
-        R, S = dx.grad_input(_x, _u)
+        if fd:                                           # util.py:10-20, batched
+            eps = 1e-4
+            tau = torch.cat((_x, _u), 1)
+            cols = []
+            for j in range(ns + nc):
+                e = torch.zeros(ns + nc, dtype=dt, device=dev)
+                e[j] = 1.
+                tp, tm = tau + eps * e, tau - eps * e
+                cols.append((dx(tp[:, :ns], tp[:, ns:]) - dx(tm[:, :ns], tm[:, ns:])) / (2. * eps))
+            J = torch.stack(cols, 2)
+            R, S = J[:, :, :ns], J[:, :, ns:]
+            new_x = dx(_x, _u)
+        else:
+            new_x = dx(_x, _u)
+            R, S = dx.grad_input(_x, _u)
+            if self.grad_method == GradMethods.AUTO_DIFF:
+                # the reference takes these Jacobians with torch.autograd.grad WITHOUT
+                # create_graph (mpc.py:544-551): they are constants for the backward pass,
+                # the network's parameters are reached through f only
+                R, S = R.detach(), S.detach()
         f = new_x - torch.bmm(R, _x.unsqueeze(2)).squeeze(2) - torch.bmm(S, _u.unsqueeze(2)).squeeze(2)
         F = torch.cat((R, S), 2).reshape(T - 1, n_batch, ns, ns + nc)
         f = f.reshape(T - 1, n_batch, ns)

@@ -149,7 +149,9 @@ typedef struct DilqrSolve {
   /* DILQR_DYN_NN only: the network of dynamics.NNDynamics(hidden_sizes=[H]) */
   const void* dyn_aux;      /* device, packed in the call's dtype: W1[H][n] (fc0.weight),
                                b1[H], W2[ns][H] (fc1.weight), b2[ns]                  */
-  int32_t dyn_ai[4];        /* {H, activation (0 sigmoid / 1 relu), passthrough, 0}   */
+  int32_t dyn_ai[4];        /* {H, activation (0 sigmoid / 1 relu), passthrough,
+                               linearisation: 0 analytic (grad_input), 1 central
+                               differences eps=1e-4 (GradMethods.FINITE_DIFF)}       */
 } DilqrSolve;
 
 const char* dilqr_version(void);

@@ -233,6 +233,40 @@ def nn_dynamics():
     torch.set_default_dtype(torch.float32)
 
 
+def nn_grad_methods():
+    """mpc.MPC + NNDynamics with grad_method AUTO_DIFF and FINITE_DIFF (mpc.py:525-601)."""
+    import dynamics as refdyn
+    torch.set_default_dtype(torch.float64)
+    out = {}
+    for name, gm in (("auto", R.mpc.GradMethods.AUTO_DIFF), ("fd", R.mpc.GradMethods.FINITE_DIFF)):
+        torch.manual_seed(9)
+        ns, nc, T, B = 3, 1, 6, 4
+        n = ns + nc
+        dx = refdyn.NNDynamics(ns, nc, hidden_sizes=[8], activation="sigmoid", passthrough=True)
+        for p_ in dx.parameters():
+            p_.data.mul_(0.5)
+        A = torch.randn(T, B, n, n)
+        C = A.transpose(2, 3) @ A + torch.eye(n)
+        c = torch.randn(T, B, n)
+        x0 = torch.randn(B, ns)
+        g = torch.Generator().manual_seed(7)
+        gx = torch.randn(T, B, ns, generator=g)
+        gu = torch.randn(T, B, nc, generator=g)
+        Cg = C.clone().requires_grad_()
+        # exit_unconverged=True + detach_unconverged=True: the reference asserts that every
+        # problem reached max|du| < eps, so the golden is a converged solve
+        m = R.mpc.MPC(ns, nc, T, lqr_iter=40, verbose=-1, exit_unconverged=True, u_lower=-2.0,
+                      u_upper=2.0, grad_method=gm, detach_unconverged=True)
+        x, u, costs = m(x0, R.mpc.QuadCost(Cg, c), dx)
+        ((x * gx).sum() + (u * gu).sum()).backward()
+        W1, b1, W2, b2 = dx.fcs[0].weight, dx.fcs[0].bias, dx.fcs[1].weight, dx.fcs[1].bias
+        out.update({name + "_" + k: v for k, v in dict(
+            C=C, c=c, x0=x0, gx=gx, gu=gu, W1=W1, b1=b1, W2=W2, b2=b2, x=x, u=u, costs=costs,
+            dC=Cg.grad, dW1=W1.grad, db1=b1.grad, dW2=W2.grad, db2=b2.grad).items()})
+    npz("ref_nn_grad_methods.npz", **out)
+    torch.set_default_dtype(torch.float32)
+
+
 def open_loop(env, mpc_T, lqr_iter, n_train, n_val, n_test):
     """IL_Env.populate_data (il_env.py:81-94): one batched open-loop expert solve."""
     torch.set_default_dtype(torch.float64)
@@ -274,3 +308,4 @@ if __name__ == "__main__":
     slew_affine()
     open_loop("pendulum", 20, 60, 5, 2, 1)
     nn_dynamics()
+    nn_grad_methods()

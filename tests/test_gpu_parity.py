@@ -691,3 +691,31 @@ def test_nn_dynamics_golden_forward_backward(dilqr, dev):
         (net.fcs[0].bias.grad, "db1"), (net.fcs[1].weight.grad, "dW2"),
         (net.fcs[1].bias.grad, "db2"))}
     assert max(errs.values()) < 1e-6, errs
+
+
+@pytest.mark.parametrize("name", ["auto", "fd"])
+def test_nn_dynamics_grad_methods_golden(dilqr, dev, name):
+    """grad_method AUTO_DIFF / FINITE_DIFF with NNDynamics (mpc.py:525-601) against the
+    reference: AUTO_DIFF is served by the analytic Jacobian of the same network,
+    FINITE_DIFF by central differences (eps = 1e-4) in the kernel and at the solution."""
+    g = golden("ref_nn_grad_methods.npz")
+    t = lambda k: g[name + "_" + k].to(dev)
+    net = dilqr.NNDynamics(3, 1, hidden_sizes=[8], activation="sigmoid").to(dev).double()
+    with torch.no_grad():
+        for prm, k in ((net.fcs[0].weight, "W1"), (net.fcs[0].bias, "b1"),
+                       (net.fcs[1].weight, "W2"), (net.fcs[1].bias, "b2")):
+            prm.copy_(t(k))
+    gm = dilqr.GradMethods.AUTO_DIFF if name == "auto" else dilqr.GradMethods.FINITE_DIFF
+    Cg = t("C").clone().requires_grad_()
+    m = dilqr.MPC(3, 1, 6, lqr_iter=40, verbose=-1, exit_unconverged=True, u_lower=-2.0,
+                  u_upper=2.0, grad_method=gm, detach_unconverged=True)
+    x, u, costs = m(t("x0"), dilqr.QuadCost(Cg, t("c")), net)
+    # both sides stop within eps = 1e-7 of the fixed point; linear convergence leaves them
+    # a few eps / (1 - rate) apart
+    assert rel(x, t("x")) < 1e-5 and rel(u, t("u")) < 1e-5 and rel(costs, t("costs")) < 1e-7
+    ((x * t("gx")).sum() + (u * t("gu")).sum()).backward()
+    errs = {k: rel(v, t(k)) for v, k in ((Cg.grad, "dC"), (net.fcs[0].weight.grad, "dW1"),
+                                          (net.fcs[0].bias.grad, "db1"),
+                                          (net.fcs[1].weight.grad, "dW2"),
+                                          (net.fcs[1].bias.grad, "db2"))}
+    assert max(errs.values()) < 1e-4, errs
