@@ -719,3 +719,38 @@ def test_nn_dynamics_grad_methods_golden(dilqr, dev, name):
                                           (net.fcs[1].weight.grad, "dW2"),
                                           (net.fcs[1].bias.grad, "db2"))}
     assert max(errs.values()) < 1e-4, errs
+
+
+def test_per_problem_outer_loop_lindx_multi_input(dilqr, port, dev):
+    """solo=2 on a box-constrained two-input LinDx batch == the oracle run once per problem
+    (every problem with its own pnqp flags, line search, stop rule)."""
+    dtype = torch.float64
+    ns, nc, T, B = 4, 2, 10, 9
+    C, c, F, f, x0 = lindx_problem(ns, nc, T, B, dtype, seed=11)
+    kw = dict(u_lower=-0.7, u_upper=0.7)
+    m = dilqr.MPC(ns, nc, T, lqr_iter=12, verbose=-1, exit_unconverged=False, solo=2, **kw)
+    with torch.no_grad():
+        x, u, costs = m(x0.to(dev), dilqr.QuadCost(C.to(dev), c.to(dev)),
+                        dilqr.LinDx(F.to(dev), f.to(dev)))
+    for j in range(B):
+        o = port.mpc_forward(x0[j:j + 1], port.QuadCost(C[:, j:j + 1], c[:, j:j + 1]),
+                             port.LinDx(F[:, j:j + 1], f[:, j:j + 1]), ns, nc, T, lqr_iter=12,
+                             final_pass=False, **kw)
+        # multi-iteration tolerance (module docstring): a problem parked next to pnqp's
+        # 1e-4 step threshold may take its last sub-eps step one iteration apart
+        assert rel(u[:, j:j + 1], o.u) < 1e-6 and rel(costs[j:j + 1], o.costs) < 1e-10, j
+
+
+def test_nn_dynamics_fp32(dilqr, port, dev):
+    """The network dynamics in FP32 against the FP32 oracle (one LQR step)."""
+    g = golden("ref_nn_dynamics.npz")
+    t = lambda k: g["sigmoid_" + k].float()
+    dyn = port.NNDynamics(t("W1"), t("b1"), t("W2"), t("b2"))
+    o = port.mpc_forward(t("x0"), port.QuadCost(t("C"), t("c")), dyn, 3, 1, 10, u_lower=-1.0,
+                         u_upper=1.0, lqr_iter=1, final_pass=False)
+    m = dilqr.MPC(3, 1, 10, lqr_iter=1, verbose=-1, exit_unconverged=False, u_lower=-1.0,
+                  u_upper=1.0, detach_unconverged=False)
+    with torch.no_grad():
+        x, u, costs = m(t("x0").to(dev), dilqr.QuadCost(t("C").to(dev), t("c").to(dev)),
+                        _nn_module(dilqr, g, "sigmoid", dev, torch.float32))
+    assert rel(x, o.x) < 3e-4 and rel(u, o.u) < 3e-4 and rel(costs, o.costs) < 3e-4
