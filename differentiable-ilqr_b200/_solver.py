@@ -104,7 +104,7 @@ def dense_cost(t, T, B, tail_ndim):
 
 def _make_problem(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower, u_upper, u_zero_I,
                   linesearch_decay, max_linesearch_iter, best_cost_eps, gain_solve,
-                  solo):
+                  solo, delta_u=None):
     L = _lib.lib()
     _require_cuda(x_init, "x_init")
     dtype = x_init.dtype
@@ -163,6 +163,9 @@ def _make_problem(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower, u_upper, u_z
         lo = dev(lo.expand(T, B, n_ctrl), "u_lower")
         hi = dev(hi.expand(T, B, n_ctrl), "u_upper")
         s.u_lower_t, s.u_upper_t = _ptr(lo), _ptr(hi)
+    if delta_u is not None:
+        assert u_lower is not None               # lqr_step.py:195
+        s.delta_u, s.has_delta_u = float(delta_u), 1
     if u_zero_I is not None:
         zi = dev(u_zero_I.expand(T, B, n_ctrl), "u_zero_I", torch.uint8)
         s.u_zero_I = _ptr(zi)
@@ -274,13 +277,13 @@ def solve_mpc(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower=None, u_upper=Non
               u_zero_I=None, u_init=None, lqr_iter=10, eps=1e-7, linesearch_decay=0.2,
               max_linesearch_iter=10, not_improved_lim=5, best_cost_eps=1e-4,
               gain_solve=_lib.GAIN_PLAIN, solo=False, verbose=0, x_cur=None,
-              want_gains=False, sync=True, gains_only=False, pipelined=True):
+              want_gains=False, sync=True, gains_only=False, pipelined=True, delta_u=None):
     """MPC.forward (mpc.py:184-306): returns (x, u, costs, info).  With ``x_cur``
     given this is a single LQRStep around (x_cur, u_init) (lqr_step.py:277-309)
     and returns the *new* iterate."""
     L, s, ws, keep = _make_problem(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower,
                                    u_upper, u_zero_I, linesearch_decay,
-                                   max_linesearch_iter, best_cost_eps, gain_solve, solo)
+                                   max_linesearch_iter, best_cost_eps, gain_solve, solo, delta_u)
     dtype, dev = x_init.dtype, x_init.device
     B = x_init.shape[0]
     if u_init is not None:

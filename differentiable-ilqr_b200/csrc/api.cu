@@ -155,6 +155,8 @@ static IterParams<Scalar> make_params(const DilqrSolve* s, int role = 1) {
   p.lo = (S)s->u_lower;
   p.hi = (S)s->u_upper;
   p.decay = (S)s->linesearch_decay;
+  p.delta_u = (S)s->delta_u;
+  p.has_delta = s->has_delta_u && s->bounds_kind != DILQR_BOUNDS_NONE;
   p.best_cost_eps = (S)s->best_cost_eps;
   p.lo_t = static_cast<const S*>(s->u_lower_t);
   p.hi_t = static_cast<const S*>(s->u_upper_t);
@@ -215,6 +217,8 @@ static int check(const DilqrSolve* s, bool need_ws) {
     return DILQR_EINVAL;
   if (s->bounds_kind == DILQR_BOUNDS_TENSOR && (!s->u_lower_t || !s->u_upper_t)) return DILQR_EINVAL;
   if (s->bounds_kind < 0 || s->bounds_kind > 2) return DILQR_EINVAL;
+  if (s->has_delta_u && (s->bounds_kind == DILQR_BOUNDS_NONE || !(s->delta_u > 0.0)))
+    return DILQR_EINVAL;                      /* lqr_step.py:195 */
   if (s->C_bcast < 0 || s->C_bcast > 2 || s->c_bcast < 0 || s->c_bcast > 2) return DILQR_EINVAL;
   auto mis = [](const void* p) { return p && (reinterpret_cast<uintptr_t>(p) & 15u); };
   if (mis(s->C) || mis(s->c) || mis(s->F) || mis(s->f) || mis(s->workspace)) return DILQR_EALIGN;

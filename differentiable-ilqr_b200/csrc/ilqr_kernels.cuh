@@ -52,6 +52,8 @@ struct IterParams {
   int has_f;
   int first_iteration;
   S lo, hi;
+  S delta_u;        // trust region on the control change (lqr_step.py:132-134,204-211)
+  int has_delta;
   S decay;
   S best_cost_eps;
   const S* lo_t;
@@ -632,6 +634,10 @@ struct IterKernel {
         for (int a = 0; a < NC; ++a) {
           lo[a] = lo[a] - tau[NS + a];
           hi[a] = hi[a] - tau[NS + a];
+          if (p.has_delta) {   // lqr_step.py:132-134
+            if (lo[a] < -p.delta_u) lo[a] = -p.delta_u;
+            if (hi[a] > p.delta_u) hi[a] = p.delta_u;
+          }
           qu[a] = qv[NS + a];
 #pragma unroll
           for (int c2 = 0; c2 < NC; ++c2) H[a][c2] = Q[NS + a][NS + c2];
@@ -761,7 +767,15 @@ struct IterKernel {
           }
           S un = (acc + tau[NS + a]) + alpha * blk.Kk[(NC * NS + a) * kWarp];
           if (p.zeroI && p.zeroI[((size_t)t * p.B + b) * NC + a]) un = S(0);  // :197-198
-          if (p.bounds_kind) un = eclamp<S>(un, lo[a], hi[a]);                  // :213
+          if (p.bounds_kind) {
+            S lb = lo[a], ub = hi[a];
+            if (p.has_delta) {   // lqr_step.py:204-211
+              const S l2 = tau[NS + a] - p.delta_u, u2 = tau[NS + a] + p.delta_u;
+              lb = l2 < lb ? lb : l2;
+              ub = u2 > ub ? ub : u2;
+            }
+            un = eclamp<S>(un, lb, ub);                                         // :213
+          }
           th[NS + a] = un;
           // full_du_norm (lqr_step.py:243-245) is the row norm of
           // (u - new_u).transpose(1,2).contiguous().view(n_batch, -1): the [T,nc,B]

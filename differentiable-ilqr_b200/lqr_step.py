@@ -20,8 +20,6 @@ def LQRStep(n_state, n_ctrl, T, u_lower=None, u_upper=None, u_zero_I=None, delta
             delta_space=True, current_x=None, current_u=None, verbose=0, back_eps=1e-3,
             no_op_forward=False, gain_solve=_lib.GAIN_PLAIN, solo=False):
     assert delta_space                                       # lqr_step.py:297-298
-    if delta_u is not None:
-        raise NotImplementedError("delta_u trust region is out of scope (SURVEY 8a-6)")
     if true_cost is not None and not isinstance(true_cost, QuadCost):
         raise NotImplementedError("only QuadCost is supported (SURVEY 8a-2)")
 
@@ -44,7 +42,7 @@ def LQRStep(n_state, n_ctrl, T, u_lower=None, u_upper=None, u_zero_I=None, delta
                 x_init, C, c, dyn, n_state, n_ctrl, T, u_lower=u_lower, u_upper=u_upper,
                 u_zero_I=u_zero_I, u_init=current_u, x_cur=current_x,
                 linesearch_decay=linesearch_decay, max_linesearch_iter=max_linesearch_iter,
-                gain_solve=gain_solve, solo=solo, verbose=verbose)
+                gain_solve=gain_solve, solo=solo, verbose=verbose, delta_u=delta_u)
             ctx.save_for_backward(x_init, C, c, F, f if f is not None else x_init.new_empty(0),
                                   x, u)
             n_qp = torch.Tensor([info.qp_iters[0]])          # float32, lqr_step.py:308

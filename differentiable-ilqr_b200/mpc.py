@@ -50,7 +50,7 @@ class _MPCFn(Function):
             linesearch_decay=mod.linesearch_decay,
             max_linesearch_iter=mod.max_linesearch_iter,
             not_improved_lim=mod.not_improved_lim, best_cost_eps=mod.best_cost_eps,
-            gain_solve=mod._gain_solve, solo=mod.solo, verbose=mod.verbose)
+            gain_solve=mod._gain_solve, solo=mod.solo, verbose=mod.verbose, delta_u=mod.delta_u)
         mod.last_info = info
         ctx.mod = mod
         ctx.dyn_kind = dyn.kind
@@ -131,8 +131,6 @@ class MPC(nn.Module):
         super().__init__()
         assert (u_lower is None) == (u_upper is None)      # mpc.py:146
         assert max_linesearch_iter > 0                     # mpc.py:147
-        if delta_u is not None:
-            raise NotImplementedError("delta_u trust region is out of scope (SURVEY 8a-13)")
         self.n_state, self.n_ctrl, self.T = n_state, n_ctrl, T
         det = lambda v: v if (v is None or isinstance(v, float)) else v.detach()
         self.u_lower, self.u_upper = det(u_lower), det(u_upper)
@@ -243,7 +241,7 @@ class MPC(nn.Module):
                     exit_unconverged=self.exit_unconverged,
                     detach_unconverged=self.detach_unconverged, backprop=self.backprop,
                     not_improved_lim=self.not_improved_lim, best_cost_eps=self.best_cost_eps,
-                    solo=self.solo)
+                    solo=self.solo, delta_u=self.delta_u)
         x, u, costs = inner(_x_init, QuadCost(_C, _c), LinDx(_F, _f))
         self.last_info = inner.last_info
         return x[:, :, nc:], u, costs
@@ -271,7 +269,8 @@ class MPC(nn.Module):
             linesearch_decay=self.linesearch_decay,
             max_linesearch_iter=self.max_linesearch_iter,
             not_improved_lim=self.not_improved_lim, best_cost_eps=self.best_cost_eps,
-            gain_solve=self._gain_solve, solo=self.solo, verbose=self.verbose)
+            gain_solve=self._gain_solve, solo=self.solo, verbose=self.verbose,
+            delta_u=self.delta_u)
         self.last_info = info
         mask = None
         eps_cmp = float(torch.tensor(self.eps, dtype=dt))

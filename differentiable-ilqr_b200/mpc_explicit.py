@@ -22,7 +22,7 @@ class _MPCExplicitFn(Function):
             linesearch_decay=mod.linesearch_decay,
             max_linesearch_iter=mod.max_linesearch_iter,
             not_improved_lim=mod.not_improved_lim, best_cost_eps=mod.best_cost_eps,
-            gain_solve=_lib.GAIN_PLAIN, solo=mod.solo, verbose=mod.verbose)
+            gain_solve=_lib.GAIN_PLAIN, solo=mod.solo, verbose=mod.verbose, delta_u=mod.delta_u)
         mod.last_info = info
         ctx.mod, ctx.dx = mod, dx
         ctx.theta_host = dyn.params

@@ -152,6 +152,11 @@ typedef struct DilqrSolve {
   int32_t dyn_ai[4];        /* {H, activation (0 sigmoid / 1 relu), passthrough,
                                linearisation: 0 analytic (grad_input), 1 central
                                differences eps=1e-4 (GradMethods.FINITE_DIFF)}       */
+  /* trust region on the control change of one LQR step (mpc.py:93, lqr_step.py:132-134,
+     204-211); needs box constraints (lqr_step.py:195) */
+  double  delta_u;
+  int32_t has_delta_u;
+  int32_t reserved0;
 } DilqrSolve;
 
 const char* dilqr_version(void);

@@ -123,7 +123,7 @@ def pnqp(H, q, lower, upper, x_init=None, n_iter=20):
 # Riccati backward recursion  (lqr_step.py:52-160, lqr_step_backup.py:163-259)
 # --------------------------------------------------------------------------
 def lqr_backward(C, c, F, f, u, n_state, n_ctrl, u_lower=None, u_upper=None,
-                 u_zero_I=None, gain_solve="pinv"):
+                 u_zero_I=None, gain_solve="pinv", delta_u=None):
     """Returns (Ks, ks, n_total_qp_iter); Ks/ks are lists in *reverse* time
     order exactly as the reference builds them (Ks[0] belongs to t=T-1).
     ``gain_solve``: "pinv" (lqr_step.py:88-94) or "chol_reg"
@@ -180,6 +180,9 @@ def lqr_backward(C, c, F, f, u, n_state, n_ctrl, u_lower=None, u_upper=None,
         else:                                          # lqr_step.py:128-148
             lb = _bound(u_lower, t) - u[t]
             ub = _bound(u_upper, t) - u[t]
+            if delta_u is not None:                    # lqr_step.py:132-134
+                lb = torch.where(lb < -delta_u, torch.full_like(lb, -delta_u), lb)
+                ub = torch.where(ub > delta_u, torch.full_like(ub, delta_u), ub)
             out = pnqp(Quu, qu, lb, ub, x_init=prev_k, n_iter=20)
             k = out.x
             n_qp += 1 + out.n_iter
@@ -229,7 +232,7 @@ LqrFwdOut = namedtuple("LqrFwdOut", "x u costs full_du_norm mean_alphas alphas n
 
 def lqr_forward(x_init, cost, dynamics, Ks, ks, x, u, n_state, n_ctrl,
                 u_lower=None, u_upper=None, u_zero_I=None,
-                linesearch_decay=0.2, max_linesearch_iter=10):
+                linesearch_decay=0.2, max_linesearch_iter=10, delta_u=None):
     """lqr_step.py:164-261.  Line search over the *true* dynamics."""
     T, B = u.shape[0], u.shape[1]
     old_cost = get_cost(T, u, cost, x)                 # lqr_step.py:169
@@ -250,7 +253,14 @@ def lqr_forward(x_init, cost, dynamics, Ks, ks, x, u, n_state, n_ctrl,
                 nu = nu.clone()
                 nu[u_zero_I[t]] = 0.0                  # lqr_step.py:197-198
             if u_lower is not None:
-                nu = _clamp(nu, _bound(u_lower, t), _bound(u_upper, t))
+                lb, ub = _bound(u_lower, t), _bound(u_upper, t)
+                if delta_u is not None:                # lqr_step.py:204-211
+                    lo_t, hi_t = u[t] - delta_u, u[t] + delta_u
+                    lb_l = lb if torch.is_tensor(lb) else torch.full_like(lo_t, lb)
+                    ub_l = ub if torch.is_tensor(ub) else torch.full_like(hi_t, ub)
+                    lb = torch.where(lo_t < lb_l, lb_l, lo_t)
+                    ub = torch.where(hi_t > ub_l, ub_l, hi_t)
+                nu = _clamp(nu, lb, ub)
             new_u.append(nu)
             xut = torch.cat((nxt, nu), 1)
             if t < T - 1:
@@ -280,17 +290,17 @@ LqrStepOut = namedtuple(
 
 def lqr_step(x_init, C, c, F, x, u, cost, dynamics, n_state, n_ctrl,
              u_lower=None, u_upper=None, u_zero_I=None, linesearch_decay=0.2,
-             max_linesearch_iter=10, gain_solve="pinv"):
+             max_linesearch_iter=10, gain_solve="pinv", delta_u=None):
     """LQRStepFn.forward, lqr_step.py:277-309 (delta-space Taylor expansion,
     f_back=None)."""
     T = C.shape[0]
     cb = torch.stack([_mv(C[t], torch.cat((x[t], u[t]), 1)) + c[t]
                       for t in range(T)])
     Ks, ks, nqp = lqr_backward(C, cb, F, None, u, n_state, n_ctrl, u_lower,
-                               u_upper, u_zero_I, gain_solve)
+                               u_upper, u_zero_I, gain_solve, delta_u)
     o = lqr_forward(x_init, cost, dynamics, Ks, ks, x, u, n_state, n_ctrl,
                     u_lower, u_upper, u_zero_I, linesearch_decay,
-                    max_linesearch_iter)
+                    max_linesearch_iter, delta_u)
     return LqrStepOut(o.x, o.u, nqp, o.costs, o.full_du_norm, o.mean_alphas,
                       Ks, ks, o.alphas)
 
@@ -446,7 +456,7 @@ def mpc_forward(x_init, cost, dynamics, n_state, n_ctrl, T, u_lower=None,
                 u_upper=None, u_zero_I=None, u_init=None, lqr_iter=10,
                 eps=1e-7, linesearch_decay=0.2, max_linesearch_iter=10,
                 not_improved_lim=5, best_cost_eps=1e-4, gain_solve="pinv",
-                final_pass=True):
+                final_pass=True, delta_u=None):
     """MPC.forward (mpc.py:184-337).  ``cost`` is a QuadCost with dense
     C[T,B,n,n], c[T,B,n]; ``dynamics`` a LinDx or an env object with
     __call__/get_linear_dyn.  Returns best iterate, costs, and (for the
@@ -472,7 +482,7 @@ def mpc_forward(x_init, cost, dynamics, n_state, n_ctrl, T, u_lower=None,
             F, _ = linearize_dynamics(x, u, dynamics)
         o = lqr_step(x_init, cost.C, cost.c, F, x, u, cost, dynamics, n_state,
                      n_ctrl, u_lower, u_upper, u_zero_I, linesearch_decay,
-                     max_linesearch_iter, gain_solve)
+                     max_linesearch_iter, gain_solve, delta_u)
         x, u = o.x, o.u
         n_not_improved += 1                            # mpc.py:266
         if best is None:                               # mpc.py:271-277

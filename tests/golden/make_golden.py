@@ -267,6 +267,37 @@ def nn_grad_methods():
     torch.set_default_dtype(torch.float32)
 
 
+def delta_u():
+    """mpc.MPC with the delta_u trust region (lqr_step.py:132-134,204-211) on a boxed LinDx
+    problem: forward + KKT gradients."""
+    torch.manual_seed(13)
+    torch.set_default_dtype(torch.float64)
+    ns, nc, T, B = 4, 2, 10, 8
+    n = ns + nc
+    A = torch.randn(T, B, n, n)
+    C = A.transpose(2, 3) @ A + torch.eye(n)
+    c = torch.randn(T, B, n)
+    F = torch.cat((torch.eye(ns).expand(T - 1, B, ns, ns) + 0.2 * torch.randn(T - 1, B, ns, ns) / ns ** 0.5,
+                   torch.randn(T - 1, B, ns, nc) / ns ** 0.5), 3)
+    f = 0.1 * torch.randn(T - 1, B, ns)
+    x0 = torch.randn(B, ns)
+    g = torch.Generator().manual_seed(7)
+    gx = torch.randn(T, B, ns, generator=g)
+    gu = torch.randn(T, B, nc, generator=g)
+    out = dict(C=C, c=c, F=F, f=f, x0=x0, gx=gx, gu=gu)
+    for L in (1, 3, 25):
+        Cg, cg, Fg, fg, x0g = [t.clone().requires_grad_() for t in (C, c, F, f, x0)]
+        m = R.mpc.MPC(ns, nc, T, lqr_iter=L, verbose=-1, exit_unconverged=False, u_lower=-1.0,
+                      u_upper=1.0, delta_u=0.25, detach_unconverged=False)
+        x, u, costs = m(x0g, R.mpc.QuadCost(Cg, cg), R.mpc.LinDx(Fg, fg))
+        out.update({"L%d_x" % L: x, "L%d_u" % L: u, "L%d_costs" % L: costs})
+        if L == 25:
+            ((x * gx).sum() + (u * gu).sum()).backward()
+            out.update(dx0=x0g.grad, dC=Cg.grad, dc=cg.grad, dF=Fg.grad, df=fg.grad)
+    npz("ref_delta_u.npz", **out)
+    torch.set_default_dtype(torch.float32)
+
+
 def open_loop(env, mpc_T, lqr_iter, n_train, n_val, n_test):
     """IL_Env.populate_data (il_env.py:81-94): one batched open-loop expert solve."""
     torch.set_default_dtype(torch.float64)
@@ -309,3 +340,4 @@ if __name__ == "__main__":
     open_loop("pendulum", 20, 60, 5, 2, 1)
     nn_dynamics()
     nn_grad_methods()
+    delta_u()

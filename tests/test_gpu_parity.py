@@ -754,3 +754,25 @@ def test_nn_dynamics_fp32(dilqr, port, dev):
         x, u, costs = m(t("x0").to(dev), dilqr.QuadCost(t("C").to(dev), t("c").to(dev)),
                         _nn_module(dilqr, g, "sigmoid", dev, torch.float32))
     assert rel(x, o.x) < 3e-4 and rel(u, o.u) < 3e-4 and rel(costs, o.costs) < 3e-4
+
+
+def test_delta_u_trust_region_golden(dilqr, dev):
+    """mpc.MPC(delta_u=...) against the reference: every LQR step moves the controls by at
+    most delta_u (pnqp bounds of the Riccati sweep and the clamp of the line search),
+    1 / 3 iterations and the converged solve with its KKT gradients."""
+    g = {k: v.to(dev) for k, v in golden("ref_delta_u.npz").items()}
+    for L in (1, 3, 25):
+        leaves = {k: g[k].clone().requires_grad_() for k in ("C", "c", "F", "f", "x0")}
+        m = dilqr.MPC(4, 2, 10, lqr_iter=L, verbose=-1, exit_unconverged=False, u_lower=-1.0,
+                      u_upper=1.0, delta_u=0.25, detach_unconverged=False)
+        x, u, costs = m(leaves["x0"], dilqr.QuadCost(leaves["C"], leaves["c"]),
+                        dilqr.LinDx(leaves["F"], leaves["f"]))
+        tol = 1e-10 if L < 25 else 1e-8
+        assert rel(x, g["L%d_x" % L]) < tol and rel(u, g["L%d_u" % L]) < tol
+        assert rel(costs, g["L%d_costs" % L]) < tol
+        if L == 1:
+            assert float(u.detach().abs().max()) <= 0.25 + 1e-12      # one step from u = 0
+        if L == 25:
+            ((x * g["gx"]).sum() + (u * g["gu"]).sum()).backward()
+            for nm, leaf in (("dx0", "x0"), ("dC", "C"), ("dc", "c"), ("dF", "F"), ("df", "f")):
+                assert rel(leaves[leaf].grad, g[nm]) < 1e-7, nm

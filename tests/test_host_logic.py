@@ -67,8 +67,8 @@ def test_unsupported_features_fail_loudly(dilqr):
     m = dilqr.mpc_explicit.MPC(3, 1, 5, slew_rate_penalty=1.0)
     with pytest.raises(NotImplementedError):       # slew rate: KKT path (mpc.MPC) only
         m(torch.zeros(2, 3), dilqr.QuadCost(torch.eye(4), torch.zeros(4)), dilqr.env_dx.PendulumDx())
-    with pytest.raises(NotImplementedError):
-        dilqr.MPC(3, 1, 5, u_lower=-1.0, u_upper=1.0, delta_u=0.1)
+    m = dilqr.MPC(3, 1, 5, u_lower=-1.0, u_upper=1.0, delta_u=0.1)   # trust region: supported
+    assert m.delta_u == 0.1
 
 
 def test_bytes_per_solve_model():

@@ -152,3 +152,15 @@ def test_nn_dynamics_bit_exact(port, act):
                          u_upper=1.0, lqr_iter=30, final_pass=False)
     assert float((o.x - t("x")).abs().max()) == 0.0
     assert float((o.u - t("u")).abs().max()) == 0.0
+
+
+def test_delta_u_bit_exact(port):
+    """mpc.MPC(delta_u=0.25) of the unmodified reference on a boxed LinDx problem
+    (lqr_step.py:132-134, 204-211): reproduced with max diff 0.0."""
+    g = golden("ref_delta_u.npz")
+    for L in (1, 3, 25):
+        o = port.mpc_forward(g["x0"], port.QuadCost(g["C"], g["c"]), port.LinDx(g["F"], g["f"]),
+                             4, 2, 10, u_lower=-1.0, u_upper=1.0, lqr_iter=L, final_pass=False,
+                             delta_u=0.25)
+        assert float((o.u - g["L%d_u" % L]).abs().max()) == 0.0
+        assert float((o.x - g["L%d_x" % L]).abs().max()) == 0.0
