@@ -290,7 +290,9 @@ def run_reference(args):
              for i in range(max(1, min(args.steps, 3)))]
     ms = 1e3 * sum(t) / len(t)
     v = Bs / (ms * 1e-3)
-    sample = "B=%d problems per step on %d host threads (reference is O(B^2); never extrapolated)" % (Bs, cores)
+    sample = ("B=%d problems per step on %d host threads, oracle port of the reference "
+              "(its matrix-free backward; the reference's own dense fix_point_equ is limited "
+              "to T*B < 1000)" % (Bs, cores))
     print(json.dumps({
         "impl": "reference",
         "metric": "MPC solves/sec (fwd+implicit bwd), cartpole T=50 B=64k",
@@ -315,7 +317,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--batch", type=int, default=65536)
-    ap.add_argument("--cpu-batch", type=int, default=2048)
+    ap.add_argument("--cpu-batch", type=int, default=32768)
     ap.add_argument("--richardson", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--broadcast-cost", action="store_true",
