@@ -212,7 +212,9 @@ static int check(const DilqrSolve* s, bool need_ws) {
   if (!s->x_init || !s->C || !s->c) return DILQR_EINVAL;
   if (s->dynamics == DILQR_DYN_LINDX && s->T > 1 && !s->F) return DILQR_EINVAL;
   if (s->dynamics == DILQR_DYN_NN &&
-      (!s->dyn_aux || s->dyn_ai[0] < 1 || s->dyn_ai[0] > 65536 || s->dyn_ai[1] < 0 || s->dyn_ai[1] > 1 ||
+      (!s->dyn_aux || s->dyn_ai[0] < 1 || (s->dyn_ai[0] & 0xffff) < 1 ||
+       ((s->dyn_ai[0] >> 16) > 0 && (s->dyn_ai[0] & 0xffff) > 128) ||   /* two layers: H1 <= 128 */
+       s->dyn_ai[1] < 0 || s->dyn_ai[1] > 1 ||
        s->dyn_ai[3] < 0 || s->dyn_ai[3] > 1))
     return DILQR_EINVAL;
   if (s->bounds_kind == DILQR_BOUNDS_TENSOR && (!s->u_lower_t || !s->u_upper_t)) return DILQR_EINVAL;

@@ -21,7 +21,7 @@ template <class S>
 struct DynParams {
   S p[8];
   const S* aux;   // DYN_NN: packed weights  W1[H][n] b1[H] W2[ns][H] b2[ns]  (device)
-  int ai[4];      // DYN_NN: {H, activation (0 sigmoid, 1 relu), passthrough,
+  int ai[4];      // DYN_NN: {H1 | H2 << 16 (H2 = 0: one hidden layer), activation (0 sigmoid, 1 relu), passthrough,
                   //          linearisation (0 analytic grad_input, 1 central differences)}
 };
 
@@ -57,8 +57,103 @@ struct Dyn<S, DYN_NN> {
     return S(1) / (S(1) + expS<S>(-a));
   }
 
+  static constexpr int kMaxH = 128;   // two hidden layers: the first layer's width (local array)
+
+  // hidden_sizes=[H1, H2]: weights W1[H1][n] b1[H1] W2[H2][H1] b2[H2] W3[ns][H2] b3[ns]
+  template <int NS, int NC>
+  DILQR_DEVICE static void step2(const DynParams<S>& P, const S* x, const S* u, S* xn) {
+    constexpr int N = NS + NC;
+    const int H1 = P.ai[0] & 0xffff, H2 = P.ai[0] >> 16;
+    const S* W1 = P.aux;
+    const S* b1 = W1 + (size_t)H1 * N;
+    const S* W2 = b1 + H1;
+    const S* b2 = W2 + (size_t)H2 * H1;
+    const S* W3 = b2 + H2;
+    const S* b3 = W3 + (size_t)NS * H2;
+    S z1[kMaxH];
+    for (int h = 0; h < H1; ++h) {
+      S a = S(0);
+#pragma unroll
+      for (int j = 0; j < NS; ++j) a = fmaS<S>(__ldg(W1 + h * N + j), x[j], a);
+#pragma unroll
+      for (int j = 0; j < NC; ++j) a = fmaS<S>(__ldg(W1 + h * N + NS + j), u[j], a);
+      z1[h] = act(a + __ldg(b1 + h), P.ai[1]);
+    }
+    S acc[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) acc[i] = S(0);
+    for (int k = 0; k < H2; ++k) {
+      S a = S(0);
+      for (int h = 0; h < H1; ++h) a = fmaS<S>(__ldg(W2 + (size_t)k * H1 + h), z1[h], a);
+      const S z2 = act(a + __ldg(b2 + k), P.ai[1]);
+#pragma unroll
+      for (int i = 0; i < NS; ++i) acc[i] = fmaS<S>(__ldg(W3 + i * H2 + k), z2, acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      S v = acc[i] + __ldg(b3 + i);
+      if (P.ai[2]) v = v + x[i];
+      xn[i] = v;
+    }
+  }
+
+  // grad_input for two hidden layers in the reference's association (dynamics.py:98-116):
+  // G = W3 (diag(d2) W2)  [ns x H1], then J = G (diag(d1) W1).
+  template <int NS, int N>
+  DILQR_DEVICE static void jacobian2(const DynParams<S>& P, const S* tau, S (&F)[NS][N]) {
+    const int H1 = P.ai[0] & 0xffff, H2 = P.ai[0] >> 16;
+    const S* W1 = P.aux;
+    const S* b1 = W1 + (size_t)H1 * N;
+    const S* W2 = b1 + H1;
+    const S* b2 = W2 + (size_t)H2 * H1;
+    const S* W3 = b2 + H2;
+    S z1[kMaxH];
+    S G[NS][kMaxH];
+    for (int h = 0; h < H1; ++h) {
+      S a = S(0);
+#pragma unroll
+      for (int j = 0; j < N; ++j) a = fmaS<S>(__ldg(W1 + h * N + j), tau[j], a);
+      z1[h] = act(a + __ldg(b1 + h), P.ai[1]);
+#pragma unroll
+      for (int i = 0; i < NS; ++i) G[i][h] = S(0);
+    }
+    for (int k = 0; k < H2; ++k) {
+      S a = S(0);
+      for (int h = 0; h < H1; ++h) a = fmaS<S>(__ldg(W2 + (size_t)k * H1 + h), z1[h], a);
+      const S z2 = act(a + __ldg(b2 + k), P.ai[1]);
+      const S d2 = (P.ai[1] == 1) ? (z2 <= S(0) ? S(0) : S(1)) : z2 * (S(1) - z2);
+      for (int h = 0; h < H1; ++h) {
+        const S w = __ldg(W2 + (size_t)k * H1 + h) * d2;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) G[i][h] = fmaS<S>(__ldg(W3 + i * H2 + k), w, G[i][h]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NS; ++i)
+#pragma unroll
+      for (int j = 0; j < N; ++j) F[i][j] = S(0);
+    for (int h = 0; h < H1; ++h) {
+      const S d1 = (P.ai[1] == 1) ? (z1[h] <= S(0) ? S(0) : S(1)) : z1[h] * (S(1) - z1[h]);
+      S w[N];
+#pragma unroll
+      for (int j = 0; j < N; ++j) w[j] = __ldg(W1 + h * N + j) * d1;
+#pragma unroll
+      for (int i = 0; i < NS; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) F[i][j] = fmaS<S>(G[i][h], w[j], F[i][j]);
+    }
+    if (P.ai[2]) {
+#pragma unroll
+      for (int i = 0; i < NS; ++i) F[i][i] = F[i][i] + S(1);
+    }
+  }
+
   template <int NS, int NC>
   DILQR_DEVICE static void step(const DynParams<S>& P, const S* x, const S* u, S* xn) {
+    if (P.ai[0] >> 16) {
+      step2<NS, NC>(P, x, u, xn);
+      return;
+    }
     constexpr int N = NS + NC;
     const int H = P.ai[0];
     const S* W1 = P.aux;
@@ -112,6 +207,10 @@ struct Dyn<S, DYN_NN> {
                                     S (&F)[NS][N]) {
     if (P.ai[3] == 1) {
       jacobian_fd<NS, N>(P, tau, F);
+      return;
+    }
+    if (P.ai[0] >> 16) {
+      jacobian2<NS, N>(P, tau, F);
       return;
     }
     const int H = P.ai[0];

@@ -82,18 +82,20 @@ class NNDynamics(nn.Module):
 
     # -- device side ---------------------------------------------------------
     def _dilqr_pack(self, dtype, device):
-        """(weight buffer, ints) for DILQR_DYN_NN: W1[H][n] b1[H] W2[ns][H] b2[ns]."""
-        if len(self.fcs) != 2:
-            raise NotImplementedError("device NNDynamics: exactly one hidden layer "
-                                      "(hidden_sizes=[H]); got %d" % (len(self.fcs) - 1))
+        """(weight buffer, ints) for DILQR_DYN_NN: weight[out][in], bias[out] per layer."""
+        if len(self.fcs) not in (2, 3):
+            raise NotImplementedError("device NNDynamics: one or two hidden layers; got %d"
+                                      % (len(self.fcs) - 1))
+        widths = [fc.weight.shape[0] for fc in self.fcs[:-1]]
+        if max(widths) >= 65536 or (len(widths) == 2 and widths[0] > 128):
+            raise NotImplementedError("device NNDynamics: hidden widths %s too large" % widths)
         if self.activation not in ('sigmoid', 'relu'):
             raise NotImplementedError("device NNDynamics: sigmoid / relu (grad_input of the "
                                       "reference supports no other, dynamics.py:104-113)")
-        fc0, fc1 = self.fcs
-        buf = torch.cat([t.detach().reshape(-1) for t in
-                         (fc0.weight, fc0.bias, fc1.weight, fc1.bias)]).to(device=device, dtype=dtype)
-        ints = [fc0.weight.shape[0], 0 if self.activation == 'sigmoid' else 1,
-                1 if self.passthrough else 0, 0]
+        buf = torch.cat([t.detach().reshape(-1) for fc in self.fcs
+                         for t in (fc.weight, fc.bias)]).to(device=device, dtype=dtype)
+        ints = [widths[0] | ((widths[1] << 16) if len(widths) == 2 else 0),
+                0 if self.activation == 'sigmoid' else 1, 1 if self.passthrough else 0, 0]
         return buf.contiguous(), ints
 
 

@@ -146,10 +146,12 @@ typedef struct DilqrSolve {
   /* scratch */
   void*  workspace;
   size_t workspace_bytes;
-  /* DILQR_DYN_NN only: the network of dynamics.NNDynamics(hidden_sizes=[H]) */
-  const void* dyn_aux;      /* device, packed in the call's dtype: W1[H][n] (fc0.weight),
-                               b1[H], W2[ns][H] (fc1.weight), b2[ns]                  */
-  int32_t dyn_ai[4];        /* {H, activation (0 sigmoid / 1 relu), passthrough,
+  /* DILQR_DYN_NN only: the network of dynamics.NNDynamics(hidden_sizes=[H] or [H1,H2]) */
+  const void* dyn_aux;      /* device, packed in the call's dtype, layer by layer:
+                               weight[out][in] then bias[out] (fc0, fc1[, fc2])        */
+  int32_t dyn_ai[4];        /* {H1 | H2 << 16 (H2 = 0: one hidden layer; two layers need
+                               H1 <= 128, H1 < 65536 otherwise), activation (0 sigmoid /
+                               1 relu), passthrough,
                                linearisation: 0 analytic (grad_input), 1 central
                                differences eps=1e-4 (GradMethods.FINITE_DIFF)}       */
   /* trust region on the control change of one LQR step (mpc.py:93, lqr_step.py:132-134,

@@ -233,6 +233,45 @@ def nn_dynamics():
     torch.set_default_dtype(torch.float32)
 
 
+def nn_two_layers():
+    """mpc.MPC + NNDynamics(hidden_sizes=[10, 6]) (dynamics.py:98-116, two factors in
+    grad_input), forward and KKT gradients wrt all six parameter tensors."""
+    import dynamics as refdyn
+    torch.set_default_dtype(torch.float64)
+    out = {}
+    for act in ("sigmoid", "relu"):
+        torch.manual_seed(21)
+        ns, nc, T, B = 3, 1, 8, 5
+        n = ns + nc
+        dx = refdyn.NNDynamics(ns, nc, hidden_sizes=[10, 6], activation=act, passthrough=True)
+        for p_ in dx.parameters():
+            p_.data.mul_(0.5)
+        A = torch.randn(T, B, n, n)
+        C = A.transpose(2, 3) @ A + torch.eye(n)
+        c = torch.randn(T, B, n)
+        x0 = torch.randn(B, ns)
+        g = torch.Generator().manual_seed(7)
+        gx = torch.randn(T, B, ns, generator=g)
+        gu = torch.randn(T, B, nc, generator=g)
+        for L in (1, 40):
+            Cg = C.clone().requires_grad_()
+            for p_ in dx.parameters():
+                p_.grad = None
+            m = R.mpc.MPC(ns, nc, T, lqr_iter=L, verbose=-1, exit_unconverged=(L > 1 and act == "sigmoid"),
+                          u_lower=-2.0, u_upper=2.0, grad_method=R.mpc.GradMethods.ANALYTIC,
+                          detach_unconverged=(L > 1 and act == "sigmoid"))
+            x, u, costs = m(x0, R.mpc.QuadCost(Cg, c), dx)
+            out.update({"%s_L%d_%s" % (act, L, k): v for k, v in dict(x=x, u=u, costs=costs).items()})
+        ((x * gx).sum() + (u * gu).sum()).backward()
+        prm = {"W%d" % (i + 1): fc.weight for i, fc in enumerate(dx.fcs)}
+        prm.update({"b%d" % (i + 1): fc.bias for i, fc in enumerate(dx.fcs)})
+        out.update({act + "_" + k: v for k, v in dict(C=C, c=c, x0=x0, gx=gx, gu=gu, dC=Cg.grad).items()})
+        out.update({act + "_" + k: v for k, v in prm.items()})
+        out.update({act + "_d" + k: v.grad for k, v in prm.items()})
+    npz("ref_nn_two_layers.npz", **out)
+    torch.set_default_dtype(torch.float32)
+
+
 def nn_grad_methods():
     """mpc.MPC + NNDynamics with grad_method AUTO_DIFF and FINITE_DIFF (mpc.py:525-601)."""
     import dynamics as refdyn
@@ -341,3 +380,4 @@ if __name__ == "__main__":
     nn_dynamics()
     nn_grad_methods()
     delta_u()
+    nn_two_layers()

@@ -776,3 +776,35 @@ def test_delta_u_trust_region_golden(dilqr, dev):
             ((x * g["gx"]).sum() + (u * g["gu"]).sum()).backward()
             for nm, leaf in (("dx0", "x0"), ("dC", "C"), ("dc", "c"), ("dF", "F"), ("df", "f")):
                 assert rel(leaves[leaf].grad, g[nm]) < 1e-7, nm
+
+
+@pytest.mark.parametrize("act", ["sigmoid", "relu"])
+def test_nn_dynamics_two_hidden_layers_golden(dilqr, dev, act):
+    """NNDynamics(hidden_sizes=[10, 6]) as device dynamics against the reference: one LQR
+    step for both activations; for sigmoid also the converged solve with the KKT gradients
+    wrt all six parameter tensors."""
+    g = golden("ref_nn_two_layers.npz")
+    t = lambda k: g[act + "_" + k].to(dev)
+    net = dilqr.NNDynamics(3, 1, hidden_sizes=[10, 6], activation=act).to(dev).double()
+    with torch.no_grad():
+        for i, fc in enumerate(net.fcs):
+            fc.weight.copy_(t("W%d" % (i + 1)))
+            fc.bias.copy_(t("b%d" % (i + 1)))
+    m = dilqr.MPC(3, 1, 8, lqr_iter=1, verbose=-1, exit_unconverged=False, u_lower=-2.0,
+                  u_upper=2.0, detach_unconverged=False)
+    with torch.no_grad():
+        x, u, costs = m(t("x0"), dilqr.QuadCost(t("C"), t("c")), net)
+    assert rel(x, t("L1_x")) < 1e-10 and rel(u, t("L1_u")) < 1e-10 and rel(costs, t("L1_costs")) < 1e-10
+    if act != "sigmoid":
+        return
+    Cg = t("C").clone().requires_grad_()
+    m = dilqr.MPC(3, 1, 8, lqr_iter=40, verbose=-1, exit_unconverged=True, u_lower=-2.0,
+                  u_upper=2.0, detach_unconverged=True)
+    x, u, costs = m(t("x0"), dilqr.QuadCost(Cg, t("c")), net)
+    assert rel(x, t("L40_x")) < 1e-5 and rel(u, t("L40_u")) < 1e-5 and rel(costs, t("L40_costs")) < 1e-7
+    ((x * t("gx")).sum() + (u * t("gu")).sum()).backward()
+    errs = {"dC": rel(Cg.grad, t("dC"))}
+    for i, fc in enumerate(net.fcs):
+        errs["dW%d" % (i + 1)] = rel(fc.weight.grad, t("dW%d" % (i + 1)))
+        errs["db%d" % (i + 1)] = rel(fc.bias.grad, t("db%d" % (i + 1)))
+    assert max(errs.values()) < 1e-4, errs

@@ -115,4 +115,6 @@ def test_nn_dynamics_container(dilqr, act):
     assert buf.numel() == 7 * 5 + 7 + 3 * 7 + 3 and ints[0] == 7 and ints[2] == 1
     assert torch.equal(buf[:35].view(7, 5), d.fcs[0].weight.detach())
     with pytest.raises(NotImplementedError):
-        dilqr.NNDynamics(3, 2, hidden_sizes=[4, 4])._dilqr_pack(torch.float64, "cpu")
+        dilqr.NNDynamics(3, 2, hidden_sizes=[4, 4, 4])._dilqr_pack(torch.float64, "cpu")
+    b2, i2 = dilqr.NNDynamics(3, 2, hidden_sizes=[9, 4])._dilqr_pack(torch.float64, "cpu")
+    assert i2[0] == (9 | (4 << 16)) and b2.numel() == 9 * 5 + 9 + 4 * 9 + 4 + 3 * 4 + 3
