@@ -93,10 +93,21 @@ class DilqrAdjoint(C.Structure):
         ("dtype", C.c_int32), ("dynamics", C.c_int32), ("bounds_kind", C.c_int32),
         ("gain_solve", C.c_int32), ("C_bcast", C.c_int32), ("c_bcast", C.c_int32),
         ("u_lower", C.c_double), ("u_upper", C.c_double), ("dyn_params", C.c_double * 8),
-        ("C", C.c_void_p), ("x", C.c_void_p), ("u", C.c_void_p), ("g", C.c_void_p),
+        ("C", C.c_void_p), ("x", C.c_void_p), ("u", C.c_void_p), ("gx", C.c_void_p),
+        ("gu", C.c_void_p),
         ("Lam", C.c_void_p), ("w", C.c_void_p), ("dC", C.c_void_p), ("dc", C.c_void_p),
         ("df", C.c_void_p), ("dx_out", C.c_void_p), ("du_out", C.c_void_p),
         ("resid", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("Cpk", C.c_void_p), ("cpk_state", C.c_void_p), ("first_pass", C.c_int32),
+        ("want_resid", C.c_int32), ("reduce_tile", C.c_int32), ("reserved0", C.c_int32),
+        ("red_out", C.c_void_p), ("df_blk", C.c_void_p),
+    ]
+
+
+class DilqrWsView(C.Structure):
+    _fields_ = [
+        ("Kk", C.c_void_p), ("Cpk", C.c_void_p), ("cpk_state", C.c_void_p),
+        ("n_warps", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -110,6 +121,13 @@ SYMBOLS = {
     "dilqr_mpc_iterate": (C.c_int, [C.POINTER(DilqrSolve), C.c_void_p]),
     "dilqr_mpc_commit": (C.c_int, [C.POINTER(DilqrSolve), C.c_void_p]),
     "dilqr_mpc_finish": (C.c_int, [C.POINTER(DilqrSolve), C.c_void_p]),
+    "dilqr_mpc_gains": (C.c_int, [C.POINTER(DilqrSolve), C.c_void_p, C.c_void_p]),
+    "dilqr_workspace_view": (C.c_int, [C.POINTER(DilqrSolve), C.POINTER(DilqrWsView)]),
+    "dilqr_lam_tables": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int]
+                         + [C.c_void_p] * 5),
+    "dilqr_sens_theta_blocked": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int,
+                                           C.c_int] + [C.c_void_p] * 8),
+    "dilqr_adjoint_dtau_offset": (C.c_size_t, [C.POINTER(DilqrAdjoint)]),
     "dilqr_kkt_grads": (C.c_int, [C.POINTER(DilqrKkt), C.c_void_p]),
     "dilqr_linearize": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -178,7 +196,8 @@ def check(code, what):
 # kernels enqueued per C-ABI call (memsets not counted)
 KERNELS_PER_CALL = {
     "dilqr_mpc_begin": 1, "dilqr_mpc_iterate": 1, "dilqr_mpc_commit": 3,
-    "dilqr_mpc_finish": 1, "dilqr_kkt_grads": 1, "dilqr_linearize": 1, "dilqr_rollout": 1,
+    "dilqr_mpc_finish": 1, "dilqr_mpc_gains": 2, "dilqr_lam_tables": 1,
+    "dilqr_sens_theta_blocked": 1, "dilqr_kkt_grads": 1, "dilqr_linearize": 1, "dilqr_rollout": 1,
     "dilqr_costate_tables": 1, "dilqr_richardson_update": 1, "dilqr_sens_theta": 1,
     "dilqr_adjoint_factor": 1, "dilqr_adjoint_pass": 1, "dilqr_adjoint_final": 1,
     "dilqr_pnqp": 2, "dilqr_env_tables": 1, "dilqr_tile_cost": 2, "dilqr_tile_cost_grad": 2,

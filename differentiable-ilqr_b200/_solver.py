@@ -22,6 +22,24 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _on_device_of(argname, pos):
+    """Run the wrapped entry point with the device of its tensor argument current, so
+    the stream the kernels are enqueued on (``_stream``), the workspace and the operands
+    always belong to the same GPU, whatever the caller's current device is."""
+    import functools
+
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrapped(*args, **kw):
+            t = kw.get(argname) if argname in kw else (args[pos] if len(args) > pos else None)
+            if torch.is_tensor(t) and t.is_cuda:
+                with torch.cuda.device(t.device):
+                    return fn(*args, **kw)
+            return fn(*args, **kw)
+        return wrapped
+    return deco
+
+
 class DynSpec:
     """What the rollouts integrate: LinDx tensors or an env_dx model id + theta."""
 
@@ -48,10 +66,50 @@ class SolveInfo:
 MAX_PIPELINED_ITERS = 1024
 
 
+class Deferred:
+    """Validation reads of a step, postponed to ONE host synchronisation at its end.
+
+    The solver's control flow never needs the host in the common case (the stop rule, the
+    pnqp trace check and the adjoint line-search test all run on the device); the host only
+    has to learn *afterwards* that nothing went wrong.  Each `add` enqueues a small D2H
+    copy into pinned memory behind the kernels that produce the data; `resolve` waits once
+    and runs the checks.  A failed check means the optimistic launches behind it computed
+    on a stale guess: the caller repeats the step with immediate checks."""
+
+    _pool = {}
+
+    def __init__(self):
+        self.items = []
+        self.ok = True
+        self.reasons = []
+
+    def add(self, dev_bytes, fn):
+        n = dev_bytes.numel()
+        key = (n, len(self.items))
+        host = Deferred._pool.get(key)
+        if host is None:
+            host = torch.empty(n, dtype=torch.uint8).pin_memory()
+            Deferred._pool[key] = host
+        host.copy_(dev_bytes, non_blocking=True)
+        self.items.append((host, fn))
+
+    def resolve(self):
+        if self.items:
+            torch.cuda.current_stream().synchronize()
+        for host, fn in self.items:
+            why = fn(host.numpy().tobytes())
+            if why:
+                self.ok = False
+                self.reasons.append(why)
+        self.items = []
+        return self.ok
+
+
 class Workspace:
     """Device scratch + status / control blocks for one (shape, dtype) family; reused."""
 
     def __init__(self, nbytes, device):
+        self.gen = 0       # bumped by every solve that (re)uses the buffer
         self.buf = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=device)
         self.status_dev = torch.zeros(64, dtype=torch.uint8, device=device)
         self.status_host = torch.zeros(64, dtype=torch.uint8).pin_memory()
@@ -69,6 +127,11 @@ def _require_cuda(t, name):
     if not t.is_cuda:
         raise _lib.DilqrLibraryError(
             "%s must be a CUDA tensor: this package has no CPU path" % name)
+
+
+def _aligned(t):
+    """TMA slabs start on 16-byte boundaries: re-materialise views that do not."""
+    return t if t.data_ptr() % 16 == 0 else t.clone()
 
 
 def _contig(t):
@@ -192,6 +255,7 @@ def _make_problem(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower, u_upper, u_z
         _ws_cache.pop(key, None)      # release the smaller buffer before allocating
         ws = Workspace(need, x_init.device)
         _ws_cache[key] = ws
+    ws.gen += 1
     s.workspace = _ptr(ws.buf)
     s.workspace_bytes = ws.buf.numel()
     s.status = _ptr(ws.status_dev)
@@ -224,10 +288,30 @@ def _iterate_committed(L, s, ws, info, sync=True):
     raise _lib.DilqrLibraryError("pnqp control-flow trace did not stabilise")
 
 
-def _solve_pipelined(L, s, ws, info, n_loops, eps_cmp, not_improved_lim, verbose):
+def _fill_info(info, raw, verbose):
+    """Decode [control | status x iterations] as read back from the device."""
+    c = _lib.DilqrControl.from_buffer_copy(raw[:64])
+    n_done = c.iters_done
+    for j in range(n_done):
+        stt = _lib.DilqrStatus.from_buffer_copy(raw[64 * (1 + j):64 * (2 + j)])
+        info.qp_iters.append(stt.n_total_qp_iter)
+        info.pnqp_unconverged += stt.pnqp_unconverged
+        info.log.append((stt.n_total_qp_iter, stt.max_full_du, stt.mean_alpha, stt.mean_best_cost))
+        if stt.pnqp_unconverged and verbose >= 0:
+            for _ in range(stt.pnqp_unconverged):
+                print("[WARNING] pnqp warning: Did not converge")   # pnqp.py:81
+        info.max_full_du, info.mean_alpha = stt.max_full_du, stt.mean_alpha
+        info.mean_best_cost = stt.mean_best_cost
+    info.n_iters = n_done
+    return c
+
+
+def _solve_pipelined(L, s, ws, info, n_loops, eps_cmp, not_improved_lim, verbose, deferred=None):
     """Outer iLQR loop with the stop rule and the trace check on the device
     (DilqrControl): all iterations are enqueued back to back, ONE host sync at the
-    end; a wrong pnqp trace guess halts the queue and the loop resumes from there."""
+    end; a wrong pnqp trace guess halts the queue and the loop resumes from there.
+    With ``deferred`` not even that: the control block is copied back asynchronously and
+    checked when the caller resolves the step (a halted queue then invalidates it)."""
     st = _stream()
     ctrl = _lib.DilqrControl()
     ctrl.eps = eps_cmp
@@ -238,6 +322,22 @@ def _solve_pipelined(L, s, ws, info, n_loops, eps_cmp, not_improved_lim, verbose
     s.control = C.c_void_p(base)
     start = 0
     nbytes = 64 * (1 + n_loops)
+    if deferred is not None:
+        for j in range(n_loops):
+            s.iteration = j
+            s.status = C.c_void_p(base + 64 * (1 + j))
+            _lib.call("dilqr_mpc_iterate", C.byref(s), st)
+            _lib.call("dilqr_mpc_commit", C.byref(s), st)
+
+        def check(raw, info=info, verbose=verbose):
+            c = _fill_info(info, raw, verbose)
+            return "pnqp trace mismatch in the forward solve" if c.halt == 2 else None
+
+        deferred.add(ws.pipe_dev[:nbytes], check)
+        # finish reads the number of committed iterations from the control block
+        s.iteration = n_loops - 1
+        s.status = _ptr(ws.status_dev)
+        return
     for _ in range(MAX_TRACE_RETRIES * 4):
         for j in range(start, n_loops):
             s.iteration = j
@@ -256,28 +356,19 @@ def _solve_pipelined(L, s, ws, info, n_loops, eps_cmp, not_improved_lim, verbose
         break
     else:
         raise _lib.DilqrLibraryError("pnqp control-flow trace did not stabilise")
-    n_done = c.iters_done
-    for j in range(n_done):
-        stt = _lib.DilqrStatus.from_buffer_copy(raw[64 * (1 + j):64 * (2 + j)])
-        info.qp_iters.append(stt.n_total_qp_iter)
-        info.pnqp_unconverged += stt.pnqp_unconverged
-        info.log.append((stt.n_total_qp_iter, stt.max_full_du, stt.mean_alpha, stt.mean_best_cost))
-        if stt.pnqp_unconverged and verbose >= 0:
-            for _ in range(stt.pnqp_unconverged):
-                print("[WARNING] pnqp warning: Did not converge")   # pnqp.py:81
-        info.max_full_du, info.mean_alpha = stt.max_full_du, stt.mean_alpha
-        info.mean_best_cost = stt.mean_best_cost
-    info.n_iters = n_done
-    s.iteration = n_done - 1
+    c = _fill_info(info, raw, verbose)
+    s.iteration = c.iters_done - 1
     s.control = None
     s.status = _ptr(ws.status_dev)
 
 
+@_on_device_of("x_init", 0)
 def solve_mpc(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower=None, u_upper=None,
               u_zero_I=None, u_init=None, lqr_iter=10, eps=1e-7, linesearch_decay=0.2,
               max_linesearch_iter=10, not_improved_lim=5, best_cost_eps=1e-4,
               gain_solve=_lib.GAIN_PLAIN, solo=False, verbose=0, x_cur=None,
-              want_gains=False, sync=True, gains_only=False, pipelined=True, delta_u=None):
+              want_gains=False, sync=True, gains_only=False, pipelined=True, delta_u=None,
+              deferred=None):
     """MPC.forward (mpc.py:184-306): returns (x, u, costs, info).  With ``x_cur``
     given this is a single LQRStep around (x_cur, u_init) (lqr_step.py:277-309)
     and returns the *new* iterate."""
@@ -312,7 +403,9 @@ def solve_mpc(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower=None, u_upper=Non
         raise ValueError("solo=2 needs lqr_iter <= %d" % MAX_PIPELINED_ITERS)
     if n_loops > 1 and n_loops <= MAX_PIPELINED_ITERS and (
             (pipelined and verbose <= 0) or int(solo) == 2):
-        _solve_pipelined(L, s, ws, info, n_loops, eps_cmp, not_improved_lim, verbose)
+        if int(solo) == 2 or s.lockstep:
+            deferred = None          # their host logic needs the statuses right away
+        _solve_pipelined(L, s, ws, info, n_loops, eps_cmp, not_improved_lim, verbose, deferred)
         n_loops = 0
     for i in range(n_loops):
         s.iteration = i
@@ -357,6 +450,9 @@ def solve_mpc(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower=None, u_upper=Non
         s.K_out, s.k_out = _ptr(K), _ptr(k)
         extra["K"], extra["k"] = K, k
     _lib.call("dilqr_mpc_finish", C.byref(s), st)
+    s.control = None
+    # what the backward pass can pick up from this solve while the workspace is untouched
+    info._problem = (s, ws, ws.gen, keep + [t for t in (x, u) if t is not None])
     info.full_du_norm = du
     info.converged = None
     for k_, v_ in extra.items():
@@ -364,6 +460,7 @@ def solve_mpc(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower=None, u_upper=Non
     return x, u, costs, info
 
 
+@_on_device_of("x", 3)
 def kkt_grads(C_, c_, F, x, u, dx, du, r, n_state, n_ctrl, want_df=True, want_dF=True):
     """Costate recursions + outer products (lqr_step.py:343-404)."""
     L = _lib.lib()
@@ -384,6 +481,7 @@ def kkt_grads(C_, c_, F, x, u, dx, du, r, n_state, n_ctrl, want_df=True, want_dF
     return dx0, dC, dc, dF, df
 
 
+@_on_device_of("x_init", 2)
 def kkt_backward(dl_dx, dl_du, x_init, C_, c_, F, f, x, u, n_state, n_ctrl, u_lower=None,
                  u_upper=None, gain_solve=_lib.GAIN_PLAIN, back_eps=1e-7):
     """LQRStepFn.backward (lqr_step.py:312-407): adjoint LQR solve with the
@@ -402,15 +500,40 @@ def kkt_backward(dl_dx, dl_du, x_init, C_, c_, F, f, x, u, n_state, n_ctrl, u_lo
     return kkt_grads(C_, c_, F, x, u, dx, du, r, n_state, n_ctrl, want_df)
 
 
+def _adjoint_struct(kind, n_state, n_ctrl, T, B, dtype, u_lower, u_upper, theta, Cb, cb):
+    a = _lib.DilqrAdjoint()
+    a.n_state, a.n_ctrl, a.T, a.n_batch, a.dtype, a.dynamics = n_state, n_ctrl, T, B, _DT[dtype], kind
+    a.bounds_kind = _lib.BOUNDS_NONE if u_lower is None else _lib.BOUNDS_SCALAR
+    a.gain_solve = _lib.GAIN_CHOL_REG
+    a.C_bcast, a.c_bcast = Cb, cb
+    if u_lower is not None:
+        a.u_lower, a.u_upper = u_lower, u_upper
+    for i in range(8):
+        a.dyn_params[i] = theta[i]
+    return a
+
+
+FUSED_BACKWARD = True      # A/B knob: False restores the round-1 kernel sequence
+
+
+@_on_device_of("x_init", 0)
 def dilqr_prepare(x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u_lower=None, u_upper=None,
-                  solo=False, theta_host=None, factored=True):
+                  solo=False, theta_host=None, factored=True, solve_info=None, deferred=None):
     """Everything of the DiLQR backward that depends only on the forward solution
     (x*, u*), the cost and theta -- NOT on the upstream gradient: the gains of the final
     no-op LQR pass (lqr_step_explicit.py:604-618), the primal costates with the
     contracted second-order tables, and the factorisation of the adjoint LQR solves.
     ``MPC.forward`` enqueues this right behind the solve when a gradient will be asked
     for, so the device works through it while the host is busy with the loss and the
-    autograd dispatch."""
+    autograd dispatch.
+
+    ``solve_info``: the SolveInfo of the forward solve.  While its workspace is untouched
+    the fused sequence is used (pendulum / cartpole, scalar bounds): ONE sweep over the
+    solver's own outputs gives gains + costates (``dilqr_mpc_gains``, C from the packed
+    workspace copy), the second-order tables are a (t, problem)-parallel kernel
+    (``dilqr_lam_tables``), and the factorisation reads the packed C as well -- no
+    re-layout of the trajectory, no gather of the gains, C streamed 2 x 21 instead of
+    3 x 36 scalars per (t, problem)."""
     T, B = x.shape[0], x.shape[1]
     dtype, dev = x.dtype, x.device
     n = n_state + n_ctrl
@@ -422,7 +545,7 @@ def dilqr_prepare(x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u_lower=None, u_
     u = u.detach().contiguous()
     scalar_bounds = u_lower is None or (isinstance(u_lower, float) and isinstance(u_upper, float))
     if not scalar_bounds or kind == _lib.DYN_ROCKET:
-        factored = False      # factored adjoint kernels: pendulum / cartpole only (round 1)
+        factored = False      # factored adjoint kernels: pendulum / cartpole only
     # cost layout: dense [T,B,..] or broadcast (C[n,n] / C[T,n,n]); the generic path
     # (LinDx kernels + kkt_grads) wants dense tensors
     C_in, c_in = C_, c_
@@ -431,6 +554,63 @@ def dilqr_prepare(x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u_lower=None, u_
     if not factored and (Cb or cb):
         C_, c_ = dense_cost(C_in.to(dtype), T, B, 2), dense_cost(c_in.to(dtype), T, B, 1)
         Cb = cb = 0
+    prep = dict(theta=theta, kind=kind, factored=factored, Cb=Cb, cb=cb, C_=C_, c_=c_, x=x, u=u,
+                x_init=x_init, C_in=C_in, c_in=c_in, fused=False)
+    nW = (B + 31) // 32
+    fused = (FUSED_BACKWARD and factored and solve_info is not None and n_ctrl == 1
+             and getattr(solve_info, "_problem", None) is not None)
+    if fused:
+        sp, ws, gen, keep = solve_info._problem
+        fused = ws.gen == gen and sp.x_out is not None and sp.u_zero_I is None
+    if fused:
+        L = _lib.lib()
+        view = _lib.DilqrWsView()
+        _lib.check(L.dilqr_workspace_view(C.byref(sp), C.byref(view)), "dilqr_workspace_view")
+        lam = torch.empty(T, nW, n_state, 32, dtype=dtype, device=dev)
+        sp.status = _ptr(ws.status_dev)
+        sp.control = None
+
+        def gains_ok(raw):
+            st = _lib.DilqrStatus.from_buffer_copy(raw)
+            return None if st.trace_match else "pnqp trace mismatch in the final LQR pass"
+
+        for attempt in range(MAX_TRACE_RETRIES):
+            rc = L.dilqr_mpc_gains(C.byref(sp), _ptr(lam), _stream())
+            if rc == -2:
+                fused = False      # shape without the fused sweep: round-1 sequence below
+                break
+            _lib.check(rc, "dilqr_mpc_gains")
+            _lib.launch_count += _lib.KERNELS_PER_CALL["dilqr_mpc_gains"]
+            if deferred is not None:
+                deferred.add(ws.status_dev, gains_ok)
+                break
+            # the trace guess was the last iteration's; a wrong guess has been corrected on
+            # the device: run the sweep again
+            if gains_ok(bytes(_read_status_raw(ws))) is None:
+                break
+            if solve_info is not None:
+                solve_info.retries += 1
+        else:
+            raise _lib.DilqrLibraryError("pnqp control-flow trace did not stabilise")
+    if fused:
+        nlam = _lib.lib().dilqr_lam_pack_size(kind)
+        Lam = torch.empty(T - 1, nW, nlam, 32, dtype=dtype, device=dev)
+        _lib.call("dilqr_lam_tables", _DT[dtype], kind, theta, T, B, _ptr(x), _ptr(u), _ptr(lam),
+                  _ptr(Lam), _stream())
+        a = _adjoint_struct(kind, n_state, n_ctrl, T, B, dtype, u_lower, u_upper, theta, Cb, cb)
+        resid = torch.zeros(3, dtype=torch.float64, device=dev)
+        a.C, a.x, a.u, a.Lam = _ptr(C_), _ptr(x), _ptr(u), _ptr(Lam)
+        a.Cpk, a.cpk_state = view.Cpk, view.cpk_state
+        a.resid = _ptr(resid)
+        need = L.dilqr_adjoint_workspace_bytes(C.byref(a))
+        aws = torch.empty(need, dtype=torch.uint8, device=dev)
+        a.workspace, a.workspace_bytes = _ptr(aws), need
+        _lib.call("dilqr_adjoint_factor", C.byref(a), _stream())
+        prep.update(fused=True, a=a, ws=aws, resid=resid, lam=lam, Lam=Lam, Kk=view.Kk,
+                    solver_ws=ws, solver_gen=gen, keep=keep,
+                    dtau_off=L.dilqr_adjoint_dtau_offset(C.byref(a)))
+        return prep
+    # ---- round-1 sequence (any env_dx model, tensor bounds, foreign workspaces) ----------
     # (1) gains of the final no-op LQR pass at tau* (lqr_step_explicit.py:604-618)
     dyn = DynSpec(kind, params=list(theta))
     _, _, _, info = solve_mpc(x_init, C_in, c_in, dyn, n_state, n_ctrl, T, u_lower=u_lower,
@@ -441,24 +621,15 @@ def dilqr_prepare(x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u_lower=None, u_
     lam = torch.empty(T, B, n_state, dtype=dtype, device=dev)
     if factored:   # packed, warp-blocked Lam (only the structurally non-zero entries)
         nlam = _lib.lib().dilqr_lam_pack_size(kind)
-        Lam = torch.empty(T - 1, (B + 31) // 32, nlam, 32, dtype=dtype, device=dev)
+        Lam = torch.empty(T - 1, nW, nlam, 32, dtype=dtype, device=dev)
     else:
         Lam = torch.empty(T - 1, B, n, n, dtype=dtype, device=dev)
     _lib.call("dilqr_costate_tables", _DT[dtype], kind, theta, T, B, _ptr(C_), _ptr(c_), _ptr(x),
               _ptr(u), _ptr(lam), _ptr(Lam), Cb, cb, 1 if factored else 0, _stream())
-    prep = dict(theta=theta, kind=kind, factored=factored, Cb=Cb, cb=cb, C_=C_, c_=c_, x=x, u=u,
-                K=K, lam=lam, Lam=Lam, x_init=x_init, C_in=C_in, c_in=c_in)
+    prep.update(K=K, lam=lam, Lam=Lam)
     if factored:
         # (3a) factor the adjoint LQR solves once (csrc/adjoint_kernels.cuh)
-        a = _lib.DilqrAdjoint()
-        a.n_state, a.n_ctrl, a.T, a.n_batch, a.dtype, a.dynamics = n_state, n_ctrl, T, B, _DT[dtype], kind
-        a.bounds_kind = _lib.BOUNDS_NONE if u_lower is None else _lib.BOUNDS_SCALAR
-        a.gain_solve = _lib.GAIN_CHOL_REG
-        a.C_bcast, a.c_bcast = Cb, cb
-        if u_lower is not None:
-            a.u_lower, a.u_upper = u_lower, u_upper
-        for i in range(8):
-            a.dyn_params[i] = theta[i]
+        a = _adjoint_struct(kind, n_state, n_ctrl, T, B, dtype, u_lower, u_upper, theta, Cb, cb)
         resid = torch.zeros(3, dtype=torch.float64, device=dev)
         a.C, a.x, a.u, a.Lam = _ptr(C_), _ptr(x), _ptr(u), _ptr(Lam)
         a.resid = _ptr(resid)
@@ -470,12 +641,28 @@ def dilqr_prepare(x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u_lower=None, u_
     return prep
 
 
+def _read_status_raw(ws):
+    ws.status_host.copy_(ws.status_dev, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return ws.status_host.numpy().tobytes()
+
+
+RICHARDSON_WARN = 1e-6     # relative residual above which a fixed-pass solve warns
+
+
+@_on_device_of("x_init", 2)
 def dilqr_backward(dl_dx, dl_du, x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u_lower=None,
                    u_upper=None, n_passes=8, tol=None, back_eps=1e-7, solo=False, stats=None,
-                   theta_host=None, factored=True, prep=None):
+                   theta_host=None, factored=True, prep=None, tile_reduce=False, deferred=None):
     """DiLQR implicit gradient (lqr_step_explicit.py:652-712 + fix_point_equ
     458-598) in matrix-free form (derivation in
-    csrc/dilqr_backward.cuh).  Returns (dC, dc, dtheta[B, n_theta]).
+    csrc/dilqr_backward.cuh).  Returns (dC, dc, dtheta[B, n_theta]); with
+    ``tile_reduce`` the first two are instead (dq[n], dp[n]), the gradient of the tiled
+    diagonal cost C[t,b] = diag(q), c[t,b] = p of il_env.py:159-162, accumulated inside the
+    final adjoint pass (the dense dC / dc are never written).
+
+    ``dl_dx`` may be None (loss independent of x): the kernels read the two halves of the
+    upstream gradient separately, nothing is concatenated or copied.
 
     n_passes Richardson passes solve A' w = g (each = one adjoint LQR solve); with
     ``tol`` the loop stops early once max|dw| <= tol * max|w| (one host sync per
@@ -497,18 +684,33 @@ def dilqr_backward(dl_dx, dl_du, x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u
     n = n_state + n_ctrl
     kind, theta, factored = prep["kind"], prep["theta"], prep["factored"]
     Cb, cb, C_d, c_d = prep["Cb"], prep["cb"], prep["C_"], prep["c_"]
-    x, u, K, lam, Lam = prep["x"], prep["u"], prep["K"], prep["lam"], prep["Lam"]
-    g = torch.cat((dl_dx, dl_du), 2).contiguous()
-    w = g.clone()
+    x, u, lam, Lam = prep["x"], prep["u"], prep["lam"], prep["Lam"]
+    fused = prep.get("fused", False)
+    if fused and prep["solver_ws"].gen != prep["solver_gen"]:
+        # another solve has reused the solver workspace since: the gains / packed C the
+        # fused kernels would read are gone -- recompute the preparation
+        prep = dilqr_prepare(x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u_lower, u_upper,
+                             solo, theta_host, factored)
+        return dilqr_backward(dl_dx, dl_du, x_init, C_, c_, x, u, dxmod, n_state, n_ctrl,
+                              u_lower, u_upper, n_passes, tol, back_eps, solo, stats, theta_host,
+                              factored, prep, tile_reduce, deferred)
+    if dl_du is None:
+        dl_du = torch.zeros(T, B, n_ctrl, dtype=dtype, device=dev)
+    gu = _aligned(dl_du.contiguous())
+    gx = None if dl_dx is None else _aligned(dl_dx.contiguous())
     passes = 0
     rel = None
     nth = len(dxmod.params)
-    # gradients of a broadcast cost come back as per-warp partial sums (summed below)
     nwarp = (B + 31) // 32
-    dC = torch.empty({0: (T, B, n, n), 1: (T, nwarp, n, n), 2: (nwarp, n, n)}[Cb], dtype=dtype,
-                     device=dev)
-    dc = torch.empty({0: (T, B, n), 1: (T, nwarp, n), 2: (nwarp, n)}[cb], dtype=dtype, device=dev)
-    df = torch.empty(T - 1, B, n_state, dtype=dtype, device=dev)
+    reduce_in_kernel = tile_reduce and factored and not Cb and not cb
+    if reduce_in_kernel:
+        dC = dc = None
+        red = torch.empty(nwarp, 2 * n, dtype=dtype, device=dev)
+    else:
+        # gradients of a broadcast cost come back as per-warp partial sums (summed below)
+        dC = torch.empty({0: (T, B, n, n), 1: (T, nwarp, n, n), 2: (nwarp, n, n)}[Cb], dtype=dtype,
+                         device=dev)
+        dc = torch.empty({0: (T, B, n), 1: (T, nwarp, n), 2: (nwarp, n)}[cb], dtype=dtype, device=dev)
     resid = prep["resid"] if factored else torch.zeros(3, dtype=torch.float64, device=dev)
 
     def converged():
@@ -517,21 +719,41 @@ def dilqr_backward(dl_dx, dl_du, x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u
 
     if factored:
         a = prep["a"]
-        dxa = torch.empty(T, B, n_state, dtype=dtype, device=dev)
-        dua = torch.empty(T, B, n_ctrl, dtype=dtype, device=dev)
-        a.g, a.w = _ptr(g), _ptr(w)
-        a.dC, a.dc, a.df, a.dx_out, a.du_out = _ptr(dC), _ptr(dc), _ptr(df), _ptr(dxa), _ptr(dua)
+        w = torch.empty(T, B, n, dtype=dtype, device=dev) if n_passes > 0 else None
+        a.gx, a.gu, a.w = _ptr(gx), _ptr(gu), _ptr(w)
+        a.want_resid = 1 if tol is not None else 0
         st = _stream()
-        for _ in range(n_passes):
+        for i in range(n_passes):
+            a.first_pass = 1 if i == 0 else 0
+            # the last pass of a fixed-count solve also measures how far w still moves
+            if tol is None and i == n_passes - 1:
+                a.want_resid = 1
             _lib.call("dilqr_adjoint_pass", C.byref(a), st)
             passes += 1
             if tol is not None:
                 rel = converged()
                 if rel <= tol:
                     break
+        a.first_pass = 1 if passes == 0 else 0
+        if fused:
+            df = torch.empty(T - 1, nwarp, n_state, 32, dtype=dtype, device=dev)
+            a.df_blk, a.df, a.dx_out, a.du_out = _ptr(df), None, None, None
+        else:
+            df = torch.empty(T - 1, B, n_state, dtype=dtype, device=dev)
+            dxa = torch.empty(T, B, n_state, dtype=dtype, device=dev)
+            dua = torch.empty(T, B, n_ctrl, dtype=dtype, device=dev)
+            a.df_blk, a.df, a.dx_out, a.du_out = None, _ptr(df), _ptr(dxa), _ptr(dua)
+        if reduce_in_kernel:
+            a.reduce_tile, a.red_out, a.dC, a.dc = 1, _ptr(red), None, None
+        else:
+            a.reduce_tile, a.red_out, a.dC, a.dc = 0, None, _ptr(dC), _ptr(dc)
         _lib.call("dilqr_adjoint_final", C.byref(a), st)
     else:
         # generic path: every adjoint solve is a full (line-searching) LQR step
+        g = torch.cat((gx if gx is not None else torch.zeros(T, B, n_state, dtype=dtype, device=dev),
+                       gu), 2).contiguous()
+        w = g.clone()
+        df = torch.empty(T - 1, B, n_state, dtype=dtype, device=dev)
         F = torch.empty(T - 1, B, n_state, n, dtype=dtype, device=dev)
         _lib.call("dilqr_linearize", _DT[dtype], kind, theta, T, B, _ptr(x), _ptr(u), _ptr(F), None,
                   _stream())
@@ -562,21 +784,53 @@ def dilqr_backward(dl_dx, dl_du, x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u
                                      want_dF=False)
     # (3) dtheta through the closed-loop sensitivity rollout
     dtheta = torch.empty(B, nth, dtype=dtype, device=dev)
-    _lib.call("dilqr_sens_theta", _DT[dtype], kind, theta, T, B, _ptr(x), _ptr(u), _ptr(K),
-              _ptr(lam), _ptr(dxa), _ptr(dua), _ptr(df), _ptr(dtheta), _stream())
+    if fused:
+        dtau = prep["ws"][prep["dtau_off"]:]
+        _lib.call("dilqr_sens_theta_blocked", _DT[dtype], kind, theta, T, B, _ptr(x), _ptr(u),
+                  C.c_void_p(prep["Kk"]), _ptr(lam), _ptr(dtau), _ptr(df), _ptr(dtheta), _stream())
+    else:
+        _lib.call("dilqr_sens_theta", _DT[dtype], kind, theta, T, B, _ptr(x), _ptr(u),
+                  _ptr(prep["K"]), _ptr(lam), _ptr(dxa), _ptr(dua), _ptr(df), _ptr(dtheta), _stream())
     if factored:
-        # one sync at the end: did the reference's line search reject any adjoint step?
-        n_rej = int(resid[2:3].view(torch.int64).item())
-        if n_rej:
-            return dilqr_backward(dl_dx, dl_du, x_init, prep["C_in"], prep["c_in"], x, u, dxmod,
-                                  n_state, n_ctrl, u_lower, u_upper, n_passes, tol, back_eps, solo,
-                                  stats, theta_host=theta_host, factored=False)
+        def check(raw, passes=passes, tol=tol, stats=stats):
+            import struct
+            dmax, wmax, n_rej = struct.unpack("ddq", raw)
+            r = dmax / (wmax + 1e-300)
+            if stats is not None and passes and stats.get("resid") is None:
+                stats["resid"] = r
+            if n_rej:
+                return "the reference's line search would reject an adjoint step"
+            if passes and tol is None and r > RICHARDSON_WARN:
+                import warnings
+                warnings.warn("DiLQR backward: after %d Richardson passes the adjoint iterate still "
+                              "moves by %.1e (relative); the gradient is approximate -- raise "
+                              "richardson_passes or set richardson_tol" % (passes, r))
+            return None
+        if deferred is not None:
+            deferred.add(resid.view(torch.uint8), check)
+        else:
+            # one sync at the end: did the reference's line search reject any adjoint step?
+            if check(bytes(resid.view(torch.uint8).cpu().numpy().tobytes())):
+                return dilqr_backward(dl_dx, dl_du, x_init, prep["C_in"], prep["c_in"], x, u, dxmod,
+                                      n_state, n_ctrl, u_lower, u_upper, n_passes, tol, back_eps,
+                                      solo, stats, theta_host=theta_host, factored=False,
+                                      tile_reduce=tile_reduce)
     if stats is not None:
         stats["passes"] = passes
-        stats["resid"] = rel
+        stats.setdefault("resid", rel)
+        if rel is not None:
+            stats["resid"] = rel
         stats["factored"] = factored
+        stats["fused"] = fused
+    if reduce_in_kernel:
+        r = red.sum(0)
+        return r[:n], r[n:], dtheta
     if Cb:
         dC = dC.sum(1 if Cb == 1 else 0)
     if cb:
         dc = dc.sum(1 if cb == 1 else 0)
+    if tile_reduce:      # the tiling's adjoint on the dense gradients (generic path)
+        dC = dC.reshape(T, B, n, n) if not Cb else dC
+        return (dC.diagonal(dim1=-2, dim2=-1).reshape(-1, n).sum(0),
+                dc.reshape(-1, n).sum(0), dtheta)
     return dC, dc, dtheta

@@ -85,6 +85,15 @@ struct AdjParams {
   S* dx_out;
   S* du_out;
   unsigned long long* resid;   // [0] max|dw| [1] max|w| (double bits), [2] #rejected problems
+  const S* Cpk;                // packed symmetric copy of C left by the solve (optional) ...
+  const uint32_t* cpk_state;   // ... valid iff *cpk_state == 1
+  const S* gx;                 // [T,B,ns] upstream gradient wrt x (NULL: zero)
+  const S* gu;                 // [T,B,nc] upstream gradient wrt u
+  int first;                   // this solve's right-hand side is g itself (w == g)
+  int want_resid;              // reduce max|dw|, max|w| (costs one extra read of w)
+  int reduce_tile;             // final pass: red_out instead of dC, dc
+  S* red_out;                  // [n_warps][2N]
+  S* df_blk;                   // final pass: df warp-blocked [T-1][Bp/32][NS][32] (optional)
   DynParams<S> dyn;
 };
 
@@ -132,15 +141,23 @@ __global__ void __launch_bounds__(128) adjoint_factor_kernel(const __grid_consta
   const int nvalid = min(kWarp, p.B - b0);
   const bool act = lane < nvalid;
   const int b = act ? b0 + lane : b0;
-  const uint32_t elems[1] = {N * N};
-  const size_t per_warp = WarpStager<S>::bytes_per_warp(1, elems) + kStages * sizeof(uint64_t);
+  // the packed symmetric copy of C the solve left in its workspace (21 instead of 36 scalars
+  // for cartpole), when the caller hands it over and it is valid
+  constexpr int NP = N * (N + 1) / 2;
+  const bool packedC = p.Cpk && p.cpk_state && !p.C_bcast &&
+                       *reinterpret_cast<const volatile uint32_t*>(p.cpk_state) == 1u;
+  const uint32_t elems_dense[1] = {N * N};
+  const uint32_t elems[1] = {packedC ? (uint32_t)NP : (uint32_t)(N * N)};
+  const size_t per_warp = WarpStager<S>::bytes_per_warp(1, elems_dense) + kStages * sizeof(uint64_t);
   char* wbase = smem + warp * per_warp;
   WarpStager<S> st;
   st.init(wbase + kStages * sizeof(uint64_t), reinterpret_cast<uint64_t*>(wbase), lane, nvalid, 1,
-          elems, 0, p.C_bcast ? 1u : 0u);
+          elems, packedC ? 1u : 0u, p.C_bcast ? 1u : 0u);
   const int T = p.T;
+  const int nWc = p.Bp / kWarp;
   auto issue = [&](int stage, int t) {
-    const S* src[1] = {cost_src<S>(p.C, p.C_bcast, t, p.B, b0, N * N)};
+    const S* src[1] = {packedC ? p.Cpk + bidx(t, 0, NP, b0, nWc)
+                               : cost_src<S>(p.C, p.C_bcast, t, p.B, b0, N * N)};
     st.issue(stage, src, 1);
   };
   S V[NS][NS], xnext[NS];
@@ -151,12 +168,20 @@ __global__ void __launch_bounds__(128) adjoint_factor_kernel(const __grid_consta
     S tau[N];
     A::load_tau(p, t, b, tau);
     st.wait(sg);
-    const S* Cs = st.lane_ptr(sg, 0);
     S Q[N][N];
+    if (packedC) {
+      const S* Cs = st.seg_ptr(sg, 0) + lane;
 #pragma unroll
-    for (int i = 0; i < N; ++i)
+      for (int i = 0; i < N; ++i)
 #pragma unroll
-      for (int j = 0; j < N; ++j) Q[i][j] = Cs[i * N + j];
+        for (int j = 0; j < N; ++j) Q[i][j] = Cs[pk_idx<N>(i, j) * kWarp];
+    } else {
+      const S* Cs = st.lane_ptr(sg, 0);
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) Q[i][j] = Cs[i * N + j];
+    }
     if (t < T - 1) {
       S Fm[NS][N];
       A::jac_at(p, tau, xnext, Fm);
@@ -290,34 +315,54 @@ __global__ void __launch_bounds__(128) adjoint_factor_kernel(const __grid_consta
 // One adjoint solve with r = w (affine sweep + linear rollout).
 //   FINAL == false: fused Richardson update  w_t <- g_t - Lam_t dtau_t.
 //   FINAL == true : keeps dtau (workspace + optional AoS dx_out/du_out), then a
-//                   costate sweep (lqr_step.py:371-385) writes dC, dc, df.
-// Every per-timestep operand (w, x*, u*, factor record, Lam, g, k, dtau, C) is
-// staged through shared memory by TMA one step ahead of its use.
+//                   costate sweep (lqr_step.py:371-385) produces dC, dc, df -- dense, or
+//                   (reduce_tile) already reduced to the gradient of the tiled diagonal
+//                   cost: sum_{t,b} diag(dC), sum_{t,b} dc, per-warp partial sums.
+// Every per-timestep operand (w / g, x*, u*, factor record, Lam, k, dtau, C) is staged
+// through shared memory by TMA one step ahead of its use; the segment table of the stage
+// is re-laid out between the sweeps (WarpStager::reconfigure).
+//   p.first: this is the first solve of the Richardson iteration, w == g: the right-hand
+//            side is read from g (no w <- g copy is ever made).
+//   g is handed over as its two halves gx[T,B,ns] (may be NULL: zero) and gu[T,B,nc],
+//            the upstream gradients as autograd delivers them (no concatenation).
 // ---------------------------------------------------------------------------
 template <class S, int DYN>
 struct AdjStage {
   using A = Adj<S, DYN>;
   static constexpr int NS = A::NS, NC = A::NC, N = A::N, NFAC = A::NFAC;
-  // segments: 0 big: packed Lam_t[NLAM] (blocked; passes) or C_t[N*N] (slab; final pass)
-  //           1 vec[N] (w_t or g_t)  2 x[NS]  3 u[NC]
-  //           4 fac[NFAC] (blocked)      5 kv[N] (blocked: kvec_t[NC] or dtau_t[N])
-  static constexpr int kNSeg = 6;
+  static constexpr int NP = N * (N + 1) / 2;
   static constexpr int NLAM = LamPack<S, DYN>::NLAM;
-  static __host__ __device__ uint32_t full_mask(bool fin) {
-    return (1u << 4) | (1u << 5) | (fin ? 0u : 1u);
+  static constexpr int kNSeg = 8;
+  using Stager = WarpStager<S, kNSeg>;
+  // sweep A (affine backward): 0 w[N]  1 x[NS]  2 u[NC]  3 fac[NFAC]*  4 gx[NS]  5 gu[NC]
+  // sweep B (rollout):         0 Lam[NLAM]*  1 x  2 u  3 K[NC*NS]* (prefix of the factor
+  //                            record)  4 gx  5 gu  6 kvec[NC]*
+  // sweep C (costates, FINAL): 0 C[N*N] (slab) or Cpk[NP]*  1 x  2 u  3 dtau[N]*  4 gx  5 gu
+  //                            7 w[N]                                  (* = warp-blocked)
+  static __host__ __device__ void elems_A(uint32_t* e) {
+    e[0] = N; e[1] = NS; e[2] = NC; e[3] = NFAC; e[4] = NS; e[5] = NC; e[6] = 0; e[7] = 0;
   }
-  static __host__ __device__ void seg_elems(uint32_t* e, bool fin) {
-    e[0] = fin ? N * N : NLAM;
-    e[1] = N;
-    e[2] = NS;
-    e[3] = NC;
-    e[4] = NFAC;
-    e[5] = N;
+  static __host__ __device__ void elems_B(uint32_t* e, bool fin) {
+    e[0] = fin ? 0 : NLAM; e[1] = NS; e[2] = NC; e[3] = NC * NS; e[4] = fin ? 0 : NS;
+    e[5] = fin ? 0 : NC; e[6] = NC; e[7] = 0;
+  }
+  static __host__ __device__ void elems_C(uint32_t* e, bool packed) {
+    e[0] = packed ? NP : N * N; e[1] = NS; e[2] = NC; e[3] = N; e[4] = NS; e[5] = NC; e[6] = 0;
+    e[7] = N;
   }
   static __host__ __device__ size_t stage_bytes(bool fin) {
     uint32_t e[kNSeg];
-    seg_elems(e, fin);
-    return WarpStager<S>::bytes_per_warp(kNSeg, e);
+    elems_A(e);
+    size_t m = Stager::bytes_per_warp(kNSeg, e);
+    elems_B(e, fin);
+    size_t v = Stager::bytes_per_warp(kNSeg, e);
+    m = v > m ? v : m;
+    if (fin) {
+      elems_C(e, false);
+      v = Stager::bytes_per_warp(kNSeg, e);
+      m = v > m ? v : m;
+    }
+    return m;
   }
   static __host__ __device__ size_t out_bytes(bool fin) {
     return fin ? (((size_t)kWarp * (N * N + N) * sizeof(S) + 15) & ~(size_t)15) : 0;
@@ -327,7 +372,7 @@ struct AdjStage {
   }
 };
 
-template <class S, int DYN, bool FINAL>
+template <class S, int DYN, bool FINAL, bool REDUCE = false>
 __global__ void __launch_bounds__(64) adjoint_pass_kernel(const __grid_constant__ AdjParams<S> p) {
   using A = Adj<S, DYN>;
   using AS = AdjStage<S, DYN>;
@@ -344,26 +389,51 @@ __global__ void __launch_bounds__(64) adjoint_pass_kernel(const __grid_constant_
   const int nW = p.Bp / kWarp;
   const size_t per_warp = AS::smem_per_warp(FINAL);
   char* wbase = smem + warp * per_warp;
-  WarpStager<S> st;
+  typename AS::Stager st;
   {
     uint32_t e[AS::kNSeg];
-    AS::seg_elems(e, FINAL);
+    AS::elems_A(e);
     st.init(wbase + kStages * sizeof(uint64_t), reinterpret_cast<uint64_t*>(wbase), lane, nvalid,
-            AS::kNSeg, e, AS::full_mask(FINAL));
+            AS::kNSeg, e, 1u << 3);
   }
   S* outC = reinterpret_cast<S*>(wbase + kStages * sizeof(uint64_t) + AS::stage_bytes(FINAL));
   S* outc = outC + kWarp * N * N;
 
-  auto slab = [&](const S* base, int t, int elems) { return base + ((size_t)t * p.B + b0) * elems; };
-
-  // ---------------- affine backward sweep
+  auto slab = [&](const S* base, int elems) {
+    return base ? base + (size_t)b0 * elems : nullptr;
+  };
   const long long sz = (long long)sizeof(S);
   const long long chunk = (long long)nW * kWarp * sz;   // bytes per timestep per component
-  st.bind(1, slab(p.w, 0, N), (long long)p.B * N * sz);
-  st.bind(2, slab(p.x, 0, NS), (long long)p.B * NS * sz);
-  st.bind(3, slab(p.u, 0, NC), (long long)p.B * NC * sz);
-  st.bind(4, p.fac + bidx(0, 0, NFAC, b0, nW), chunk * NFAC);
-  auto issue_a = [&](int stage, int t) { st.issue_bound(stage, t, 0x1eu); };
+  const bool first = p.first != 0;
+  // right-hand side r_t of this solve: w_t, or (first) g_t = [gx_t; gu_t]
+  const uint32_t rmask = first ? ((p.gx ? 1u << 4 : 0u) | (1u << 5)) : 1u;
+  auto bind_common = [&]() {
+    st.bind(1, slab(p.x, NS), (long long)p.B * NS * sz);
+    st.bind(2, slab(p.u, NC), (long long)p.B * NC * sz);
+    st.bind(4, slab(p.gx, NS), (long long)p.B * NS * sz);
+    st.bind(5, slab(p.gu, NC), (long long)p.B * NC * sz);
+  };
+  // r_t[i] from the staged right-hand side
+  auto rhs = [&](int sg, int wseg, S* r) {
+    if (first) {
+      const S* gxs = st.lane_ptr(sg, 4);
+      const S* gus = st.lane_ptr(sg, 5);
+#pragma unroll
+      for (int i = 0; i < NS; ++i) r[i] = p.gx ? gxs[i] : S(0);
+#pragma unroll
+      for (int a = 0; a < NC; ++a) r[NS + a] = gus[a];
+    } else {
+      const S* ws_ = st.lane_ptr(sg, wseg);
+#pragma unroll
+      for (int i = 0; i < N; ++i) r[i] = ws_[i];
+    }
+  };
+
+  // ---------------- affine backward sweep
+  bind_common();
+  st.bind(0, slab(p.w, N), (long long)p.B * N * sz);
+  st.bind(3, p.fac + bidx(0, 0, NFAC, b0, nW), chunk * NFAC);
+  auto issue_a = [&](int stage, int t) { st.issue_bound(stage, t, 0xeu | rmask); };
   S v[NS], xnext[NS];
   S pred = S(0);
   issue_a(0, T - 1);
@@ -371,17 +441,17 @@ __global__ void __launch_bounds__(64) adjoint_pass_kernel(const __grid_constant_
     const int sg = (T - 1 - t) & 1;
     if (t > 0) issue_a(sg ^ 1, t - 1);
     st.wait(sg);
-    const S* ws_ = st.lane_ptr(sg, 1);
-    const S* xs_ = st.lane_ptr(sg, 2);
-    const S* us_ = st.lane_ptr(sg, 3);
-    const S* f = st.seg_ptr(sg, 4) + lane;
+    const S* xs_ = st.lane_ptr(sg, 1);
+    const S* us_ = st.lane_ptr(sg, 2);
+    const S* f = st.seg_ptr(sg, 3) + lane;
     S tau[N], q[N];
 #pragma unroll
     for (int i = 0; i < NS; ++i) tau[i] = xs_[i];
 #pragma unroll
     for (int a = 0; a < NC; ++a) tau[NS + a] = us_[a];
+    rhs(sg, 0, q);
 #pragma unroll
-    for (int i = 0; i < N; ++i) q[i] = -ws_[i];
+    for (int i = 0; i < N; ++i) q[i] = -q[i];
     if (t < T - 1) {
       S Fm[NS][N];
       A::jac_at(p, tau, xnext, Fm);
@@ -436,13 +506,18 @@ __global__ void __launch_bounds__(64) adjoint_pass_kernel(const __grid_constant_
   __syncwarp();
 
   // ---------------- linear rollout (+ Richardson update)
-  if (!FINAL) {
-    st.bind(0, p.Lam + bidx(0, 0, AS::NLAM, b0, nW), chunk * AS::NLAM);
-    st.bind(1, slab(p.g, 0, N), (long long)p.B * N * sz);
+  {
+    uint32_t e[AS::kNSeg];
+    AS::elems_B(e, FINAL);
+    st.reconfigure(AS::kNSeg, e, (1u << 0) | (1u << 3) | (1u << 6));
   }
-  st.bind(5, p.kvec + bidx(0, 0, NC, b0, nW), chunk * NC);
+  bind_common();
+  if (!FINAL) st.bind(0, p.Lam + bidx(0, 0, AS::NLAM, b0, nW), chunk * AS::NLAM);
+  st.bind(3, p.fac + bidx(0, 0, NFAC, b0, nW), chunk * NFAC);   // K = leading NC*NS components
+  st.bind(6, p.kvec + bidx(0, 0, NC, b0, nW), chunk * NC);
+  const uint32_t gmask = (p.gx ? 1u << 4 : 0u) | (1u << 5);
   auto issue_f = [&](int stage, int t) {
-    st.issue_bound(stage, t, FINAL ? 0x3cu : ((t < T - 1) ? 0x3fu : 0x3eu));
+    st.issue_bound(stage, t, FINAL ? 0x4eu : (0x4eu | gmask | ((t < T - 1) ? 1u : 0u)));
   };
   S dt[N], tprev[N];
   double dmax = 0.0, wmax = 0.0;
@@ -451,16 +526,24 @@ __global__ void __launch_bounds__(64) adjoint_pass_kernel(const __grid_constant_
     const int sg = t & 1;
     if (t + 1 < T) issue_f(sg ^ 1, t + 1);
     st.wait(sg);
-    const S* xs_ = st.lane_ptr(sg, 2);
-    const S* us_ = st.lane_ptr(sg, 3);
-    const S* f = st.seg_ptr(sg, 4) + lane;
-    const S* kv = st.seg_ptr(sg, 5) + lane;
-    // previous iterate w_t (for the residual of the Richardson update): fetched now, used
-    // at the end of the step, so the global-load latency hides behind the step's arithmetic
+    const S* xs_ = st.lane_ptr(sg, 1);
+    const S* us_ = st.lane_ptr(sg, 2);
+    const S* f = st.seg_ptr(sg, 3) + lane;
+    const S* kv = st.seg_ptr(sg, 6) + lane;
+    // previous iterate w_t (only for the residual of the Richardson update): fetched now,
+    // used at the end of the step, so the global-load latency hides behind the arithmetic
     S wold[N];
-    if (!FINAL) {
+    if (!FINAL && p.want_resid) {
 #pragma unroll
-      for (int k2 = 0; k2 < N; ++k2) wold[k2] = act ? p.w[((size_t)t * p.B + b) * N + k2] : S(0);
+      for (int k2 = 0; k2 < N; ++k2) {
+        S wv = S(0);
+        if (act) {
+          if (!first) wv = p.w[((size_t)t * p.B + b) * N + k2];
+          else if (k2 < NS) wv = p.gx ? p.gx[((size_t)t * p.B + b) * NS + k2] : S(0);
+          else wv = p.gu[((size_t)t * p.B + b) * NC + (k2 - NS)];
+        }
+        wold[k2] = wv;
+      }
     }
     S tau[N];
 #pragma unroll
@@ -515,7 +598,8 @@ __global__ void __launch_bounds__(64) adjoint_pass_kernel(const __grid_constant_
       }
     } else {
       const S* Ls = st.seg_ptr(sg, 0) + lane;     // packed Lam_t, lane-interleaved
-      const S* gs = st.lane_ptr(sg, 1);
+      const S* gxs = st.lane_ptr(sg, 4);
+      const S* gus = st.lane_ptr(sg, 5);
       const size_t tb = (size_t)t * p.B + b;
       using LP = LamPack<S, DYN>;
       static_for<0, N>([&](auto K2) {
@@ -530,24 +614,29 @@ __global__ void __launch_bounds__(64) adjoint_pass_kernel(const __grid_constant_
             }
           });
         }
-        const S wn = gs[k2] - acc;
+        const S gk = k2 < NS ? (p.gx ? gxs[k2 < NS ? k2 : 0] : S(0)) : gus[k2 < NS ? 0 : k2 - NS];
+        const S wn = gk - acc;
         if (act) {
-          const S wo = wold[k2];
-          dmax = fmax(dmax, fabs((double)wn - (double)wo));
-          wmax = fmax(wmax, fabs((double)wn));
+          if (p.want_resid) {
+            const S wo = wold[k2];
+            dmax = fmax(dmax, fabs((double)wn - (double)wo));
+            wmax = fmax(wmax, fabs((double)wn));
+          }
           p.w[tb * N + k2] = wn;
         }
       });
     }
   }
   if (!FINAL) {
-    for (int o = 16; o > 0; o >>= 1) {
-      dmax = fmax(dmax, __shfl_xor_sync(kFull, dmax, o));
-      wmax = fmax(wmax, __shfl_xor_sync(kFull, wmax, o));
-    }
-    if (lane == 0) {
-      atomicMax(&p.resid[0], dbits(dmax));
-      atomicMax(&p.resid[1], dbits(wmax));
+    if (p.want_resid) {
+      for (int o = 16; o > 0; o >>= 1) {
+        dmax = fmax(dmax, __shfl_xor_sync(kFull, dmax, o));
+        wmax = fmax(wmax, __shfl_xor_sync(kFull, wmax, o));
+      }
+      if (lane == 0) {
+        atomicMax(&p.resid[0], dbits(dmax));
+        atomicMax(&p.resid[1], dbits(wmax));
+      }
     }
     return;
   }
@@ -558,10 +647,27 @@ __global__ void __launch_bounds__(64) adjoint_pass_kernel(const __grid_constant_
   __threadfence();
   asm volatile("fence.proxy.async;" ::: "memory");
   __syncwarp();
-  st.bind(1, slab(p.w, 0, N), (long long)p.B * N * sz);
-  st.bind(5, p.dtau + bidx(0, 0, N, b0, nW), chunk * N);
-  auto issue_b = [&](int stage, int t) { st.issue_bound(stage, t, 0x2fu); };
-  const bool bulk_out = (nvalid == kWarp) && ((((size_t)N * N * sizeof(S) * kWarp) & 15) == 0) &&
+  const bool packedC = p.Cpk && p.cpk_state && !p.C_bcast &&
+                       *reinterpret_cast<const volatile uint32_t*>(p.cpk_state) == 1u;
+  {
+    uint32_t e[AS::kNSeg];
+    AS::elems_C(e, packedC);
+    st.reconfigure(AS::kNSeg, e, (1u << 3) | (packedC ? 1u : 0u), p.C_bcast ? 1u : 0u);
+  }
+  bind_common();
+  if (packedC)
+    st.bind(0, p.Cpk + bidx(0, 0, AS::NP, b0, nW), chunk * AS::NP);
+  else
+    st.bind(0, cost_src<S>(p.C, p.C_bcast, 0, p.B, b0, N * N),
+            p.C_bcast == 0 ? (long long)p.B * N * N * sz : (p.C_bcast == 1 ? (long long)N * N * sz : 0));
+  st.bind(3, p.dtau + bidx(0, 0, N, b0, nW), chunk * N);
+  st.bind(7, slab(p.w, N), (long long)p.B * N * sz);
+  auto issue_b = [&](int stage, int t) {
+    st.issue_bound(stage, t, 0xfu | (first ? rmask : (1u << 7)));
+  };
+  constexpr bool reduce = REDUCE;
+  const bool bulk_out = !reduce && (nvalid == kWarp) &&
+                        ((((size_t)N * N * sizeof(S) * kWarp) & 15) == 0) &&
                         ((((size_t)N * sizeof(S) * kWarp) & 15) == 0) &&
                         (p.C_bcast == 0 || p.c_bcast == 0);
   const int gwarp = b0 / kWarp;
@@ -570,39 +676,60 @@ __global__ void __launch_bounds__(64) adjoint_pass_kernel(const __grid_constant_
     for (int o = 16; o > 0; o >>= 1) v = v + __shfl_xor_sync(kFull, v, o);
     return v;
   };
-  S accC[N][N], accc[N];   // mode-2 accumulators (sum over t of this lane's contributions)
+  // mode-2 accumulators (sum over t of this lane's contributions); none in REDUCE mode
+  S accC[REDUCE ? 1 : N][REDUCE ? 1 : N], accc[N];
+  S redq[N];               // reduce_tile: sum over t of diag(dC_t)  (dc sums go to accc)
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     accc[i] = S(0);
-#pragma unroll
-    for (int j = 0; j < N; ++j) accC[i][j] = S(0);
+    redq[i] = S(0);
   }
-  st.set_shared(p.C_bcast ? 1u : 0u);   // segment 0 now carries C
-  st.bind(0, cost_src<S>(p.C, p.C_bcast, 0, p.B, b0, N * N),
-          p.C_bcast == 0 ? (long long)p.B * N * N * sz : (p.C_bcast == 1 ? (long long)N * N * sz : 0));
+  if constexpr (!REDUCE) {
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int j = 0; j < N; ++j) accC[i][j] = S(0);
+  }
   S dlam[NS];
   issue_b(0, T - 1);
   for (int t = T - 1; t >= 0; --t) {
     const int sg = (T - 1 - t) & 1;
     if (t > 0) issue_b(sg ^ 1, t - 1);
     st.wait(sg);
-    const S* Cs = st.lane_ptr(sg, 0);
-    const S* ws_ = st.lane_ptr(sg, 1);
-    const S* xs_ = st.lane_ptr(sg, 2);
-    const S* us_ = st.lane_ptr(sg, 3);
-    const S* ds_ = st.seg_ptr(sg, 5) + lane;
-    S tt[N], dtv[N];
+    const S* Cs = packedC ? st.seg_ptr(sg, 0) + lane : st.lane_ptr(sg, 0);
+    const S* xs_ = st.lane_ptr(sg, 1);
+    const S* us_ = st.lane_ptr(sg, 2);
+    const S* ds_ = st.seg_ptr(sg, 3) + lane;
+    S tt[N], dtv[N], rv[N];
 #pragma unroll
     for (int i = 0; i < NS; ++i) tt[i] = xs_[i];
 #pragma unroll
     for (int a = 0; a < NC; ++a) tt[NS + a] = us_[a];
 #pragma unroll
     for (int i = 0; i < N; ++i) dtv[i] = ds_[i * kWarp];
+    rhs(sg, 7, rv);
     const size_t tb = (size_t)t * p.B + b;
-    if (t < T - 1 && p.df && act) {
+    if (t < T - 1) {
+      if (p.df_blk) {
+        S* o = p.df_blk + bidx(t, 0, NS, bw, nW);
 #pragma unroll
-      for (int i = 0; i < NS; ++i) p.df[tb * NS + i] = -dlam[i];
+        for (int i = 0; i < NS; ++i) o[i * kWarp] = -dlam[i];
+      } else if (p.df && act) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) p.df[tb * NS + i] = -dlam[i];
+      }
     }
+    if constexpr (reduce) {
+      // gradient of the tiled diagonal cost (il_env.py:159-162): only diag(dC) and dc survive
+      // the adjoint of the tiling -- accumulated here instead of writing dC, dc out
+      if (act) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          redq[i] = redq[i] + S(-0.5) * (dtv[i] * tt[i] + tt[i] * dtv[i]);
+          accc[i] = accc[i] + (-dtv[i]);
+        }
+      }
+    } else {
     // dense outputs go through shared memory, one bulk store per warp slab
     if (bulk_out) {
       bulk_wait_read0();
@@ -663,15 +790,23 @@ __global__ void __launch_bounds__(64) adjoint_pass_kernel(const __grid_constant_
         bulk_commit();
       }
     }
+    }
     S nd[NS];
 #pragma unroll
     for (int i = 0; i < NS; ++i) {
       S d1 = S(0), d2 = S(0);
+      if (packedC) {
 #pragma unroll
-      for (int j = 0; j < NS; ++j) d1 = fmaS<S>(Cs[i * N + j], dtv[j], d1);
+        for (int j = 0; j < NS; ++j) d1 = fmaS<S>(Cs[pk_idx<N>(i, j) * kWarp], dtv[j], d1);
 #pragma unroll
-      for (int a = 0; a < NC; ++a) d2 = fmaS<S>(Cs[i * N + NS + a], dtv[NS + a], d2);
-      nd[i] = (d1 + d2) - ws_[i];
+        for (int a = 0; a < NC; ++a) d2 = fmaS<S>(Cs[pk_idx<N>(i, NS + a) * kWarp], dtv[NS + a], d2);
+      } else {
+#pragma unroll
+        for (int j = 0; j < NS; ++j) d1 = fmaS<S>(Cs[i * N + j], dtv[j], d1);
+#pragma unroll
+        for (int a = 0; a < NC; ++a) d2 = fmaS<S>(Cs[i * N + NS + a], dtv[NS + a], d2);
+      }
+      nd[i] = (d1 + d2) - rv[i];
     }
     if (t < T - 1) {
       S Fm[NS][N];
@@ -691,6 +826,20 @@ __global__ void __launch_bounds__(64) adjoint_pass_kernel(const __grid_constant_
     }
   }
   if (bulk_out) bulk_wait0();
+  if constexpr (reduce) {
+    // red_out[n_warps][2N]: per-warp partial sums, summed over the warp axis by the caller
+    // (fixed order: deterministic)
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const S rq = warp_sum(redq[i]);
+      const S rc = warp_sum(accc[i]);
+      if (lane == 0) {
+        p.red_out[(size_t)gwarp * (2 * N) + i] = rq;
+        p.red_out[(size_t)gwarp * (2 * N) + N + i] = rc;
+      }
+    }
+    return;
+  } else {
   if (p.dC && p.C_bcast == 2) {
 #pragma unroll
     for (int i = 0; i < N; ++i)
@@ -706,6 +855,7 @@ __global__ void __launch_bounds__(64) adjoint_pass_kernel(const __grid_constant_
       const S r = warp_sum(accc[i]);
       if (lane == 0) p.dc[(size_t)gwarp * N + i] = r;
     }
+  }
   }
 }
 

@@ -173,6 +173,8 @@ static IterParams<Scalar> make_params(const DilqrSolve* s, int role = 1) {
     p.traj_cur = reinterpret_cast<const S*>(ws + w.traj[cur]);
     p.traj_new = reinterpret_cast<S*>(ws + w.traj[cur ^ 1]);
     p.traj_best = reinterpret_cast<S*>(ws + w.best);
+    p.traj_buf[0] = reinterpret_cast<S*>(ws + w.traj[0]);
+    p.traj_buf[1] = reinterpret_cast<S*>(ws + w.traj[1]);
   }
   p.Kk = reinterpret_cast<S*>(ws + w.Kk);
   p.cost_cur = reinterpret_cast<S*>(ws + w.cost_cur);
@@ -318,6 +320,43 @@ static int launch_iterate(const DilqrSolve* s, cudaStream_t st) {
   return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
 }
 
+// gains of the final no-op LQR pass + costates at the solution (ilqr_gains_kernel)
+template <int NS, int NC, int DYN>
+static int launch_gains(const DilqrSolve* s, void* lam_blk, cudaStream_t st) {
+  using S = Scalar;
+  using G = Geometry<S, NS, NC, DYN>;
+  if constexpr (!G::STAGED || DYN == DYN_LINDX || DYN == DYN_NN) {
+    return DILQR_EUNSUPPORTED;
+  } else {
+    if (!s->x_out || !s->u_out) return DILQR_EINVAL;
+    if (s->u_zero_I || (s->bounds_kind && !s->solo && NC > 1)) return DILQR_EUNSUPPORTED;
+    IterParams<S> p = make_params(s);
+    p.gains_only = 1;
+    p.lockstep = 0;
+    p.lam_blk = static_cast<S*>(lam_blk);
+    using IK = typename G::IK;
+    size_t per = IK::smem_per_warp(true);
+    int wpb = (int)((112 * 1024) / per);
+    if (wpb > 4) wpb = 4;
+    if (wpb < 1) wpb = 1;
+    const int warps = (p.B + kWarp - 1) / kWarp;
+    const int blocks = (warps + wpb - 1) / wpb;
+    const size_t smem = per * wpb;
+    auto kern = ilqr_gains_kernel<S, NS, NC, DYN, G::STAGED>;
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // pnqp trace guess: whatever the workspace holds -- the verified trace of the solve's
+    // last iteration (the best predictor of this sweep, which runs at the iterate that
+    // iteration produced), or the correction a previous call of this function left
+    if (p.bounds_kind && !p.solo)
+      cudaMemsetAsync(p.votes, 0, (size_t)p.T * kPnqpMaxIter * sizeof(uint32_t), st);
+    kern<<<blocks, wpb * kWarp, smem, st>>>(p);
+    trace_verify_kernel<<<1, 256, 0, st>>>(p.guess, p.votes, p.T, p.bounds_kind != 0, p.solo,
+                                           s->status, 0, nullptr);
+    return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
+  }
+}
+
 template <int NS, int NC>
 static int launch_commit(const DilqrSolve* s, cudaStream_t st) {
   using S = Scalar;
@@ -400,6 +439,18 @@ int DILQR_SUFFIX(supported)(int n_state, int n_ctrl, int dynamics) {
 size_t DILQR_SUFFIX(workspace_bytes)(const DilqrSolve* s) {
   return ws_layout(s, sizeof(Scalar)).total;
 }
+int DILQR_SUFFIX(workspace_view)(const DilqrSolve* s, DilqrWsView* v) {
+  if (!s->workspace) return DILQR_EINVAL;
+  const WsLayout w = ws_layout(s, sizeof(Scalar));
+  if (s->workspace_bytes < w.total) return DILQR_EWORKSPACE;
+  char* ws = static_cast<char*>(s->workspace);
+  v->Kk = ws + w.Kk;
+  v->Cpk = ws + w.Cpk;
+  v->cpk_state = reinterpret_cast<const uint32_t*>(ws + w.cpk_state);
+  v->n_warps = w.Bp / 32;
+  v->reserved = 0;
+  return DILQR_OK;
+}
 
 #endif
 
@@ -422,6 +473,16 @@ int DILQR_SUFFIX(mpc_finish)(const DilqrSolve* s, void* stream) {
   int e = check(s, true);
   if (e) return e;
   return dispatch(s, OP_FINISH, static_cast<cudaStream_t>(stream));
+}
+int DILQR_SUFFIX(mpc_gains)(const DilqrSolve* s, void* lam_blk, void* stream) {
+  int e = check(s, true);
+  if (e) return e;
+#define X(NS_, NC_, DYN_)                                                       \
+  if (s->n_state == NS_ && s->n_ctrl == NC_ && s->dynamics == DYN_)             \
+    return launch_gains<NS_, NC_, DYN_>(s, lam_blk, static_cast<cudaStream_t>(stream));
+  DILQR_CONFIGS(X)
+#undef X
+  return DILQR_EUNSUPPORTED;
 }
 
 int DILQR_SUFFIX(kkt_grads)(const DilqrKkt* k, void* stream) {
@@ -562,7 +623,15 @@ static int adj_run(const DilqrAdjoint* a, int what, cudaStream_t st) {
   p.C = static_cast<const S*>(a->C);
   p.x = static_cast<const S*>(a->x);
   p.u = static_cast<const S*>(a->u);
-  p.g = static_cast<const S*>(a->g);
+  p.gx = static_cast<const S*>(a->gx);
+  p.gu = static_cast<const S*>(a->gu);
+  p.Cpk = static_cast<const S*>(a->Cpk);
+  p.cpk_state = a->cpk_state;
+  p.first = a->first_pass;
+  p.want_resid = a->want_resid;
+  p.reduce_tile = (what == 2) ? a->reduce_tile : 0;
+  p.red_out = static_cast<S*>(a->red_out);
+  p.df_blk = static_cast<S*>(a->df_blk);
   p.Lam = static_cast<const S*>(a->Lam);
   p.w = static_cast<S*>(a->w);
   p.fac = reinterpret_cast<S*>(ws + w.fac);
@@ -589,12 +658,13 @@ static int adj_run(const DilqrAdjoint* a, int what, cudaStream_t st) {
     const size_t smem = AdjStage<S, DYN>::smem_per_warp(false) * wpb;
     auto kern = adjoint_pass_kernel<S, DYN, false>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaMemsetAsync(p.resid, 0, 16, st);   // max|dw|, max|w|; the reject counter accumulates
+    if (p.want_resid) cudaMemsetAsync(p.resid, 0, 16, st);   // max|dw|, max|w|; the reject counter accumulates
     kern<<<(warps + wpb - 1) / wpb, wpb * kWarp, smem, st>>>(p);
   } else {
     const int wpb = 1;
     const size_t smem = AdjStage<S, DYN>::smem_per_warp(true) * wpb;
-    auto kern = adjoint_pass_kernel<S, DYN, true>;
+    auto kern = p.reduce_tile ? adjoint_pass_kernel<S, DYN, true, true>
+                              : adjoint_pass_kernel<S, DYN, true, false>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<(warps + wpb - 1) / wpb, wpb * kWarp, smem, st>>>(p);
   }
@@ -604,12 +674,15 @@ static int adj_run(const DilqrAdjoint* a, int what, cudaStream_t st) {
 static int adj_check(const DilqrAdjoint* a, int what) {
   if (!a || a->T < 2 || a->n_batch <= 0 || !a->C || !a->x || !a->u || !a->resid)
     return DILQR_EINVAL;
-  if (what != 0 && !a->w) return DILQR_EINVAL;     // the factorisation needs no right-hand side
-  if (what == 1 && (!a->g || !a->Lam)) return DILQR_EINVAL;
+  if (what != 0 && !a->gu) return DILQR_EINVAL;    // the factorisation needs no right-hand side
+  if (what == 1 && (!a->w || !a->Lam)) return DILQR_EINVAL;
+  if (what == 2 && !a->first_pass && !a->w) return DILQR_EINVAL;
+  if (what == 2 && a->reduce_tile && (!a->red_out || a->C_bcast || a->c_bcast)) return DILQR_EINVAL;
   if (a->bounds_kind != DILQR_BOUNDS_NONE && a->bounds_kind != DILQR_BOUNDS_SCALAR)
     return DILQR_EINVAL;
   auto mis = [](const void* p) { return p && (reinterpret_cast<uintptr_t>(p) & 15u); };
-  if (mis(a->C) || mis(a->g) || mis(a->Lam) || mis(a->dC) || mis(a->dc) || mis(a->workspace))
+  if (mis(a->C) || mis(a->gx) || mis(a->gu) || mis(a->w) || mis(a->Lam) || mis(a->dC) ||
+      mis(a->dc) || mis(a->workspace) || mis(a->Cpk))
     return DILQR_EALIGN;
   return DILQR_OK;
 }
@@ -618,6 +691,13 @@ size_t DILQR_SUFFIX(adjoint_workspace_bytes)(const DilqrAdjoint* a) {
   if (!a) return 0;
   if (a->dynamics == DYN_PENDULUM) return adj_layout<DYN_PENDULUM>(a).total;
   if (a->dynamics == DYN_CARTPOLE) return adj_layout<DYN_CARTPOLE>(a).total;
+  return 0;
+}
+
+size_t DILQR_SUFFIX(adjoint_dtau_offset)(const DilqrAdjoint* a) {
+  if (!a) return 0;
+  if (a->dynamics == DYN_PENDULUM) return adj_layout<DYN_PENDULUM>(a).dtau;
+  if (a->dynamics == DYN_CARTPOLE) return adj_layout<DYN_CARTPOLE>(a).dtau;
   return 0;
 }
 
@@ -666,6 +746,60 @@ int DILQR_SUFFIX(costate_tables)(int dynamics, const double* dp, int T, int B, c
   if (dynamics == DYN_PENDULUM) return launch_costate<DYN_PENDULUM>(dp, T, B, C, c, x, u, lam, Lam, Cb, cb, packed, st);
   if (dynamics == DYN_CARTPOLE) return launch_costate<DYN_CARTPOLE>(dp, T, B, C, c, x, u, lam, Lam, Cb, cb, packed, st);
   if (dynamics == DYN_ROCKET) return launch_costate<DYN_ROCKET>(dp, T, B, C, c, x, u, lam, Lam, Cb, cb, packed, st);
+  return DILQR_EUNSUPPORTED;
+}
+
+template <int DYN>
+static int launch_lam_tables(const double* dp, int T, int B, const void* x, const void* u,
+                             const void* lam_blk, void* Lam, cudaStream_t st) {
+  using S = Scalar;
+  DynParams<S> P;
+  memset(&P, 0, sizeof(P));
+  for (int i = 0; i < 8; ++i) P.p[i] = (S)dp[i];
+  if (T < 2) return DILQR_OK;
+  const int Bp = (B + kWarp - 1) / kWarp * kWarp;
+  dim3 grid((Bp + 127) / 128, T - 1);
+  lam_tables_kernel<S, DYN><<<grid, 128, 0, st>>>(P, T, B, static_cast<const S*>(x),
+                                                   static_cast<const S*>(u),
+                                                   static_cast<const S*>(lam_blk),
+                                                   static_cast<S*>(Lam));
+  return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
+}
+
+int DILQR_SUFFIX(lam_tables)(int dynamics, const double* dp, int T, int B, const void* x,
+                             const void* u, const void* lam_blk, void* Lam, void* stream) {
+  if (!dp || !x || !u || !lam_blk || !Lam || T <= 0 || B <= 0) return DILQR_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dynamics == DYN_PENDULUM) return launch_lam_tables<DYN_PENDULUM>(dp, T, B, x, u, lam_blk, Lam, st);
+  if (dynamics == DYN_CARTPOLE) return launch_lam_tables<DYN_CARTPOLE>(dp, T, B, x, u, lam_blk, Lam, st);
+  if (dynamics == DYN_ROCKET) return launch_lam_tables<DYN_ROCKET>(dp, T, B, x, u, lam_blk, Lam, st);
+  return DILQR_EUNSUPPORTED;
+}
+
+template <int DYN>
+static int launch_sens_blocked(const double* dp, int T, int B, const void* x, const void* u,
+                               const void* Kk, const void* lam, const void* dtau, const void* df,
+                               void* dtheta, cudaStream_t st) {
+  using S = Scalar;
+  DynParams<S> P;
+  memset(&P, 0, sizeof(P));
+  for (int i = 0; i < 8; ++i) P.p[i] = (S)dp[i];
+  const int Bp = (B + kWarp - 1) / kWarp * kWarp;
+  sens_theta_kernel<S, DYN, true><<<(Bp + 63) / 64, 64, 0, st>>>(
+      P, T, B, static_cast<const S*>(x), static_cast<const S*>(u), static_cast<const S*>(Kk),
+      static_cast<const S*>(lam), static_cast<const S*>(dtau), nullptr,
+      static_cast<const S*>(df), static_cast<S*>(dtheta));
+  return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
+}
+
+int DILQR_SUFFIX(sens_theta_blocked)(int dynamics, const double* dp, int T, int B, const void* x,
+                                     const void* u, const void* Kk, const void* lam,
+                                     const void* dtau, const void* df, void* dtheta, void* stream) {
+  if (!dp || !x || !u || !Kk || !lam || !dtau || !df || !dtheta || T <= 1 || B <= 0)
+    return DILQR_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dynamics == DYN_PENDULUM) return launch_sens_blocked<DYN_PENDULUM>(dp, T, B, x, u, Kk, lam, dtau, df, dtheta, st);
+  if (dynamics == DYN_CARTPOLE) return launch_sens_blocked<DYN_CARTPOLE>(dp, T, B, x, u, Kk, lam, dtau, df, dtheta, st);
   return DILQR_EUNSUPPORTED;
 }
 

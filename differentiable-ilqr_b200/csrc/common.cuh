@@ -116,7 +116,6 @@ DILQR_DEVICE void prefetch_l1(const void* p) {
 // to a lane-strided copy.
 // ---------------------------------------------------------------------------
 constexpr int kStages = 2;
-constexpr int kMaxSeg = 6;
 
 // rarely taken path (tail warps / unaligned slabs): kept out of line so the hot
 // sweeps stay small
@@ -125,7 +124,7 @@ __device__ __noinline__ void lane_copy(S* dst, const S* src, int cnt, int lane) 
   for (int e = lane; e < cnt; e += kWarp) dst[e] = __ldg(src + e);
 }
 
-template <class S>
+template <class S, int kMaxSeg = 6>
 struct WarpStager {
   char* base;        // this warp's staging area (kStages * stage_bytes)
   uint64_t* bar;     // kStages barriers
@@ -192,6 +191,31 @@ struct WarpStager {
       mbar_fence_init();
     }
     __syncwarp();
+  }
+
+  // New segment table for the next sweep of the same kernel (all copies of the previous
+  // sweep have been waited for): offsets / sizes are recomputed, barriers and their
+  // parity are kept, bound sources are cleared.
+  DILQR_DEVICE void reconfigure(int nseg, const uint32_t* elems, uint32_t full_mask = 0,
+                                uint32_t shared_mask = 0) {
+    __syncwarp();
+    seg_full = full_mask;
+    seg_shared = shared_mask;
+    bnd_fast = 0;
+    uint32_t off = 0;
+    seg_sized = 0;
+#pragma unroll
+    for (int i = 0; i < kMaxSeg; ++i) {
+      bnd_base[i] = nullptr;
+      bnd_stride[i] = 0;
+      seg_off[i] = off;
+      seg_elems[i] = i < nseg ? elems[i] : 0;
+      seg_nbytes[i] = seg_bytes(i);
+      if (seg_nbytes[i] && !(seg_nbytes[i] & 15u)) seg_sized |= 1u << i;
+      uint32_t full = seg_elems[i] * kWarp * sizeof(S);
+      off += (full + 15u) & ~15u;
+    }
+    stage_bytes = off;
   }
 
   // change which segments are shared blocks (a stage reused for different tensors)

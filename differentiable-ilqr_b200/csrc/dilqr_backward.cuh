@@ -181,6 +181,61 @@ static_for<0, N>([&](auto KK) {
 }
 
 // ---------------------------------------------------------------------------
+// Contracted second-order tables alone: Lam_t (packed, warp-blocked) from tau*_t and
+// lam_{t+1} (blocked [T][B/32][NS][32], written by the gains sweep).  No recursion in t is
+// left once the costates are known, so this is ONE THREAD PER (t, problem): 50x the
+// parallelism of the costate sweep, throughput- instead of latency-bound.
+// ---------------------------------------------------------------------------
+template <class S, int DYN>
+__global__ void __launch_bounds__(128)
+lam_tables_kernel(DynParams<S> P, int T, int B, const S* __restrict__ x, const S* __restrict__ u,
+                  const S* __restrict__ lam_blk, S* __restrict__ Lam_out) {
+  using D = Dyn<S, DYN>;
+  using TB = EnvTables<S, DYN>;
+  using LP = LamPack<S, DYN>;
+  constexpr int NS = D::NS, NC = D::NC, N = D::N, NTH = TB::NTH;
+  const int bw = blockIdx.x * blockDim.x + threadIdx.x;   // own (padded) column
+  const int t = blockIdx.y;
+  const int nW = (B + kWarp - 1) / kWarp;
+  if (bw >= nW * kWarp || t >= T - 1) return;
+  const int b = bw < B ? bw : B - 1;
+  const size_t tb = (size_t)t * B + b;
+  S tau[N], lam[NS];
+#pragma unroll
+  for (int i = 0; i < NS; ++i) tau[i] = __ldg(x + tb * NS + i);
+#pragma unroll
+  for (int a = 0; a < NC; ++a) tau[NS + a] = __ldg(u + tb * NC + a);
+  {
+    const S* ls = lam_blk + bidx(t + 1, 0, NS, bw, nW);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) lam[i] = ls[i * kWarp];
+  }
+  S Dm[NS][N], Dth[NS][N][NTH], Dx[NS][N][NS], Du[NS][N][NC], xth[NS][NTH], xx[NS][NS], xu[NS][NC];
+  TB::eval(P, tau, &tau[NS], Dm, Dth, Dx, Du, xth, xx, xu);
+  S* Lo = Lam_out + bidx(t, 0, LP::NLAM, bw, nW);
+  static_for<0, N>([&](auto KK) {
+    constexpr int k = decltype(KK)::value;
+    static_for<0, N>([&](auto JJ) {
+      constexpr int j = decltype(JJ)::value;
+      if constexpr (LP::nz(k, j)) {
+        S acc = S(0);
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+          if (k < NS) {
+            if (TB::nz_Dx(i, j, k < NS ? k : 0)) acc = fmaS<S>(lam[i], Dx[i][j][k < NS ? k : 0], acc);
+          } else {
+            if (TB::nz_Du(i, j, k < NS ? 0 : k - NS))
+              acc = fmaS<S>(lam[i], Du[i][j][k < NS ? 0 : k - NS], acc);
+          }
+        }
+        constexpr int e = LP::idx(k, j);
+        Lo[e * kWarp] = acc;
+      }
+    });
+  });
+}
+
+// ---------------------------------------------------------------------------
 // Richardson update  w_t = g_t - Lam_t dtau_t  (t < T-1),  w_{T-1} = g_{T-1};
 // also writes -w (the linear cost of the next adjoint solve) and reduces
 // max|w_new - w_old| and max|w_new| into resid[0], resid[1] (ordered-uint max).
@@ -237,7 +292,11 @@ __global__ void richardson_update_kernel(int T, int B, const S* __restrict__ g,
 //   lam    [T,B,ns]     primal costates           dx,du: adjoint solution (r = w)
 //   df     [T-1,B,ns]   = -dlam_{t+1}             dtheta [B,nth]
 // ---------------------------------------------------------------------------
-template <class S, int DYN>
+// BLK: K, lam, dtau, df come in the warp-blocked workspace layouts the fused backward keeps
+// them in (Kk[T][B/32][NC*NS+NC][32] of the gains sweep, lam[T][B/32][NS][32],
+// dtau[T][B/32][N][32] and df[T-1][B/32][NS][32] of the final adjoint pass): coalesced reads,
+// and none of them is ever gathered into the API layout.
+template <class S, int DYN, bool BLK = false>
 __global__ void __launch_bounds__(128)
 sens_theta_kernel(DynParams<S> P, int T, int B, const S* __restrict__ x,
                   const S* __restrict__ u, const S* __restrict__ K, const S* __restrict__ lam,
@@ -246,8 +305,24 @@ sens_theta_kernel(DynParams<S> P, int T, int B, const S* __restrict__ x,
   using D = Dyn<S, DYN>;
   using TB = EnvTables<S, DYN>;
   constexpr int NS = D::NS, NC = D::NC, N = D::N, NTH = TB::NTH;
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
+  constexpr int NK = NC * NS + NC;
+  const int bw = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nW = (B + kWarp - 1) / kWarp;
+  if (BLK ? (bw >= nW * kWarp) : (bw >= B)) return;
+  const int b = bw < B ? bw : B - 1;
+  auto ldK = [&](int t, int e) -> S {
+    return BLK ? K[bidx(t, e, NK, bw, nW)] : K[((size_t)t * B + b) * (NC * NS) + e];
+  };
+  auto ldlam = [&](int t, int i) -> S {
+    return BLK ? lam[bidx(t, i, NS, bw, nW)] : lam[((size_t)t * B + b) * NS + i];
+  };
+  auto lddtau = [&](int t, int i) -> S {
+    if (BLK) return dx[bidx(t, i, N, bw, nW)];
+    return i < NS ? dx[((size_t)t * B + b) * NS + i] : du[((size_t)t * B + b) * NC + (i - NS)];
+  };
+  auto lddf = [&](int t, int i) -> S {
+    return BLK ? df[bidx(t, i, NS, bw, nW)] : df[((size_t)t * B + b) * NS + i];
+  };
   S G[NS][NTH], Gp[NS][NTH], Dprev[NS][N], Kp[NC][NS];
   S acc[NTH];
 #pragma unroll
@@ -261,35 +336,30 @@ sens_theta_kernel(DynParams<S> P, int T, int B, const S* __restrict__ x,
     if (t + 1 < T) {   // next step's operands on their way while this step's tables are evaluated
       const size_t nb = tb + B;
       prefetch_l1(x + nb * NS);
-      prefetch_l1(dx + nb * NS);
       prefetch_l1(u + nb * NC);
-      prefetch_l1(du + nb * NC);
-      prefetch_l1(lam + nb * NS);
-      prefetch_l1(df + tb * NS);
-      if (t + 2 < T) prefetch_l1(K + ((size_t)(T - 2 - t) * B + b) * (NC * NS));
+      if (!BLK) {
+        prefetch_l1(dx + nb * NS);
+        prefetch_l1(du + nb * NC);
+        prefetch_l1(lam + nb * NS);
+        prefetch_l1(df + tb * NS);
+        if (t + 2 < T) prefetch_l1(K + ((size_t)(T - 2 - t) * B + b) * (NC * NS));
+      }
     }
     S tau[N], dtau[N];
 #pragma unroll
-    for (int i = 0; i < NS; ++i) {
-      tau[i] = x[tb * NS + i];
-      dtau[i] = dx[tb * NS + i];
-    }
+    for (int i = 0; i < NS; ++i) tau[i] = x[tb * NS + i];
 #pragma unroll
-    for (int a = 0; a < NC; ++a) {
-      tau[NS + a] = u[tb * NC + a];
-      dtau[NS + a] = du[tb * NC + a];
-    }
+    for (int a = 0; a < NC; ++a) tau[NS + a] = u[tb * NC + a];
+#pragma unroll
+    for (int i = 0; i < N; ++i) dtau[i] = lddtau(t, i);
     S Dm[NS][N], Dth[NS][N][NTH], Dx[NS][N][NS], Du[NS][N][NC], xth[NS][NTH], xx[NS][NS],
         xu[NS][NC];
     TB::eval(P, tau, &tau[NS], Dm, Dth, Dx, Du, xth, xx, xu);
     S Kt[NC][NS];   // K_ref[t] = K_{T-1-t}
-    {
-      const size_t kb = ((size_t)(T - 1 - t) * B + b) * (NC * NS);
 #pragma unroll
-      for (int a = 0; a < NC; ++a)
+    for (int a = 0; a < NC; ++a)
 #pragma unroll
-        for (int j = 0; j < NS; ++j) Kt[a][j] = K[kb + a * NS + j];
-    }
+      for (int j = 0; j < NS; ++j) Kt[a][j] = ldK(T - 1 - t, a * NS + j);
     if (t > 0) {
       // G_t = xth + (xx + xu K_ref[t-1]) G_{t-1}                 (cartpole.py:768)
       S A[NS][NS];
@@ -330,10 +400,9 @@ sens_theta_kernel(DynParams<S> P, int T, int B, const S* __restrict__ x,
           Z[NS + a][q] = s;
         }
       }
-      const size_t pb = (size_t)(t - 1) * B + b;
 #pragma unroll
       for (int i = 0; i < NS; ++i) {
-        const S dfi = df[pb * NS + i];
+        const S dfi = lddf(t - 1, i);
 #pragma unroll
         for (int q = 0; q < NTH; ++q) {
           S s = S(0);
@@ -347,10 +416,9 @@ sens_theta_kernel(DynParams<S> P, int T, int B, const S* __restrict__ x,
     if (t < T - 1) {
       // sum_ij W[i][j] gradD_t[i][j][:],  W = -lam_{t+1} dtau_t'
       // gradD = Dth + (Dx + Du K_ref[t]) G_t                      (cartpole.py:773-775)
-      const size_t nb = (size_t)(t + 1) * B + b;
       S lm[NS];
 #pragma unroll
-      for (int i = 0; i < NS; ++i) lm[i] = lam[nb * NS + i];
+      for (int i = 0; i < NS; ++i) lm[i] = ldlam(t + 1, i);
       S om[NS];   // om[k] = sum_ij W_ij (Dx[i][j][k] + sum_a Du[i][j][a] K[a][k])
 #pragma unroll
       for (int k = 0; k < NS; ++k) om[k] = S(0);
@@ -389,8 +457,10 @@ sens_theta_kernel(DynParams<S> P, int T, int B, const S* __restrict__ x,
 #pragma unroll
       for (int j = 0; j < NS; ++j) Kp[a][j] = Kt[a][j];
   }
+  if (bw < B) {
 #pragma unroll
-  for (int q = 0; q < NTH; ++q) dtheta[(size_t)b * NTH + q] = acc[q];
+    for (int q = 0; q < NTH; ++q) dtheta[(size_t)b * NTH + q] = acc[q];
+  }
 }
 
 }  // namespace dilqr

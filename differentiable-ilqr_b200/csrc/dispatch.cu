@@ -11,6 +11,7 @@ namespace dilqr {
   int mpc_iterate_##sfx(const DilqrSolve*, void*);                                        \
   int mpc_commit_##sfx(const DilqrSolve*, void*);                                         \
   int mpc_finish_##sfx(const DilqrSolve*, void*);                                         \
+  int mpc_gains_##sfx(const DilqrSolve*, void*, void*);                                   \
   int kkt_grads_##sfx(const DilqrKkt*, void*);                                            \
   int richardson_update_##sfx(int, int, int, int, const void*, const void*, const void*,   \
                               const void*, void*, void*, void*, void*);
@@ -29,6 +30,12 @@ namespace dilqr {
   int pnqp_##sfx(int, int, const void*, const void*, const void*, const void*, const void*, \
                  void*, void*, int32_t*, void*, uint32_t*, int, DilqrStatus*, void*);     \
   size_t adjoint_workspace_bytes_##sfx(const DilqrAdjoint*);                              \
+  size_t adjoint_dtau_offset_##sfx(const DilqrAdjoint*);                                  \
+  int workspace_view_##sfx(const DilqrSolve*, DilqrWsView*);                              \
+  int lam_tables_##sfx(int, const double*, int, int, const void*, const void*, const void*, \
+                       void*, void*);                                                     \
+  int sens_theta_blocked_##sfx(int, const double*, int, int, const void*, const void*,    \
+                               const void*, const void*, const void*, const void*, void*, void*); \
   int adjoint_run_##sfx(const DilqrAdjoint*, int, void*);
 DECL_G(f32_g0) DECL_G(f32_g1) DECL_G(f32_g2) DECL_G(f32_g3)
 DECL_G(f64_g0) DECL_G(f64_g1) DECL_G(f64_g2) DECL_G(f64_g3)
@@ -100,6 +107,33 @@ int dilqr_mpc_commit(const DilqrSolve* s, void* st) {
 int dilqr_mpc_finish(const DilqrSolve* s, void* st) {
   if (!s) return DILQR_EINVAL;
   BY_DTYPE_GROUPS(s->dtype, mpc_finish, s, st);
+}
+int dilqr_mpc_gains(const DilqrSolve* s, void* lam_blk, void* st) {
+  if (!s) return DILQR_EINVAL;
+  BY_DTYPE_GROUPS(s->dtype, mpc_gains, s, lam_blk, st);
+}
+int dilqr_workspace_view(const DilqrSolve* s, DilqrWsView* v) {
+  if (!s || !v) return DILQR_EINVAL;
+  return ROUTE(s->dtype, dilqr::workspace_view_f32_g0(s, v), dilqr::workspace_view_f64_g0(s, v));
+}
+int dilqr_lam_tables(int dtype, int dyn, const double* dp, int T, int B, const void* x,
+                     const void* u, const void* lam_blk, void* Lam, void* st) {
+  return ROUTE(dtype, dilqr::lam_tables_f32_g0(dyn, dp, T, B, x, u, lam_blk, Lam, st),
+               dilqr::lam_tables_f64_g0(dyn, dp, T, B, x, u, lam_blk, Lam, st));
+}
+int dilqr_sens_theta_blocked(int dtype, int dyn, const double* dp, int T, int B, const void* x,
+                             const void* u, const void* Kk, const void* lam_blk,
+                             const void* dtau_blk, const void* df_blk, void* dtheta, void* st) {
+  return ROUTE(dtype,
+               dilqr::sens_theta_blocked_f32_g0(dyn, dp, T, B, x, u, Kk, lam_blk, dtau_blk, df_blk,
+                                                dtheta, st),
+               dilqr::sens_theta_blocked_f64_g0(dyn, dp, T, B, x, u, Kk, lam_blk, dtau_blk, df_blk,
+                                                dtheta, st));
+}
+size_t dilqr_adjoint_dtau_offset(const DilqrAdjoint* a) {
+  if (!a) return 0;
+  return a->dtype == DILQR_F32 ? dilqr::adjoint_dtau_offset_f32_g0(a)
+                               : dilqr::adjoint_dtau_offset_f64_g0(a);
 }
 int dilqr_kkt_grads(const DilqrKkt* k, void* st) {
   if (!k) return DILQR_EINVAL;

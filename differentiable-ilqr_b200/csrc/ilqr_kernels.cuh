@@ -72,6 +72,7 @@ struct IterParams {
   const S* traj_cur;  // [T][Bp/32][N][32]  current iterate (read)
   S* traj_new;        // [T][Bp/32][N][32]  new iterate (written)
   S* traj_best;       // [T][Bp/32][N][32]  best iterate so far
+  S* traj_buf[2];     // the two ping-pong buffers (finish picks by the device-side iteration count)
   S* Kk;              // [T][Bp/32][NC*NS+NC][32]
   int nW;             // Bp / 32
   S* dusq;            // [T][NC][B] squared control changes of the first line-search pass
@@ -98,6 +99,7 @@ struct IterParams {
   S* alpha_out;
   S* K_out;
   S* k_out;
+  S* lam_blk;   // gains-at-the-solution sweep: primal costates [T][Bp/32][NS][32] (optional)
   DynParams<S> dyn;
 };
 
@@ -365,18 +367,20 @@ struct IterKernel {
     return STAGED && p.cpk_state && !p.C_bcast && *reinterpret_cast<const volatile uint32_t*>(p.cpk_state) == 1u;
   }
 
-  static __host__ __device__ void seg_elems(uint32_t* e) {
+  // sol: the sweep runs at a given solution handed over in the API layout (x_out[T,B,ns],
+  // u_out[T,B,nc]): segments 2 / 3 carry those slabs, the workspace chunks are not staged
+  static __host__ __device__ void seg_elems(uint32_t* e, bool sol = false) {
     e[0] = N * N;
     e[1] = N;
-    e[2] = kEnv ? 0 : NS * N;
-    e[3] = kEnv ? 0 : NS;
-    e[4] = N;
-    e[5] = NK;
+    e[2] = sol ? NS : (kEnv ? 0 : NS * N);
+    e[3] = sol ? NC : (kEnv ? 0 : NS);
+    e[4] = sol ? 0 : N;
+    e[5] = sol ? 0 : NK;
   }
-  static __host__ __device__ size_t smem_per_warp() {
+  static __host__ __device__ size_t smem_per_warp(bool sol = false) {
     if (!STAGED) return 0;
     uint32_t e[kNSeg];
-    seg_elems(e);
+    seg_elems(e, sol);
     return WarpStager<S>::bytes_per_warp(kNSeg, e) + kStages * sizeof(uint64_t);
   }
 
@@ -391,13 +395,23 @@ struct IterKernel {
     const S* f;
     const S* tau;
     const S* Kk;
+    const S* xs;      // SOL sweeps: this lane's x_t[NS] / u_t[NC] of the API slabs
+    const S* us;
     int tstride;
   };
+  template <bool SOL = false>
   DILQR_DEVICE static Blk blocks(const IterParams<S>& p, const WarpStager<S>& st, int sg, int t,
                                  int b, int bw, int lane) {
     Blk k;
     k.packed = STAGED && ((st.seg_full >> 0) & 1u);
-    if (STAGED) {
+    k.xs = k.us = nullptr;
+    if (STAGED && SOL) {
+      k.C = k.packed ? st.seg_ptr(sg, 0) + lane : st.lane_ptr(sg, 0);
+      k.c = st.lane_ptr(sg, 1);
+      k.F = k.f = k.tau = k.Kk = nullptr;
+      k.xs = st.lane_ptr(sg, 2);
+      k.us = st.lane_ptr(sg, 3);
+    } else if (STAGED) {
       k.C = k.packed ? st.seg_ptr(sg, 0) + lane : st.lane_ptr(sg, 0);
       k.c = st.lane_ptr(sg, 1);
       k.F = kEnv ? nullptr : st.lane_ptr(sg, 2);
@@ -434,6 +448,7 @@ struct IterKernel {
 
   // Tell the stager where this warp's slabs / chunks of each segment live (once per
   // kernel): address of timestep 0 and the byte stride between timesteps.
+  template <bool SOL = false>
   DILQR_DEVICE static void bind_sources(WarpStager<S>& st, const IterParams<S>& p, int b0) {
     if (!STAGED) return;
     const long long sz = (long long)sizeof(S);
@@ -444,6 +459,11 @@ struct IterKernel {
               p.C_bcast == 0 ? (long long)p.B * N * N * sz : (p.C_bcast == 1 ? (long long)N * N * sz : 0));
     st.bind(1, cost_src<S>(p.c, p.c_bcast, 0, p.B, b0, N),
             p.c_bcast == 0 ? (long long)p.B * N * sz : (p.c_bcast == 1 ? (long long)N * sz : 0));
+    if (SOL) {
+      st.bind(2, p.x_out + (size_t)b0 * NS, (long long)p.B * NS * sz);
+      st.bind(3, p.u_out + (size_t)b0 * NC, (long long)p.B * NC * sz);
+      return;
+    }
     if (!kEnv) {
       st.bind(2, p.F ? p.F + (size_t)b0 * (NS * N) : nullptr, (long long)p.B * NS * N * sz);
       st.bind(3, (p.has_f && p.f) ? p.f + (size_t)b0 * NS : nullptr, (long long)p.B * NS * sz);
@@ -453,10 +473,15 @@ struct IterKernel {
   }
 
   // issue the operands of timestep t for this warp into `stage`
+  template <bool SOL = false>
   DILQR_DEVICE static void issue_t(WarpStager<S>& st, const IterParams<S>& p, int stage, int t,
                                    int b0, bool want_f, bool want_traj, bool want_K) {
     if (!STAGED) return;
     uint32_t mask = 3u;   // C, c
+    if (SOL) {
+      st.issue_bound(stage, t, mask | (1u << 2) | (1u << 3));
+      return;
+    }
     if (!kEnv && t < p.T - 1) {
       if (p.F) mask |= 1u << 2;
       if (want_f && p.has_f && p.f) mask |= 1u << 3;
@@ -471,30 +496,43 @@ struct IterKernel {
   // ======================================================================
   // b: problem index for the API tensors (clamped for padded lanes); bw: this
   // lane's own column of the (padded) workspace.
+  // SOL (gains at the solution, lqr_step_explicit.py:604-618): tau* comes from the API
+  // slabs x_out / u_out, nothing of the solver state is touched except the gains, and the
+  // primal costates lam_t = C_xx x + C_xu u + c_x + F_x' lam_{t+1} (lqr_step.py:355-369) ride
+  // along (p.lam_blk) -- they need exactly the operands this sweep has in hand.
+  template <bool SOL = false>
   DILQR_DEVICE static void backward_sweep(const IterParams<S>& p, WarpStager<S>& st, int b0,
                                           int b, int bw, bool active, int lane) {
     S V[NS][NS], v[NS];
+    S lam[SOL ? NS : 1];
     S kprev[NC];
     S xnext[NS];  // x_{t+1} of the nominal trajectory (trig reuse for env Jacobians)
     bool have_prev = false;
     const int T = p.T;
     // lazy best-iterate tracking (mpc.py:272-285): if the previous iteration made the
     // current trajectory this problem's best, park it in traj_best while it streams by.
-    const bool flush = (p.take[bw] & 1) != 0;
-    issue_t(st, p, 0, T - 1, b0, false, true, false);
+    const bool flush = !SOL && (p.take[bw] & 1) != 0;
+    issue_t<SOL>(st, p, 0, T - 1, b0, false, true, false);
     for (int t = T - 1; t >= 0; --t) {
       const int sg = (T - 1 - t) & 1;
-      if (t > 0) issue_t(st, p, sg ^ 1, t - 1, b0, false, true, false);
+      if (t > 0) issue_t<SOL>(st, p, sg ^ 1, t - 1, b0, false, true, false);
       uint4 gpre = make_uint4(0, 0, 0, 0);
       if (p.bounds_kind && !p.solo && !LOCKSTEP)
         gpre = __ldg(reinterpret_cast<const uint4*>(p.guess + (size_t)t * kPnqpMaxIter));
       if (STAGED) st.wait(sg);
-      const Blk blk = blocks(p, st, sg, t, b, bw, lane);
+      const Blk blk = blocks<SOL>(p, st, sg, t, b, bw, lane);
       const S* Cs = blk.C;
       const S* cs = blk.c;
       S tau[N];
+      if constexpr (SOL) {
 #pragma unroll
-      for (int i = 0; i < N; ++i) tau[i] = blk.tau[i * kWarp];
+        for (int i = 0; i < NS; ++i) tau[i] = blk.xs[i];
+#pragma unroll
+        for (int a = 0; a < NC; ++a) tau[NS + a] = blk.us[a];
+      } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) tau[i] = blk.tau[i * kWarp];
+      }
       if (flush) {
         S* bo = p.traj_best + bidx(t, 0, N, bw, p.nW);
 #pragma unroll
@@ -519,6 +557,18 @@ struct IterKernel {
 #pragma unroll
         for (int j = 0; j < N; ++j) acc = fmaS<S>(Q[i][j], tau[j], acc);
         qv[i] = acc + cs[i];
+      }
+      S nl[SOL ? NS : 1];
+      if constexpr (SOL) {   // cost part of lam_t, same association as costate_tables_kernel
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+          S a1 = S(0), a2 = S(0);
+#pragma unroll
+          for (int j = 0; j < NS; ++j) a1 = fmaS<S>(Q[i][j], tau[j], a1);
+#pragma unroll
+          for (int a = 0; a < NC; ++a) a2 = fmaS<S>(Q[i][NS + a], tau[NS + a], a2);
+          nl[i] = (a1 + a2) + cs[i];
+        }
       }
       if (t < T - 1) {
         S Fm[NS][N];
@@ -557,6 +607,24 @@ struct IterKernel {
           for (int l = 0; l < NS; ++l)
             if (D::nz(l, i)) acc = fmaS<S>(Fm[l][i], v[l], acc);
           qv[i] = qv[i] + acc;
+        }
+        if constexpr (SOL) {
+#pragma unroll
+          for (int i = 0; i < NS; ++i) {
+            S a1 = S(0);
+#pragma unroll
+            for (int l = 0; l < NS; ++l)
+              if (D::nz(l, i)) a1 = fmaS<S>(Fm[l][i], lam[l], a1);
+            nl[i] = nl[i] + a1;
+          }
+        }
+      }
+      if constexpr (SOL) {
+        S* lo_ = p.lam_blk ? p.lam_blk + bidx(t, 0, NS, bw, p.nW) : nullptr;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+          lam[i] = nl[i];
+          if (lo_) lo_[i * kWarp] = nl[i];
         }
       }
 #pragma unroll
@@ -856,6 +924,42 @@ ilqr_iter_kernel(const __grid_constant__ IterParams<S> p) {
   const int bsafe = active ? b : b0;
   if (PHASE != 2) IK::backward_sweep(p, st, b0, bsafe, b, active, lane);
   if (PHASE != 1 && !p.gains_only) IK::forward_linesearch(p, st, b0, bsafe, b, active, lane);
+}
+
+// ---------------------------------------------------------------------------
+// Gains of the final no-op LQR pass at the solution (lqr_step_explicit.py:604-618:
+// LQRStep(...)(x*, u*) whose new iterate is discarded) + the primal costates, straight
+// from the solver's outputs x_out / u_out and the packed C the solve left in the
+// workspace: no re-layout of the trajectory (begin) and no gather of the gains (finish).
+// Writes Kk (workspace, blocked) and lam_blk.
+// ---------------------------------------------------------------------------
+template <class S, int NS, int NC, int DYN, bool STAGED>
+__global__ void __launch_bounds__(128)
+ilqr_gains_kernel(const __grid_constant__ IterParams<S> p) {
+  using IK = IterKernel<S, NS, NC, DYN, STAGED, false>;
+  extern __shared__ __align__(128) char smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int wpb = blockDim.x >> 5;
+  const int b0 = (blockIdx.x * wpb + warp) * kWarp;
+  if (b0 >= p.B) return;
+  const int nvalid = min(kWarp, p.B - b0);
+  const bool active = lane < nvalid;
+  const int b = b0 + lane;
+  const size_t per_warp = IK::smem_per_warp(true);
+  char* wbase = smem + warp * per_warp;
+  WarpStager<S> st;
+  if (STAGED) {
+    uint32_t e[IK::kNSeg];
+    IK::seg_elems(e, true);
+    const bool packed = IK::use_packed(p);
+    if (packed) e[0] = IK::NP;
+    st.init(wbase + kStages * sizeof(uint64_t), reinterpret_cast<uint64_t*>(wbase), lane, nvalid,
+            IK::kNSeg, e, packed ? 1u : 0u, (p.C_bcast ? 1u : 0u) | (p.c_bcast ? 2u : 0u));
+    IK::template bind_sources<true>(st, p, b0);
+  }
+  const int bsafe = active ? b : b0;
+  IK::template backward_sweep<true>(p, st, b0, bsafe, b, active, lane);
 }
 
 // ---------------------------------------------------------------------------

@@ -201,8 +201,15 @@ __global__ void finish_kernel(const __grid_constant__ IterParams<S> p) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   const int t = blockIdx.y;
   if (b >= p.B) return;
-  // best iterate: parked in traj_best, or still the latest trajectory (take flag)
-  const S* src = ((p.take[b] & 1) ? p.traj_new : p.traj_best) + bidx(t, 0, N, b, p.nW);
+  // best iterate: parked in traj_best, or still the latest trajectory (take flag).  With a
+  // device-side outer loop (DilqrControl) the host may not know yet how many iterations were
+  // committed: the latest trajectory is the one iteration iters_done-1 wrote.
+  const S* latest = p.traj_new;
+  if (p.control) {
+    const int it = (int)reinterpret_cast<const DilqrControl*>(p.control)->iters_done - 1;
+    latest = p.traj_buf[(it + 1) & 1];
+  }
+  const S* src = ((p.take[b] & 1) ? latest : p.traj_best) + bidx(t, 0, N, b, p.nW);
   if (p.x_out) {
 #pragma unroll
     for (int i = 0; i < NS; ++i) p.x_out[((size_t)t * p.B + b) * NS + i] = src[i * kWarp];

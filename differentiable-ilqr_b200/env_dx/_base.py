@@ -24,6 +24,18 @@ class EnvDx(nn.Module):
             self._theta_key = key
         return self._theta_cache
 
+    def set_host_params(self, values):
+        """Tell the model the current parameter values from a host copy the caller keeps
+        (e.g. the training loop's master copy): no device->host read is ever needed."""
+        p = self.params
+        self._theta_cache = [float(v) for v in values]
+        self._theta_key = (p.data_ptr(), p._version)
+
+    def invalidate_params(self):
+        """Forget the cached host copy (call after updating ``params`` through ``.data``,
+        which does not bump the tensor version the cache is keyed on)."""
+        self._theta_key = None
+
     def _theta(self):
         th = (C.c_double * 8)()
         for i, v in enumerate(self._theta_list()):

@@ -11,7 +11,7 @@ import ctypes as C
 from torch.autograd import Function
 
 from . import _lib, mpc_explicit, parallel
-from ._solver import _DT, _ptr, _stream
+from ._solver import _DT, _ptr, _stream, Deferred
 from .definitions import QuadCost
 
 
@@ -49,6 +49,19 @@ class TileCost(Function):
         return dq, dp, None, None
 
 
+def tile_cost(q, p, T, B):
+    """il_env.py:159-162 as one call: (C[T,B,n,n] = diag(q), c[T,B,n] = p).  The pair is
+    tagged with its source so that ``mpc_explicit.MPC`` can hand the gradient wrt (q, p)
+    back directly -- the adjoint of the tiling is then accumulated inside the final adjoint
+    pass and the dense dC (0.94 GB at T=50, B=65536) is neither written nor re-read.
+    Used on their own (any other consumer), C and c are ordinary autograd tensors."""
+    Cm, cv = TileCost.apply(q, p, T, B)
+    tag = (q, p)
+    Cm._dilqr_tile = tag
+    cv._dilqr_tile = tag
+    return Cm, cv
+
+
 class ImitationStep:
     def __init__(self, dx_cls, T, lqr_iter, dtype, device, n_richardson=4, richardson_tol=None,
                  group=None, tile=True):
@@ -68,41 +81,67 @@ class ImitationStep:
             richardson_passes=n_richardson, richardson_tol=richardson_tol)
         self.group = group
         self.retries = 0
+        self.redone = 0           # steps repeated because a deferred check failed
         self.backward_name = "DiLQR implicit (%d Richardson passes)" % n_richardson
         self.d2h_bytes = 0
+        self.defer = True         # one host sync per step (see _solver.Deferred)
+        self._out_host = None
 
     # -- pieces -----------------------------------------------------------
     def tile_cost(self, q, p, B):
         """il_env.py:159-162: Q = diag(q) tiled to [T,B,n,n], p tiled to [T,B,n]."""
         if not self.tile:
             return torch.diag(q), p
-        return TileCost.apply(q, p, self.T, B)
+        return tile_cost(q, p, self.T, B)
 
     def prepare(self, x0, q, p, theta):
         return {"x0": x0, "q": q.clone().requires_grad_(), "p": p.clone().requires_grad_(),
-                "theta": theta.clone().requires_grad_()}
+                "theta": theta.clone().requires_grad_(),
+                "theta_host": theta.detach().double().cpu().tolist()}
 
-    def _step(self, x0, uexp, q, p, theta, world_frac=1.0):
+    def _step(self, x0, uexp, q, p, theta, world_frac=1.0, theta_host=None, defer=None):
+        """One il_exp step.  Nothing in it waits for the device: the kernels take theta
+        by value from ``theta_host`` (the caller's host copy; without it the parameters are
+        read back once, before anything is queued) and every validation read is deferred to
+        the end of the step (``_solver.Deferred``), where the caller synchronises anyway to
+        fetch the loss.  Returns (flat, deferred)."""
+        defer = self.defer if defer is None else defer
         for t in (q, p, theta):
             t.grad = None
         B = x0.shape[0]
         self.mpc.n_batch = B
         dx = self.dx_cls(theta)
-        dx._theta_list()          # the one device->host read of a step, before anything is queued
+        if theta_host is not None:
+            dx.set_host_params(theta_host)
+        else:
+            dx._theta_list()      # the one device->host read of a step, before anything is queued
+        self.mpc.defer_checks = defer
+        self.mpc.deferred = Deferred() if defer else None
         C, c = self.tile_cost(q, p, B)
         x, u, _ = self.mpc(x0, QuadCost(C, c), dx)
         loss = (u - uexp).pow(2).mean() * world_frac      # il_exp.py:346
         loss.backward()                                    # il_exp.py:373
-        self.retries += self.mpc.last_info.retries
         flat = torch.cat((theta.grad, q.grad, p.grad, loss.detach().reshape(1)))
-        return parallel.allreduce_sum_(flat, self.group)
+        return parallel.allreduce_sum_(flat, self.group), self.mpc.deferred
+
+    def _checked(self, run):
+        """Run a step optimistically; if one of its deferred checks fails (a pnqp trace
+        guess was wrong, or an adjoint step would have been rejected) repeat it with
+        immediate checks -- still entirely on the device."""
+        flat, d = run(None)
+        if d is not None and not d.resolve():
+            self.redone += 1
+            flat, _ = run(False)
+        self.retries += self.mpc.last_info.retries
+        return flat
 
     # -- resident inputs (device timing) -----------------------------------
     def run_resident(self, res, uexp):
         w = 1.0
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             w = 1.0 / torch.distributed.get_world_size()
-        return self._step(res["x0"], uexp, res["q"], res["p"], res["theta"], w)
+        return self._checked(lambda defer: self._step(
+            res["x0"], uexp, res["q"], res["p"], res["theta"], w, res.get("theta_host"), defer))
 
     # -- host inputs (end to end) -------------------------------------------
     def run_host(self, x0_h, uexp_h, q_h, p_h, theta_h):
@@ -115,8 +154,22 @@ class ImitationStep:
         w = 1.0
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             w = 1.0 / torch.distributed.get_world_size()
-        flat = self._step(x0, uexp, q, p, theta, w)
-        out = flat.cpu()                                   # loss + gradients back to the host
+        th_host = theta_h.double().tolist()
+        out = None
+
+        def run(defer):
+            nonlocal out
+            flat, d = self._step(x0, uexp, q, p, theta, w, th_host, defer)
+            # loss + gradients back to the host: enqueued behind the step, ONE sync serves
+            # this copy and the deferred checks
+            if self._out_host is None or self._out_host.numel() != flat.numel():
+                self._out_host = torch.empty(flat.numel(), dtype=flat.dtype).pin_memory()
+            self._out_host.copy_(flat, non_blocking=True)
+            return flat, d
+
+        self._checked(run)
+        torch.cuda.current_stream().synchronize()
+        out = self._out_host.clone()
         self.d2h_bytes = out.numel() * out.element_size()
         return out
 

@@ -49,25 +49,22 @@ class IL_Env:
 
     # ------------------------------------------------------------------ sampling
     def sample_xinit(self, n_batch=1):
-        """il_env.py:57-79, same draw order from the CPU generator so that a seed
-        reproduces the reference's initial states (returned on the host)."""
-        def uniform(shape, low, high):
-            r = high - low
-            return torch.rand(shape) * r + low
-
-        if self.env in ['pendulum', 'pendulum-complex']:
-            th = uniform(n_batch, -(1 / 2) * np.pi, (1 / 2) * np.pi)
-            thdot = uniform(n_batch, -1., 1.)
-            xinit = torch.stack((torch.cos(th), torch.sin(th), thdot), dim=1)
-        elif self.env == 'cartpole':
-            x = uniform(n_batch, -0.5, 0.5) * 0
-            dx = uniform(n_batch, -0.5, 0.5) * 0
-            th = uniform(n_batch, -np.pi, np.pi) * 0 + torch.ones(n_batch) * 3.1415926 / 1.05
-            dth = uniform(n_batch, -1., 1.) * 0
-            xinit = torch.stack((x, dx, torch.cos(th), torch.sin(th), dth), dim=1)
-        else:
-            assert False
-        return xinit
+        """Initial states of il_env.py:57-79, returned on the host.  The reference draws
+        from the global CPU generator -- pendulum: angle then angular velocity; cartpole:
+        four draws that it multiplies by zero (every cartpole problem starts at rest with
+        the pole at pi/1.05) -- so the same number of draws is consumed here, in the same
+        order, and a seed reproduces both the states and the generator state afterwards."""
+        draw = lambda lo, hi: lo + (hi - lo) * torch.rand(n_batch)
+        if self.env in ('pendulum', 'pendulum-complex'):
+            angle = draw(-0.5 * np.pi, 0.5 * np.pi)
+            rate = draw(-1., 1.)
+            return torch.stack((angle.cos(), angle.sin(), rate), dim=1)
+        assert self.env == 'cartpole'
+        for _ in range(4):                       # x, dx, th, dth: drawn, then discarded
+            torch.rand(n_batch)
+        rest = torch.zeros(n_batch)
+        angle = torch.full((n_batch,), 3.1415926 / 1.05)
+        return torch.stack((rest, rest, angle.cos(), angle.sin(), rest), dim=1)
 
     def _dev(self, t):
         return t.detach().to(device=self.device, dtype=self.dtype)
@@ -80,17 +77,18 @@ class IL_Env:
 
     # ------------------------------------------------------------------ open loop
     def populate_data(self, n_train, n_val, n_test, seed=0):
-        """il_env.py:81-94."""
+        """Expert data by ONE batched open-loop solve with the true model and the true
+        cost (il_env.py:81-94): rows are [T, ns+nc] trajectories, split train / val / test."""
         torch.manual_seed(seed)
-        n_data = n_train + n_val + n_test
-        xinit = self.sample_xinit(n_batch=n_data)
-        true_q, true_p = self.true_dx.get_true_obj()
+        sizes = (n_train, n_val, n_test)
+        x0 = self.sample_xinit(n_batch=sum(sizes))
+        q_true, p_true = self.true_dx.get_true_obj()
         with torch.no_grad():     # expert data: no gradient is ever asked for
-            true_x_mpc, true_u_mpc = self.mpc(self.true_dx, xinit, true_q, true_p)
-        tau = torch.cat((true_x_mpc, true_u_mpc), dim=2).transpose(0, 1)
-        self.train_data = tau[:n_train]
-        self.val_data = tau[n_train:n_train + n_val]
-        self.test_data = tau[-n_test:]
+            xs, us = self.mpc(self.true_dx, x0, q_true, p_true)
+        rows = torch.cat((xs, us), dim=2).transpose(0, 1)          # [n_data, T, ns+nc]
+        self.train_data = rows[:n_train]
+        self.val_data = rows[n_train:n_train + n_val]
+        self.test_data = rows[-n_test:]                            # il_env.py:94 (tail slice)
 
     # ------------------------------------------------------------------ closed loop
     def closed_loop(self, x_init, n_steps=None):

@@ -12,9 +12,24 @@ from .mpc import MPC as _BaseMPC, GradMethods, _dyn_spec  # noqa: F401
 
 
 class _MPCExplicitFn(Function):
+    """``q, p``: set when (C, c) is the tiled diagonal cost of il_env.py:159-162 built by
+    ``il.tile_cost`` -- C, c then come in detached and the backward returns the gradient wrt
+    (q, p) directly (the adjoint of the tiling is accumulated inside the final adjoint pass;
+    the dense dC[T,B,n,n] is never written)."""
+
     @staticmethod
-    def forward(ctx, mod, dx, x_init, C, c, theta):
+    def forward(ctx, mod, dx, x_init, C, c, theta, q=None, p=None):
+        ctx.set_materialize_grads(False)
+        ctx.tiled = q is not None
+        deferred = mod.deferred if (mod.defer_checks and not mod.detach_unconverged) else None
         dyn = _dyn_spec(dx)
+        # A 4-D stride-0 cost (e.g. Q[None, None].expand(T, B, n, n)) is read as the broadcast
+        # block it is -- unless its gradient is wanted: autograd then expects a [T,B,n,n]
+        # gradient per (t, b) like the reference returns, so the dense tensor is used.
+        if C.ndimension() == 4 and ctx.needs_input_grad[3]:
+            C = C.contiguous()
+        if c.ndimension() == 3 and ctx.needs_input_grad[4]:
+            c = c.contiguous()
         x, u, costs, info = _solver.solve_mpc(
             x_init, C, c, dyn, mod.n_state, mod.n_ctrl, mod.T,
             u_lower=mod.u_lower, u_upper=mod.u_upper, u_zero_I=mod.u_zero_I,
@@ -22,9 +37,11 @@ class _MPCExplicitFn(Function):
             linesearch_decay=mod.linesearch_decay,
             max_linesearch_iter=mod.max_linesearch_iter,
             not_improved_lim=mod.not_improved_lim, best_cost_eps=mod.best_cost_eps,
-            gain_solve=_lib.GAIN_PLAIN, solo=mod.solo, verbose=mod.verbose, delta_u=mod.delta_u)
+            gain_solve=_lib.GAIN_PLAIN, solo=mod.solo, verbose=mod.verbose, delta_u=mod.delta_u,
+            deferred=deferred)
         mod.last_info = info
         ctx.mod, ctx.dx = mod, dx
+        ctx.deferred = deferred
         ctx.theta_host = dyn.params
         ctx.mask = None
         eps_cmp = float(torch.tensor(mod.eps, dtype=x.dtype))
@@ -42,10 +59,10 @@ class _MPCExplicitFn(Function):
         # backward that only needs the solution right behind the solve (the final no-op
         # LQR pass is part of the reference's forward too, mpc_explicit.py:325-340)
         ctx.prep = None
-        if mod.backprop and mod.prepare_in_forward and any(ctx.needs_input_grad[3:6]):
+        if mod.backprop and mod.prepare_in_forward and any(ctx.needs_input_grad[3:8]):
             ctx.prep = _solver.dilqr_prepare(
                 x_init, C, c, x, u, dx, mod.n_state, mod.n_ctrl, mod.u_lower, mod.u_upper,
-                solo=mod.solo, theta_host=dyn.params)
+                solo=mod.solo, theta_host=dyn.params, solve_info=info, deferred=deferred)
         return x, u, costs
 
     @staticmethod
@@ -53,20 +70,26 @@ class _MPCExplicitFn(Function):
         mod, dx = ctx.mod, ctx.dx
         x_init, C, c, x, u = ctx.saved_tensors
         if ctx.mask is not None:
-            dl_dx = dl_dx * ctx.mask.view(1, -1, 1)
-            dl_du = dl_du * ctx.mask.view(1, -1, 1)
+            dl_dx = None if dl_dx is None else dl_dx * ctx.mask.view(1, -1, 1)
+            dl_du = None if dl_du is None else dl_du * ctx.mask.view(1, -1, 1)
         stats = {}
         dC, dc, dtheta = _solver.dilqr_backward(
-            dl_dx.contiguous(), dl_du.contiguous(), x_init, C, c, x, u, dx, mod.n_state,
+            dl_dx, dl_du, x_init, C, c, x, u, dx, mod.n_state,
             mod.n_ctrl, mod.u_lower, mod.u_upper, n_passes=mod.richardson_passes,
             tol=mod.richardson_tol, back_eps=mod.back_eps, solo=mod.solo, stats=stats,
-            theta_host=ctx.theta_host, prep=ctx.prep)
+            theta_host=ctx.theta_host, prep=ctx.prep, tile_reduce=ctx.tiled,
+            deferred=ctx.deferred)
         ctx.prep = None
         mod.last_backward = stats
         # dC / dc come back in the layout of the cost tensors handed in (dense, or already
         # summed over the broadcast axes for C[n,n] / C[T,n,n]); the reference returns
         # dtheta[B, n_theta] and autograd sums it to theta's shape
-        return None, None, None, dC.reshape(C.shape), dc.reshape(c.shape), dtheta.sum(0)
+        dth = None
+        if ctx.needs_input_grad[5]:      # dx.params may live on the host (PendulumDx() default)
+            dth = dtheta.sum(0).to(device=dx.params.device, dtype=dx.params.dtype)
+        if ctx.tiled:                    # (dC, dc) are already (dq, dp)
+            return None, None, None, None, None, dth, dC, dc
+        return None, None, None, dC.reshape(C.shape), dc.reshape(c.shape), dth, None, None
 
 
 class MPC(_BaseMPC):
@@ -78,6 +101,12 @@ class MPC(_BaseMPC):
                  prepare_in_forward=True, **kw):
         super().__init__(*args, **kw)
         self.prepare_in_forward = prepare_in_forward
+        # defer_checks: postpone every validation read of a step (pnqp trace, stop-rule
+        # status, adjoint line-search test) to ONE host sync when the caller resolves
+        # `self.deferred` (il.ImitationStep does); a failed check means "repeat the step
+        # with immediate checks".  Off by default: MPC.forward then returns validated data.
+        self.defer_checks = False
+        self.deferred = None
         self.richardson_passes = richardson_passes
         self.richardson_tol = richardson_tol
         self.last_backward = None
@@ -102,4 +131,9 @@ class MPC(_BaseMPC):
         assert x_init.ndimension() == 2 and x_init.size(0) == n_batch
         # broadcast costs (C[n,n], C[T,n,n]) are NOT tiled: the kernels read the shared
         # block and the backward returns the gradient already reduced to that shape
+        tile = getattr(cost.C, "_dilqr_tile", None)
+        if tile is not None and getattr(cost.c, "_dilqr_tile", None) is tile:
+            q, p = tile
+            return _MPCExplicitFn.apply(self, dx, x_init, cost.C.detach(), cost.c.detach(),
+                                        dx.params, q, p)
         return _MPCExplicitFn.apply(self, dx, x_init, cost.C, cost.c, dx.params)

@@ -173,6 +173,19 @@ int dilqr_lockstep_capacity(int dtype, int n_state, int n_ctrl, int dynamics);
 /* Bytes of workspace the dilqr_mpc_* calls need. */
 size_t dilqr_workspace_bytes(const DilqrSolve* s);
 
+/* What the solve leaves in its workspace for the backward pass (valid until the workspace is
+ * reused): the gains Kk warp-blocked [T][ceil(B/32)][nc*ns+nc][32] (K then k; written by
+ * iterate / dilqr_mpc_gains), the packed upper triangle of C [T][ceil(B/32)][n(n+1)/2][32]
+ * with its validity word (1: every C[t,b] was bitwise symmetric and the copy exists). */
+typedef struct DilqrWsView {
+  void* Kk;
+  const void* Cpk;
+  const uint32_t* cpk_state;
+  int32_t n_warps;          /* ceil(B/32) */
+  int32_t reserved;
+} DilqrWsView;
+int dilqr_workspace_view(const DilqrSolve* s, DilqrWsView* view);
+
 /* ---- iLQR outer loop, MPC.forward (mpc.py:184-337, mpc_explicit.py:182-358) -- */
 
 /* Initial nominal rollout x = get_traj(u_init) (util.py:104-127) and its cost
@@ -194,6 +207,14 @@ int dilqr_mpc_commit(const DilqrSolve* s, void* stream);
 
 /* Gather the best iterate into x_out,u_out,cost_out,du_out (mpc.py:304-306). */
 int dilqr_mpc_finish(const DilqrSolve* s, void* stream);
+
+/* Gains of the final no-op LQR pass at the solution (lqr_step_explicit.py:604-618) and the
+ * primal costates (lqr_step.py:355-369) in ONE sweep over s->x_out, s->u_out (the solution as
+ * dilqr_mpc_finish returned it), C read from the packed workspace copy when valid.  Writes
+ * the gains into the workspace (DilqrWsView.Kk) and lam_blk [T][ceil(B/32)][ns][32]
+ * (optional); verifies the pnqp trace into *s->status like dilqr_mpc_commit.  Staged env_dx
+ * shapes only (DILQR_EUNSUPPORTED otherwise: use the LQR-step call sequence below). */
+int dilqr_mpc_gains(const DilqrSolve* s, void* lam_blk, void* stream);
 
 /* A single LQR step, LQRStep(...)(x_init,C,c,F,f) (lqr_step.py:22-38,277-309), is
  * the same call sequence with `x_cur` (and `u_init` = current u) set: dilqr_mpc_begin
@@ -257,6 +278,12 @@ int dilqr_costate_tables(int dtype, int dynamics, const double* dyn_params, int 
                          const void* C, const void* c, const void* x, const void* u, void* lam,
                          void* Lam, int C_bcast, int c_bcast, int packed, void* stream);
 
+/* The contracted second-order tables alone, from tau* and the warp-blocked costates of
+ * dilqr_mpc_gains: one thread per (t, problem) -- no recursion in t is left.  Lam is the packed
+ * layout of dilqr_costate_tables(packed = 1). */
+int dilqr_lam_tables(int dtype, int dynamics, const double* dyn_params, int T, int n_batch,
+                     const void* x, const void* u, const void* lam_blk, void* Lam, void* stream);
+
 /* One Richardson update of A' w = g:  w_t = g_t - Lam_t dtau_t (t < T-1),
  * w_{T-1} = g_{T-1}; writes w and -w, and resid[0] = max|w_new - w_old|,
  * resid[1] = max|w_new| (two doubles, device).  (dx,du) is the adjoint LQR
@@ -287,17 +314,34 @@ typedef struct DilqrAdjoint {
   double dyn_params[8];
   const void *C;         /* [T,B,n,n]                                                  */
   const void *x, *u;     /* solution tau* [T,B,ns], [T,B,nc]                           */
-  const void *g;         /* [T,B,n]  cat(dl_dx, dl_du)                                 */
-  const void *Lam;       /* packed Lam from dilqr_costate_tables(packed = 1)            */
-  void *w;               /* [T,B,n]  Richardson iterate, in/out (initialise to g)      */
+  const void *gx, *gu;   /* upstream gradient g = [dl_dx; dl_du] as its two halves [T,B,ns]
+                            (NULL: zero) and [T,B,nc] -- never concatenated               */
+  const void *Lam;       /* packed Lam from dilqr_costate_tables(packed = 1) / dilqr_lam_tables */
+  void *w;               /* [T,B,n]  Richardson iterate; with first_pass = 1 the solve reads
+                            its right-hand side from g and w is only written               */
   void *dC, *dc, *df;    /* final pass outputs: [T,B,n,n], [T,B,n], [T-1,B,ns]         */
   void *dx_out, *du_out; /* final pass: adjoint solution (optional)                    */
   void *resid;           /* device, 3 x 8 bytes: max|dw|, max|w| (doubles), #problems
                             whose adjoint step the reference's line search would reject */
   void *workspace;
   size_t workspace_bytes;
+  /* --- fused-backward options (all optional, zero = round-1 behaviour) ------------------ */
+  const void *Cpk;       /* packed symmetric copy of C the forward solve left in its workspace */
+  const uint32_t *cpk_state; /* device word, 1: Cpk valid (dilqr_workspace_view)              */
+  int32_t first_pass;    /* the Richardson iterate equals g (first solve): no w <- g copy      */
+  int32_t want_resid;    /* pass: reduce resid[0..1] (one extra read of w per pass)            */
+  int32_t reduce_tile;   /* final: gradient of the TILED DIAGONAL cost of il_env.py:159-162
+                            instead of dC, dc: red_out[ceil(B/32)][2n] per-warp partial sums of
+                            sum_{t,b} diag(dC) and sum_{t,b} dc (sum over axis 0 = dq, dp)    */
+  int32_t reserved0;
+  void *red_out;
+  void *df_blk;          /* final: df warp-blocked [T-1][ceil(B/32)][ns][32] for
+                            dilqr_sens_theta_blocked (instead of df)                          */
 } DilqrAdjoint;
 size_t dilqr_adjoint_workspace_bytes(const DilqrAdjoint* a);
+/* Byte offset, inside the adjoint workspace, of the adjoint solution the final pass keeps:
+ * dtau warp-blocked [T][ceil(B/32)][n][32] (input of dilqr_sens_theta_blocked). */
+size_t dilqr_adjoint_dtau_offset(const DilqrAdjoint* a);
 /* Masked Riccati sweep at tau*: gains and the r-independent blocks.  Needs only C, x, u,
  * bounds, dyn_params, resid and the workspace (not w, g, Lam or the outputs), so it can be
  * enqueued right behind the forward solve, before any upstream gradient exists. */
@@ -314,6 +358,13 @@ int dilqr_adjoint_final(const DilqrAdjoint* a, void* stream);
 int dilqr_sens_theta(int dtype, int dynamics, const double* dyn_params, int T, int n_batch,
                      const void* x, const void* u, const void* K, const void* lam, const void* dx,
                      const void* du, const void* df, void* dtheta, void* stream);
+
+/* Same with every solver-internal operand in the warp-blocked layout it was produced in:
+ * Kk (DilqrWsView), lam_blk (dilqr_mpc_gains), dtau_blk (adjoint workspace +
+ * dilqr_adjoint_dtau_offset), df_blk (DilqrAdjoint.df_blk). */
+int dilqr_sens_theta_blocked(int dtype, int dynamics, const double* dyn_params, int T, int n_batch,
+                             const void* x, const void* u, const void* Kk, const void* lam_blk,
+                             const void* dtau_blk, const void* df_blk, void* dtheta, void* stream);
 
 /* The cost plumbing either side of the solve in the imitation-learning loop.
  * dilqr_tile_cost: C[T,B,n,n] = diag(q), c[T,B,n] = p for every (t, b) -- what
