@@ -8,7 +8,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdilqr.so")
+# DILQR_LIB: load another build of the same library (A/B variants, tools/build_variant.sh)
+LIB_PATH = os.environ.get("DILQR_LIB") or os.path.join(_HERE, "libdilqr.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 F32, F64 = 0, 1
@@ -206,9 +207,10 @@ launch_count = 0     # running total of kernels launched through this binding
 profile = None       # set to a dict {name: [(start_event, end_event), ...]} to time calls
 
 
-def call(name, *args):
+def call(name, *args, allow=()):
     """Invoke a C-ABI entry point; counts launches and (optionally) brackets the
-    call with CUDA events on the current stream for per-kernel timing."""
+    call with CUDA events on the current stream for per-kernel timing.  Error codes listed
+    in ``allow`` are returned instead of raised (nothing was enqueued)."""
     global launch_count
     fn = getattr(lib(), name)
     if profile is not None:
@@ -221,5 +223,8 @@ def call(name, *args):
         profile.setdefault(name, []).append((e0, e1))
     else:
         rc = fn(*args)
+    if rc in allow:
+        return rc
     check(rc, name)
     launch_count += KERNELS_PER_CALL.get(name, 0)
+    return rc

@@ -575,12 +575,10 @@ def dilqr_prepare(x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u_lower=None, u_
             return None if st.trace_match else "pnqp trace mismatch in the final LQR pass"
 
         for attempt in range(MAX_TRACE_RETRIES):
-            rc = L.dilqr_mpc_gains(C.byref(sp), _ptr(lam), _stream())
+            rc = _lib.call("dilqr_mpc_gains", C.byref(sp), _ptr(lam), _stream(), allow=(-2,))
             if rc == -2:
                 fused = False      # shape without the fused sweep: round-1 sequence below
                 break
-            _lib.check(rc, "dilqr_mpc_gains")
-            _lib.launch_count += _lib.KERNELS_PER_CALL["dilqr_mpc_gains"]
             if deferred is not None:
                 deferred.add(ws.status_dev, gains_ok)
                 break

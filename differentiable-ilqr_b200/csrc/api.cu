@@ -248,7 +248,11 @@ struct Geometry {
     if (forced >= 1 && forced <= w) w = forced;
     return w;
   }
-  static size_t smem(int wpb) { return STAGED ? IK::smem_per_warp() * wpb : 0; }
+  static size_t smem(int wpb) {
+    // DILQR_SMEM_PAD: extra dynamic shared memory per block (occupancy experiments)
+    static const size_t pad = getenv("DILQR_SMEM_PAD") ? (size_t)atol(getenv("DILQR_SMEM_PAD")) : 0;
+    return STAGED ? IK::smem_per_warp() * wpb + pad : 0;
+  }
 };
 
 template <int NS, int NC, int DYN>

@@ -13,6 +13,10 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef DILQR_RCP_PARAMS
+#define DILQR_RCP_PARAMS 1
+#endif
+
 namespace dilqr {
 
 enum { DYN_LINDX = 0, DYN_PENDULUM = 1, DYN_CARTPOLE = 2, DYN_ROCKET = 3, DYN_NN = 4 };
@@ -408,10 +412,20 @@ struct Dyn<S, DYN_CARTPOLE> {
     const S gs = g - c * w2lmp * iM;              // dG/ds
     const S mpc = mp * c * iM * iden;             // m_p c / (M den)
     // d th_acc / d(c, s, w, u)
+#if DILQR_RCP_PARAMS
+    // 1/l is a property of theta (loop invariant): three divisions per Jacobian become
+    // multiplications (<= 1 ulp each; ~120 cycles of dependent latency each saved)
+    const S il = S(1.0) / l;
+    const S ta_c = (S(2.0) * mpc * G * iden - A * iM * iden) * il;
+    const S ta_s = gs * iden * il;
+    const S ta_w = S(-2.0) * c * w * mp * s * iM * iden;
+    const S ta_u = -c * iM * iden * il;
+#else
     const S ta_c = (S(2.0) * mpc * G * iden - A * iM * iden) / l;
     const S ta_s = gs * iden / l;
     const S ta_w = S(-2.0) * c * w * mp * s * iM * iden;
     const S ta_u = -c * iM * iden / l;
+#endif
     // d xacc / d(c, s, w, u)
     const S xa_c = -mp * G * iM * iden + mpc * A * iM - S(2.0) * mpc * mpc * G;
     const S xa_s = w2lmp * iM - mpc * gs;

@@ -350,11 +350,25 @@ DILQR_DEVICE void pnqp_thread(const S (&H)[N][N], const S (&q)[N], const S (&lo)
 // ---------------------------------------------------------------------------
 // The fused iLQR iteration.
 // ---------------------------------------------------------------------------
+// Association of the Riccati update.  0: every product of lqr_step.py:66-70,155-158 is rounded
+// on its own and the terms are added in the reference's order (what torch computes op by
+// op).  1: the same terms accumulated as ONE fused-multiply-add chain per entry (the addend
+// C_ij / q_i / Q_ij opens the chain): ~14 % fewer FP64 instructions in the sweep and fewer
+// roundings; results differ from mode 0 by a few ulp (both are within the rounding error of
+// the reference's own BLAS-ordered sums).
+#ifndef DILQR_CHAIN_FMA
+#define DILQR_CHAIN_FMA 1
+#endif
+constexpr bool kChainFmaOn = DILQR_CHAIN_FMA != 0;
+
 template <class S, int NS, int NC, int DYN, bool STAGED, bool LOCKSTEP = false>
 struct IterKernel {
   static constexpr int N = NS + NC;
   static constexpr int NK = NC * NS + NC;
   static constexpr bool kEnv = (DYN != DYN_LINDX);
+  // env_dx models only: user-supplied LinDx problems keep the op-by-op association (their
+  // parity tests pin pnqp iteration counts on borderline |dx| >= 1e-4 decisions)
+  static constexpr bool kChainFma = kChainFmaOn && kEnv;
   using D = Dyn<S, DYN>;
   // stage segments: 0 C[n*n]  1 c[n]  2 F[ns*n]  3 f[ns]  (API slabs)
   //                 4 traj_cur[t] chunk [N][32]   5 Kk[t] chunk [NK][32]   (workspace)
@@ -553,10 +567,10 @@ struct IterKernel {
       }
 #pragma unroll
       for (int i = 0; i < N; ++i) {  // c_back = C tau + c   (lqr_step.py:294)
-        S acc = S(0);
+        S acc = kChainFma ? cs[i] : S(0);
 #pragma unroll
         for (int j = 0; j < N; ++j) acc = fmaS<S>(Q[i][j], tau[j], acc);
-        qv[i] = acc + cs[i];
+        qv[i] = kChainFma ? acc : acc + cs[i];
       }
       S nl[SOL ? NS : 1];
       if constexpr (SOL) {   // cost part of lam_t, same association as costate_tables_kernel
@@ -596,17 +610,17 @@ struct IterKernel {
           }
 #pragma unroll
           for (int j = 0; j < N; ++j) {
-            S acc = S(0);
+            S acc = kChainFma ? Q[i][j] : S(0);
 #pragma unroll
             for (int k = 0; k < NS; ++k)
               if (D::nz(k, j)) acc = fmaS<S>(M[k], Fm[k][j], acc);
-            Q[i][j] = Q[i][j] + acc;
+            Q[i][j] = kChainFma ? acc : Q[i][j] + acc;
           }
-          S acc = S(0);
+          S acc = kChainFma ? qv[i] : S(0);
 #pragma unroll
           for (int l = 0; l < NS; ++l)
             if (D::nz(l, i)) acc = fmaS<S>(Fm[l][i], v[l], acc);
-          qv[i] = qv[i] + acc;
+          qv[i] = kChainFma ? acc : qv[i] + acc;
         }
         if constexpr (SOL) {
 #pragma unroll
@@ -763,23 +777,45 @@ struct IterKernel {
       for (int i = 0; i < NS; ++i) {
 #pragma unroll
         for (int j = 0; j < NS; ++j) {
+          if constexpr (kChainFma) {
+            S acc = Q[i][j];
+#pragma unroll
+            for (int a = 0; a < NC; ++a) acc = fmaS<S>(Q[i][NS + a], K[a][j], acc);
+#pragma unroll
+            for (int a = 0; a < NC; ++a) acc = fmaS<S>(K[a][i], Q[NS + a][j], acc);
+#pragma unroll
+            for (int a = 0; a < NC; ++a) acc = fmaS<S>(KQ[i][a], K[a][j], acc);
+            V[i][j] = acc;
+          } else {
+            S t1 = S(0), t2 = S(0), t3 = S(0);
+#pragma unroll
+            for (int a = 0; a < NC; ++a) {
+              t1 = fmaS<S>(Q[i][NS + a], K[a][j], t1);
+              t2 = fmaS<S>(K[a][i], Q[NS + a][j], t2);
+              t3 = fmaS<S>(KQ[i][a], K[a][j], t3);
+            }
+            V[i][j] = ((Q[i][j] + t1) + t2) + t3;
+          }
+        }
+        if constexpr (kChainFma) {
+          S acc = qv[i];
+#pragma unroll
+          for (int a = 0; a < NC; ++a) acc = fmaS<S>(Q[i][NS + a], k[a], acc);
+#pragma unroll
+          for (int a = 0; a < NC; ++a) acc = fmaS<S>(K[a][i], qv[NS + a], acc);
+#pragma unroll
+          for (int a = 0; a < NC; ++a) acc = fmaS<S>(KQ[i][a], k[a], acc);
+          v[i] = acc;
+        } else {
           S t1 = S(0), t2 = S(0), t3 = S(0);
 #pragma unroll
           for (int a = 0; a < NC; ++a) {
-            t1 = fmaS<S>(Q[i][NS + a], K[a][j], t1);
-            t2 = fmaS<S>(K[a][i], Q[NS + a][j], t2);
-            t3 = fmaS<S>(KQ[i][a], K[a][j], t3);
+            t1 = fmaS<S>(Q[i][NS + a], k[a], t1);
+            t2 = fmaS<S>(K[a][i], qv[NS + a], t2);
+            t3 = fmaS<S>(KQ[i][a], k[a], t3);
           }
-          V[i][j] = ((Q[i][j] + t1) + t2) + t3;
+          v[i] = ((qv[i] + t1) + t2) + t3;
         }
-        S t1 = S(0), t2 = S(0), t3 = S(0);
-#pragma unroll
-        for (int a = 0; a < NC; ++a) {
-          t1 = fmaS<S>(Q[i][NS + a], k[a], t1);
-          t2 = fmaS<S>(K[a][i], qv[NS + a], t2);
-          t3 = fmaS<S>(KQ[i][a], k[a], t3);
-        }
-        v[i] = ((qv[i] + t1) + t2) + t3;
       }
     }
   }

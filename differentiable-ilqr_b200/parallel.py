@@ -16,5 +16,11 @@ def shard_range(n_batch, rank, world):
 def allreduce_sum_(flat, group=None):
     """In-place SUM all-reduce of a small flat buffer (d theta, dq, dp, loss)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        if flat.is_cuda and dist.get_backend(group) == "gloo":
+            # gloo (CPU tests, two ranks sharing one GPU): stage through the host
+            host = flat.cpu()
+            dist.all_reduce(host, op=dist.ReduceOp.SUM, group=group)
+            flat.copy_(host)
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     return flat

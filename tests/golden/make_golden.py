@@ -147,6 +147,45 @@ def dilqr(env, T, B, lqr_iter, sigma):
         gx=gx, gu=gu, dC=C.grad, dc=c.grad, dtheta=theta.grad, T=T, lqr_iter=lqr_iter)
 
 
+def dilqr_t50(B=16, sigma=0.05, presolve=250):
+    """DiLQR gradient at the HEADLINE horizon (cartpole T=50) in the regime where the
+    implicit gradient is well posed: perturbation +-0.05, controls
+    warm-started from an untimed pre-solve, so the differentiated solve stops after one
+    iteration at a converged fixed point.  T*B = 800 < 1000 keeps the reference on its CPU
+    KKT_gradient path (lqr_step_explicit.py:664-705)."""
+    torch.manual_seed(0)
+    torch.set_default_dtype(torch.float64)
+    dt = torch.float64
+    T = 50
+    theta = torch.tensor((9.8, 1.0, 0.1, 0.5), dtype=dt, requires_grad=True)
+    dx = R.cartpole.CartpoleDx(theta)
+    r = (torch.rand(B, 4) * 2 - 1) * sigma
+    x0 = torch.stack((r[:, 0], r[:, 1], torch.cos(r[:, 2]), torch.sin(r[:, 2]), r[:, 3]), 1)
+    q, p = dx.get_true_obj()
+    q, p = q.to(dt), p.to(dt)
+    kw = dict(u_lower=dx.lower, u_upper=dx.upper, verbose=-1, exit_unconverged=False,
+              detach_unconverged=False, linesearch_decay=dx.linesearch_decay,
+              max_linesearch_iter=dx.max_linesearch_iter, eps=1e-9,
+              grad_method=R.mpc_explicit.GradMethods.ANALYTIC)
+    C0 = torch.diag(q)[None, None].repeat(T, B, 1, 1)
+    c0 = p[None, None].repeat(T, B, 1)
+    with torch.no_grad():
+        pre = R.mpc_explicit.MPC(dx.n_state, dx.n_ctrl, T, lqr_iter=presolve, **kw)
+        _, u_warm, _ = pre(x0, R.mpc_explicit.QuadCost(C0, c0), R.cartpole.CartpoleDx(theta.detach()))
+    C = C0.clone().requires_grad_()
+    c = c0.clone().requires_grad_()
+    m = R.mpc_explicit.MPC(dx.n_state, dx.n_ctrl, T, lqr_iter=5, u_init=u_warm.clone(), **kw)
+    x, u, costs = m(x0, R.mpc_explicit.QuadCost(C, c), dx)
+    g = torch.Generator().manual_seed(7)
+    gx = torch.randn(x.shape, generator=g)
+    gu = torch.randn(u.shape, generator=g)
+    ((x * gx).sum() + (u * gu).sum()).backward()
+    npz("ref_dilqr_cartpole_T50.npz", x0=x0, q=q, p=p, theta=theta.detach(), u_init=u_warm, x=x,
+        u=u, costs=costs, gx=gx, gu=gu, dC=C.grad, dc=c.grad, dtheta=theta.grad, T=T, lqr_iter=5,
+        du_warm=(u - u_warm).abs().max())
+    torch.set_default_dtype(torch.float32)
+
+
 def tables():
     torch.manual_seed(1)
     torch.set_default_dtype(torch.float64)
@@ -363,12 +402,16 @@ def closed_loop(env, mpc_T, lqr_iter, n_train, n_val, n_test):
 
 
 if __name__ == "__main__":
+    if sys.argv[1:] == ["t50"]:      # only the headline-horizon DiLQR golden (about a minute)
+        dilqr_t50()
+        sys.exit(0)
     fixtures()
     lindx(False)
     lindx(True)
     dilqr("pendulum", 20, 4, 60, None)
     dilqr("cartpole", 12, 8, 80, 0.05)
     dilqr("rocket", 10, 4, 60, None)
+    dilqr_t50()
     tables()
     env_forward("cartpole", 25, 16, 6, torch.float64)
     env_forward("pendulum", 20, 16, 8, torch.float64)

@@ -60,3 +60,48 @@ def test_shard_range_covers_batch_exactly():
             assert r[0][0] == 0 and r[-1][1] == B
             assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
             assert max(h - l for l, h in r) - min(h - l for l, h in r) <= 1
+
+
+import pytest
+
+
+def _run_workers(backend, tmp_path):
+    import subprocess
+    out = str(tmp_path / "dist.pt")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(ROOT, "tests", "dist_worker.py"), out, backend]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:]
+    return torch.load(out)
+
+
+def _check(res):
+    full, sh = res["full"], res["sharded"]
+    # (d theta[4], dq[6], dp[6], loss): all-reduced shard results == the full batch alone
+    err = float((full - sh).abs().max() / full.abs().max())
+    assert err < 1e-12, (err, full, sh)
+    assert abs(res["learner_loss"] - res["full_loss"]) <= 1e-12 * abs(res["full_loss"])
+    assert float((res["learner_theta"] - res["full_theta"]).abs().max()) < 1e-12
+
+
+@pytest.mark.gpu
+def test_two_rank_step_equals_full_batch(tmp_path):
+    """a 2-rank ImitationStep / ImitationLearner step (problems sharded by
+    batch index, one all-reduce of the gradient scalars) equals the 1-rank full-batch result
+    to 1e-12.  gloo, both ranks on cuda:0, so it runs on the single-GPU box.
+
+    The identity is asserted under per-problem pnqp flags (``solo``): with the reference's
+    batch-global flags (pnqp.py:56-59: every problem keeps iterating while ANY problem of
+    the batch still moves) what a problem computes depends on who shares its batch -- the
+    sharded and the full-batch results then differ at ~1e-7, in this framework exactly as
+    they would in the reference run on the two shards."""
+    _check(_run_workers("gloo", tmp_path))
+
+
+@pytest.mark.gpu
+def test_two_rank_step_equals_full_batch_nccl(tmp_path):
+    """Same over NCCL, one GPU per rank (needs `gpurun --gpus 2`)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _check(_run_workers("nccl", tmp_path))

@@ -97,8 +97,8 @@ def test_fused_vs_oracle(dilqr, port, env, dev, name):
     # multi-iteration solves: see test_gpu_parity.test_dilqr_gradient_vs_oracle (1e-8) and
     # test_teacher_forced.py for the per-iteration 1e-10 statement
     assert rel(a[0], o.x) < 1e-8 and rel(a[1], o.u) < 1e-8
-    assert rel(a[2], ref.dtheta.sum(0)) < 1e-8
-    assert rel(a[3], ref.dC) < 1e-8 and rel(a[4], ref.dc) < 1e-8
+    assert rel(a[2], ref.dtheta.sum(0)) < 1e-7
+    assert rel(a[3], ref.dC) < 1e-7 and rel(a[4], ref.dc) < 1e-7
 
 
 @pytest.mark.parametrize("B", [64, 45])

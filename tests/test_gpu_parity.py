@@ -211,6 +211,70 @@ def test_dilqr_gradient_golden(dilqr, env, dev, name):
     assert rel(c.grad, g["dc"]) < 1e-10
 
 
+@pytest.mark.parametrize("dtype,passes", [(torch.float64, 4), (torch.float64, 12),
+                                          (torch.float32, 12)])
+def test_dilqr_gradient_golden_headline_horizon(dilqr, env, dev, dtype, passes):
+    """Cartpole T=50 (the benchmark horizon), B=16, warm-started converged regime (SURVEY
+    8d-2b: the point where the implicit gradient is well posed) against the reference's
+    dense fix_point_equ solve, end to end (CUDA forward, then CUDA backward) -- already with
+    the 4 Richardson passes the benchmark runs -- and the FP32 build against the same FP64
+    golden.
+
+    x, u, dC, dc hold 1e-10.  dtheta is asserted at 1e-9 here and at 1e-10 in
+    test_dilqr_backward_from_the_reference_solution: the CUDA forward's x* differs from the
+    reference's by ~5e-12 (an open-loop rollout of the inverted pendulum over T=50 steps
+    amplifies the last-bit differences of sin / cos / atan2 by e^(sqrt(g/l) T dt) ~ 6e4),
+    and dtheta -- a sum over the horizon of products with the sensitivity rollout -- carries
+    that to 2e-10.  The same conditioning, ~1e6 x eps, is what limits the FP32 build: its
+    dtheta agrees to ~2e-2 (1e6 x 6e-8), its x, u, dC, dc to 1e-4."""
+    g = golden("ref_dilqr_cartpole_T50.npz")
+    T, B = int(g["T"]), g["x0"].shape[0]
+    theta = g["theta"].to(dev, dtype).requires_grad_()
+    dx = env.CartpoleDx(theta)
+    C = torch.diag(g["q"]).to(dev, dtype)[None, None].repeat(T, B, 1, 1).requires_grad_()
+    c = g["p"].to(dev, dtype)[None, None].repeat(T, B, 1).requires_grad_()
+    m = dilqr.mpc_explicit.MPC(5, 1, T, u_lower=dx.lower, u_upper=dx.upper,
+                               u_init=g["u_init"].to(dev, dtype), lqr_iter=int(g["lqr_iter"]),
+                               verbose=-1, exit_unconverged=False, detach_unconverged=False,
+                               linesearch_decay=dx.linesearch_decay,
+                               max_linesearch_iter=dx.max_linesearch_iter, eps=1e-9,
+                               richardson_passes=passes, richardson_tol=None)
+    x, u, costs = m(g["x0"].to(dev, dtype), dilqr.QuadCost(C, c), dx)
+    ((x * g["gx"].to(dev, dtype)).sum() + (u * g["gu"].to(dev, dtype)).sum()).backward()
+    if dtype == torch.float64:
+        assert m.last_info.n_iters == 1          # the reference stops after one iteration
+        assert rel(x, g["x"]) < 1e-10 and rel(u, g["u"]) < 1e-10
+        assert rel(theta.grad, g["dtheta"]) < 1e-9
+        assert rel(C.grad, g["dC"]) < 1e-10 and rel(c.grad, g["dc"]) < 1e-10
+    else:
+        e = (rel(x, g["x"]), rel(u, g["u"]), rel(theta.grad, g["dtheta"]), rel(C.grad, g["dC"]),
+             rel(c.grad, g["dc"]))
+        print("fp32 DiLQR at T=50 vs the fp64 reference: x %.1e u %.1e dtheta %.1e dC %.1e dc %.1e" % e)
+        assert max(e[0], e[1], e[3], e[4]) < 1e-4 and e[2] < 1e-1
+
+
+@pytest.mark.parametrize("passes", [4, 12])
+def test_dilqr_backward_from_the_reference_solution(dilqr, env, dev, passes):
+    """The backward pass alone at the headline horizon: the REFERENCE's own converged
+    solution (x*, u*) of the T=50 golden is handed to the CUDA backward (gains at the
+    solution, costates, second-order tables, factored adjoint passes, sensitivity rollout);
+    every gradient, dtheta included, matches the reference's dense fix_point_equ solve to
+    1e-10."""
+    solver = importlib.import_module("differentiable-ilqr_b200._solver")
+    g = golden("ref_dilqr_cartpole_T50.npz")
+    T, B = int(g["T"]), g["x0"].shape[0]
+    dx = env.CartpoleDx(g["theta"].to(dev))
+    C = torch.diag(g["q"]).to(dev)[None, None].repeat(T, B, 1, 1)
+    c = g["p"].to(dev)[None, None].repeat(T, B, 1)
+    stats = {}
+    dC, dc, dth = solver.dilqr_backward(
+        g["gx"].to(dev), g["gu"].to(dev), g["x0"].to(dev), C, c, g["x"].to(dev), g["u"].to(dev),
+        dx, 5, 1, dx.lower, dx.upper, n_passes=passes, stats=stats)
+    assert stats["factored"]
+    assert rel(dth.sum(0), g["dtheta"]) < 1e-10
+    assert rel(dC, g["dC"]) < 1e-10 and rel(dc, g["dc"]) < 1e-10
+
+
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 def test_dilqr_gradient_vs_oracle(dilqr, port, env, dev, dtype):
     pdx, x0, C, c, kw = env_problem(port, "cartpole", 30, 40, dtype, sigma=0.05)

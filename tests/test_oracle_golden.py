@@ -68,6 +68,26 @@ def test_lindx_forward_and_kkt_backward(port, tag):
         assert rel(a, g[nm]) < 1e-13, nm
 
 
+def test_dilqr_backward_at_the_headline_horizon(port):
+    """Cartpole T=50 (the benchmark horizon), warm-started converged regime:
+    the oracle's matrix-free backward against the reference's dense fix_point_equ solve --
+    and how few Richardson passes that regime needs."""
+    g = golden("ref_dilqr_cartpole_T50.npz")
+    T, B = int(g["T"]), g["x0"].shape[0]
+    pdx = port.CartpoleDx(params=g["theta"], dtype=torch.float64)
+    C = torch.diag(g["q"])[None, None].repeat(T, B, 1, 1)
+    c = g["p"][None, None].repeat(T, B, 1)
+    o = port.mpc_forward(g["x0"], port.QuadCost(C, c), pdx, 5, 1, T, u_init=g["u_init"],
+                         final_pass=False, **_mpc_kw(pdx, int(g["lqr_iter"]), eps=1e-9))
+    assert o.n_iters == 1                    # the reference stops after one iteration too
+    assert rel(o.x, g["x"]) < 1e-13 and rel(o.u, g["u"]) < 1e-13
+    for n_passes in (4, 12):
+        r = port.dilqr_backward(g["gx"], g["gu"], g["x0"], C, c, o.x, o.u, pdx, 5, 1, pdx.lower,
+                                pdx.upper, n_passes=n_passes)
+        assert rel(r.dtheta.sum(0), g["dtheta"]) < 1e-10
+        assert rel(r.dC, g["dC"]) < 1e-12 and rel(r.dc, g["dc"]) < 1e-12
+
+
 @pytest.mark.parametrize("env", ["pendulum", "cartpole", "rocket"])
 def test_dilqr_backward_matches_reference_dense_solve(port, env):
     """Matrix-free DiLQR gradient == the reference's fix_point_equ (dense solve)."""
