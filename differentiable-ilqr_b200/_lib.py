@@ -72,7 +72,8 @@ class DilqrSolve(C.Structure):
         ("status", C.c_void_p), ("control", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
         ("dyn_aux", C.c_void_p), ("dyn_ai", C.c_int32 * 4),
-        ("delta_u", C.c_double), ("has_delta_u", C.c_int32), ("reserved0", C.c_int32),
+        ("delta_u", C.c_double), ("has_delta_u", C.c_int32), ("gains_guess_reset", C.c_int32),
+        ("keep_trace_guess", C.c_int32), ("reserved1", C.c_int32),
     ]
 
 

@@ -110,6 +110,8 @@ class Workspace:
 
     def __init__(self, nbytes, device):
         self.gen = 0       # bumped by every solve that (re)uses the buffer
+        self.gains_guess = None   # (shape key) the gains sweep's own trace guess is valid for
+        self.solve_guess = None   # (shape key) of the solve whose final trace guess is in place
         self.buf = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=device)
         self.status_dev = torch.zeros(64, dtype=torch.uint8, device=device)
         self.status_host = torch.zeros(64, dtype=torch.uint8).pin_memory()
@@ -368,7 +370,7 @@ def solve_mpc(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower=None, u_upper=Non
               max_linesearch_iter=10, not_improved_lim=5, best_cost_eps=1e-4,
               gain_solve=_lib.GAIN_PLAIN, solo=False, verbose=0, x_cur=None,
               want_gains=False, sync=True, gains_only=False, pipelined=True, delta_u=None,
-              deferred=None):
+              deferred=None, reuse_trace=True):
     """MPC.forward (mpc.py:184-306): returns (x, u, costs, info).  With ``x_cur``
     given this is a single LQRStep around (x_cur, u_init) (lqr_step.py:277-309)
     and returns the *new* iterate."""
@@ -393,6 +395,12 @@ def solve_mpc(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower=None, u_upper=Non
     if gains_only:
         s.gains_only = 1
         want_gains = True
+    # warm-started repeats of the same solve (training loops, closed loops): the trace the
+    # previous solve ended with predicts this one's first iteration better than the default
+    shape_key = (s.n_state, s.n_ctrl, s.T, s.n_batch, s.dtype, s.dynamics, s.bounds_kind, int(solo))
+    s.keep_trace_guess = 1 if (reuse_trace and u_init is not None and x_cur is None
+                               and ws.solve_guess == shape_key) else 0
+    ws.solve_guess = shape_key if x_cur is None else None
     _lib.call("dilqr_mpc_begin", C.byref(s), st)
     # python float eps is compared in the data dtype by torch (mpc.py:299)
     eps_cmp = float(torch.tensor(eps, dtype=dtype))
@@ -574,7 +582,10 @@ def dilqr_prepare(x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u_lower=None, u_
             st = _lib.DilqrStatus.from_buffer_copy(raw)
             return None if st.trace_match else "pnqp trace mismatch in the final LQR pass"
 
+        shape_key = (sp.n_state, sp.n_ctrl, sp.T, sp.n_batch, sp.dtype, sp.dynamics)
         for attempt in range(MAX_TRACE_RETRIES):
+            sp.gains_guess_reset = 0 if ws.gains_guess == shape_key else 1
+            ws.gains_guess = shape_key
             rc = _lib.call("dilqr_mpc_gains", C.byref(sp), _ptr(lam), _stream(), allow=(-2,))
             if rc == -2:
                 fused = False      # shape without the fused sweep: round-1 sequence below

@@ -92,7 +92,7 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
   size_t traj[2], best, Kk, cost_cur, cost_new, cost_best, du_new, du_best, alpha_new, dusq, take,
-      guess, votes, cpk_state, Cpk, total;
+      guess, votes, guess_gains, cpk_state, Cpk, total;
   int Bp;
 };
 
@@ -121,6 +121,7 @@ static WsLayout ws_layout(const DilqrSolve* s, size_t esz) {
   w.take = take((size_t)w.Bp * sizeof(int));
   w.guess = take((size_t)s->T * kPnqpMaxIter * sizeof(uint32_t));
   w.votes = take((size_t)s->T * kPnqpMaxIter * sizeof(uint32_t));
+  w.guess_gains = take((size_t)s->T * kPnqpMaxIter * sizeof(uint32_t));
   w.cpk_state = take(sizeof(uint32_t));
   // packed symmetric copy of C: only shapes whose sweeps are staged use it (staged_v)
   {
@@ -271,9 +272,11 @@ static int launch_begin(const DilqrSolve* s, cudaStream_t st) {
   // minimiser); at t < T-1 one Newton step then convergence (SURVEY a-5).
   const WsLayout w = ws_layout(s, sizeof(S));
   static_assert(kPnqpMaxIter == DILQR_PNQP_MAX_ITER, "trace width");
-  cudaMemsetAsync(p.guess, 0, (size_t)p.T * kPnqpMaxIter * sizeof(uint32_t), st);
-  if (p.T > 1)
-    cudaMemset2DAsync(p.guess, kPnqpMaxIter * sizeof(uint32_t), 3, 1, p.T - 1, st);
+  if (!s->keep_trace_guess) {
+    cudaMemsetAsync(p.guess, 0, (size_t)p.T * kPnqpMaxIter * sizeof(uint32_t), st);
+    if (p.T > 1)
+      cudaMemset2DAsync(p.guess, kPnqpMaxIter * sizeof(uint32_t), 3, 1, p.T - 1, st);
+  }
   (void)w;
   {  // 1: begin packs the upper triangle of C for the sweeps (ilqr_kernels.cuh), 0: dense
     static const bool off = getenv("DILQR_NO_PACK") != nullptr;   // tuning / A-B knob
@@ -349,9 +352,14 @@ static int launch_gains(const DilqrSolve* s, void* lam_blk, cudaStream_t st) {
     auto kern = ilqr_gains_kernel<S, NS, NC, DYN, G::STAGED>;
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    // pnqp trace guess: whatever the workspace holds -- the verified trace of the solve's
-    // last iteration (the best predictor of this sweep, which runs at the iterate that
-    // iteration produced), or the correction a previous call of this function left
+    // pnqp trace guess: this sweep's own, kept in the workspace from call to call (the
+    // correction a mismatching call leaves is the right guess for the next call / step)
+    p.guess = reinterpret_cast<uint32_t*>(static_cast<char*>(s->workspace) +
+                                          ws_layout(s, sizeof(S)).guess_gains);
+    if (s->gains_guess_reset) {   // default: nothing moves at T-1, one Newton step elsewhere
+      cudaMemsetAsync(p.guess, 0, (size_t)p.T * kPnqpMaxIter * sizeof(uint32_t), st);
+      if (p.T > 1) cudaMemset2DAsync(p.guess, kPnqpMaxIter * sizeof(uint32_t), 3, 1, p.T - 1, st);
+    }
     if (p.bounds_kind && !p.solo)
       cudaMemsetAsync(p.votes, 0, (size_t)p.T * kPnqpMaxIter * sizeof(uint32_t), st);
     kern<<<blocks, wpb * kWarp, smem, st>>>(p);

@@ -64,7 +64,7 @@ def tile_cost(q, p, T, B):
 
 class ImitationStep:
     def __init__(self, dx_cls, T, lqr_iter, dtype, device, n_richardson=4, richardson_tol=None,
-                 group=None, tile=True):
+                 group=None, tile=True, detach_unconverged=False):
         # tile=True: materialise Q,p as [T,B,n,n] / [T,B,n] exactly like il_env.py:159-162;
         # tile=False: hand MPC the [n,n] / [n] tensors (mpc.py:205-219 broadcasts them)
         self.tile = tile
@@ -75,7 +75,7 @@ class ImitationStep:
         self.ns, self.nc = proto.n_state, proto.n_ctrl
         self.mpc = mpc_explicit.MPC(
             self.ns, self.nc, T, u_lower=proto.lower, u_upper=proto.upper, lqr_iter=lqr_iter,
-            verbose=-1, exit_unconverged=False, detach_unconverged=False,
+            verbose=-1, exit_unconverged=False, detach_unconverged=detach_unconverged,
             linesearch_decay=proto.linesearch_decay,
             max_linesearch_iter=proto.max_linesearch_iter, eps=proto.mpc_eps,
             richardson_passes=n_richardson, richardson_tol=richardson_tol)

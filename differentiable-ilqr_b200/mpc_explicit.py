@@ -21,7 +21,8 @@ class _MPCExplicitFn(Function):
     def forward(ctx, mod, dx, x_init, C, c, theta, q=None, p=None):
         ctx.set_materialize_grads(False)
         ctx.tiled = q is not None
-        deferred = mod.deferred if (mod.defer_checks and not mod.detach_unconverged) else None
+        deferred = mod.deferred if (mod.defer_checks and not (
+            mod.detach_unconverged and (mod.exit_unconverged or mod.verbose >= 0))) else None
         dyn = _dyn_spec(dx)
         # A 4-D stride-0 cost (e.g. Q[None, None].expand(T, B, n, n)) is read as the broadcast
         # block it is -- unless its gradient is wanted: autograd then expects a [T,B,n,n]
@@ -46,13 +47,18 @@ class _MPCExplicitFn(Function):
         ctx.mask = None
         eps_cmp = float(torch.tensor(mod.eps, dtype=x.dtype))
         if mod.detach_unconverged:                       # mpc_explicit.py:343-356
-            if float(info.full_du_norm.max()) > eps_cmp:
-                if mod.exit_unconverged:
-                    assert False
-                if mod.verbose >= 0:
+            # the mask is a device op; only the reference's warning / assert needs the host
+            # to look at the norms (one sync), so a quiet caller (verbose < 0) pays none
+            mask = (info.full_du_norm < eps_cmp).to(x.dtype)
+            if mod.exit_unconverged or mod.verbose >= 0:
+                if float(info.full_du_norm.max()) > eps_cmp:
+                    if mod.exit_unconverged:
+                        assert False
                     print("LQR Warning: All examples did not converge to a fixed point.")
                     print("Detaching and *not* backpropping through the bad examples.")
-                ctx.mask = (info.full_du_norm < eps_cmp).to(x.dtype)
+                else:
+                    mask = None
+            ctx.mask = mask
         ctx.save_for_backward(x_init, C, c, x, u)
         ctx.mark_non_differentiable(costs)
         # a gradient wrt the cost or theta will be asked for: enqueue the part of the

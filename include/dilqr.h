@@ -158,7 +158,14 @@ typedef struct DilqrSolve {
      204-211); needs box constraints (lqr_step.py:195) */
   double  delta_u;
   int32_t has_delta_u;
-  int32_t reserved0;
+  int32_t gains_guess_reset; /* dilqr_mpc_gains keeps its own pnqp trace guess in the workspace,
+                                carried from call to call (a training loop revisits nearly the
+                                same solutions, so the guess of the previous step is right);
+                                1: start from the default guess (first use of a workspace)      */
+  int32_t keep_trace_guess;  /* dilqr_mpc_begin: 1 keeps the pnqp trace guess the previous solve in
+                                this workspace ended with (same shape; steady-state loops) instead
+                                of resetting it to the default                                    */
+  int32_t reserved1;
 } DilqrSolve;
 
 const char* dilqr_version(void);
