@@ -73,7 +73,7 @@ class DilqrSolve(C.Structure):
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
         ("dyn_aux", C.c_void_p), ("dyn_ai", C.c_int32 * 4),
         ("delta_u", C.c_double), ("has_delta_u", C.c_int32), ("gains_guess_reset", C.c_int32),
-        ("keep_trace_guess", C.c_int32), ("reserved1", C.c_int32),
+        ("keep_trace_guess", C.c_int32), ("group_sweep", C.c_int32),
     ]
 
 
@@ -118,6 +118,8 @@ SYMBOLS = {
     "dilqr_version": (C.c_char_p, []),
     "dilqr_supported": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "dilqr_lockstep_capacity": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "dilqr_group_sweep_capacity": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "dilqr_shape_staged": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "dilqr_workspace_bytes": (C.c_size_t, [C.POINTER(DilqrSolve)]),
     "dilqr_mpc_begin": (C.c_int, [C.POINTER(DilqrSolve), C.c_void_p]),
     "dilqr_mpc_iterate": (C.c_int, [C.POINTER(DilqrSolve), C.c_void_p]),

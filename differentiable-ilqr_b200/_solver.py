@@ -122,7 +122,11 @@ class Workspace:
 
 _ws_cache = {}
 _lockstep_cap = {}
+_group_cap = {}
 LOCKSTEP_AUTO = True
+GROUP_SWEEP = "auto"          # "auto" | "always" | "never"
+GROUP_SWEEP_BOXED = True      # auto: box-constrained multi-input batches use it even when the
+                              # register-resident lockstep kernel would fit
 
 
 def _require_cuda(t, name):
@@ -240,13 +244,30 @@ def _make_problem(x_init, C_, c_, dyn, n_state, n_ctrl, T, u_lower, u_upper, u_z
             "(add it to DILQR_CONFIGS in csrc/api.cu)" % (dtype, n_state, n_ctrl, dyn.kind))
     # multi-input box-constrained problems have long, unstable pnqp traces: resolve the
     # batch-global decisions with grid barriers when the whole batch fits on the device
-    if s.bounds_kind != _lib.BOUNDS_NONE and not solo and n_ctrl > 1 and LOCKSTEP_AUTO:
-        cap = _lockstep_cap.get((s.dtype, n_state, n_ctrl, dyn.kind))
+    key = (s.dtype, n_state, n_ctrl, dyn.kind)
+    boxed_multi = s.bounds_kind != _lib.BOUNDS_NONE and not solo and n_ctrl > 1
+    cap = 0
+    if boxed_multi and LOCKSTEP_AUTO:
+        cap = _lockstep_cap.get(key)
         if cap is None:
-            cap = L.dilqr_lockstep_capacity(s.dtype, n_state, n_ctrl, dyn.kind)
-            _lockstep_cap[(s.dtype, n_state, n_ctrl, dyn.kind)] = cap
+            cap = L.dilqr_lockstep_capacity(*key)
+            _lockstep_cap[key] = cap
         if B <= cap:
             s.lockstep = 1
+    # Thread-group sweep (csrc/group_kernels.cuh): shapes too large for one thread per
+    # problem (their matrices would spill to local memory), and box-constrained multi-input
+    # batches -- its barriers need no problem to be resident, so it is exact at any size
+    if GROUP_SWEEP != "never":
+        gs = _group_cap.get(key)
+        if gs is None:
+            gs = (L.dilqr_group_sweep_capacity(*key), L.dilqr_shape_staged(*key))
+            _group_cap[key] = gs
+        gcap, staged = gs
+        want = GROUP_SWEEP == "always" or staged == 0 or (
+            boxed_multi and (B > cap or GROUP_SWEEP_BOXED))
+        if want and 0 < B <= gcap:
+            s.group_sweep = 1
+            s.lockstep = 0
     need = L.dilqr_workspace_bytes(C.byref(s))
     # one workspace per (device, stream): solves on different streams never share scratch;
     # it only ever grows (the layout comes from the problem struct, not the buffer size)

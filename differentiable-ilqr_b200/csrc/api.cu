@@ -12,6 +12,7 @@
 #include "misc_kernels.cuh"
 #include "dilqr_backward.cuh"
 #include "adjoint_kernels.cuh"
+#include "group_kernels.cuh"
 
 namespace dilqr {
 
@@ -92,7 +93,7 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
   size_t traj[2], best, Kk, cost_cur, cost_new, cost_best, du_new, du_best, alpha_new, dusq, take,
-      guess, votes, guess_gains, cpk_state, Cpk, total;
+      guess, votes, guess_gains, cpk_state, gs_barrier, Cpk, gsQ, gsG, total;
   int Bp;
 };
 
@@ -123,14 +124,19 @@ static WsLayout ws_layout(const DilqrSolve* s, size_t esz) {
   w.votes = take((size_t)s->T * kPnqpMaxIter * sizeof(uint32_t));
   w.guess_gains = take((size_t)s->T * kPnqpMaxIter * sizeof(uint32_t));
   w.cpk_state = take(sizeof(uint32_t));
+  w.gs_barrier = take(sizeof(uint32_t));
   // packed symmetric copy of C: only shapes whose sweeps are staged use it (staged_v)
   {
     const bool env = s->dynamics != DILQR_DYN_LINDX;
     const size_t per = (size_t)kWarp * esz *
                        ((size_t)N * N + N + (env ? 0 : (size_t)s->n_state * N + s->n_state));
     const bool staged = per * kStages <= kStageBudget;
-    w.Cpk = take(staged && !s->C_bcast ? (size_t)s->T * w.Bp * (N * (N + 1) / 2) * esz : 0);
+    (void)staged;   // every shape keeps the packed copy (staged: TMA chunks; else: coalesced reads)
+    w.Cpk = take(!s->C_bcast ? (size_t)s->T * w.Bp * (N * (N + 1) / 2) * esz : 0);
   }
+  // group sweep: one Q_t / q_t record per problem
+  w.gsQ = take(s->group_sweep ? (size_t)w.Bp * ((size_t)N * N + N) * esz : 0);
+  w.gsG = take(s->group_sweep ? (size_t)w.Bp * ((size_t)s->n_ctrl * N + s->n_ctrl) * esz : 0);
   w.total = off;
   return w;
 }
@@ -191,7 +197,10 @@ static IterParams<Scalar> make_params(const DilqrSolve* s, int role = 1) {
   p.gains_only = s->gains_only;
   p.C_bcast = s->C_bcast;
   p.c_bcast = s->c_bcast;
-  p.lockstep = s->lockstep;
+  p.lockstep = s->lockstep || s->group_sweep;   // either way the votes ARE the pnqp trace
+  p.gsQ = reinterpret_cast<S*>(ws + w.gsQ);
+  p.gsG = reinterpret_cast<S*>(ws + w.gsG);
+  p.gs_barrier = reinterpret_cast<unsigned int*>(ws + w.gs_barrier);
   p.guess = reinterpret_cast<uint32_t*>(ws + w.guess);
   p.votes = reinterpret_cast<uint32_t*>(ws + w.votes);
   p.status = s->status;
@@ -280,7 +289,7 @@ static int launch_begin(const DilqrSolve* s, cudaStream_t st) {
   (void)w;
   {  // 1: begin packs the upper triangle of C for the sweeps (ilqr_kernels.cuh), 0: dense
     static const bool off = getenv("DILQR_NO_PACK") != nullptr;   // tuning / A-B knob
-    const bool pack = G::STAGED && !p.C_bcast && !(p.gains_only && p.x_cur) && !off;
+    const bool pack = !p.C_bcast && !(p.gains_only && p.x_cur) && !off;
     cudaMemsetAsync(p.cpk_state, 0, sizeof(uint32_t), st);
     if (pack) cudaMemsetAsync(p.cpk_state, 1, 1, st);   // little-endian: word value 1
   }
@@ -288,11 +297,89 @@ static int launch_begin(const DilqrSolve* s, cudaStream_t st) {
   return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
 }
 
+// Shapes the batch-synchronous group sweep (group_kernels.cuh) is compiled for: everything
+// too large for one thread per problem, and every multi-input shape (whose box-constrained
+// batches otherwise need the whole batch co-resident or a replayed trace).
+template <class S, int NS, int NC, int DYN>
+constexpr bool group_sweep_v() {
+  return (DYN == DYN_LINDX || DYN == DYN_ROCKET) && (!staged_v<S, NS, NC, DYN>() || NC > 1);
+}
+
+template <int NS, int NC, int DYN>
+static int group_sweep_blocks(int* max_blocks) {
+  using S = Scalar;
+  if constexpr (!group_sweep_v<S, NS, NC, DYN>()) {
+    *max_blocks = 0;
+    return 0;
+  } else {
+    using GS = GroupSweep<S, NS, NC, DYN>;
+    auto kern = group_sweep_kernel<S, NS, NC, DYN>;
+    const size_t smem = GS::smem_bytes();
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 0, dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GS::kThreads, smem) != cudaSuccess)
+      return 0;
+    *max_blocks = per_sm * sms;
+    return per_sm * sms * GS::kThreads;     // one phase-B thread per problem
+  }
+}
+
+template <int NS, int NC, int DYN>
+static int launch_group_sweep(const DilqrSolve* s, IterParams<Scalar>& p, cudaStream_t st) {
+  using S = Scalar;
+  if constexpr (!group_sweep_v<S, NS, NC, DYN>()) {
+    return DILQR_EUNSUPPORTED;
+  } else {
+    using GS = GroupSweep<S, NS, NC, DYN>;
+    int max_blocks = 0;
+    const int cap = group_sweep_blocks<NS, NC, DYN>(&max_blocks);
+    if (p.B > cap) return DILQR_ELOCKSTEP;
+    const int need_b = (p.B + GS::kThreads - 1) / GS::kThreads;       // phase B: thread per problem
+    const int want_ac = (p.B + GS::GPB - 1) / GS::GPB;               // phase AC: group per problem
+    int blocks = want_ac < max_blocks ? want_ac : max_blocks;
+    if (blocks < need_b) blocks = need_b;
+    if (p.bounds_kind && !p.solo)
+      cudaMemsetAsync(p.votes, 0, (size_t)p.T * kPnqpMaxIter * sizeof(uint32_t), st);
+    cudaMemsetAsync(p.gs_barrier, 0, sizeof(unsigned int), st);
+    auto kern = group_sweep_kernel<S, NS, NC, DYN>;
+    void* args[] = {(void*)&p};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)kern, dim3(blocks), dim3(GS::kThreads), args,
+                                                GS::smem_bytes(), st);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return DILQR_ELOCKSTEP;
+    }
+    (void)s;
+    return DILQR_OK;
+  }
+}
+
 template <int NS, int NC, int DYN>
 static int launch_iterate(const DilqrSolve* s, cudaStream_t st) {
   using S = Scalar;
   using G = Geometry<S, NS, NC, DYN>;
   IterParams<S> p = make_params(s);
+  if (s->group_sweep) {
+    // Riccati / pnqp sweep by thread groups, all problems in step; then the line-search
+    // rollout (one thread per problem: its state is small) as a second launch
+    int rc = launch_group_sweep<NS, NC, DYN>(s, p, st);
+    if (rc != DILQR_OK) return rc;
+    if (p.gains_only) return DILQR_OK;
+    if constexpr (group_sweep_v<S, NS, NC, DYN>()) {
+      const int wpb = G::warps_per_block();
+      const int warps = (p.B + kWarp - 1) / kWarp;
+      const size_t smem = G::smem(wpb);
+      auto fwd = ilqr_iter_kernel<S, NS, NC, DYN, G::STAGED, false, 2>;
+      if (smem > 48 * 1024)
+        cudaFuncSetAttribute(fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      p.lockstep = 0;
+      fwd<<<(warps + wpb - 1) / wpb, wpb * kWarp, smem, st>>>(p);
+    }
+    return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
+  }
   const int wpb = G::warps_per_block();
   const int warps = (p.B + kWarp - 1) / kWarp;
   const int blocks = (warps + wpb - 1) / wpb;
@@ -437,6 +524,23 @@ int DILQR_SUFFIX(lockstep_capacity)(int n_state, int n_ctrl, int dynamics) {
   DILQR_CONFIGS(X)
 #undef X
   return 0;
+}
+
+int DILQR_SUFFIX(group_sweep_capacity)(int n_state, int n_ctrl, int dynamics) {
+  int mb = 0;
+#define X(NS_, NC_, DYN_) \
+  if (n_state == NS_ && n_ctrl == NC_ && dynamics == DYN_) return group_sweep_blocks<NS_, NC_, DYN_>(&mb);
+  DILQR_CONFIGS(X)
+#undef X
+  return 0;
+}
+
+int DILQR_SUFFIX(shape_staged)(int n_state, int n_ctrl, int dynamics) {
+#define X(NS_, NC_, DYN_) \
+  if (n_state == NS_ && n_ctrl == NC_ && dynamics == DYN_) return staged_v<Scalar, NS_, NC_, DYN_>() ? 1 : 0;
+  DILQR_CONFIGS(X)
+#undef X
+  return -1;
 }
 
 int DILQR_SUFFIX(supported)(int n_state, int n_ctrl, int dynamics) {

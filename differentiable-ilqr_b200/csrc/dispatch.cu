@@ -7,6 +7,8 @@ namespace dilqr {
 #define DECL_G(sfx)                                                                       \
   int supported_##sfx(int, int, int);                                                     \
   int lockstep_capacity_##sfx(int, int, int);                                             \
+  int group_sweep_capacity_##sfx(int, int, int);                                          \
+  int shape_staged_##sfx(int, int, int);                                                  \
   int mpc_begin_##sfx(const DilqrSolve*, void*);                                          \
   int mpc_iterate_##sfx(const DilqrSolve*, void*);                                        \
   int mpc_commit_##sfx(const DilqrSolve*, void*);                                         \
@@ -85,6 +87,29 @@ int dilqr_lockstep_capacity(int dtype, int ns, int nc, int dyn) {
     return dilqr::lockstep_capacity_f64_g0(ns, nc, dyn) + dilqr::lockstep_capacity_f64_g1(ns, nc, dyn) +
            dilqr::lockstep_capacity_f64_g2(ns, nc, dyn) + dilqr::lockstep_capacity_f64_g3(ns, nc, dyn);
   return 0;
+}
+
+int dilqr_group_sweep_capacity(int dtype, int ns, int nc, int dyn) {
+  if (dtype == DILQR_F32)
+    return dilqr::group_sweep_capacity_f32_g0(ns, nc, dyn) + dilqr::group_sweep_capacity_f32_g1(ns, nc, dyn) +
+           dilqr::group_sweep_capacity_f32_g2(ns, nc, dyn) + dilqr::group_sweep_capacity_f32_g3(ns, nc, dyn);
+  if (dtype == DILQR_F64)
+    return dilqr::group_sweep_capacity_f64_g0(ns, nc, dyn) + dilqr::group_sweep_capacity_f64_g1(ns, nc, dyn) +
+           dilqr::group_sweep_capacity_f64_g2(ns, nc, dyn) + dilqr::group_sweep_capacity_f64_g3(ns, nc, dyn);
+  return 0;
+}
+
+int dilqr_shape_staged(int dtype, int ns, int nc, int dyn) {
+  int r = -1;
+  for (int g = 0; g < 4 && r < 0; ++g) {
+    if (dtype == DILQR_F32)
+      r = g == 0 ? dilqr::shape_staged_f32_g0(ns, nc, dyn) : g == 1 ? dilqr::shape_staged_f32_g1(ns, nc, dyn)
+        : g == 2 ? dilqr::shape_staged_f32_g2(ns, nc, dyn) : dilqr::shape_staged_f32_g3(ns, nc, dyn);
+    else if (dtype == DILQR_F64)
+      r = g == 0 ? dilqr::shape_staged_f64_g0(ns, nc, dyn) : g == 1 ? dilqr::shape_staged_f64_g1(ns, nc, dyn)
+        : g == 2 ? dilqr::shape_staged_f64_g2(ns, nc, dyn) : dilqr::shape_staged_f64_g3(ns, nc, dyn);
+  }
+  return r;
 }
 
 size_t dilqr_workspace_bytes(const DilqrSolve* s) {

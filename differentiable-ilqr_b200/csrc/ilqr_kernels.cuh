@@ -100,6 +100,9 @@ struct IterParams {
   S* K_out;
   S* k_out;
   S* lam_blk;   // gains-at-the-solution sweep: primal costates [T][Bp/32][NS][32] (optional)
+  S* gsQ;       // group sweep (group_kernels.cuh): per-problem record Q_t[N][N], q_t[N]
+  S* gsG;       // group sweep: rows n_state.. of Q_t and q_u, lane-interleaved [Bp/32][NC*N+NC][32]
+  unsigned int* gs_barrier;   // group sweep: SubBarrier counter (zeroed before the launch)
   DynParams<S> dyn;
 };
 
@@ -176,13 +179,37 @@ DILQR_DEVICE void lin_step(const S* __restrict__ Fs, const S* __restrict__ fs, b
 // last evaluated iteration -- exactly what lqr_backward consumes
 // (lqr_step.py:135-148).
 // ---------------------------------------------------------------------------
-template <class S, int N, bool LOCKSTEP = false>
+// Barrier among the first `n` blocks of a (co-resident) grid: one monotonically increasing
+// counter in global memory, episode k is complete once it reaches k * n.  Used by the group
+// sweep for the pnqp decisions, which only involve the blocks that own problems (a fraction
+// of the grid, so it is cheaper than a full grid.sync and the other blocks stay out of it).
+struct SubBarrier {
+  unsigned int* counter;   // zeroed before the launch
+  unsigned int n;
+  unsigned int episode;
+  DILQR_DEVICE void sync() {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned int target = (++episode) * n;
+      atomicAdd(counter, 1u);
+      while (*reinterpret_cast<volatile unsigned int*>(counter) < target) {
+      }
+      __threadfence();
+    }
+    __syncthreads();
+  }
+};
+
+// LOCKSTEP: 0 replay a guessed trace; 1 decide with grid-wide barriers (cooperative launch,
+// every thread of the grid takes part); 2 decide with a SubBarrier (`sb`).
+template <class S, int N, int LOCKSTEP = 0>
 DILQR_DEVICE void pnqp_thread(const S (&H)[N][N], const S (&q)[N], const S (&lo)[N],
                               const S (&hi)[N], bool have_init, S (&x)[N], bool (&If)[N],
                               LUpp<S, N>& lu, const uint32_t* __restrict__ guess, uint4 gpre,
                               uint32_t* __restrict__ votes, bool solo, bool active, int lane,
-                              S* rinv_out = nullptr) {
-  constexpr bool lockstep = LOCKSTEP;
+                              S* rinv_out = nullptr, SubBarrier* sb = nullptr) {
+  constexpr bool lockstep = LOCKSTEP != 0;
   // N == 1: 1 / (masked Hessian) of the last evaluated iteration, handed to the caller
   // (which needs the same quotient for K, lqr_step.py:144-146) and reused across
   // iterations while the operand is unchanged -- same value, one division instead of three.
@@ -193,9 +220,13 @@ DILQR_DEVICE void pnqp_thread(const S (&H)[N][N], const S (&q)[N], const S (&lo)
   // barrier (no guessing, no re-runs) -- the better trade when the control-flow trace
   // is long and unstable (multi-input problems with many active constraints).
   auto grid_decide = [&](uint32_t* word, uint32_t mine) -> uint32_t {
-    if constexpr (LOCKSTEP) {
+    if constexpr (LOCKSTEP == 1) {
       if (mine && lane == 0) atomicOr(word, mine);
       cooperative_groups::this_grid().sync();
+      return *reinterpret_cast<volatile uint32_t*>(word);
+    } else if constexpr (LOCKSTEP == 2) {
+      if (mine && lane == 0) atomicOr(word, mine);
+      sb->sync();
       return *reinterpret_cast<volatile uint32_t*>(word);
     } else {
       return 0u;
@@ -433,7 +464,12 @@ struct IterKernel {
       k.tau = st.seg_ptr(sg, 4) + lane;
       k.Kk = st.seg_ptr(sg, 5) + lane;
     } else {
-      k.C = cost_src<S>(p.C, p.C_bcast, t, p.B, b, N * N);
+      // shapes too large to stage: the packed, lane-interleaved copy of C (written by begin)
+      // turns the per-thread reads of a 2 KB row-major block into coalesced ones
+      k.packed = !p.C_bcast && p.cpk_state &&
+                 *reinterpret_cast<const volatile uint32_t*>(p.cpk_state) == 1u;
+      k.C = k.packed ? p.Cpk + bidx(t, 0, NP, bw, p.nW)
+                     : cost_src<S>(p.C, p.C_bcast, t, p.B, b, N * N);
       k.c = cost_src<S>(p.c, p.c_bcast, t, p.B, b, N);
       k.F = (kEnv || t >= p.T - 1) ? nullptr : p.F + ((size_t)t * p.B + b) * (NS * N);
       k.f = (kEnv || !p.has_f || t >= p.T - 1) ? nullptr : p.f + ((size_t)t * p.B + b) * NS;
@@ -728,7 +764,7 @@ struct IterKernel {
         bool If[NC];
         LUpp<S, NC> lu;
         S rinv = S(0);
-        pnqp_thread<S, NC, LOCKSTEP>(H, qu, lo, hi, have_prev, k, If, lu,
+        pnqp_thread<S, NC, LOCKSTEP ? 1 : 0>(H, qu, lo, hi, have_prev, k, If, lu,
                                      p.guess + (size_t)t * kPnqpMaxIter, gpre,
                                      p.votes + (size_t)t * kPnqpMaxIter, p.solo != 0, active, lane,
                                      &rinv);
@@ -1040,7 +1076,7 @@ ilqr_begin_kernel(const __grid_constant__ IterParams<S> p) {
   const bool want_cost = !(p.gains_only && p.x_cur);
   // the sweeps read C twice per iteration: when every block is bitwise symmetric they
   // stream this packed copy (N(N+1)/2 instead of N*N scalars) instead
-  const bool do_pack = STAGED && want_cost && !p.C_bcast && p.cpk_state &&
+  const bool do_pack = want_cost && !p.C_bcast && p.cpk_state &&
                        *reinterpret_cast<const volatile uint32_t*>(p.cpk_state) == 1u;
   bool asym = false;
   if (want_cost) IK::issue_t(st, p, 0, 0, b0, true, false, false);
@@ -1065,7 +1101,11 @@ ilqr_begin_kernel(const __grid_constant__ IterParams<S> p) {
     }
     if (!want_cost) continue;
     if (STAGED) st.wait(sg);
-    const typename IK::Blk blk = IK::blocks(p, st, sg, t, b, b0 + lane, lane);
+    typename IK::Blk blk = IK::blocks(p, st, sg, t, b, b0 + lane, lane);
+    if (!STAGED) {   // begin WRITES the packed copy: it reads the dense API tensor itself
+      blk.C = cost_src<S>(p.C, p.C_bcast, t, p.B, b, N * N);
+      blk.packed = false;
+    }
     cost = cost + stage_cost<S, N>(blk.C, blk.c, th);
     if (do_pack) {   // upper triangle into the warp-blocked workspace copy; symmetry check
       S* po = p.Cpk + bidx(t, 0, IK::NP, b0 + lane, p.nW);

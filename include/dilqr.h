@@ -165,7 +165,11 @@ typedef struct DilqrSolve {
   int32_t keep_trace_guess;  /* dilqr_mpc_begin: 1 keeps the pnqp trace guess the previous solve in
                                 this workspace ended with (same shape; steady-state loops) instead
                                 of resetting it to the default                                    */
-  int32_t reserved1;
+  int32_t group_sweep;       /* iterate: run the Riccati / pnqp sweep with the batch-synchronous
+                                thread-group kernel (csrc/group_kernels.cuh): G lanes per problem,
+                                every batch-global pnqp decision a grid barrier -- exact on any batch
+                                up to dilqr_group_sweep_capacity() problems, no trace replay.  Must
+                                be set before dilqr_workspace_bytes (it adds a scratch record)      */
 } DilqrSolve;
 
 const char* dilqr_version(void);
@@ -176,6 +180,16 @@ int dilqr_supported(int dtype, int n_state, int n_ctrl, int dynamics);
 /* Largest n_batch the lockstep (cooperative) variant of dilqr_mpc_iterate can hold
  * resident on the current device for this shape; 0 if unsupported. */
 int dilqr_lockstep_capacity(int dtype, int n_state, int n_ctrl, int dynamics);
+
+/* Largest n_batch the group sweep handles for this shape on the current device (one
+ * phase-B thread per problem in a co-resident cooperative grid); 0: not compiled for it
+ * (single-input shapes that fit one thread per problem keep the register-resident sweep). */
+int dilqr_group_sweep_capacity(int dtype, int n_state, int n_ctrl, int dynamics);
+
+/* 1: the shape's sweeps keep a problem in one thread's registers with TMA-staged operands;
+ * 0: too large for that (its matrices would live in local memory: use the group sweep);
+ * -1: shape not compiled in. */
+int dilqr_shape_staged(int dtype, int n_state, int n_ctrl, int dynamics);
 
 /* Bytes of workspace the dilqr_mpc_* calls need. */
 size_t dilqr_workspace_bytes(const DilqrSolve* s);
