@@ -172,19 +172,26 @@ class MPC(nn.Module):
         return C, c
 
     def forward(self, x_init, cost, dx):
-        if not isinstance(cost, QuadCost):
-            raise NotImplementedError("only QuadCost is supported (SURVEY 8a-2)")
+        quad = isinstance(cost, QuadCost)
+        if not quad and not isinstance(cost, nn.Module):
+            raise TypeError("cost must be a QuadCost or an nn.Module (mpc.py:447-487)")
         if self.n_batch is not None:
             n_batch = self.n_batch
-        elif cost.C.ndimension() == 4:
+        elif quad and cost.C.ndimension() == 4:
             n_batch = cost.C.size(1)
         else:
             print('MPC Error: Could not infer batch size, pass in as n_batch')
             sys.exit(-1)
-        C, c = self._expand_cost(cost, n_batch)
         assert x_init.ndimension() == 2 and x_init.size(0) == n_batch
         if isinstance(dx, AffineDynamics):      # time-invariant LinDx (dynamics.py:159-202)
             dx = LinDx(*dx.as_lindx(self.T, n_batch, x_init.dtype, x_init.device))
+        generic_dx = not isinstance(dx, (LinDx, NNDynamics)) and getattr(dx, "_dilqr_kind", None) is None
+        if not quad or generic_dx:
+            # Module cost (approximate_cost, mpc.py:447-487) and / or a dynamics Module
+            # without device kernels (AUTO_DIFF / FINITE_DIFF / ANALYTIC grad_input,
+            # mpc.py:490-601): torch evaluates the Modules, the kernels run the sweeps
+            return self._forward_generic(x_init, cost, dx, n_batch)
+        C, c = self._expand_cost(cost, n_batch)
         if self.slew_rate_penalty is not None:
             return self._forward_slew(x_init, C, c, dx, n_batch)
         if isinstance(dx, NNDynamics):
@@ -245,6 +252,211 @@ class MPC(nn.Module):
         x, u, costs = inner(_x_init, QuadCost(_C, _c), LinDx(_F, _f))
         self.last_info = inner.last_info
         return x[:, :, nc:], u, costs
+
+    # ------------------------------------------------------------------ generic Modules
+    def approximate_cost(self, x, u, Cf, diff=True):
+        """Second-order Taylor expansion of a cost Module along a trajectory (mpc.py:447-487):
+        hessians [T,B,n,n], grads - H tau [T,B,n], costs [T,B].  All T timesteps go through
+        the Module as one [T*B, n] batch (it acts row-wise), one autograd pass per column
+        of the Hessian, on the device."""
+        T, B = x.shape[0], x.shape[1]
+        n = self.n_state + self.n_ctrl
+        with torch.enable_grad():
+            tau = torch.cat((x, u), 2).detach().reshape(T * B, n).requires_grad_()
+            cost = Cf(tau)
+            grad = torch.autograd.grad(cost.sum(), tau, create_graph=True, retain_graph=True)[0]
+            cols = [torch.autograd.grad(grad[:, i].sum(), tau, retain_graph=True)[0] for i in range(n)]
+            hess = torch.stack(cols, -1)
+            grads = grad - torch.bmm(hess, tau.unsqueeze(2)).squeeze(2)
+        out = (hess.reshape(T, B, n, n), grads.reshape(T, B, n), cost.reshape(T, B))
+        return out if diff else tuple(t.detach() for t in out)
+
+    def linearize_dynamics(self, x, u, dynamics, diff):
+        """F[T-1,B,ns,n], f[T-1,B,ns] of a dynamics Module along (x, u) (mpc.py:490-601), all
+        T-1 steps as one batch: ANALYTIC through ``dynamics.grad_input``, AUTO_DIFF through
+        one autograd pass per state component, FINITE_DIFF by central differences
+        (eps = 1e-4, util.py:10-20)."""
+        T, B, ns, nc = self.T, x.shape[1], self.n_state, self.n_ctrl
+        with torch.enable_grad():
+            _x = x[:-1].reshape(-1, ns).detach().requires_grad_()
+            _u = u[:-1].reshape(-1, nc).detach().requires_grad_()
+            new_x = dynamics(_x, _u)
+            if self.grad_method == GradMethods.ANALYTIC:
+                if not diff:
+                    R, S = dynamics.grad_input(_x.detach(), _u.detach())
+                else:
+                    R, S = dynamics.grad_input(_x, _u)
+            elif self.grad_method == GradMethods.AUTO_DIFF:
+                Rs, Ss = [], []
+                for j in range(ns):
+                    Rj, Sj = torch.autograd.grad(new_x[:, j].sum(), [_x, _u], retain_graph=True)
+                    Rs.append(Rj)
+                    Ss.append(Sj)
+                R, S = torch.stack(Rs, 1), torch.stack(Ss, 1)
+            elif self.grad_method == GradMethods.FINITE_DIFF:
+                eps = 1e-4
+                tau = torch.cat((_x, _u), 1).detach()
+                cols = []
+                for j in range(ns + nc):
+                    e = torch.zeros(ns + nc, dtype=tau.dtype, device=tau.device)
+                    e[j] = 1.
+                    tp, tm = tau + eps * e, tau - eps * e
+                    cols.append((dynamics(tp[:, :ns], tp[:, ns:]) - dynamics(tm[:, :ns], tm[:, ns:]))
+                                / (2. * eps))
+                J = torch.stack(cols, 2)
+                if not diff:
+                    J = J.detach()
+                R, S = J[:, :, :ns], J[:, :, ns:]
+            else:
+                raise NotImplementedError("grad_method %s" % self.grad_method)
+            if not diff:
+                new_x, _x, _u = new_x.detach(), _x.detach(), _u.detach()
+                R, S = R.detach(), S.detach()
+            f = new_x - torch.bmm(R, _x.unsqueeze(2)).squeeze(2) - torch.bmm(S, _u.unsqueeze(2)).squeeze(2)
+        F = torch.cat((R, S), 2).reshape(T - 1, B, ns, ns + nc)
+        return F, f.reshape(T - 1, B, ns)
+
+    def _forward_generic(self, x_init, cost, dx, n_batch):
+        """MPC.forward for a cost Module and / or a dynamics Module without device kernels
+        (mpc.py:248-337).  Per iLQR iteration torch evaluates and differentiates the
+        Modules on the device (quadratic cost model, linearised dynamics, and the TRUE cost /
+        dynamics inside the line search, lqr_step.py:164-261), batched over the problems and
+        the horizon; the Riccati / pnqp sweep of every LQR step -- the hot part -- runs in
+        the kernels on the resulting (C, c, F, f).  The gradient is the KKT adjoint at the
+        solution with (C, c, F, f) re-derived under autograd (mpc.py:308-319)."""
+        if self.slew_rate_penalty is not None:
+            raise NotImplementedError("slew_rate_penalty with Module cost / dynamics: the reference "
+                                      "itself exits here (mpc.py:451-457)")
+        T, ns, nc = self.T, self.n_state, self.n_ctrl
+        dt, dev = x_init.dtype, x_init.device
+        quad = isinstance(cost, QuadCost)
+        lin = isinstance(dx, LinDx)
+        env = getattr(dx, "_dilqr_kind", None) is not None and not lin
+        if quad:
+            C, c = [t.detach().contiguous() for t in self._expand_cost(cost, n_batch)]
+
+        def step(xt, ut, t):
+            if lin:
+                nx = torch.bmm(dx.F[t], torch.cat((xt, ut), 1).unsqueeze(2)).squeeze(2)
+                return nx + dx.f[t] if (dx.f is not None and dx.f.nelement() > 0) else nx
+            return dx(xt, ut).detach()
+
+        def traj_cost(x, u):                                  # util.py:130-153
+            tau = torch.cat((x, u), 2)
+            if quad:
+                return (0.5 * (torch.matmul(tau.unsqueeze(2), C) @ tau.unsqueeze(3)).reshape(T, -1)
+                        + (tau * c).sum(2)).sum(0)
+            return cost(tau.reshape(T * n_batch, ns + nc)).reshape(T, n_batch).sum(0)
+
+        def bound(t, ut_nom):
+            lo = self.u_lower if isinstance(self.u_lower, float) else self.u_lower[t]
+            hi = self.u_upper if isinstance(self.u_upper, float) else self.u_upper[t]
+            if self.delta_u is not None:                      # lqr_step.py:204-211
+                lo = torch.maximum(ut_nom - self.delta_u, torch.as_tensor(lo, dtype=dt, device=dev))
+                hi = torch.minimum(ut_nom + self.delta_u, torch.as_tensor(hi, dtype=dt, device=dev))
+            return lo, hi
+
+        if self.u_init is None:
+            u = torch.zeros(T, n_batch, nc, dtype=dt, device=dev)
+        else:
+            u = self.u_init.detach().to(dt)
+            if u.ndimension() == 2:
+                u = u.unsqueeze(1).expand(T, n_batch, -1)
+            u = u.clone()
+        info = _solver.SolveInfo()
+        eps_cmp = float(torch.tensor(self.eps, dtype=dt))
+        best = None
+        n_not_improved = 0
+        with torch.no_grad():
+            for i in range(self.lqr_iter):
+                xs = [x_init.detach()]
+                for t in range(T - 1):
+                    xs.append(step(xs[t], u[t], t))
+                x = torch.stack(xs, 0)
+                if lin:
+                    F, f = dx.F.detach(), (dx.f.detach() if dx.f is not None and dx.f.nelement() > 0 else None)
+                elif env:
+                    F, f = dx.linearize_traj(x, u)
+                else:
+                    F, f = self.linearize_dynamics(x, u, dx, diff=False)
+                if not quad:
+                    C, c, _ = self.approximate_cost(x, u, cost, diff=False)
+                    C, c = C.contiguous(), c.contiguous()
+                # lqr_backward (lqr_step.py:52-160) in the kernels: the gains of this LQR step
+                _, _, _, li = _solver.solve_mpc(
+                    x_init.detach(), C, c, _solver.DynSpec(_lib.DYN_LINDX, F=F, f=f), ns, nc, T,
+                    u_lower=self.u_lower, u_upper=self.u_upper, u_zero_I=self.u_zero_I, u_init=u,
+                    x_cur=x, lqr_iter=1, gain_solve=self._gain_solve, solo=self.solo, verbose=-1,
+                    gains_only=True, delta_u=self.delta_u)
+                K, k = li.K, li.k
+                info.qp_iters.append(li.qp_iters[0] if li.qp_iters else 0)
+                info.retries += li.retries
+                # lqr_forward: line search on the TRUE cost / dynamics (lqr_step.py:164-261)
+                old_cost = traj_cost(x, u)
+                alphas = torch.ones(n_batch, dtype=dt, device=dev)
+                cur, full_du, j = None, None, 0
+                while (cur is None or bool((cur > old_cost).any())) and j < self.max_linesearch_iter:
+                    nx, nu = [x_init.detach()], []
+                    for t in range(T):
+                        ut = torch.bmm(K[t], (nx[t] - x[t]).unsqueeze(2)).squeeze(2) + u[t] \
+                            + alphas.unsqueeze(1) * k[t]
+                        if self.u_zero_I is not None:
+                            ut = ut.masked_fill(self.u_zero_I[t].to(torch.bool), 0.)
+                        if self.u_lower is not None:
+                            lo, hi = bound(t, u[t])
+                            ut = torch.minimum(torch.maximum(ut, torch.as_tensor(lo, dtype=dt, device=dev)),
+                                               torch.as_tensor(hi, dtype=dt, device=dev))
+                        nu.append(ut)
+                        if t < T - 1:
+                            nx.append(step(nx[t], ut, t))
+                    new_x, new_u = torch.stack(nx, 0), torch.stack(nu, 0)
+                    cur = traj_cost(new_x, new_u)
+                    if full_du is None:                       # lqr_step.py:243-245 (rows mix problems)
+                        full_du = (u - new_u).transpose(1, 2).contiguous().view(n_batch, -1).norm(2, 1)
+                    alphas = torch.where(cur > old_cost, alphas * self.linesearch_decay, alphas)
+                    j += 1
+                x, u, costs = new_x, new_u, cur
+                n_not_improved += 1
+                if best is None:                              # mpc.py:271-285
+                    best = {"x": x.clone(), "u": u.clone(), "costs": costs.clone(), "du": full_du.clone()}
+                else:
+                    imp = costs <= best["costs"] + self.best_cost_eps
+                    if bool(imp.any()):
+                        n_not_improved = 0
+                    best["x"][:, imp], best["u"][:, imp] = x[:, imp], u[:, imp]
+                    best["costs"][imp], best["du"][imp] = costs[imp], full_du[imp]
+                info.n_iters = i + 1
+                if float(full_du.max()) < eps_cmp or n_not_improved > self.not_improved_lim:
+                    break                                     # mpc.py:299-301
+        x, u, costs = best["x"], best["u"], best["costs"]
+        info.full_du_norm = best["du"]
+        self.last_info = info
+        mask = None
+        if self.detach_unconverged and float(best["du"].max()) > eps_cmp:   # mpc.py:321-334
+            if self.exit_unconverged:
+                assert False
+            if self.verbose >= 0:
+                print("LQR Warning: All examples did not converge to a fixed point.")
+                print("Detaching and *not* backpropping through the bad examples.")
+            mask = (best["du"] < eps_cmp).to(dt)
+        if not (self.backprop and torch.is_grad_enabled()):
+            return x, u, costs
+        # the final no-op LQR step under autograd (mpc.py:308-319)
+        if lin:
+            F = dx.F
+            f = dx.f if (dx.f is not None and dx.f.nelement() > 0) else torch.zeros(
+                T - 1, n_batch, ns, dtype=dt, device=dev)
+        elif env:
+            F, f = dx.linearize_traj(x, u)            # kernels: constants for autograd
+        else:
+            F, f = self.linearize_dynamics(x, u, dx, diff=True)
+        if quad:
+            Cg, cg = self._expand_cost(cost, n_batch)
+        else:
+            Cg, cg, _ = self.approximate_cost(x, u, cost, diff=True)
+        xo, uo = _KKTAtSolutionFn.apply(self, mask, x_init, Cg.contiguous(), cg.contiguous(),
+                                        F.contiguous(), f.contiguous(), x, u)
+        return xo, uo, costs
 
     def _forward_network(self, x_init, C, c, dx, n_batch):
         """Module dynamics ``dynamics.NNDynamics`` (mpc.py:248-337 with

@@ -60,3 +60,33 @@ def env_problem(port, name, T, B, dtype, sigma=0.5, seed=0):
               linesearch_decay=pdx.linesearch_decay,
               max_linesearch_iter=pdx.max_linesearch_iter)
     return pdx, x0.to(dtype), C, c, kw
+
+
+class SoftCost(torch.nn.Module):
+    """A convex, non-quadratic cost Module: 1/2 tau' (A'A + I) tau + p' tau + w sum log cosh(tau)."""
+
+    def __init__(self, n, seed):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        self.A = torch.nn.Parameter(0.3 * torch.randn(n, n, generator=g, dtype=torch.float64))
+        self.p = torch.nn.Parameter(0.5 * torch.randn(n, generator=g, dtype=torch.float64))
+        self.w = torch.nn.Parameter(torch.tensor(0.7, dtype=torch.float64))
+
+    def forward(self, tau):
+        Q = self.A.t() @ self.A + torch.eye(self.A.shape[0], dtype=tau.dtype, device=tau.device)
+        return 0.5 * ((tau @ Q) * tau).sum(1) + (tau * self.p).sum(1) \
+            + self.w * torch.log(torch.cosh(tau)).sum(1)
+
+
+class SoftDyn(torch.nn.Module):
+    """A smooth dynamics Module without grad_input: x' = x + dt (A x + B u + 0.3 tanh(W x))."""
+
+    def __init__(self, ns, nc, seed):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        self.A = torch.nn.Parameter(0.4 * torch.randn(ns, ns, generator=g, dtype=torch.float64))
+        self.B = torch.nn.Parameter(torch.randn(ns, nc, generator=g, dtype=torch.float64))
+        self.W = torch.nn.Parameter(0.5 * torch.randn(ns, ns, generator=g, dtype=torch.float64))
+
+    def forward(self, x, u):
+        return x + 0.1 * (x @ self.A.t() + u @ self.B.t() + 0.3 * torch.tanh(x @ self.W.t()))

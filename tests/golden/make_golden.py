@@ -18,6 +18,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import ref_harness  # noqa: E402
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from common import SoftCost as _SoftCost, SoftDyn as _SoftDyn  # noqa: E402
 
 R = ref_harness.load()
 
@@ -183,6 +185,52 @@ def dilqr_t50(B=16, sigma=0.05, presolve=250):
     npz("ref_dilqr_cartpole_T50.npz", x0=x0, q=q, p=p, theta=theta.detach(), u_init=u_warm, x=x,
         u=u, costs=costs, gx=gx, gu=gu, dC=C.grad, dc=c.grad, dtheta=theta.grad, T=T, lqr_iter=5,
         du_warm=(u - u_warm).abs().max())
+    torch.set_default_dtype(torch.float32)
+
+
+def module_cost_and_dynamics():
+    """mpc.MPC with a cost Module (approximate_cost, mpc.py:447-487) on LinDx dynamics, and with
+    a dynamics Module under AUTO_DIFF / FINITE_DIFF (mpc.py:525-601) on a QuadCost: forward
+    solutions and the gradients wrt the Modules' parameters."""
+    torch.set_default_dtype(torch.float64)
+    out = {}
+    ns, nc, T, B = 4, 2, 8, 6
+    n = ns + nc
+    g = torch.Generator().manual_seed(21)
+    F = (torch.eye(ns).unsqueeze(0).unsqueeze(0).repeat(T - 1, B, 1, 1)
+         + 0.2 * torch.randn(T - 1, B, ns, ns, generator=g))
+    F = torch.cat((F, torch.randn(T - 1, B, ns, nc, generator=g)), 3)
+    f = 0.1 * torch.randn(T - 1, B, ns, generator=g)
+    x0 = torch.randn(B, ns, generator=g)
+    gx = torch.randn(T, B, ns, generator=g)
+    gu = torch.randn(T, B, nc, generator=g)
+    cost = _SoftCost(n, 5)
+    Fg, fg, x0g = F.clone().requires_grad_(), f.clone().requires_grad_(), x0.clone().requires_grad_()
+    m = R.mpc.MPC(ns, nc, T, u_lower=-1.0, u_upper=1.0, lqr_iter=20, verbose=-1, n_batch=B,
+                  exit_unconverged=False, detach_unconverged=False, eps=1e-9, backprop=True,
+                  max_linesearch_iter=10, linesearch_decay=0.2)
+    x, u, costs = m(x0g, cost, R.mpc.LinDx(Fg, fg))
+    ((x * gx).sum() + (u * gu).sum()).backward()
+    out.update(c_F=F, c_f=f, c_x0=x0, c_gx=gx, c_gu=gu, c_x=x, c_u=u, c_costs=costs,
+               c_dA=cost.A.grad, c_dp=cost.p.grad, c_dw=cost.w.grad, c_dF=Fg.grad, c_df=fg.grad,
+               c_dx0=x0g.grad)
+    # dynamics Module, two linearisation methods
+    q = torch.cat((torch.ones(ns), 0.1 * torch.ones(nc)))
+    Cq = torch.diag(q)[None, None].repeat(T, B, 1, 1)
+    cq = 0.3 * torch.randn(T, B, n, generator=g)
+    for name, gm in (("ad", R.mpc.GradMethods.AUTO_DIFF), ("fd", R.mpc.GradMethods.FINITE_DIFF)):
+        dyn = _SoftDyn(ns, nc, 9)
+        Cg, cg = Cq.clone().requires_grad_(), cq.clone().requires_grad_()
+        m = R.mpc.MPC(ns, nc, T, u_lower=-1.0, u_upper=1.0, lqr_iter=20, verbose=-1, n_batch=B,
+                      exit_unconverged=False, detach_unconverged=False, eps=1e-9, grad_method=gm,
+                      max_linesearch_iter=10, linesearch_decay=0.2)
+        x, u, costs = m(x0, R.mpc.QuadCost(Cg, cg), dyn)
+        ((x * gx).sum() + (u * gu).sum()).backward()
+        out.update({"d_%s_x" % name: x, "d_%s_u" % name: u, "d_%s_costs" % name: costs,
+                    "d_%s_dA" % name: dyn.A.grad, "d_%s_dB" % name: dyn.B.grad,
+                    "d_%s_dW" % name: dyn.W.grad, "d_%s_dC" % name: Cg.grad, "d_%s_dc" % name: cg.grad})
+    out.update(d_C=Cq, d_c=cq)
+    npz("ref_module_cost_dynamics.npz", **out)
     torch.set_default_dtype(torch.float32)
 
 
@@ -405,6 +453,9 @@ if __name__ == "__main__":
     if sys.argv[1:] == ["t50"]:      # only the headline-horizon DiLQR golden (about a minute)
         dilqr_t50()
         sys.exit(0)
+    if sys.argv[1:] == ["modules"]:
+        module_cost_and_dynamics()
+        sys.exit(0)
     fixtures()
     lindx(False)
     lindx(True)
@@ -424,3 +475,4 @@ if __name__ == "__main__":
     nn_grad_methods()
     delta_u()
     nn_two_layers()
+    module_cost_and_dynamics()

@@ -872,3 +872,48 @@ def test_nn_dynamics_two_hidden_layers_golden(dilqr, dev, act):
         errs["dW%d" % (i + 1)] = rel(fc.weight.grad, t("dW%d" % (i + 1)))
         errs["db%d" % (i + 1)] = rel(fc.bias.grad, t("db%d" % (i + 1)))
     assert max(errs.values()) < 1e-4, errs
+
+
+def test_module_cost_golden(dilqr, dev):
+    """mpc.MPC with a cost Module (approximate_cost, mpc.py:447-487) on LinDx dynamics vs the
+    reference: torch quadraticises the Module and evaluates it in the line search, the
+    kernels run the sweeps; solution and every gradient (Module parameters, F, f, x_init)."""
+    from common import SoftCost
+    g = golden("ref_module_cost_dynamics.npz")
+    T, B, ns = g["c_x"].shape
+    nc = g["c_u"].shape[2]
+    cost = SoftCost(ns + nc, 5).to(dev)
+    F, f, x0 = [g[k].to(dev).requires_grad_() for k in ("c_F", "c_f", "c_x0")]
+    m = dilqr.MPC(ns, nc, T, u_lower=-1.0, u_upper=1.0, lqr_iter=20, verbose=-1, n_batch=B,
+                  exit_unconverged=False, detach_unconverged=False, eps=1e-9,
+                  max_linesearch_iter=10, linesearch_decay=0.2)
+    x, u, costs = m(x0, cost, dilqr.LinDx(F, f))
+    assert rel(x, g["c_x"]) < 1e-9 and rel(u, g["c_u"]) < 1e-9 and rel(costs, g["c_costs"]) < 1e-9
+    ((x * g["c_gx"].to(dev)).sum() + (u * g["c_gu"].to(dev)).sum()).backward()
+    for got, key in ((cost.A.grad, "c_dA"), (cost.p.grad, "c_dp"), (cost.w.grad, "c_dw"),
+                     (F.grad, "c_dF"), (f.grad, "c_df"), (x0.grad, "c_dx0")):
+        assert rel(got, g[key]) < 1e-8, key
+
+
+@pytest.mark.parametrize("name", ["ad", "fd"])
+def test_module_dynamics_golden(dilqr, dev, name):
+    """A dynamics Module without device kernels under AUTO_DIFF / FINITE_DIFF
+    (mpc.py:525-601) vs the reference, gradients wrt the Module's parameters included."""
+    from common import SoftDyn
+    g = golden("ref_module_cost_dynamics.npz")
+    T, B, ns = g["d_ad_x"].shape
+    nc = g["d_ad_u"].shape[2]
+    dyn = SoftDyn(ns, nc, 9).to(dev)
+    C, c = g["d_C"].to(dev).requires_grad_(), g["d_c"].to(dev).requires_grad_()
+    gm = dilqr.GradMethods.AUTO_DIFF if name == "ad" else dilqr.GradMethods.FINITE_DIFF
+    m = dilqr.MPC(ns, nc, T, u_lower=-1.0, u_upper=1.0, lqr_iter=20, verbose=-1, n_batch=B,
+                  exit_unconverged=False, detach_unconverged=False, eps=1e-9, grad_method=gm,
+                  max_linesearch_iter=10, linesearch_decay=0.2)
+    x, u, costs = m(g["c_x0"].to(dev), dilqr.QuadCost(C, c), dyn)
+    tol = 1e-9 if name == "ad" else 1e-6
+    assert rel(x, g["d_%s_x" % name]) < tol and rel(u, g["d_%s_u" % name]) < tol
+    ((x * g["c_gx"].to(dev)).sum() + (u * g["c_gu"].to(dev)).sum()).backward()
+    gt = 1e-8 if name == "ad" else 1e-5
+    for got, key in ((dyn.A.grad, "dA"), (dyn.B.grad, "dB"), (dyn.W.grad, "dW"), (C.grad, "dC"),
+                     (c.grad, "dc")):
+        assert rel(got, g["d_%s_%s" % (name, key)]) < gt, key
