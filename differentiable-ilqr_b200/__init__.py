@@ -8,7 +8,8 @@ The directory name is not a valid Python identifier; import it with
 from . import _lib
 from .definitions import QuadCost, LinDx
 from .mpc import MPC, GradMethods
-from . import mpc, mpc_explicit, env_dx, il, il_env, parallel, lqr_step, util, dynamics  # noqa: F401
+from . import (mpc, mpc_explicit, env_dx, il, il_env, parallel, lqr_step, lqr_step_explicit,  # noqa: F401
+               util, dynamics, dropin)
 from .dynamics import AffineDynamics, CtrlPassthroughDynamics, NNDynamics
 from . import pnqp as _pnqp_mod  # noqa: F401
 from .pnqp import pnqp

@@ -22,6 +22,7 @@ ALIASES = {
     "mpc_explicit": "mpc_explicit",
     "mpc_explicit_backup": "mpc_explicit",
     "lqr_step": "lqr_step",
+    "lqr_step_explicit": "lqr_step_explicit",
     "pnqp": "pnqp",
     "util": "util",
     "dynamics": "dynamics",

@@ -186,6 +186,13 @@ class MPC(nn.Module):
         if isinstance(dx, AffineDynamics):      # time-invariant LinDx (dynamics.py:159-202)
             dx = LinDx(*dx.as_lindx(self.T, n_batch, x_init.dtype, x_init.device))
         generic_dx = not isinstance(dx, (LinDx, NNDynamics)) and getattr(dx, "_dilqr_kind", None) is None
+        if isinstance(dx, NNDynamics):
+            # networks the device dynamics do not cover (more than two hidden layers, wide
+            # layers, other activations): torch runs the network (grad_input / autograd)
+            try:
+                dx._dilqr_pack(x_init.dtype, x_init.device)
+            except NotImplementedError:
+                generic_dx = True
         if not quad or generic_dx:
             # Module cost (approximate_cost, mpc.py:447-487) and / or a dynamics Module
             # without device kernels (AUTO_DIFF / FINITE_DIFF / ANALYTIC grad_input,

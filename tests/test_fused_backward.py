@@ -195,3 +195,48 @@ def test_host_resident_theta_gets_host_gradient(dilqr, env, dev):
     assert q.grad is not None and q.grad.device.type == "cpu"
     assert e.true_dx.params.grad is not None and e.true_dx.params.grad.device.type == "cpu"
     assert torch.isfinite(q.grad).all() and torch.isfinite(e.true_dx.params.grad).all()
+
+
+def test_lqr_step_explicit_entry(dilqr, port, env, dev):
+    """lqr_step_explicit.LQRStep(..., no_op_forward=True)(x_init, C, c, F, f, theta): the
+    reference's own entry to the DiLQR backward (lqr_step_explicit.py:24-44, 599-712) gives
+    the gradients mpc_explicit.MPC gives at the same solution."""
+    T, B = 20, 32
+    pdx, x0, C, c, kw = env_problem(port, "cartpole", T, B, torch.float64, sigma=0.05)
+    kw["eps"] = 1e-9
+    g = torch.Generator().manual_seed(4)
+    gx = torch.randn(T, B, 5, generator=g, dtype=torch.float64).to(dev)
+    gu = torch.randn(T, B, 1, generator=g, dtype=torch.float64).to(dev)
+    th1 = pdx.params.to(dev).requires_grad_()
+    C1, c1 = C.to(dev).requires_grad_(), c.to(dev).requires_grad_()
+    m = dilqr.mpc_explicit.MPC(5, 1, T, lqr_iter=60, verbose=-1, exit_unconverged=False,
+                               detach_unconverged=False, richardson_passes=30, **kw)
+    x, u, _ = m(x0.to(dev), dilqr.QuadCost(C1, c1), env.CartpoleDx(th1))
+    ((x * gx).sum() + (u * gu).sum()).backward()
+    th2 = pdx.params.to(dev).requires_grad_()
+    C2, c2 = C.to(dev).requires_grad_(), c.to(dev).requires_grad_()
+    dx2 = env.CartpoleDx(th2)
+    step = dilqr.lqr_step_explicit.LQRStep(
+        5, 1, T, u_lower=pdx.lower, u_upper=pdx.upper, true_cost=dilqr.QuadCost(C2, c2),
+        true_dynamics=dx2, current_x=x.detach(), current_u=u.detach(), no_op_forward=True)
+    F, f = dx2.linearize_traj(x.detach(), u.detach())
+    xs, us = step(x0.to(dev), C2, c2, F, f, th2)
+    assert torch.equal(xs, x.detach()) and torch.equal(us, u.detach())
+    ((xs * gx).sum() + (us * gu).sum()).backward()
+    assert rel(th2.grad, th1.grad) < 1e-10
+    assert rel(C2.grad, C1.grad) < 1e-10 and rel(c2.grad, c1.grad) < 1e-10
+    # and one real step (lqr_step_explicit.py:620-650) == lqr_step.LQRStep on the same iterate
+    u0 = torch.zeros(T, B, 1, dtype=torch.float64, device=dev)
+    x_roll = dilqr.util.get_traj(T, u0, x0.to(dev), env.CartpoleDx(pdx.params.to(dev)))
+    a = dilqr.lqr_step_explicit.LQRStep(5, 1, T, u_lower=pdx.lower, u_upper=pdx.upper,
+                                        true_dynamics=env.CartpoleDx(pdx.params.to(dev)),
+                                        current_x=x_roll, current_u=u0,
+                                        linesearch_decay=pdx.linesearch_decay,
+                                        max_linesearch_iter=pdx.max_linesearch_iter)(
+        x0.to(dev), C.to(dev), c.to(dev))
+    b = dilqr.LQRStep(5, 1, T, u_lower=pdx.lower, u_upper=pdx.upper,
+                      true_dynamics=env.CartpoleDx(pdx.params.to(dev)), current_x=x_roll,
+                      current_u=u0, linesearch_decay=pdx.linesearch_decay,
+                      max_linesearch_iter=pdx.max_linesearch_iter)(
+        x0.to(dev), C.to(dev), c.to(dev), None)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
