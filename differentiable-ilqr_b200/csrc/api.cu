@@ -93,7 +93,7 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
   size_t traj[2], best, Kk, cost_cur, cost_new, cost_best, du_new, du_best, alpha_new, dusq, take,
-      guess, votes, guess_gains, cpk_state, gs_barrier, Cpk, gsQ, gsG, total;
+      guess, votes, guess_gains, cpk_state, gs_barrier, commit_ticket, commit_part, Cpk, gsQ, gsG, total;
   int Bp;
 };
 
@@ -125,6 +125,8 @@ static WsLayout ws_layout(const DilqrSolve* s, size_t esz) {
   w.guess_gains = take((size_t)s->T * kPnqpMaxIter * sizeof(uint32_t));
   w.cpk_state = take(sizeof(uint32_t));
   w.gs_barrier = take(sizeof(uint32_t));
+  w.commit_ticket = take(sizeof(uint32_t));
+  w.commit_part = take((size_t)((w.Bp + 127) / 128) * sizeof(CommitPart));
   // packed symmetric copy of C: only shapes whose sweeps are staged use it (staged_v)
   {
     const bool env = s->dynamics != DILQR_DYN_LINDX;
@@ -292,6 +294,8 @@ static int launch_begin(const DilqrSolve* s, cudaStream_t st) {
     const bool pack = !p.C_bcast && !(p.gains_only && p.x_cur) && !off;
     cudaMemsetAsync(p.cpk_state, 0, sizeof(uint32_t), st);
     if (pack) cudaMemsetAsync(p.cpk_state, 1, 1, st);   // little-endian: word value 1
+    // ticket counter of the one-launch commit (returns to zero after every commit)
+    cudaMemsetAsync(static_cast<char*>(s->workspace) + w.commit_ticket, 0, sizeof(uint32_t), st);
   }
   kern<<<blocks, wpb * kWarp, smem, st>>>(p);
   return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
@@ -460,10 +464,15 @@ template <int NS, int NC>
 static int launch_commit(const DilqrSolve* s, cudaStream_t st) {
   using S = Scalar;
   IterParams<S> p = make_params(s);
-  trace_verify_kernel<<<1, 256, 0, st>>>(p.guess, p.votes, p.T, p.bounds_kind != 0, p.solo,
-                                         s->status, p.lockstep, s->control);
-  commit_kernel<S, NS + NC, NC><<<(p.B + 127) / 128, 128, 0, st>>>(p);
-  if (s->control) control_kernel<<<1, 1, 0, st>>>(s->control, s->status, s->iteration, s->solo);
+  const WsLayout w = ws_layout(s, sizeof(S));
+  char* ws = static_cast<char*>(s->workspace);
+  CommitAux aux;
+  aux.part = reinterpret_cast<CommitPart*>(ws + w.commit_part);
+  aux.ticket = reinterpret_cast<unsigned int*>(ws + w.commit_ticket);
+  aux.ctrl = s->control;
+  aux.lockstep = p.lockstep;
+  aux.iteration = s->iteration;
+  commit_kernel<S, NS + NC, NC><<<(p.B + 127) / 128, 128, 0, st>>>(p, aux);
   return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
 }
 

@@ -183,6 +183,12 @@ DILQR_DEVICE void lin_step(const S* __restrict__ Fs, const S* __restrict__ fs, b
 // counter in global memory, episode k is complete once it reaches k * n.  Used by the group
 // sweep for the pnqp decisions, which only involve the blocks that own problems (a fraction
 // of the grid, so it is cheaper than a full grid.sync and the other blocks stay out of it).
+// Fire-and-forget OR into a vote word: a RED has no destination register, so nothing in the
+// sweep ever waits for the L2 round trip of the (heavily shared) word.
+DILQR_DEVICE void vote_or(uint32_t* word, uint32_t bits) {
+  asm volatile("red.relaxed.gpu.global.or.b32 [%0], %1;" ::"l"(word), "r"(bits) : "memory");
+}
+
 struct SubBarrier {
   unsigned int* counter;   // zeroed before the launch
   unsigned int n;
@@ -232,12 +238,11 @@ DILQR_DEVICE void pnqp_thread(const S (&H)[N][N], const S (&q)[N], const S (&lo)
       return 0u;
     }
   };
-  // gpre = guess[0..3], loaded by the caller long before this point (the common
-  // case never looks past the first two words; a global load here would sit on
-  // the critical path of the sweep).
+  // gpre.x/.y = guess[0..1], obtained by the caller without a global load at this point (the
+  // common case never looks past the first two words; an L2 round trip here would sit on the
+  // critical path of the sweep).
   auto gword_at = [&](int it) -> uint32_t {
-    return it == 0 ? gpre.x : it == 1 ? gpre.y : it == 2 ? gpre.z : it == 3 ? gpre.w
-                                                                            : __ldg(&guess[it]);
+    return it == 0 ? gpre.x : it == 1 ? gpre.y : __ldg(&guess[it]);
   };
   const S GAMMA = S(0.1);
   if (!have_init) {  // pnqp.py:14-19
@@ -315,7 +320,7 @@ DILQR_DEVICE void pnqp_thread(const S (&H)[N][N], const S (&q)[N], const S (&lo)
       any_moving = (gword_at(it) & 1u) != 0;
     }
     if (!any_moving) {  // pnqp.py:57-59
-      if (!solo && !lockstep && vote && lane == 0) atomicOr(&votes[it], vote);
+      if (!solo && !lockstep && vote && lane == 0) vote_or(&votes[it], vote);
       return;
     }
     // Armijo backtracking with a batch-global exit test (pnqp.py:61-76).
@@ -372,7 +377,7 @@ DILQR_DEVICE void pnqp_thread(const S (&H)[N][N], const S (&q)[N], const S (&lo)
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) x[i] = mx[i];  // pnqp.py:78
-    if (!solo && !lockstep && vote && lane == 0) atomicOr(&votes[it], vote);
+    if (!solo && !lockstep && vote && lane == 0) vote_or(&votes[it], vote);
   }
   // fell through n_iter iterations: the reference returns the factors / If of the
   // last iteration together with the stepped x (pnqp.py:81-82).
@@ -563,12 +568,21 @@ struct IterKernel {
     // current trajectory this problem's best, park it in traj_best while it streams by.
     const bool flush = !SOL && (p.take[bw] & 1) != 0;
     issue_t<SOL>(st, p, 0, T - 1, b0, false, true, false);
+    // First two words of the guessed pnqp trace: lane l keeps those of timestep (t & ~31) + l
+    // (one 8-byte load per lane per 32 timesteps), the sweep fetches its timestep's pair with
+    // two shuffles.  A global load per timestep -- wherever it is placed -- costs an exposed L2
+    // round trip: ptxas makes an unrelated instruction next to it wait on the shared scoreboard
+    // (ncu: 400 cycles per timestep, profiles/r2_iter_stalls.txt).
+    const bool use_guess = p.bounds_kind && !p.solo && !LOCKSTEP;
+    uint2 glane = make_uint2(0, 0);
     for (int t = T - 1; t >= 0; --t) {
       const int sg = (T - 1 - t) & 1;
       if (t > 0) issue_t<SOL>(st, p, sg ^ 1, t - 1, b0, false, true, false);
-      uint4 gpre = make_uint4(0, 0, 0, 0);
-      if (p.bounds_kind && !p.solo && !LOCKSTEP)
-        gpre = __ldg(reinterpret_cast<const uint4*>(p.guess + (size_t)t * kPnqpMaxIter));
+      if (use_guess && (t == T - 1 || (t & 31) == 31)) {
+        const int tt = (t & ~31) + lane;
+        glane = tt < T ? __ldg(reinterpret_cast<const uint2*>(p.guess + (size_t)tt * kPnqpMaxIter))
+                       : make_uint2(0, 0);
+      }
       if (STAGED) st.wait(sg);
       const Blk blk = blocks<SOL>(p, st, sg, t, b, bw, lane);
       const S* Cs = blk.C;
@@ -764,6 +778,11 @@ struct IterKernel {
         bool If[NC];
         LUpp<S, NC> lu;
         S rinv = S(0);
+        uint4 gpre = make_uint4(0, 0, 0, 0);
+        if (use_guess) {
+          gpre.x = __shfl_sync(kFull, glane.x, t & 31);
+          gpre.y = __shfl_sync(kFull, glane.y, t & 31);
+        }
         pnqp_thread<S, NC, LOCKSTEP ? 1 : 0>(H, qu, lo, hi, have_prev, k, If, lu,
                                      p.guess + (size_t)t * kPnqpMaxIter, gpre,
                                      p.votes + (size_t)t * kPnqpMaxIter, p.solo != 0, active, lane,
@@ -883,10 +902,13 @@ struct IterKernel {
 #pragma unroll
       for (int i = 0; i < NS; ++i) xh[i] = x0[i];
       S cost = S(0);
+      // two timesteps in flight: the stage of t is re-issued for t+2 as soon as its last
+      // reader (the cost of t; the linear dynamics for LinDx) is done, i.e. before the
+      // dynamics step -- a rollout timestep is shorter than a DRAM round trip under load
       issue_t(st, p, 0, 0, b0, true, true, true);
+      if (T > 1) issue_t(st, p, 1, 1, b0, true, true, true);
       for (int t = 0; t < T; ++t) {
         const int sg = t & 1;
-        if (t + 1 < T) issue_t(st, p, sg ^ 1, t + 1, b0, true, true, true);
         if (STAGED) st.wait(sg);
         const Blk blk = blocks(p, st, sg, t, b, bw, lane);
         S tau[N];   // nominal (x_t, u_t)
@@ -933,6 +955,7 @@ struct IterKernel {
         }
         cost = cost + (blk.packed ? stage_cost_packed<S, N>(blk.C, blk.c, th)
                                   : stage_cost<S, N>(blk.C, blk.c, th));
+        if (kEnv && t + 2 < T) issue_t(st, p, sg, t + 2, b0, true, true, true);
         if (t < T - 1) {
           if constexpr (kEnv) {
             dyn_step<S, NS, NC, DYN>(p.dyn, th, &th[NS], xh);
@@ -940,6 +963,7 @@ struct IterKernel {
             lin_step<S, NS, N>(blk.F, blk.f, p.has_f != 0, th, xh);
           }
         }
+        if (!kEnv && t + 2 < T) issue_t(st, p, sg, t + 2, b0, true, true, true);
       }
       if (run) {
         res_cost = cost;

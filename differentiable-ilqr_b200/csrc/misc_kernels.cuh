@@ -74,36 +74,69 @@ static __global__ void trace_verify_kernel(uint32_t* __restrict__ guess, const u
   }
 }
 
-// Device-side stop rule of the outer loop (mpc.py:266,281,299-301), one thread.
-static __global__ void control_kernel(DilqrControl* ctrl, const DilqrStatus* status, int iteration,
-                                      int solo) {
-  if (ctrl->halt) return;
-  if (solo == 2) {   // per-problem stop rule lives in commit_kernel; halt once nobody is left
-    ctrl->iters_done = (uint32_t)iteration + 1u;
-    if (status->n_active == 0u) ctrl->halt = 1u;
-    return;
-  }
-  uint32_t n = ctrl->n_not_improved + 1u;
-  if (iteration > 0 && status->any_improved) n = 0u;
-  ctrl->n_not_improved = n;
-  ctrl->iters_done = (uint32_t)iteration + 1u;
-  if (status->max_full_du < ctrl->eps || n > ctrl->not_improved_lim) ctrl->halt = 1u;
-}
+// ---------------------------------------------------------------------------
+// Commit of one iLQR iteration, ONE launch (round 1 used three: trace_verify<<<1,256>>>,
+// commit<<<B/128,128>>>, control<<<1,1>>>):
+//   1. every block checks the replayed pnqp trace against the votes on its own (a few KB of
+//      L2-resident words), so no block waits for a verdict;
+//   2. per-problem best-iterate bookkeeping (mpc.py:271-285), block-level partial reductions
+//      written to `part[blockIdx]`;
+//   3. the block that finishes last (ticket counter) folds the partials in a fixed order,
+//      corrects the trace guess on a mismatch, fills the status block and runs the stop rule
+//      of the outer loop (mpc.py:266,281,299-301).
+// ---------------------------------------------------------------------------
+struct CommitPart {
+  double du, al, bc;
+  uint32_t flags;   // bit 0: some problem improved, bit 1: NaN in ||du||
+  uint32_t n_active;
+};
+struct CommitAux {
+  CommitPart* part;         // one record per block
+  unsigned int* ticket;     // zero between launches
+  DilqrControl* ctrl;       // may be nullptr
+  int lockstep;             // votes ARE the trace (lockstep / group sweep): nothing to compare
+  int iteration;
+};
 
-// ---------------------------------------------------------------------------
-// Per-problem commit: best-iterate bookkeeping (mpc.py:271-285) + the batch
-// reductions the host needs for the stop rule (mpc.py:299-301).
-// ---------------------------------------------------------------------------
 template <class S, int N, int NCc>
-__global__ void commit_kernel(const __grid_constant__ IterParams<S> p) {
+__global__ void __launch_bounds__(128) commit_kernel(const __grid_constant__ IterParams<S> p,
+                                                     const CommitAux aux) {
   DilqrStatus* status = reinterpret_cast<DilqrStatus*>(p.status);
-  if (p.halt && *p.halt) return;
-  if (status->trace_match == 0) return;
+  if (p.halt && *reinterpret_cast<const volatile uint32_t*>(p.halt)) return;   // uniform
+  __shared__ int s_first;
+  __shared__ unsigned s_nqp, s_unconv, s_last;
+  __shared__ double s_du[4], s_al[4], s_bc[4];
+  __shared__ unsigned s_fl[4], s_act[4];
+  const int n = p.T * kPnqpMaxIter;
+  const bool traced = p.bounds_kind != 0 && !p.solo;
+  if (threadIdx.x == 0) {
+    s_first = n;
+    s_nqp = 0;
+    s_unconv = 0;
+  }
+  __syncthreads();
+  if (traced && !aux.lockstep) {
+    // Normalised vote of a slot: if nobody was moving the sweep left the slot right there, so
+    // Armijo bits voted under a wrong "moving" guess are void.  Processing order of the sweep
+    // is t = T-1 .. 0, it = 0 .. 19.
+    int first = n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int t = p.T - 1 - i / kPnqpMaxIter, it = i % kPnqpMaxIter;
+      const int slot = t * kPnqpMaxIter + it;
+      uint32_t v = p.votes[slot];
+      if (!(v & 1u)) v = 0;
+      if (p.guess[slot] != v && i < first) first = i;
+    }
+    if (first < n) atomicMin(&s_first, first);
+    __syncthreads();
+  }
+  const bool match = s_first >= n;
+
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   double du = 0.0, al = 0.0, bc = 0.0;
   bool improved = false;
   bool active = false;
-  if (b < p.B && p.solo == 2) {
+  if (match && b < p.B && p.solo == 2) {
     // Every problem is its own batch of one (the closed-loop driver il_env.py:96-151 calls
     // MPC with n_batch = 1): plain per-problem ||du||, and the stop rule mpc.py:266,281,
     // 299-301 per problem.  take[b]: bit 0 = take, bits 8..29 = n_not_improved, bit 30 =
@@ -130,10 +163,7 @@ __global__ void commit_kernel(const __grid_constant__ IterParams<S> p) {
         p.cost_best[b] = cn;
         p.du_best[b] = dn;
       }
-      if (p.control) {
-        const DilqrControl* ctl = reinterpret_cast<const DilqrControl*>(p.control);
-        stop = (double)dn < ctl->eps || (uint32_t)nni > ctl->not_improved_lim;
-      }
+      if (aux.ctrl) stop = (double)dn < aux.ctrl->eps || (uint32_t)nni > aux.ctrl->not_improved_lim;
       active = !stop;
       du = (double)dn;
       al = (double)p.alpha_new[b];
@@ -141,7 +171,7 @@ __global__ void commit_kernel(const __grid_constant__ IterParams<S> p) {
     p.take[b] = (take ? 1 : 0) | (nni << 8) | (stop ? (1 << 30) : 0);
     p.cost_cur[b] = cn;
     bc = (double)p.cost_best[b];
-  } else if (b < p.B) {
+  } else if (match && b < p.B) {
     // full_du_norm[b]: norm of row b of the [T,nc,B] squares re-read as [B, T*nc]
     // (lqr_step.py:243-245, see the note in forward_linesearch)
     {
@@ -169,8 +199,8 @@ __global__ void commit_kernel(const __grid_constant__ IterParams<S> p) {
     al = (double)p.alpha_new[b];
     bc = (double)p.cost_best[b];
   }
-  // warp reductions, then one atomic per warp
-  bool nan_du = du != du;
+  // warp reductions -> block partial
+  const bool nan_du = du != du;
   for (int o = 16; o > 0; o >>= 1) {
     du = fmax(du, __shfl_xor_sync(kFull, du, o));
     al += __shfl_xor_sync(kFull, al, o);
@@ -179,14 +209,112 @@ __global__ void commit_kernel(const __grid_constant__ IterParams<S> p) {
   const unsigned imp = __ballot_sync(kFull, improved);
   const unsigned nn = __ballot_sync(kFull, nan_du);
   const unsigned act = __ballot_sync(kFull, active);
+  const int w = threadIdx.x >> 5;
   if ((threadIdx.x & 31) == 0) {
-    if (act) atomicAdd(&status->n_active, (uint32_t)__popc(act));
-    if (nn) du = __longlong_as_double(0x7ff8000000000000LL);  // propagate NaN like python max()
-    atomicMax(reinterpret_cast<unsigned long long*>(&status->max_full_du), dbits(du));
-    atomicAdd(&status->mean_alpha, al / p.B);
-    atomicAdd(&status->mean_best_cost, bc / p.B);
-    if (imp) atomicOr(&status->any_improved, 1u);
+    s_du[w] = du;
+    s_al[w] = al;
+    s_bc[w] = bc;
+    s_fl[w] = (imp ? 1u : 0u) | (nn ? 2u : 0u);
+    s_act[w] = (unsigned)__popc(act);
   }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    CommitPart r;
+    r.du = fmax(fmax(s_du[0], s_du[1]), fmax(s_du[2], s_du[3]));
+    r.al = (s_al[0] + s_al[1]) + (s_al[2] + s_al[3]);
+    r.bc = (s_bc[0] + s_bc[1]) + (s_bc[2] + s_bc[3]);
+    r.flags = s_fl[0] | s_fl[1] | s_fl[2] | s_fl[3];
+    r.n_active = s_act[0] + s_act[1] + s_act[2] + s_act[3];
+    aux.part[blockIdx.x] = r;
+    __threadfence();
+    s_last = (atomicAdd(aux.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+
+  // ---- last block: fold the partials, finish the trace bookkeeping, status + stop rule
+  if (traced) {
+    for (int t = threadIdx.x; t < p.T; t += blockDim.x) {
+      int it = 0;
+      while (it < kPnqpMaxIter && (p.votes[t * kPnqpMaxIter + it] & 1u)) ++it;
+      if (it == kPnqpMaxIter) {
+        atomicAdd(&s_unconv, 1u);
+        it = kPnqpMaxIter - 1;   // pnqp.py:82 returns i = n_iter-1
+      }
+      atomicAdd(&s_nqp, 1u + (unsigned)it);
+    }
+    if (!match) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        uint32_t v = p.votes[i];
+        if (!(v & 1u)) v = 0;
+        // moving, but the sweep exited here on a wrong guess so no Armijo pass was
+        // observed: guess the overwhelmingly common "exit after the first pass".
+        else if (!(p.guess[i] & 1u)) v = 3u;
+        p.guess[i] = v;
+      }
+    }
+  }
+  du = 0.0; al = 0.0; bc = 0.0;
+  unsigned fl = 0, na = 0;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+    const CommitPart* r = &aux.part[i];   // written by other blocks: read through L2
+    du = fmax(du, __ldcg(&r->du));
+    al += __ldcg(&r->al);
+    bc += __ldcg(&r->bc);
+    fl |= __ldcg(&r->flags);
+    na += __ldcg(&r->n_active);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    du = fmax(du, __shfl_xor_sync(kFull, du, o));
+    al += __shfl_xor_sync(kFull, al, o);
+    bc += __shfl_xor_sync(kFull, bc, o);
+    fl |= __shfl_xor_sync(kFull, fl, o);
+    na += __shfl_xor_sync(kFull, na, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_du[w] = du;
+    s_al[w] = al;
+    s_bc[w] = bc;
+    s_fl[w] = fl;
+    s_act[w] = na;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  du = fmax(fmax(s_du[0], s_du[1]), fmax(s_du[2], s_du[3]));
+  al = (s_al[0] + s_al[1]) + (s_al[2] + s_al[3]);
+  bc = (s_bc[0] + s_bc[1]) + (s_bc[2] + s_bc[3]);
+  fl = s_fl[0] | s_fl[1] | s_fl[2] | s_fl[3];
+  na = s_act[0] + s_act[1] + s_act[2] + s_act[3];
+  if (fl & 2u) du = __longlong_as_double(0x7ff8000000000000LL);  // propagate NaN like python max()
+  *aux.ticket = 0u;
+  status->trace_match = match ? 1u : 0u;
+  status->first_mismatch = (uint32_t)s_first;
+  status->n_total_qp_iter = s_nqp;
+  status->pnqp_unconverged = s_unconv;
+  status->any_improved = match ? (fl & 1u) : 0u;
+  status->n_active = match ? na : 0u;
+  status->max_full_du = match ? du : 0.0;
+  status->mean_alpha = match ? al / p.B : 0.0;
+  status->mean_best_cost = match ? bc / p.B : 0.0;
+  DilqrControl* ctrl = aux.ctrl;
+  if (!ctrl) return;
+  if (!match) {
+    ctrl->halt = 2u;
+    return;
+  }
+  // device-side stop rule of the outer loop (mpc.py:266,281,299-301)
+  if (p.solo == 2) {   // per-problem stop rule above; halt once nobody is left
+    ctrl->iters_done = (uint32_t)aux.iteration + 1u;
+    if (na == 0u) ctrl->halt = 1u;
+    return;
+  }
+  uint32_t nni = ctrl->n_not_improved + 1u;
+  if (aux.iteration > 0 && (fl & 1u)) nni = 0u;
+  ctrl->n_not_improved = nni;
+  ctrl->iters_done = (uint32_t)aux.iteration + 1u;
+  // the comparison of mpc.py:299 is on the python max() of the batch: NaN never compares below eps
+  if (du < ctrl->eps || nni > ctrl->not_improved_lim) ctrl->halt = 1u;
 }
 
 // ---------------------------------------------------------------------------
