@@ -131,6 +131,8 @@ SYMBOLS = {
                          + [C.c_void_p] * 5),
     "dilqr_sens_theta_blocked": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int,
                                            C.c_int] + [C.c_void_p] * 8),
+    "dilqr_sens_theta_adjoint": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int,
+                                           C.c_int] + [C.c_void_p] * 9),
     "dilqr_adjoint_dtau_offset": (C.c_size_t, [C.POINTER(DilqrAdjoint)]),
     "dilqr_kkt_grads": (C.c_int, [C.POINTER(DilqrKkt), C.c_void_p]),
     "dilqr_linearize": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int,
@@ -201,7 +203,7 @@ def check(code, what):
 KERNELS_PER_CALL = {
     "dilqr_mpc_begin": 1, "dilqr_mpc_iterate": 1, "dilqr_mpc_commit": 1,
     "dilqr_mpc_finish": 1, "dilqr_mpc_gains": 2, "dilqr_lam_tables": 1,
-    "dilqr_sens_theta_blocked": 1, "dilqr_kkt_grads": 1, "dilqr_linearize": 1, "dilqr_rollout": 1,
+    "dilqr_sens_theta_blocked": 1, "dilqr_sens_theta_adjoint": 1, "dilqr_kkt_grads": 1, "dilqr_linearize": 1, "dilqr_rollout": 1,
     "dilqr_costate_tables": 1, "dilqr_richardson_update": 1, "dilqr_sens_theta": 1,
     "dilqr_adjoint_factor": 1, "dilqr_adjoint_pass": 1, "dilqr_adjoint_final": 1,
     "dilqr_pnqp": 2, "dilqr_env_tables": 1, "dilqr_tile_cost": 2, "dilqr_tile_cost_grad": 2,

@@ -6,12 +6,15 @@ Nothing here computes on the CPU; torch is used for device memory, streams and
 autograd plumbing only.
 """
 import ctypes as C
+import os
 
 import torch
 
 from . import _lib
 
 _DT = {torch.float32: _lib.F32, torch.float64: _lib.F64}
+# A/B knob: dtheta by the forward sensitivity rollout (round 1) instead of its adjoint form
+_SENS_ROLLOUT = bool(os.environ.get("DILQR_SENS_ROLLOUT"))
 
 
 def _ptr(t):
@@ -816,8 +819,14 @@ def dilqr_backward(dl_dx, dl_du, x_init, C_, c_, x, u, dxmod, n_state, n_ctrl, u
     dtheta = torch.empty(B, nth, dtype=dtype, device=dev)
     if fused:
         dtau = prep["ws"][prep["dtau_off"]:]
-        _lib.call("dilqr_sens_theta_blocked", _DT[dtype], kind, theta, T, B, _ptr(x), _ptr(u),
-                  C.c_void_p(prep["Kk"]), _ptr(lam), _ptr(dtau), _ptr(df), _ptr(dtheta), _stream())
+        if _SENS_ROLLOUT:   # A/B knob: the forward sensitivity rollout of round 1
+            _lib.call("dilqr_sens_theta_blocked", _DT[dtype], kind, theta, T, B, _ptr(x), _ptr(u),
+                      C.c_void_p(prep["Kk"]), _ptr(lam), _ptr(dtau), _ptr(df), _ptr(dtheta),
+                      _stream())
+        else:               # adjoint form: reverse sweep, second-order tables via the packed Lam
+            _lib.call("dilqr_sens_theta_adjoint", _DT[dtype], kind, theta, T, B, _ptr(x), _ptr(u),
+                      C.c_void_p(prep["Kk"]), _ptr(lam), _ptr(dtau), _ptr(df), _ptr(Lam),
+                      _ptr(dtheta), _stream())
     else:
         _lib.call("dilqr_sens_theta", _DT[dtype], kind, theta, T, B, _ptr(x), _ptr(u),
                   _ptr(prep["K"]), _ptr(lam), _ptr(dxa), _ptr(dua), _ptr(df), _ptr(dtheta), _stream())

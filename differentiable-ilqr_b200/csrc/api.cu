@@ -929,6 +929,34 @@ int DILQR_SUFFIX(sens_theta_blocked)(int dynamics, const double* dp, int T, int 
 }
 
 template <int DYN>
+static int launch_sens_adjoint(const double* dp, int T, int B, const void* x, const void* u,
+                               const void* Kk, const void* lam, const void* dtau, const void* df,
+                               const void* Lam, void* dtheta, cudaStream_t st) {
+  using S = Scalar;
+  DynParams<S> P;
+  memset(&P, 0, sizeof(P));
+  for (int i = 0; i < 8; ++i) P.p[i] = (S)dp[i];
+  const int Bp = (B + kWarp - 1) / kWarp * kWarp;
+  sens_theta_adjoint_kernel<S, DYN><<<(Bp + 63) / 64, 64, 0, st>>>(
+      P, T, B, static_cast<const S*>(x), static_cast<const S*>(u), static_cast<const S*>(Kk),
+      static_cast<const S*>(lam), static_cast<const S*>(dtau), static_cast<const S*>(df),
+      static_cast<const S*>(Lam), static_cast<S*>(dtheta));
+  return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
+}
+
+int DILQR_SUFFIX(sens_theta_adjoint)(int dynamics, const double* dp, int T, int B, const void* x,
+                                     const void* u, const void* Kk, const void* lam,
+                                     const void* dtau, const void* df, const void* Lam,
+                                     void* dtheta, void* stream) {
+  if (!dp || !x || !u || !Kk || !lam || !dtau || !df || !Lam || !dtheta || T <= 1 || B <= 0)
+    return DILQR_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dynamics == DYN_PENDULUM) return launch_sens_adjoint<DYN_PENDULUM>(dp, T, B, x, u, Kk, lam, dtau, df, Lam, dtheta, st);
+  if (dynamics == DYN_CARTPOLE) return launch_sens_adjoint<DYN_CARTPOLE>(dp, T, B, x, u, Kk, lam, dtau, df, Lam, dtheta, st);
+  return DILQR_EUNSUPPORTED;
+}
+
+template <int DYN>
 static int launch_sens(const double* dp, int T, int B, const void* x, const void* u,
                        const void* K, const void* lam, const void* dx, const void* du,
                        const void* df, void* dtheta, cudaStream_t st) {

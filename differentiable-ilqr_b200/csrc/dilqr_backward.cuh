@@ -463,6 +463,144 @@ sens_theta_kernel(DynParams<S> P, int T, int B, const S* __restrict__ x,
   }
 }
 
+// ---------------------------------------------------------------------------
+// dtheta again, in ADJOINT form: same sum as sens_theta_kernel, but the 5 x n_theta
+// sensitivity matrix G_t of the forward rollout is never formed.  With (loop variables of
+// sens_theta_kernel) A_t = xx_t + xu_t K_ref[t-1], G_t = xth_t + A_t G_{t-1}, G_0 = 0,
+//   dtheta = sum_{t<=T-2} W_t : Dth_t + sum_t c_t' G_t,      W_t = -lam_{t+1} dtau_t',
+//   c_t = [t>=1] df_{t-1} + [t<=T-2] (om_t - (D_t,x + D_t,u K_ref[t])' df_t),
+//   om_t = -(Lam_t,x dtau_t + K_ref[t]' Lam_t,u dtau_t)          (Lam_t: lam_tables_kernel),
+// and  sum_t c_t' G_t = sum_{t>=1} mu_t' xth_t  with the reverse recursion
+//   mu_{T-1} = c_{T-1},  mu_t = c_t + A_{t+1}' mu_{t+1}.
+// One reverse sweep per problem carrying a vector of n_state scalars; the second-order tables
+// Dx, Du (the bulk of EnvTables::eval) are not evaluated at all -- their contraction with
+// lam is the packed Lam the Richardson passes already use.  Every operand in its blocked
+// workspace layout.  (cartpole.py:717-788, pendulum.py:383-443)
+// ---------------------------------------------------------------------------
+template <class S, int DYN>
+__global__ void __launch_bounds__(64)
+sens_theta_adjoint_kernel(DynParams<S> P, int T, int B, const S* __restrict__ x,
+                          const S* __restrict__ u, const S* __restrict__ K,
+                          const S* __restrict__ lam, const S* __restrict__ dtau_b,
+                          const S* __restrict__ df, const S* __restrict__ Lam,
+                          S* __restrict__ dtheta) {
+  using D = Dyn<S, DYN>;
+  using TB = EnvTables<S, DYN>;
+  using LP = LamPack<S, DYN>;
+  constexpr int NS = D::NS, NC = D::NC, N = D::N, NTH = TB::NTH;
+  constexpr int NK = NC * NS + NC;
+  const int bw = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nW = (B + kWarp - 1) / kWarp;
+  if (bw >= nW * kWarp) return;
+  const int b = bw < B ? bw : B - 1;
+  S acc[NTH], nu[NS], dfn[NS], Kt[NC][NS];
+#pragma unroll
+  for (int q = 0; q < NTH; ++q) acc[q] = S(0);
+#pragma unroll
+  for (int i = 0; i < NS; ++i) nu[i] = dfn[i] = S(0);
+#pragma unroll
+  for (int a = 0; a < NC; ++a)
+#pragma unroll
+    for (int j = 0; j < NS; ++j) Kt[a][j] = K[bidx(0, a * NS + j, NK, bw, nW)];   // K_ref[T-1] = K_0
+  for (int t = T - 1; t >= 0; --t) {
+    const size_t tb = (size_t)t * B + b;
+    if (t > 0) {
+      prefetch_l1(x + (tb - B) * NS);
+      prefetch_l1(u + (tb - B) * NC);
+    }
+    S tau[N];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) tau[i] = x[tb * NS + i];
+#pragma unroll
+    for (int a = 0; a < NC; ++a) tau[NS + a] = u[tb * NC + a];
+    S Dm[NS][N], Dth[NS][N][NTH], Dx[NS][N][NS], Du[NS][N][NC], xth[NS][NTH], xx[NS][NS],
+        xu[NS][NC];
+    TB::eval(P, tau, &tau[NS], Dm, Dth, Dx, Du, xth, xx, xu);   // Dx, Du unused: eliminated
+    S dfm[NS], mu[NS];   // df_{t-1}
+#pragma unroll
+    for (int i = 0; i < NS; ++i) dfm[i] = t >= 1 ? df[bidx(t - 1, i, NS, bw, nW)] : S(0);
+    if (t <= T - 2) {
+      S dtau[N], lm[NS], Ld[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) dtau[i] = dtau_b[bidx(t, i, N, bw, nW)];
+#pragma unroll
+      for (int i = 0; i < NS; ++i) lm[i] = lam[bidx(t + 1, i, NS, bw, nW)];
+      static_for<0, N>([&](auto KK) {
+        constexpr int k = decltype(KK)::value;
+        S s = S(0);
+        static_for<0, N>([&](auto JJ) {
+          constexpr int j = decltype(JJ)::value;
+          if constexpr (LP::nz(k, j)) s = fmaS<S>(Lam[bidx(t, LP::idx(k, j), LP::NLAM, bw, nW)], dtau[j], s);
+        });
+        Ld[k] = s;
+      });
+#pragma unroll
+      for (int k = 0; k < NS; ++k) {
+        S om = Ld[k];
+#pragma unroll
+        for (int a = 0; a < NC; ++a) om = fmaS<S>(Kt[a][k], Ld[NS + a], om);
+        S s = S(0);   // ((D_x + D_u K_ref[t])' df_t)[k]
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+          S e = TB::nz_D(i, k) ? Dm[i][k] : S(0);
+#pragma unroll
+          for (int a = 0; a < NC; ++a)
+            if (TB::nz_D(i, NS + a)) e = fmaS<S>(Dm[i][NS + a], Kt[a][k], e);
+          s = fmaS<S>(dfn[i], e, s);
+        }
+        mu[k] = (dfm[k] - (om + s)) + nu[k];
+      }
+#pragma unroll
+      for (int i = 0; i < NS; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          const S wij = -(lm[i] * dtau[j]);
+#pragma unroll
+          for (int q = 0; q < NTH; ++q)
+            if (TB::nz_Dth(i, j, q)) acc[q] = fmaS<S>(wij, Dth[i][j][q], acc[q]);
+        }
+    } else {
+#pragma unroll
+      for (int k = 0; k < NS; ++k) mu[k] = dfm[k];
+    }
+    if (t >= 1) {
+#pragma unroll
+      for (int i = 0; i < NS; ++i)
+#pragma unroll
+        for (int q = 0; q < NTH; ++q)
+          if (TB::nz_xth(i, q)) acc[q] = fmaS<S>(mu[i], xth[i][q], acc[q]);
+      // nu_{t-1} = (xx_t + xu_t K_ref[t-1])' mu_t ; K_ref[t-1] = K_{T-t}
+#pragma unroll
+      for (int a = 0; a < NC; ++a)
+#pragma unroll
+        for (int j = 0; j < NS; ++j) Kt[a][j] = K[bidx(T - t, a * NS + j, NK, bw, nW)];
+#pragma unroll
+      for (int k = 0; k < NS; ++k) {
+        S s = S(0);
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+          bool any = TB::nz_xx(i, k);
+          S e = any ? xx[i][k] : S(0);
+#pragma unroll
+          for (int a = 0; a < NC; ++a)
+            if (TB::nz_xu(i, a)) {
+              e = fmaS<S>(xu[i][a], Kt[a][k], e);
+              any = true;
+            }
+          if (any) s = fmaS<S>(mu[i], e, s);
+        }
+        nu[k] = s;
+      }
+#pragma unroll
+      for (int i = 0; i < NS; ++i) dfn[i] = dfm[i];
+    }
+  }
+  if (bw < B) {
+#pragma unroll
+    for (int q = 0; q < NTH; ++q) dtheta[(size_t)b * NTH + q] = acc[q];
+  }
+}
+
 }  // namespace dilqr
 
 namespace dilqr {

@@ -38,6 +38,9 @@ namespace dilqr {
                        void*, void*);                                                     \
   int sens_theta_blocked_##sfx(int, const double*, int, int, const void*, const void*,    \
                                const void*, const void*, const void*, const void*, void*, void*); \
+  int sens_theta_adjoint_##sfx(int, const double*, int, int, const void*, const void*,    \
+                               const void*, const void*, const void*, const void*, const void*, \
+                               void*, void*);                                             \
   int adjoint_run_##sfx(const DilqrAdjoint*, int, void*);
 DECL_G(f32_g0) DECL_G(f32_g1) DECL_G(f32_g2) DECL_G(f32_g3)
 DECL_G(f64_g0) DECL_G(f64_g1) DECL_G(f64_g2) DECL_G(f64_g3)
@@ -154,6 +157,16 @@ int dilqr_sens_theta_blocked(int dtype, int dyn, const double* dp, int T, int B,
                                                 dtheta, st),
                dilqr::sens_theta_blocked_f64_g0(dyn, dp, T, B, x, u, Kk, lam_blk, dtau_blk, df_blk,
                                                 dtheta, st));
+}
+int dilqr_sens_theta_adjoint(int dtype, int dyn, const double* dp, int T, int B, const void* x,
+                             const void* u, const void* Kk, const void* lam_blk,
+                             const void* dtau_blk, const void* df_blk, const void* Lam_packed,
+                             void* dtheta, void* st) {
+  return ROUTE(dtype,
+               dilqr::sens_theta_adjoint_f32_g0(dyn, dp, T, B, x, u, Kk, lam_blk, dtau_blk, df_blk,
+                                                Lam_packed, dtheta, st),
+               dilqr::sens_theta_adjoint_f64_g0(dyn, dp, T, B, x, u, Kk, lam_blk, dtau_blk, df_blk,
+                                                Lam_packed, dtheta, st));
 }
 size_t dilqr_adjoint_dtau_offset(const DilqrAdjoint* a) {
   if (!a) return 0;

@@ -387,6 +387,16 @@ int dilqr_sens_theta_blocked(int dtype, int dynamics, const double* dyn_params, 
                              const void* x, const void* u, const void* Kk, const void* lam_blk,
                              const void* dtau_blk, const void* df_blk, void* dtheta, void* stream);
 
+/* Same sum in adjoint form (one reverse sweep carrying n_state scalars per problem instead of
+ * the n_state x n_theta sensitivity matrix; the second-order tables enter through
+ * Lam_packed [T-1][ceil(B/32)][dilqr_lam_pack_size][32] of dilqr_lam_tables).  Pendulum and
+ * cartpole.  Replaces the loop of cartpole.py:755-782 / pendulum.py:412-437 contracted with
+ * dF, df (lqr_step_explicit.py:700-708). */
+int dilqr_sens_theta_adjoint(int dtype, int dynamics, const double* dyn_params, int T, int n_batch,
+                             const void* x, const void* u, const void* Kk, const void* lam_blk,
+                             const void* dtau_blk, const void* df_blk, const void* Lam_packed,
+                             void* dtheta, void* stream);
+
 /* The cost plumbing either side of the solve in the imitation-learning loop.
  * dilqr_tile_cost: C[T,B,n,n] = diag(q), c[T,B,n] = p for every (t, b) -- what
  * il_env.py:159-162 builds with .repeat (C or c may be NULL to skip one).
