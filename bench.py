@@ -426,9 +426,22 @@ def run_other(args):
         L = None
     else:
         T, ns, nc = args.horizon or 50, args.ns, args.nc
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        from common import lindx_problem
-        Cc, cc, F, f, x0 = [t.to(dev) for t in lindx_problem(ns, nc, T, B, dtype, seed=rank)]
+        # SURVEY 8d config 5 generator (tests/common.lindx_problem), drawn on the device: at
+        # B = 1 M the host generator alone would take minutes
+        gd = torch.Generator(device=dev).manual_seed(rank)
+        nn_ = ns + nc
+        rn = lambda *sh: torch.randn(*sh, generator=gd, dtype=dtype, device=dev)
+        A = rn(T, B, nn_, nn_)
+        Cc = torch.baddbmm(torch.eye(nn_, dtype=dtype, device=dev).expand(T * B, nn_, nn_),
+                           A.view(T * B, nn_, nn_).transpose(1, 2), A.view(T * B, nn_, nn_)
+                           ).view(T, B, nn_, nn_)
+        del A
+        cc = rn(T, B, nn_)
+        F = torch.cat((torch.eye(ns, dtype=dtype, device=dev).expand(T - 1, B, ns, ns)
+                       + 0.2 * rn(T - 1, B, ns, ns) / ns ** 0.5,
+                       rn(T - 1, B, ns, nc) / ns ** 0.5), 3).contiguous()
+        f = 0.1 * rn(T - 1, B, ns)
+        x0 = rn(B, ns)
         kw = dict(u_lower=-1.0, u_upper=1.0) if args.boxed else {}
         m = d.MPC(ns, nc, T, lqr_iter=LQR_ITER, verbose=-1, exit_unconverged=False,
                   detach_unconverged=False, n_batch=B, **kw)

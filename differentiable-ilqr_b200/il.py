@@ -86,6 +86,8 @@ class ImitationStep:
         self.d2h_bytes = 0
         self.defer = True         # one host sync per step (see _solver.Deferred)
         self._out_host = None
+        self._h2d = None          # side stream of run_host
+        self._uexp_ready = None
 
     # -- pieces -----------------------------------------------------------
     def tile_cost(self, q, p, B):
@@ -119,6 +121,8 @@ class ImitationStep:
         self.mpc.deferred = Deferred() if defer else None
         C, c = self.tile_cost(q, p, B)
         x, u, _ = self.mpc(x0, QuadCost(C, c), dx)
+        if self._uexp_ready is not None:   # run_host: uexp was copied on a side stream
+            torch.cuda.current_stream().wait_event(self._uexp_ready)
         loss = (u - uexp).pow(2).mean() * world_frac      # il_exp.py:346
         loss.backward()                                    # il_exp.py:373
         flat = torch.cat((theta.grad, q.grad, p.grad, loss.detach().reshape(1)))
@@ -146,8 +150,21 @@ class ImitationStep:
     # -- host inputs (end to end) -------------------------------------------
     def run_host(self, x0_h, uexp_h, q_h, p_h, theta_h):
         dev = self.device
+        main = torch.cuda.current_stream(dev)
         x0 = x0_h.to(dev, non_blocking=True)
-        uexp = uexp_h.to(dev, non_blocking=True)
+        # the expert controls (the bulk of the inputs: T*B*nc scalars) are first needed by the
+        # loss, after the solve: their copy runs on a side stream next to the solve instead of
+        # in front of it.  The side stream starts behind everything already queued on the
+        # caller's stream, so the copy stays inside the step.
+        if self._h2d is None:
+            self._h2d = torch.cuda.Stream(dev)
+        self._h2d.wait_stream(main)
+        with torch.cuda.stream(self._h2d):
+            uexp = uexp_h.to(dev, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self._h2d)
+        uexp.record_stream(main)
+        self._uexp_ready = ready
         q = q_h.to(dev, non_blocking=True).requires_grad_()
         p = p_h.to(dev, non_blocking=True).requires_grad_()
         theta = theta_h.to(dev, non_blocking=True).requires_grad_()
@@ -168,6 +185,7 @@ class ImitationStep:
             return flat, d
 
         self._checked(run)
+        self._uexp_ready = None
         torch.cuda.current_stream().synchronize()
         out = self._out_host.clone()
         self.d2h_bytes = out.numel() * out.element_size()
