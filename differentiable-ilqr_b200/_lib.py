@@ -133,6 +133,7 @@ SYMBOLS = {
                                            C.c_int] + [C.c_void_p] * 8),
     "dilqr_sens_theta_adjoint": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int,
                                            C.c_int] + [C.c_void_p] * 9),
+    "dilqr_last_iterate_launches": (C.c_int, []),
     "dilqr_adjoint_dtau_offset": (C.c_size_t, [C.POINTER(DilqrAdjoint)]),
     "dilqr_kkt_grads": (C.c_int, [C.POINTER(DilqrKkt), C.c_void_p]),
     "dilqr_linearize": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int,
@@ -231,5 +232,10 @@ def call(name, *args, allow=()):
     if rc in allow:
         return rc
     check(rc, name)
-    launch_count += KERNELS_PER_CALL.get(name, 0)
+    launch_count += (fn_iter_launches() if name == "dilqr_mpc_iterate"
+                     else KERNELS_PER_CALL.get(name, 0))
     return rc
+
+
+def fn_iter_launches():
+    return int(lib().dilqr_last_iterate_launches())

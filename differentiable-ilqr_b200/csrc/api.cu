@@ -89,6 +89,11 @@ constexpr bool staged_v() {
   return per * kStages <= kStageBudget;
 }
 
+}  // namespace dilqr
+extern "C" int g_dilqr_iterate_launches;   // dispatch.cu: kernels of the last dilqr_mpc_iterate
+namespace dilqr {
+#define g_iterate_launches g_dilqr_iterate_launches
+
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
@@ -411,6 +416,30 @@ static int launch_iterate(const DilqrSolve* s, cudaStream_t st) {
   }
   if (s->lockstep && NC == 1 && p.bounds_kind && !p.solo) return DILQR_ELOCKSTEP;
   p.lockstep = 0;
+  g_iterate_launches = 1;
+  // Split iteration, an experiment kept behind DILQR_SPLIT=1 (measured): the
+  // sweep needs ~240 registers in FP64 (8 warps/SM, two rounds of resident warps at B = 65536),
+  // the line-search rollout only 128 -- as its own launch (one thread per problem, operands
+  // straight from the blocked workspace through L2 prefetches, 16 warps/SM) the whole batch is
+  // one wave.  It is SLOWER (0.51 vs 0.45 ms per iteration in FP64, 0.32 vs 0.28 in FP32): with
+  // every warp in the rollout at once that launch is HBM-bound (1.2 GB, >= 0.19 ms), while the
+  // fused kernel hides the rollout's traffic behind the sweeps of the other warps.
+  if constexpr (G::STAGED && DYN != DYN_LINDX && DYN != DYN_NN && NS + NC <= 6) {
+    static const int knob = getenv("DILQR_SPLIT") ? atoi(getenv("DILQR_SPLIT")) : -1;
+    const bool split = knob > 0;
+    if (split) {
+      auto sweep = ilqr_iter_kernel<S, NS, NC, DYN, G::STAGED, false, 1>;
+      if (smem > 48 * 1024)
+        cudaFuncSetAttribute(sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      sweep<<<blocks, wpb * kWarp, smem, st>>>(p);
+      if (!p.gains_only) {
+        auto roll = ilqr_iter_kernel<S, NS, NC, DYN, false, false, 2>;
+        roll<<<(warps + 3) / 4, 4 * kWarp, 0, st>>>(p);
+        g_iterate_launches = 2;
+      }
+      return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
+    }
+  }
   auto kern = ilqr_iter_kernel<S, NS, NC, DYN, G::STAGED, false>;
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -49,6 +49,10 @@ DECL_0(f32_g0) DECL_0(f64_g0)
 #undef DECL_0
 }  // namespace dilqr
 
+extern "C" int g_dilqr_iterate_launches;
+int g_dilqr_iterate_launches = 1;
+int dilqr_last_iterate_launches(void) { return g_dilqr_iterate_launches; }
+
 #define ROUTE(dtype, call32, call64)                   \
   ((dtype) == DILQR_F32 ? (call32) : ((dtype) == DILQR_F64 ? (call64) : DILQR_EINVAL))
 

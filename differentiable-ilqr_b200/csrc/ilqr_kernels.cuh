@@ -417,6 +417,32 @@ struct IterKernel {
     return STAGED && p.cpk_state && !p.C_bcast && *reinterpret_cast<const volatile uint32_t*>(p.cpk_state) == 1u;
   }
 
+  // Same question for the kernels that read their operands straight from global memory.
+  DILQR_DEVICE static bool use_packed_direct(const IterParams<S>& p) {
+    return !p.C_bcast && p.cpk_state &&
+           *reinterpret_cast<const volatile uint32_t*>(p.cpk_state) == 1u;
+  }
+
+  // Non-staged rollout: ask L2 for the operands of timestep t (this warp's chunks / slabs)
+  // one timestep before they are loaded -- the loads then cost an L2 hit, not a DRAM round trip.
+  DILQR_DEVICE static void prefetch_span_l2(const void* base, size_t bytes, int lane) {
+    const char* pc = static_cast<const char*>(base);
+    for (size_t o = (size_t)lane * 128; o < bytes; o += 32 * 128)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + o));
+  }
+  DILQR_DEVICE static void prefetch_step_l2(const IterParams<S>& p, const WarpStager<S>& st, int t,
+                                            int b0, int lane) {
+    const int nvalid = min(kWarp, p.B - b0);
+    if ((st.seg_full >> 0) & 1u)
+      prefetch_span_l2(p.Cpk + bidx(t, 0, NP, b0, p.nW), (size_t)NP * kWarp * sizeof(S), lane);
+    else if (!p.C_bcast)
+      prefetch_span_l2(cost_src<S>(p.C, 0, t, p.B, b0, N * N), (size_t)nvalid * N * N * sizeof(S), lane);
+    if (!p.c_bcast)
+      prefetch_span_l2(cost_src<S>(p.c, 0, t, p.B, b0, N), (size_t)nvalid * N * sizeof(S), lane);
+    prefetch_span_l2(p.traj_cur + bidx(t, 0, N, b0, p.nW), (size_t)N * kWarp * sizeof(S), lane);
+    prefetch_span_l2(p.Kk + bidx(t, 0, NK, b0, p.nW), (size_t)NK * kWarp * sizeof(S), lane);
+  }
+
   // sol: the sweep runs at a given solution handed over in the API layout (x_out[T,B,ns],
   // u_out[T,B,nc]): segments 2 / 3 carry those slabs, the workspace chunks are not staged
   static __host__ __device__ void seg_elems(uint32_t* e, bool sol = false) {
@@ -471,8 +497,7 @@ struct IterKernel {
     } else {
       // shapes too large to stage: the packed, lane-interleaved copy of C (written by begin)
       // turns the per-thread reads of a 2 KB row-major block into coalesced ones
-      k.packed = !p.C_bcast && p.cpk_state &&
-                 *reinterpret_cast<const volatile uint32_t*>(p.cpk_state) == 1u;
+      k.packed = (st.seg_full >> 0) & 1u;   // set once per kernel (use_packed_direct)
       k.C = k.packed ? p.Cpk + bidx(t, 0, NP, bw, p.nW)
                      : cost_src<S>(p.C, p.C_bcast, t, p.B, b, N * N);
       k.c = cost_src<S>(p.c, p.c_bcast, t, p.B, b, N);
@@ -910,6 +935,7 @@ struct IterKernel {
       for (int t = 0; t < T; ++t) {
         const int sg = t & 1;
         if (STAGED) st.wait(sg);
+        if (!STAGED && kEnv && t + 1 < T) prefetch_step_l2(p, st, t + 1, b0, lane);
         const Blk blk = blocks(p, st, sg, t, b, bw, lane);
         S tau[N];   // nominal (x_t, u_t)
 #pragma unroll
@@ -983,13 +1009,16 @@ struct IterKernel {
 // one SM: a 65536-problem batch (2048 warps, 13.8 per SM) then runs as ONE wave instead of
 // two, which saves a whole per-warp latency (cartpole: 0.445 -> 0.30 ms per launch).  The
 // FP64 build needs 252 registers and 27.6 KB of stage per warp and stays at 8 warps/SM.
-template <class S, int NS, int NC, int DYN, bool STAGED>
+template <class S, int NS, int NC, int DYN, bool STAGED, int PHASE = 0>
 constexpr int iter_min_blocks() {
+  // the stand-alone rollout of the small env models (split iteration, api.cu): its state is
+  // small, 128 registers give 16 warps/SM and the whole 65536-problem batch is one wave
+  if (PHASE == 2 && !STAGED && DYN != DYN_LINDX && NS + NC <= 6) return 4;
   return (sizeof(S) == 4 && STAGED && DYN != DYN_LINDX && NS + NC <= 6) ? 4 : 1;
 }
 
 template <class S, int NS, int NC, int DYN, bool STAGED, bool LOCKSTEP = false, int PHASE = 0>
-__global__ void __launch_bounds__(128, iter_min_blocks<S, NS, NC, DYN, STAGED>())
+__global__ void __launch_bounds__(128, iter_min_blocks<S, NS, NC, DYN, STAGED, PHASE>())
 ilqr_iter_kernel(const __grid_constant__ IterParams<S> p) {
   using IK = IterKernel<S, NS, NC, DYN, STAGED, LOCKSTEP>;
   extern __shared__ __align__(128) char smem[];
@@ -1015,6 +1044,8 @@ ilqr_iter_kernel(const __grid_constant__ IterParams<S> p) {
     st.init(wbase + kStages * sizeof(uint64_t), bars, lane, nvalid, IK::kNSeg, e,
             IK::kFullMask | (packed ? 1u : 0u), (p.C_bcast ? 1u : 0u) | (p.c_bcast ? 2u : 0u));
     IK::bind_sources(st, p, b0);
+  } else {
+    st.seg_full = IK::use_packed_direct(p) ? 1u : 0u;   // blocks(): packed copy of C or the API tensor
   }
   // padded lanes (tail warp) read the API tensors of the warp's first problem
   const int bsafe = active ? b : b0;

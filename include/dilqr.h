@@ -397,6 +397,10 @@ int dilqr_sens_theta_adjoint(int dtype, int dynamics, const double* dyn_params, 
                              const void* dtau_blk, const void* df_blk, const void* Lam_packed,
                              void* dtheta, void* stream);
 
+/* Kernels the most recent dilqr_mpc_iterate enqueued (1: fused sweep + rollout, 2: split) --
+ * launch accounting of the host bindings only. */
+int dilqr_last_iterate_launches(void);
+
 /* The cost plumbing either side of the solve in the imitation-learning loop.
  * dilqr_tile_cost: C[T,B,n,n] = diag(q), c[T,B,n] = p for every (t, b) -- what
  * il_env.py:159-162 builds with .repeat (C or c may be NULL to skip one).
