@@ -203,7 +203,7 @@ def check(code, what):
 # kernels enqueued per C-ABI call (memsets not counted)
 KERNELS_PER_CALL = {
     "dilqr_mpc_begin": 1, "dilqr_mpc_iterate": 1, "dilqr_mpc_commit": 1,
-    "dilqr_mpc_finish": 1, "dilqr_mpc_gains": 2, "dilqr_lam_tables": 1,
+    "dilqr_mpc_finish": 1, "dilqr_mpc_gains": 3, "dilqr_lam_tables": 1,
     "dilqr_sens_theta_blocked": 1, "dilqr_sens_theta_adjoint": 1, "dilqr_kkt_grads": 1, "dilqr_linearize": 1, "dilqr_rollout": 1,
     "dilqr_costate_tables": 1, "dilqr_richardson_update": 1, "dilqr_sens_theta": 1,
     "dilqr_adjoint_factor": 1, "dilqr_adjoint_pass": 1, "dilqr_adjoint_final": 1,

@@ -94,6 +94,13 @@ extern "C" int g_dilqr_iterate_launches;   // dispatch.cu: kernels of the last d
 namespace dilqr {
 #define g_iterate_launches g_dilqr_iterate_launches
 
+// shapes whose sweeps exist in a symmetric-Riccati form next to the general one
+template <class S, int NS, int NC, int DYN>
+constexpr bool sym_pair_v() {
+  return kSymRiccatiOn && kChainFmaOn && staged_v<S, NS, NC, DYN>() &&
+         (DYN == DYN_PENDULUM || DYN == DYN_CARTPOLE);
+}
+
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
@@ -299,6 +306,8 @@ static int launch_begin(const DilqrSolve* s, cudaStream_t st) {
     const bool pack = !p.C_bcast && !(p.gains_only && p.x_cur) && !off;
     cudaMemsetAsync(p.cpk_state, 0, sizeof(uint32_t), st);
     if (pack) cudaMemsetAsync(p.cpk_state, 1, 1, st);   // little-endian: word value 1
+    // 3: broadcast C, symmetry of the shared block(s) to be verified by begin
+    if (p.C_bcast && !(p.gains_only && p.x_cur) && !off) cudaMemsetAsync(p.cpk_state, 3, 1, st);
     // ticket counter of the one-launch commit (returns to zero after every commit)
     cudaMemsetAsync(static_cast<char*>(s->workspace) + w.commit_ticket, 0, sizeof(uint32_t), st);
   }
@@ -443,6 +452,16 @@ static int launch_iterate(const DilqrSolve* s, cudaStream_t st) {
   auto kern = ilqr_iter_kernel<S, NS, NC, DYN, G::STAGED, false>;
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if constexpr (sym_pair_v<S, NS, NC, DYN>()) {
+    // symmetric Riccati update when the packed copy of C is valid (ilqr_kernels.cuh, kSym): the
+    // flag is on the device, so both kernels of the pair are enqueued and one exits at once
+    auto ksym = ilqr_iter_kernel<S, NS, NC, DYN, G::STAGED, false, 0, true>;
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(ksym, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    p.sym_pair = 1;
+    ksym<<<blocks, wpb * kWarp, smem, st>>>(p);
+    g_iterate_launches = 2;
+  }
   kern<<<blocks, wpb * kWarp, smem, st>>>(p);
   return cudaGetLastError() == cudaSuccess ? DILQR_OK : DILQR_ECUDA;
 }
@@ -482,6 +501,13 @@ static int launch_gains(const DilqrSolve* s, void* lam_blk, cudaStream_t st) {
     }
     if (p.bounds_kind && !p.solo)
       cudaMemsetAsync(p.votes, 0, (size_t)p.T * kPnqpMaxIter * sizeof(uint32_t), st);
+    if constexpr (sym_pair_v<S, NS, NC, DYN>()) {
+      auto ksym = ilqr_gains_kernel<S, NS, NC, DYN, G::STAGED, true>;
+      if (smem > 48 * 1024)
+        cudaFuncSetAttribute(ksym, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      p.sym_pair = 1;
+      ksym<<<blocks, wpb * kWarp, smem, st>>>(p);
+    }
     kern<<<blocks, wpb * kWarp, smem, st>>>(p);
     trace_verify_kernel<<<1, 256, 0, st>>>(p.guess, p.votes, p.T, p.bounds_kind != 0, p.solo,
                                            s->status, 0, nullptr);
