@@ -149,20 +149,24 @@ def live_traffic(args):
         cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control",
                "none", "--print-units", "base", "--kernel-name", "regex:ilqr_iter_kernel",
                "--launch-skip",
-               str(NCU_CHILD_SKIP), "--launch-count", "1", "--csv", sys.executable,
+               str(NCU_CHILD_SKIP), "--launch-count", "2", "--csv", sys.executable,
                os.path.abspath(__file__), "--ncu-child", "--dtype", args.dtype, "--batch",
                str(args.batch)]
         out = subprocess.run(cmd, capture_output=True, text=True, timeout=240).stdout
-        tot, unit_scale = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        n = 0
+        # an iteration enqueues the (symmetric, general) kernel pair and one of the two exits at
+        # once (csrc/ilqr_kernels.cuh, kSym): capture two consecutive launches, keep the working one
+        unit_scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        per_launch, n = {}, 0
         for line in out.splitlines():
             if "dram__bytes_" in line:
                 f = [c.strip('"') for c in line.split('","')]
-                tot += float(f[-1].replace(",", "")) * unit_scale.get(f[-2], 1.0)
+                per_launch[f[0]] = per_launch.get(f[0], 0.0) + \
+                    float(f[-1].replace(",", "")) * unit_scale.get(f[-2], 1.0)
                 n += 1
-        if n != 2:
+        if n != 4 or len(per_launch) != 2:
             raise RuntimeError("ncu output not understood")
-        return tot, "ncu, this run (1 launch, after %d warm launches)" % NCU_CHILD_SKIP
+        return max(per_launch.values()), \
+            "ncu, this run (the working launch of one iteration, after %d warm launches)" % NCU_CHILD_SKIP
     except Exception as e:   # noqa: BLE001
         if args.dtype == "f64" and os.path.isfile(fallback):
             with open(fallback) as f:

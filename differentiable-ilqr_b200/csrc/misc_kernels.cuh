@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(128) commit_kernel(const __grid_constant__ Ite
     // Armijo bits voted under a wrong "moving" guess are void.  Processing order of the sweep
     // is t = T-1 .. 0, it = 0 .. 19.
     int first = n;
+#pragma unroll 4
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
       const int t = p.T - 1 - i / kPnqpMaxIter, it = i % kPnqpMaxIter;
       const int slot = t * kPnqpMaxIter + it;
@@ -178,7 +179,15 @@ __global__ void __launch_bounds__(128) commit_kernel(const __grid_constant__ Ite
       const int row = p.T * NCc;
       const S* src = p.dusq + (size_t)b * row;
       S acc = S(0);
-      for (int k = 0; k < row; ++k) acc = acc + src[k];
+      int k = 0;
+      for (; k + 8 <= row; k += 8) {   // eight loads in flight, summed in the same order
+        S v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = src[k + j];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc = acc + v[j];
+      }
+      for (; k < row; ++k) acc = acc + src[k];
       p.du_new[b] = sqrtS<S>(acc);
     }
     const S cn = p.cost_new[b];
@@ -257,6 +266,7 @@ __global__ void __launch_bounds__(128) commit_kernel(const __grid_constant__ Ite
   }
   du = 0.0; al = 0.0; bc = 0.0;
   unsigned fl = 0, na = 0;
+#pragma unroll 4
   for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
     const CommitPart* r = &aux.part[i];   // written by other blocks: read through L2
     du = fmax(du, __ldcg(&r->du));

@@ -123,9 +123,17 @@ class ImitationStep:
         x, u, _ = self.mpc(x0, QuadCost(C, c), dx)
         if self._uexp_ready is not None:   # run_host: uexp was copied on a side stream
             torch.cuda.current_stream().wait_event(self._uexp_ready)
-        loss = (u - uexp).pow(2).mean() * world_frac      # il_exp.py:346
-        loss.backward()                                    # il_exp.py:373
-        flat = torch.cat((theta.grad, q.grad, p.grad, loss.detach().reshape(1)))
+        # loss = mean((u - u_expert)^2) (il_exp.py:346) and loss.backward() (il_exp.py:373) with
+        # the gradient of the loss written out by hand: d loss / du = 2 (u - u_expert) / numel.
+        # Three small kernels instead of the dozen of the pow / mean / mul autograd chain -- at
+        # this point of the step the device is waiting for the host.
+        with torch.no_grad():
+            d = u - uexp
+            scale = world_frac / d.numel()
+            loss = torch.dot(d.reshape(-1), d.reshape(-1)) * scale
+            gu = d * (2.0 * scale)
+        torch.autograd.backward([u], [gu])
+        flat = torch.cat((theta.grad, q.grad, p.grad, loss.reshape(1)))
         return parallel.allreduce_sum_(flat, self.group), self.mpc.deferred
 
     def _checked(self, run):
