@@ -366,9 +366,19 @@ struct Dyn<S, DYN_CARTPOLE> {
     uc = uc > S(100.0) ? S(100.0) : uc;
     const S c = x[2], s = x[3], w = x[4];
     const S th = atan2S<S>(s, c);
+#if DILQR_RCP_PARAMS
+    // 1/M is a property of theta (loop invariant): the three divisions by M -- two of them on
+    // the dependent chain cart_in -> th_acc -> xacc, 124 cycles each -- become multiplications
+    // (<= 1 ulp each, the order of the libdevice / glibc trig differences already in the rollout)
+    const S iM = S(1.0) / M;
+    const S cart_in = (uc + pml * (w * w) * s) * iM;
+    const S th_acc = (g * s - c * cart_in) / (l * (S(4.0 / 3.0) - mp * (c * c) * iM));
+    const S xacc = cart_in - pml * th_acc * c * iM;
+#else
     const S cart_in = (uc + pml * (w * w) * s) / M;
     const S th_acc = (g * s - c * cart_in) / (l * (S(4.0 / 3.0) - mp * (c * c) / M));
     const S xacc = cart_in - pml * th_acc * c / M;
+#endif
     xn[0] = x[0] + dt * x[1];
     xn[1] = x[1] + dt * xacc;
     const S nth = th + dt * w;
